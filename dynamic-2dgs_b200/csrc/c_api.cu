@@ -1,0 +1,366 @@
+// C-ABI entry points of libd2gs.so (see include/d2gs.h).  Host-side orchestration only: workspace carving,
+// stage sequencing on the caller's stream, CUB scan / radix sort for the binning stage.
+#include <cub/cub.cuh>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/d2gs.h"
+#include "raster_common.cuh"
+#include "deform.cuh"
+
+namespace d2gs {
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define D2GS_CUDA_OK(expr)                                                                       \
+  do {                                                                                           \
+    cudaError_t e__ = (expr);                                                                    \
+    if (e__ != cudaSuccess)                                                                      \
+      return fail(D2GS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));           \
+  } while (0)
+
+// after a stage: launch errors always, execution errors too when debug is on (reference: auxiliary.h:271-278)
+#define D2GS_STAGE(name, debug, stream)                                                          \
+  do {                                                                                           \
+    cudaError_t e__ = cudaGetLastError();                                                        \
+    if (e__ == cudaSuccess && (debug)) e__ = cudaStreamSynchronize(stream);                      \
+    if (e__ != cudaSuccess)                                                                      \
+      return fail(D2GS_ERR_CUDA, std::string("stage ") + name + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+GeomLayout geom_layout(int P) {
+  GeomLayout L{};
+  size_t o = 0;
+  L.rec = o; o = align_up(o + sizeof(SurfelRec) * (size_t)P);
+  L.clamped = o; o = align_up(o + (size_t)P);
+  L.tiles_touched = o; o = align_up(o + 4 * (size_t)P);
+  L.point_offsets = o; o = align_up(o + 4 * (size_t)P);
+  size_t tmp = 0;
+  cub::DeviceScan::InclusiveSum(nullptr, tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, P > 0 ? P : 1);
+  L.scan_temp_bytes = tmp;
+  L.scan_temp = o; o = align_up(o + tmp);
+  L.total = o + 256;
+  return L;
+}
+
+ImgLayout img_layout(int W, int H) {
+  ImgLayout L{};
+  const size_t HW = (size_t)W * H;
+  const size_t tiles = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
+  size_t o = 0;
+  L.ranges = o; o = align_up(o + 8 * tiles);
+  L.final_T = o; o = align_up(o + 4 * 3 * HW);
+  L.n_contrib = o; o = align_up(o + 4 * 2 * HW);
+  L.total = o + 256;
+  return L;
+}
+
+BinLayout bin_layout(int64_t R) {
+  BinLayout L{};
+  const size_t n = R > 0 ? (size_t)R : 1;
+  size_t o = 0;
+  L.keys_unsorted = o; o = align_up(o + 8 * n);
+  L.keys_sorted = o; o = align_up(o + 8 * n);
+  L.vals_unsorted = o; o = align_up(o + 4 * n);
+  L.point_list = o; o = align_up(o + 4 * n);
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, (int)n);
+  L.sort_temp_bytes = tmp;
+  L.sort_temp = o; o = align_up(o + tmp);
+  L.total = o + 256;
+  return L;
+}
+
+static char* aligned_base(const void* p) {
+  return reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + 255) & ~(uintptr_t)255);
+}
+
+// number of key bits above the 32 depth bits (reference: rasterizer_impl.cu:35-50)
+static uint32_t higher_msb(uint32_t n) {
+  uint32_t msb = 16, step = 16;
+  while (step > 1) {
+    step /= 2;
+    if (n >> msb) msb += step; else msb -= step;
+  }
+  if (n >> msb) msb++;
+  return msb;
+}
+
+}  // namespace d2gs
+
+using namespace d2gs;
+
+extern "C" {
+
+const char* d2gs_last_error(void) { return g_last_error.c_str(); }
+const char* d2gs_version(void) { return "d2gs-b200 0.1 (sm_100a)"; }
+
+int d2gs_get_config(D2gsConfig* c) {
+  if (!c) return fail(D2GS_ERR_INVALID_ARG, "null config");
+  c->num_channels = NUM_CH; c->block_x = TILE_X; c->block_y = TILE_Y;
+  c->tight_bbox = 0; c->render_auxiliary = 1; c->backface_cull = 1; c->dual_visible = 1; c->detach_weight = 0;
+  c->near_plane = D2GS_NEAR_PLANE; c->far_plane = D2GS_FAR_PLANE; c->filter_size = D2GS_FILTER_SIZE;
+  c->sm_arch = 100;
+  return D2GS_OK;
+}
+
+int d2gs_raster_workspace(int P, int width, int height, int64_t num_rendered, size_t* geom_bytes, size_t* img_bytes,
+                          size_t* binning_bytes) {
+  if (P < 0 || width <= 0 || height <= 0 || num_rendered < 0) return fail(D2GS_ERR_INVALID_ARG, "negative size");
+  if (geom_bytes) *geom_bytes = geom_layout(P).total;
+  if (img_bytes) *img_bytes = img_layout(width, height).total;
+  if (binning_bytes) *binning_bytes = bin_layout(num_rendered).total;
+  return D2GS_OK;
+}
+
+int d2gs_raster_forward(const D2gsRasterFwdArgs* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!a) return fail(D2GS_ERR_INVALID_ARG, "null args");
+  if (a->P < 0 || a->width <= 0 || a->height <= 0) return fail(D2GS_ERR_INVALID_ARG, "bad sizes");
+  if (!a->out_color || !a->out_others || !a->num_rendered) return fail(D2GS_ERR_INVALID_ARG, "missing outputs");
+  const int P = a->P, W = a->width, H = a->height;
+  const size_t HW = (size_t)W * H;
+  if (P == 0) {   // reference returns zero images for an empty scene (rasterize_points.cu:92-94,106)
+    D2GS_CUDA_OK(cudaMemsetAsync(a->out_color, 0, 4 * 3 * HW, stream));
+    D2GS_CUDA_OK(cudaMemsetAsync(a->out_others, 0, 4 * 8 * HW, stream));
+    *a->num_rendered = 0;
+    return D2GS_OK;
+  }
+  if (!a->means3D || !a->opacities || !a->viewmatrix || !a->projmatrix || !a->campos || !a->background || !a->radii)
+    return fail(D2GS_ERR_INVALID_ARG, "missing inputs");
+  if ((a->shs == nullptr) == (a->colors_precomp == nullptr))
+    return fail(D2GS_ERR_INVALID_ARG, "provide exactly one of SHs or precomputed colours");
+  if (((a->scales == nullptr) || (a->rotations == nullptr)) == (a->transMat_precomp == nullptr))
+    return fail(D2GS_ERR_INVALID_ARG, "provide exactly one of scale/rotation pair or precomputed transMat");
+  if (a->shs && (a->M < 1 || a->M > 16 || a->D < 0 || a->D > 3 || (a->D + 1) * (a->D + 1) > a->M))
+    return fail(D2GS_ERR_INVALID_ARG, "SH degree / coefficient count out of range (deg<=3, M<=16)");
+
+  const GeomLayout GL = geom_layout(P);
+  const ImgLayout IL = img_layout(W, H);
+  if (a->geom_bytes < GL.total || !a->geom_buffer) return fail(D2GS_ERR_WORKSPACE, "geometry workspace too small");
+  if (a->img_bytes < IL.total || !a->img_buffer) return fail(D2GS_ERR_WORKSPACE, "image workspace too small");
+  char* gb = aligned_base(a->geom_buffer);
+  char* ib = aligned_base(a->img_buffer);
+  SurfelRec* rec = (SurfelRec*)(gb + GL.rec);
+  uint8_t* clamped = (uint8_t*)(gb + GL.clamped);
+  uint32_t* tiles_touched = (uint32_t*)(gb + GL.tiles_touched);
+  uint32_t* point_offsets = (uint32_t*)(gb + GL.point_offsets);
+  uint2* ranges = (uint2*)(ib + IL.ranges);
+  float* final_T = (float*)(ib + IL.final_T);
+  uint32_t* n_contrib = (uint32_t*)(ib + IL.n_contrib);
+
+  FwdParams p{};
+  p.P = P; p.D = a->D; p.M = a->M; p.W = W; p.H = H;
+  p.bg = a->background; p.means3D = a->means3D; p.shs = a->shs; p.sh_rest = a->sh_rest;
+  p.colors_precomp = a->colors_precomp; p.opacities = a->opacities; p.scales = a->scales; p.rotations = a->rotations;
+  p.transMat_precomp = a->transMat_precomp; p.view = a->viewmatrix; p.proj = a->projmatrix; p.campos = a->campos;
+  p.tan_fovx = a->tan_fovx; p.tan_fovy = a->tan_fovy;
+  p.focal_y = H / (2.0f * a->tan_fovy);
+  p.focal_x = W / (2.0f * a->tan_fovx);
+  p.prefiltered = a->prefiltered;
+  p.gx = (W + TILE_X - 1) / TILE_X; p.gy = (H + TILE_Y - 1) / TILE_Y;
+
+  if (!a->resume) {
+    launch_preprocess_fwd(p, rec, clamped, a->radii, tiles_touched, stream);
+    D2GS_STAGE("preprocess", a->debug, stream);
+    size_t tmp = GL.scan_temp_bytes;
+    D2GS_CUDA_OK(cub::DeviceScan::InclusiveSum(gb + GL.scan_temp, tmp, tiles_touched, point_offsets, P, stream));
+    D2GS_STAGE("scan", a->debug, stream);
+  }
+  uint32_t R32 = 0;
+  D2GS_CUDA_OK(cudaMemcpyAsync(&R32, point_offsets + P - 1, 4, cudaMemcpyDeviceToHost, stream));
+  D2GS_CUDA_OK(cudaStreamSynchronize(stream));
+  const int64_t R = R32;
+  *a->num_rendered = R;
+  const BinLayout BL = bin_layout(R);
+  if (a->binning_required) *a->binning_required = BL.total;
+  if (a->binning_bytes < BL.total || !a->binning_buffer) return D2GS_NEED_BINNING;
+
+  char* bb = aligned_base(a->binning_buffer);
+  uint64_t* keys_unsorted = (uint64_t*)(bb + BL.keys_unsorted);
+  uint64_t* keys_sorted = (uint64_t*)(bb + BL.keys_sorted);
+  uint32_t* vals_unsorted = (uint32_t*)(bb + BL.vals_unsorted);
+  uint32_t* point_list = (uint32_t*)(bb + BL.point_list);
+
+  launch_duplicate(P, rec, a->radii, point_offsets, keys_unsorted, vals_unsorted, p.gx, p.gy, stream);
+  D2GS_STAGE("duplicate", a->debug, stream);
+  if (R > 0) {
+    const int bit = (int)higher_msb(p.gx * p.gy);
+    size_t tmp = BL.sort_temp_bytes;
+    D2GS_CUDA_OK(cub::DeviceRadixSort::SortPairs(bb + BL.sort_temp, tmp, keys_unsorted, keys_sorted, vals_unsorted,
+                                                 point_list, (int)R, 0, 32 + bit, stream));
+    D2GS_STAGE("sort", a->debug, stream);
+  }
+  D2GS_CUDA_OK(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)p.gx * p.gy, stream));
+  launch_ranges(R, keys_sorted, ranges, stream);
+  D2GS_STAGE("ranges", a->debug, stream);
+  launch_blend_fwd(p, ranges, point_list, rec, final_T, n_contrib, a->out_color, a->out_others, stream);
+  D2GS_STAGE("blend", a->debug, stream);
+  return D2GS_OK;
+}
+
+int d2gs_raster_backward(const D2gsRasterBwdArgs* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!a) return fail(D2GS_ERR_INVALID_ARG, "null args");
+  const int P = a->P, W = a->width, H = a->height;
+  if (P == 0) return D2GS_OK;
+  if (P < 0 || W <= 0 || H <= 0) return fail(D2GS_ERR_INVALID_ARG, "bad sizes");
+  if (!a->geom_buffer || !a->img_buffer || !a->binning_buffer || !a->grad_scratch || !a->radii ||
+      !a->dL_dout_color || !a->dL_dout_others)
+    return fail(D2GS_ERR_INVALID_ARG, "missing buffers");
+  const GeomLayout GL = geom_layout(P);
+  const ImgLayout IL = img_layout(W, H);
+  const BinLayout BL = bin_layout(a->num_rendered);
+  char* gb = aligned_base(a->geom_buffer);
+  char* ib = aligned_base(a->img_buffer);
+  char* bb = aligned_base(a->binning_buffer);
+  const SurfelRec* rec = (const SurfelRec*)(gb + GL.rec);
+  const uint8_t* clamped = (const uint8_t*)(gb + GL.clamped);
+  const uint2* ranges = (const uint2*)(ib + IL.ranges);
+  const float* final_T = (const float*)(ib + IL.final_T);
+  const uint32_t* n_contrib = (const uint32_t*)(ib + IL.n_contrib);
+  const uint32_t* point_list = (const uint32_t*)(bb + BL.point_list);
+
+  BwdParams p{};
+  p.P = P; p.D = a->D; p.M = a->M; p.W = W; p.H = H;
+  p.bg = a->background; p.means3D = a->means3D; p.shs = a->shs; p.sh_rest = a->sh_rest;
+  p.colors_precomp = a->colors_precomp; p.scales = a->scales; p.rotations = a->rotations;
+  p.transMat_precomp = a->transMat_precomp; p.view = a->viewmatrix; p.proj = a->projmatrix; p.campos = a->campos;
+  p.tan_fovx = a->tan_fovx; p.tan_fovy = a->tan_fovy;
+  p.focal_y = H / (2.0f * a->tan_fovy);
+  p.focal_x = W / (2.0f * a->tan_fovx);
+  p.gx = (W + TILE_X - 1) / TILE_X; p.gy = (H + TILE_Y - 1) / TILE_Y;
+
+  if (a->num_rendered > 0) {
+    launch_blend_bwd(p, ranges, point_list, rec, final_T, n_contrib, a->dL_dout_color, a->dL_dout_others,
+                     a->grad_scratch, stream);
+    D2GS_STAGE("blend_bwd", a->debug, stream);
+  }
+  launch_preprocess_bwd(p, rec, clamped, a->radii, a->grad_scratch, a->dL_dmeans2D, a->dL_dcolors, a->dL_dopacity,
+                        a->dL_dmeans3D, a->dL_dtransMat, a->dL_dsh, a->dL_dsh_rest, a->dL_dscales, a->dL_drotations,
+                        stream);
+  D2GS_STAGE("preprocess_bwd", a->debug, stream);
+  return D2GS_OK;
+}
+
+int d2gs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,
+                      void* stream) {
+  (void)projmatrix;
+  if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return fail(D2GS_ERR_INVALID_ARG, "bad args");
+  launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(D2GS_ERR_CUDA, cudaGetErrorString(e));
+  return D2GS_OK;
+}
+
+__global__ void export_geom_kernel(int P, const SurfelRec* rec, const uint8_t* clamped, D2gsRasterState o) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const SurfelRec r = rec[i];
+  if (o.means2D) { o.means2D[2 * i] = r.q2.y; o.means2D[2 * i + 1] = r.q2.z; }
+  if (o.depths) o.depths[i] = r.q3.w;
+  if (o.transMat) {
+    float* t = o.transMat + 9 * (size_t)i;
+    t[0] = r.q0.x; t[1] = r.q0.y; t[2] = r.q0.z; t[3] = r.q0.w; t[4] = r.q1.x; t[5] = r.q1.y; t[6] = r.q1.z;
+    t[7] = r.q1.w; t[8] = r.q2.x;
+  }
+  if (o.normal_opacity) {
+    float* t = o.normal_opacity + 4 * (size_t)i;
+    t[0] = r.q3.x; t[1] = r.q3.y; t[2] = r.q3.z; t[3] = r.q2.w;
+  }
+  if (o.rgb) { o.rgb[3 * i] = r.q4.x; o.rgb[3 * i + 1] = r.q4.y; o.rgb[3 * i + 2] = r.q4.z; }
+  if (o.clamped) {
+    const uint8_t c = clamped[i];
+    o.clamped[3 * i] = c & 1; o.clamped[3 * i + 1] = (c >> 1) & 1; o.clamped[3 * i + 2] = (c >> 2) & 1;
+  }
+}
+
+int d2gs_raster_export_state(int P, int width, int height, int64_t R, const void* geom_buffer,
+                             const void* binning_buffer, const void* img_buffer, const D2gsRasterState* out,
+                             void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!out || P <= 0) return fail(D2GS_ERR_INVALID_ARG, "bad args");
+  const GeomLayout GL = geom_layout(P);
+  const ImgLayout IL = img_layout(width, height);
+  const BinLayout BL = bin_layout(R);
+  const size_t HW = (size_t)width * height;
+  const size_t tiles = (size_t)((width + TILE_X - 1) / TILE_X) * ((height + TILE_Y - 1) / TILE_Y);
+  if (geom_buffer) {
+    char* gb = aligned_base(geom_buffer);
+    export_geom_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, (const SurfelRec*)(gb + GL.rec),
+                                                           (const uint8_t*)(gb + GL.clamped), *out);
+    if (out->tiles_touched)
+      D2GS_CUDA_OK(cudaMemcpyAsync(out->tiles_touched, gb + GL.tiles_touched, 4 * (size_t)P, cudaMemcpyDeviceToDevice, stream));
+    if (out->point_offsets)
+      D2GS_CUDA_OK(cudaMemcpyAsync(out->point_offsets, gb + GL.point_offsets, 4 * (size_t)P, cudaMemcpyDeviceToDevice, stream));
+  }
+  if (binning_buffer && R > 0) {
+    char* bb = aligned_base(binning_buffer);
+    if (out->keys_unsorted) D2GS_CUDA_OK(cudaMemcpyAsync(out->keys_unsorted, bb + BL.keys_unsorted, 8 * (size_t)R, cudaMemcpyDeviceToDevice, stream));
+    if (out->keys_sorted) D2GS_CUDA_OK(cudaMemcpyAsync(out->keys_sorted, bb + BL.keys_sorted, 8 * (size_t)R, cudaMemcpyDeviceToDevice, stream));
+    if (out->values_unsorted) D2GS_CUDA_OK(cudaMemcpyAsync(out->values_unsorted, bb + BL.vals_unsorted, 4 * (size_t)R, cudaMemcpyDeviceToDevice, stream));
+    if (out->point_list) D2GS_CUDA_OK(cudaMemcpyAsync(out->point_list, bb + BL.point_list, 4 * (size_t)R, cudaMemcpyDeviceToDevice, stream));
+  }
+  if (img_buffer) {
+    char* ib = aligned_base(img_buffer);
+    if (out->ranges) D2GS_CUDA_OK(cudaMemcpyAsync(out->ranges, ib + IL.ranges, 8 * tiles, cudaMemcpyDeviceToDevice, stream));
+    if (out->final_T) D2GS_CUDA_OK(cudaMemcpyAsync(out->final_T, ib + IL.final_T, 4 * 3 * HW, cudaMemcpyDeviceToDevice, stream));
+    if (out->n_contrib) D2GS_CUDA_OK(cudaMemcpyAsync(out->n_contrib, ib + IL.n_contrib, 4 * 2 * HW, cudaMemcpyDeviceToDevice, stream));
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(D2GS_ERR_CUDA, cudaGetErrorString(e));
+  return D2GS_OK;
+}
+
+int d2gs_deform_forward(const D2gsDeformFwdArgs* a, void* stream) {
+  if (!a) return fail(D2GS_ERR_INVALID_ARG, "null args");
+  if (a->P < 0 || a->M <= 0) return fail(D2GS_ERR_INVALID_ARG, "bad sizes");
+  if (a->P > 0 && (!a->xyz || !a->nodes || !a->node_radius_log || !a->node_trans || !a->node_rot || !a->node_scale ||
+                   !a->d_xyz || !a->d_rotation || !a->d_scaling))
+    return fail(D2GS_ERR_INVALID_ARG, "missing buffers");
+  DeformFwdHost h{};
+  h.P = a->P; h.M = a->M; h.K = a->K; h.hyper = a->hyper_dim;
+  h.xyz = a->xyz; h.feature = a->feature; h.fstride = a->feature_stride;
+  h.nodes = a->nodes; h.radius_log = a->node_radius_log; h.weight_logit = a->node_weight_logit;
+  h.trans = a->node_trans; h.rot = a->node_rot; h.scale = a->node_scale; h.local_rot = a->node_local_rot;
+  h.mask = a->motion_mask; h.nn_idx = a->nn_idx; h.nn_dist = a->nn_dist; h.nn_weight = a->nn_weight;
+  h.d_xyz = a->d_xyz; h.d_rot = a->d_rotation; h.d_scale = a->d_scaling;
+  const char* err = nullptr;
+  if (deform_forward_launch(h, (cudaStream_t)stream, &err) != 0) return fail(D2GS_ERR_INVALID_ARG, err);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(D2GS_ERR_CUDA, cudaGetErrorString(e));
+  return D2GS_OK;
+}
+
+int d2gs_deform_backward(const D2gsDeformBwdArgs* a, void* stream) {
+  if (!a) return fail(D2GS_ERR_INVALID_ARG, "null args");
+  if (a->P < 0 || a->M <= 0) return fail(D2GS_ERR_INVALID_ARG, "bad sizes");
+  if (a->P > 0 && (!a->xyz || !a->nodes || !a->nn_idx || !a->nn_dist || !a->nn_weight || !a->dL_d_xyz ||
+                   !a->dL_d_rotation || !a->dL_d_scaling || !a->dL_dnode_trans || !a->dL_dnode_rot ||
+                   !a->dL_dnode_scale || !a->dL_dnodes || !a->dL_dnode_radius_log))
+    return fail(D2GS_ERR_INVALID_ARG, "missing buffers");
+  DeformBwdHost h{};
+  h.P = a->P; h.M = a->M; h.K = a->K; h.hyper = a->hyper_dim;
+  h.xyz = a->xyz; h.feature = a->feature; h.fstride = a->feature_stride;
+  h.nodes = a->nodes; h.radius_log = a->node_radius_log; h.weight_logit = a->node_weight_logit;
+  h.trans = a->node_trans; h.rot = a->node_rot; h.scale = a->node_scale; h.local_rot = a->node_local_rot;
+  h.mask = a->motion_mask; h.nn_idx = a->nn_idx; h.nn_dist = a->nn_dist; h.nn_weight = a->nn_weight;
+  h.g_xyz = a->dL_d_xyz; h.g_rot = a->dL_d_rotation; h.g_scale = a->dL_d_scaling;
+  h.d_trans = a->dL_dnode_trans; h.d_rot = a->dL_dnode_rot; h.d_scale = a->dL_dnode_scale;
+  h.d_local_rot = a->dL_dnode_local_rot; h.d_nodes = a->dL_dnodes; h.d_radius_log = a->dL_dnode_radius_log;
+  h.d_weight_logit = a->dL_dnode_weight_logit; h.d_feature = a->dL_dfeature; h.d_mask = a->dL_dmotion_mask;
+  const char* err = nullptr;
+  if (deform_backward_launch(h, (cudaStream_t)stream, &err) != 0) return fail(D2GS_ERR_INVALID_ARG, err);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(D2GS_ERR_CUDA, cudaGetErrorString(e));
+  return D2GS_OK;
+}
+
+}  // extern "C"

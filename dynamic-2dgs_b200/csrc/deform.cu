@@ -1,0 +1,368 @@
+// Node-controlled deformation on sm_100a: brute-force K-nearest control nodes in the (3+hyper)-D embedding,
+// radial-basis weights, and the blend of per-node MLP outputs onto the surfels — one fused kernel each way.
+// Behavioural contract: utils/time_utils.py:934-967 (cal_nn_weight; knn_points = squared L2, K smallest, ascending),
+// :1145-1157 (local-frame translation), :1190-1193 (rotation / scaling residuals), :115-132 (quaternion_to_matrix with
+// the 2/|q|^2 factor, quaternion NOT normalised).  The reference materialises P*K*{3,4,9} temporaries across ~25
+// eager kernels; here nothing of size P*K*c is written except the (idx, dist, weight) triple the backward needs.
+#include "raster_common.cuh"
+#include "deform.cuh"
+
+namespace d2gs {
+
+constexpr int MAX_K = 8;
+constexpr int MAX_D = 3 + 16;   // 3 spatial + up to 16 hyper coordinates
+
+// rotation matrix rows from an un-normalised quaternion (r,i,j,k)
+__device__ __forceinline__ void quat_to_matrix_raw(const float q[4], float R[9]) {
+  const float r = q[0], i = q[1], j = q[2], k = q[3];
+  const float two_s = 2.0f / (r * r + i * i + j * j + k * k);
+  R[0] = 1 - two_s * (j * j + k * k); R[1] = two_s * (i * j - k * r);     R[2] = two_s * (i * k + j * r);
+  R[3] = two_s * (i * j + k * r);     R[4] = 1 - two_s * (i * i + k * k); R[5] = two_s * (j * k - i * r);
+  R[6] = two_s * (i * k - j * r);     R[7] = two_s * (j * k + i * r);     R[8] = 1 - two_s * (i * i + j * j);
+}
+
+// VJP of quat_to_matrix_raw: given dL/dR (row-major 9) returns dL/dq
+__device__ __forceinline__ void quat_to_matrix_raw_vjp(const float q[4], const float dR[9], float dq[4]) {
+  const float r = q[0], i = q[1], j = q[2], k = q[3];
+  const float n2 = r * r + i * i + j * j + k * k;
+  const float ts = 2.0f / n2;
+  // R = I + ts * A(q), with A the quadratic forms below; dL/dts = <dR, A>, dts/dq = -2*ts/n2 * q
+  const float A[9] = {-(j * j + k * k), i * j - k * r, i * k + j * r,
+                      i * j + k * r, -(i * i + k * k), j * k - i * r,
+                      i * k - j * r, j * k + i * r, -(i * i + j * j)};
+  float dts = 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; t++) dts += dR[t] * A[t];
+  const float c = -ts / n2 * 2.0f * dts;   // multiplies q
+  // ts * dA/dq contracted with dR
+  const float gr = ts * (-k * dR[1] + j * dR[2] + k * dR[3] - i * dR[5] - j * dR[6] + i * dR[7]);
+  const float gi = ts * (j * dR[1] + k * dR[2] + j * dR[3] - 2 * i * dR[4] - r * dR[5] + k * dR[6] + r * dR[7] - 2 * i * dR[8]);
+  const float gj = ts * (-2 * j * dR[0] + i * dR[1] + r * dR[2] + i * dR[3] + k * dR[5] - r * dR[6] + k * dR[7] - 2 * j * dR[8]);
+  const float gk = ts * (-2 * k * dR[0] - r * dR[1] + i * dR[2] + r * dR[3] - 2 * k * dR[4] + j * dR[5] + i * dR[6] + j * dR[7]);
+  dq[0] = gr + c * r; dq[1] = gi + c * i; dq[2] = gj + c * j; dq[3] = gk + c * k;
+}
+
+struct DeformFwdP {
+  int P, M, K, D, hyper;
+  const float* xyz; const float* feature; int fstride;
+  const float* nodes; const float* radius_log; const float* weight_logit;
+  const float* trans; const float* rot; const float* scale; const float* local_rot;
+  const float* mask;
+  int64_t* nn_idx; float* nn_dist; float* nn_weight;
+  float* d_xyz; float* d_rot; float* d_scale;
+};
+
+__global__ void __launch_bounds__(256) deform_fwd_kernel(DeformFwdP a) {
+  extern __shared__ float s_nodes[];   // M * D, node-major
+  const int D = a.D;
+  const int nstride = 3 + a.hyper;
+  for (int t = threadIdx.x; t < a.M * D; t += blockDim.x) {
+    const int m = t / D, d = t - m * D;
+    s_nodes[t] = a.nodes[(size_t)m * nstride + d];
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.P) return;
+
+  float q[MAX_D];
+  q[0] = a.xyz[3 * (size_t)i]; q[1] = a.xyz[3 * (size_t)i + 1]; q[2] = a.xyz[3 * (size_t)i + 2];
+#pragma unroll
+  for (int d = 3; d < MAX_D; d++) q[d] = (d < D) ? a.feature[(size_t)i * a.fstride + (d - 3)] : 0.f;
+
+  // K smallest squared distances, ascending; ties keep the lower node index (strict < while scanning upwards)
+  float bd[MAX_K];
+  int bi[MAX_K];
+#pragma unroll
+  for (int k = 0; k < MAX_K; k++) { bd[k] = INFINITY; bi[k] = -1; }
+  const int K = a.K;
+  for (int m = 0; m < a.M; m++) {
+    const float* n = s_nodes + m * D;
+    float dist = 0.f;
+#pragma unroll
+    for (int d = 0; d < MAX_D; d++) {
+      if (d < D) {
+        const float df = q[d] - n[d];
+        dist = fmaf(df, df, dist);
+      }
+    }
+    if (dist < bd[K - 1] || bi[K - 1] < 0) {
+      float cd = dist; int ci = m;
+#pragma unroll
+      for (int k = 0; k < MAX_K; k++) {
+        if (k < K) {
+          const bool take = (cd < bd[k]) || (bi[k] < 0 && ci >= 0);
+          if (take) {
+            const float td = bd[k]; const int ti = bi[k];
+            bd[k] = cd; bi[k] = ci; cd = td; ci = ti;
+          }
+        }
+      }
+    }
+  }
+
+  // radial-basis weights
+  float w[MAX_K];
+  float wsum = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAX_K; k++) {
+    w[k] = 0.f;
+    if (k < K) {
+      const int m = bi[k];
+      const float r = expf(__ldg(a.radius_log + m));
+      float wk = expf(-bd[k] / (2 * (r * r)));
+      if (a.weight_logit) wk = wk * (1.0f / (1.0f + expf(-__ldg(a.weight_logit + m))));
+      wk = wk + 1e-7f;
+      w[k] = wk;
+      wsum += wk;
+    }
+  }
+  const float x0 = q[0], x1 = q[1], x2 = q[2];
+  float t0 = 0.f, t1 = 0.f, t2 = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAX_K; k++) {
+    if (k < K) {
+      const int m = bi[k];
+      const float wk = w[k] / wsum;
+      w[k] = wk;
+      const float tr0 = __ldg(a.trans + 3 * m), tr1 = __ldg(a.trans + 3 * m + 1), tr2 = __ldg(a.trans + 3 * m + 2);
+      if (a.local_rot) {
+        float lq[4] = {__ldg(a.local_rot + 4 * m) + 1.0f, __ldg(a.local_rot + 4 * m + 1), __ldg(a.local_rot + 4 * m + 2),
+                       __ldg(a.local_rot + 4 * m + 3)};
+        float R[9];
+        quat_to_matrix_raw(lq, R);
+        const float n0 = s_nodes[m * D], n1 = s_nodes[m * D + 1], n2 = s_nodes[m * D + 2];
+        const float e0 = x0 - n0, e1 = x1 - n1, e2 = x2 - n2;
+        const float A0 = (R[0] * e0 + R[1] * e1 + R[2] * e2) + n0 + tr0;
+        const float A1 = (R[3] * e0 + R[4] * e1 + R[5] * e2) + n1 + tr1;
+        const float A2 = (R[6] * e0 + R[7] * e1 + R[8] * e2) + n2 + tr2;
+        t0 += A0 * wk; t1 += A1 * wk; t2 += A2 * wk;
+      } else {
+        t0 += tr0 * wk; t1 += tr1 * wk; t2 += tr2 * wk;
+      }
+      r0 += __ldg(a.rot + 4 * m) * wk; r1 += __ldg(a.rot + 4 * m + 1) * wk;
+      r2 += __ldg(a.rot + 4 * m + 2) * wk; r3 += __ldg(a.rot + 4 * m + 3) * wk;
+      s0 += __ldg(a.scale + 2 * m) * wk; s1 += __ldg(a.scale + 2 * m + 1) * wk;
+      if (a.nn_idx) a.nn_idx[(size_t)i * K + k] = m;
+      if (a.nn_dist) a.nn_dist[(size_t)i * K + k] = bd[k];
+      if (a.nn_weight) a.nn_weight[(size_t)i * K + k] = wk;
+    }
+  }
+  if (a.local_rot) { t0 -= x0; t1 -= x1; t2 -= x2; }
+  const float mk = a.mask ? a.mask[i] : 1.0f;
+  a.d_xyz[3 * (size_t)i] = t0 * mk; a.d_xyz[3 * (size_t)i + 1] = t1 * mk; a.d_xyz[3 * (size_t)i + 2] = t2 * mk;
+  a.d_rot[4 * (size_t)i] = r0 * mk; a.d_rot[4 * (size_t)i + 1] = r1 * mk; a.d_rot[4 * (size_t)i + 2] = r2 * mk;
+  a.d_rot[4 * (size_t)i + 3] = r3 * mk;
+  a.d_scale[2 * (size_t)i] = s0 * mk; a.d_scale[2 * (size_t)i + 1] = s1 * mk;
+}
+
+struct DeformBwdP {
+  int P, M, K, D, hyper;
+  const float* xyz; const float* feature; int fstride;
+  const float* nodes; const float* radius_log; const float* weight_logit;
+  const float* trans; const float* rot; const float* scale; const float* local_rot;
+  const float* mask;
+  const int64_t* nn_idx; const float* nn_dist; const float* nn_weight;
+  const float* g_xyz; const float* g_rot; const float* g_scale;
+  float* d_trans; float* d_rot; float* d_scale; float* d_local_rot; float* d_nodes; float* d_radius_log;
+  float* d_weight_logit;
+  float* d_feature; float* d_mask;
+  int use_smem;   // 1: per-CTA shared accumulators for the node gradients
+};
+
+// per-node gradient row inside the accumulator: [0..2] trans [3..6] rot [7..8] scale [9..12] local_rot
+// [13] radius_log [14] weight_logit [15..15+hyper) hyper coordinates
+constexpr int NG_FIXED = 15;
+
+__global__ void __launch_bounds__(256) deform_bwd_kernel(DeformBwdP a) {
+  extern __shared__ float s_acc[];   // M * (NG_FIXED + hyper) when use_smem
+  const int NG = NG_FIXED + a.hyper;
+  const int nstride = 3 + a.hyper;
+  if (a.use_smem) {
+    for (int t = threadIdx.x; t < a.M * NG; t += blockDim.x) s_acc[t] = 0.f;
+    __syncthreads();
+  }
+  auto add = [&](int m, int c, float v) {
+    if (a.use_smem) { atomicAdd(&s_acc[m * NG + c], v); return; }
+    if (c < 3) atomicAdd(a.d_trans + 3 * m + c, v);
+    else if (c < 7) atomicAdd(a.d_rot + 4 * m + (c - 3), v);
+    else if (c < 9) atomicAdd(a.d_scale + 2 * m + (c - 7), v);
+    else if (c < 13) { if (a.d_local_rot) atomicAdd(a.d_local_rot + 4 * m + (c - 9), v); }
+    else if (c == 13) atomicAdd(a.d_radius_log + m, v);
+    else if (c == 14) { if (a.d_weight_logit) atomicAdd(a.d_weight_logit + m, v); }
+    else atomicAdd(a.d_nodes + (size_t)m * nstride + 3 + (c - NG_FIXED), v);
+  };
+
+  const int K = a.K;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.P; i += gridDim.x * blockDim.x) {
+    const float mk = a.mask ? a.mask[i] : 1.0f;
+    const float x0 = a.xyz[3 * (size_t)i], x1 = a.xyz[3 * (size_t)i + 1], x2 = a.xyz[3 * (size_t)i + 2];
+    const float gx0 = a.g_xyz[3 * (size_t)i], gx1 = a.g_xyz[3 * (size_t)i + 1], gx2 = a.g_xyz[3 * (size_t)i + 2];
+    const float gr0 = a.g_rot[4 * (size_t)i], gr1 = a.g_rot[4 * (size_t)i + 1], gr2 = a.g_rot[4 * (size_t)i + 2],
+                gr3 = a.g_rot[4 * (size_t)i + 3];
+    const float gs0 = a.g_scale[2 * (size_t)i], gs1 = a.g_scale[2 * (size_t)i + 1];
+    const float Gx0 = gx0 * mk, Gx1 = gx1 * mk, Gx2 = gx2 * mk;
+    const float Gr0 = gr0 * mk, Gr1 = gr1 * mk, Gr2 = gr2 * mk, Gr3 = gr3 * mk;
+    const float Gs0 = gs0 * mk, Gs1 = gs1 * mk;
+
+    float dw[MAX_K], wk[MAX_K];
+    int idx[MAX_K];
+    float sum_w_dw = 0.f;
+    float acc_x0 = 0.f, acc_x1 = 0.f, acc_x2 = 0.f, acc_r0 = 0.f, acc_r1 = 0.f, acc_r2 = 0.f, acc_r3 = 0.f, acc_s0 = 0.f,
+          acc_s1 = 0.f;   // un-masked blended outputs, for the mask gradient
+#pragma unroll
+    for (int k = 0; k < MAX_K; k++) {
+      dw[k] = 0.f; wk[k] = 0.f; idx[k] = 0;
+      if (k < K) {
+        const int m = (int)a.nn_idx[(size_t)i * K + k];
+        const float w = a.nn_weight[(size_t)i * K + k];
+        idx[k] = m; wk[k] = w;
+        const float tr0 = __ldg(a.trans + 3 * m), tr1 = __ldg(a.trans + 3 * m + 1), tr2 = __ldg(a.trans + 3 * m + 2);
+        float A0 = tr0, A1 = tr1, A2 = tr2;
+        if (a.local_rot) {
+          float lq[4] = {__ldg(a.local_rot + 4 * m) + 1.0f, __ldg(a.local_rot + 4 * m + 1), __ldg(a.local_rot + 4 * m + 2),
+                         __ldg(a.local_rot + 4 * m + 3)};
+          float R[9];
+          quat_to_matrix_raw(lq, R);
+          const float n0 = __ldg(a.nodes + (size_t)m * nstride), n1 = __ldg(a.nodes + (size_t)m * nstride + 1),
+                      n2 = __ldg(a.nodes + (size_t)m * nstride + 2);
+          const float e0 = x0 - n0, e1 = x1 - n1, e2 = x2 - n2;
+          A0 = (R[0] * e0 + R[1] * e1 + R[2] * e2) + n0 + tr0;
+          A1 = (R[3] * e0 + R[4] * e1 + R[5] * e2) + n1 + tr1;
+          A2 = (R[6] * e0 + R[7] * e1 + R[8] * e2) + n2 + tr2;
+          // dL/dR = (w G_x) (x - node)^T  -> quaternion
+          const float wg0 = w * Gx0, wg1 = w * Gx1, wg2 = w * Gx2;
+          const float dR[9] = {wg0 * e0, wg0 * e1, wg0 * e2, wg1 * e0, wg1 * e1, wg1 * e2, wg2 * e0, wg2 * e1, wg2 * e2};
+          float dq[4];
+          quat_to_matrix_raw_vjp(lq, dR, dq);
+          add(m, 9, dq[0]); add(m, 10, dq[1]); add(m, 11, dq[2]); add(m, 12, dq[3]);
+        }
+        const float rr0 = __ldg(a.rot + 4 * m), rr1 = __ldg(a.rot + 4 * m + 1), rr2 = __ldg(a.rot + 4 * m + 2),
+                    rr3 = __ldg(a.rot + 4 * m + 3);
+        const float ss0 = __ldg(a.scale + 2 * m), ss1 = __ldg(a.scale + 2 * m + 1);
+        add(m, 0, w * Gx0); add(m, 1, w * Gx1); add(m, 2, w * Gx2);
+        add(m, 3, w * Gr0); add(m, 4, w * Gr1); add(m, 5, w * Gr2); add(m, 6, w * Gr3);
+        add(m, 7, w * Gs0); add(m, 8, w * Gs1);
+        const float d = Gx0 * A0 + Gx1 * A1 + Gx2 * A2 + Gr0 * rr0 + Gr1 * rr1 + Gr2 * rr2 + Gr3 * rr3 + Gs0 * ss0 + Gs1 * ss1;
+        dw[k] = d;
+        sum_w_dw += w * d;
+        acc_x0 += w * A0; acc_x1 += w * A1; acc_x2 += w * A2;
+        acc_r0 += w * rr0; acc_r1 += w * rr1; acc_r2 += w * rr2; acc_r3 += w * rr3;
+        acc_s0 += w * ss0; acc_s1 += w * ss1;
+      }
+    }
+    if (a.d_mask) {
+      if (a.local_rot) { acc_x0 -= x0; acc_x1 -= x1; acc_x2 -= x2; }
+      a.d_mask[i] = gx0 * acc_x0 + gx1 * acc_x1 + gx2 * acc_x2 + gr0 * acc_r0 + gr1 * acc_r1 + gr2 * acc_r2 + gr3 * acc_r3 +
+                    gs0 * acc_s0 + gs1 * acc_s1;
+    }
+    // un-normalised weights: u_k = e_k*sigma_k + 1e-7, w_k = u_k / S.  S is recovered from any (w,u) pair.
+    float dq_h[MAX_D - 3];
+#pragma unroll
+    for (int d = 0; d < MAX_D - 3; d++) dq_h[d] = 0.f;
+    float S = 0.f;
+    {
+      const int m = idx[0];
+      const float r = expf(__ldg(a.radius_log + m));
+      float e = expf(-a.nn_dist[(size_t)i * K] / (2 * (r * r)));
+      const float sg = a.weight_logit ? 1.0f / (1.0f + expf(-__ldg(a.weight_logit + m))) : 1.0f;
+      S = (e * sg + 1e-7f) / wk[0];
+    }
+#pragma unroll
+    for (int k = 0; k < MAX_K; k++) {
+      if (k < K) {
+        const int m = idx[k];
+        const float du = (dw[k] - sum_w_dw) / S;
+        const float r = expf(__ldg(a.radius_log + m));
+        const float dist = a.nn_dist[(size_t)i * K + k];
+        const float inv2r2 = 1.0f / (2 * (r * r));
+        const float e = expf(-dist * inv2r2);
+        const float sg = a.weight_logit ? 1.0f / (1.0f + expf(-__ldg(a.weight_logit + m))) : 1.0f;
+        const float de = du * sg;
+        if (a.weight_logit) add(m, 14, du * e * sg * (1.0f - sg));
+        const float dd = -de * e * inv2r2;                 // dL/d dist
+        add(m, 13, de * e * dist * 2.0f * inv2r2);          // dL/d log r  (= de * e * dist / r^2)
+        if (a.hyper > 0 && a.feature) {
+#pragma unroll
+          for (int d = 0; d < MAX_D - 3; d++) {
+            if (d < a.hyper) {
+              const float df = a.feature[(size_t)i * a.fstride + d] - __ldg(a.nodes + (size_t)m * nstride + 3 + d);
+              const float gq = dd * 2.0f * df;
+              dq_h[d] += gq;
+              add(m, NG_FIXED + d, -gq);
+            }
+          }
+        }
+      }
+    }
+    if (a.d_feature) {
+      for (int d = 0; d < a.fstride; d++) a.d_feature[(size_t)i * a.fstride + d] = (d < a.hyper) ? dq_h[d < MAX_D - 3 ? d : 0] : 0.f;
+    }
+  }
+
+  if (a.use_smem) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < a.M * NG; t += blockDim.x) {
+      const float v = s_acc[t];
+      if (v == 0.f) continue;
+      const int m = t / NG, c = t - m * NG;
+      if (c < 3) atomicAdd(a.d_trans + 3 * m + c, v);
+      else if (c < 7) atomicAdd(a.d_rot + 4 * m + (c - 3), v);
+      else if (c < 9) atomicAdd(a.d_scale + 2 * m + (c - 7), v);
+      else if (c < 13) { if (a.d_local_rot) atomicAdd(a.d_local_rot + 4 * m + (c - 9), v); }
+      else if (c == 13) atomicAdd(a.d_radius_log + m, v);
+      else if (c == 14) { if (a.d_weight_logit) atomicAdd(a.d_weight_logit + m, v); }
+      else atomicAdd(a.d_nodes + (size_t)m * nstride + 3 + (c - NG_FIXED), v);
+    }
+  }
+}
+
+int deform_forward_launch(const DeformFwdHost& h, cudaStream_t s, const char** err) {
+  if (h.K < 1 || h.K > MAX_K || h.K > h.M) { *err = "K must be in [1, min(8, M)]"; return -1; }
+  if (h.hyper < 0 || h.hyper > MAX_D - 3) { *err = "hyper_dim must be <= 16"; return -1; }
+  if (h.P == 0) return 0;
+  DeformFwdP a{};
+  a.P = h.P; a.M = h.M; a.K = h.K;
+  a.hyper = h.hyper;                       // stride of the node table is always 3 + hyper_dim
+  a.D = h.feature ? 3 + h.hyper : 3;       // the query is 3-D when no hyper feature is given
+  a.xyz = h.xyz; a.feature = h.feature; a.fstride = h.fstride;
+  a.nodes = h.nodes; a.radius_log = h.radius_log; a.weight_logit = h.weight_logit;
+  a.trans = h.trans; a.rot = h.rot; a.scale = h.scale; a.local_rot = h.local_rot; a.mask = h.mask;
+  a.nn_idx = h.nn_idx; a.nn_dist = h.nn_dist; a.nn_weight = h.nn_weight;
+  a.d_xyz = h.d_xyz; a.d_rot = h.d_rot; a.d_scale = h.d_scale;
+  const size_t smem = sizeof(float) * (size_t)a.M * a.D;
+  if (smem > 200 * 1024) { *err = "node table exceeds shared memory (M*(3+hyper) floats > 200 KB)"; return -1; }
+  cudaFuncSetAttribute(deform_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  deform_fwd_kernel<<<(h.P + 255) / 256, 256, smem, s>>>(a);
+  return 0;
+}
+
+int deform_backward_launch(const DeformBwdHost& h, cudaStream_t s, const char** err) {
+  DeformBwdP a{};
+  a.P = h.P; a.M = h.M; a.K = h.K; a.hyper = h.hyper; a.D = 3 + h.hyper;
+  a.xyz = h.xyz; a.feature = h.feature; a.fstride = h.fstride;
+  a.nodes = h.nodes; a.radius_log = h.radius_log; a.weight_logit = h.weight_logit;
+  a.trans = h.trans; a.rot = h.rot; a.scale = h.scale; a.local_rot = h.local_rot; a.mask = h.mask;
+  a.nn_idx = h.nn_idx; a.nn_dist = h.nn_dist; a.nn_weight = h.nn_weight;
+  a.g_xyz = h.g_xyz; a.g_rot = h.g_rot; a.g_scale = h.g_scale;
+  a.d_trans = h.d_trans; a.d_rot = h.d_rot; a.d_scale = h.d_scale; a.d_local_rot = h.d_local_rot;
+  a.d_nodes = h.d_nodes; a.d_radius_log = h.d_radius_log; a.d_weight_logit = h.d_weight_logit;
+  a.d_feature = h.d_feature; a.d_mask = h.d_mask;
+  if (h.K < 1 || h.K > MAX_K) { *err = "K must be in [1, 8]"; return -1; }
+  if (h.hyper < 0 || h.hyper > MAX_D - 3) { *err = "hyper_dim must be <= 16"; return -1; }
+  if (h.P == 0) return 0;
+  const size_t smem = sizeof(float) * (size_t)h.M * (NG_FIXED + h.hyper);
+  a.use_smem = smem <= 200 * 1024;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int blocks = (h.P + 255) / 256;
+  if (a.use_smem) {
+    cudaFuncSetAttribute(deform_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int per_sm = smem <= 48 * 1024 ? 4 : (smem <= 100 * 1024 ? 2 : 1);
+    blocks = min(blocks, sms * per_sm);
+  }
+  deform_bwd_kernel<<<blocks, 256, a.use_smem ? smem : 0, s>>>(a);
+  return 0;
+}
+
+}  // namespace d2gs

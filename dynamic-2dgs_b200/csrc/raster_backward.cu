@@ -1,0 +1,501 @@
+// Backward kernels of the surfel rasterizer for sm_100a.
+// Behavioural contract: DSR/cuda_rasterizer/backward.cu:143-449 (blend), :599-649 (AABB), :451-597 (per surfel),
+// :20-139 (SH).  Design differences (results agree to fp32 re-association):
+//   * the reference issues up to 16 global float atomics per contributing (pixel, surfel) pair; here each warp
+//     first reduces its 32 pixels with a transposed butterfly (16 shuffles for 16 values), adds the warp totals
+//     into a per-instance shared-memory accumulator, and the CTA issues one global reduction per
+//     (tile, instance, component) — R*18 instead of pairs*16;
+//   * traversal starts at the deepest instance any pixel of the tile actually consumed (block max of n_contrib)
+//     instead of the end of the tile list;
+//   * AABB backward, the transMat/normal/SH backward and the clearing of the gradient scratch are one
+//     per-surfel kernel; all outputs are fully written, so callers need no zero-fill.
+#include "raster_common.cuh"
+
+namespace d2gs {
+
+constexpr int BWD_BATCH = 256;
+constexpr int ACC_STRIDE = 19;   // 18 components, odd stride keeps the flush free of bank conflicts
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ void pixel_of_thread_b(int tid, int& lx, int& ly) {
+  const int w = tid >> 5, l = tid & 31;
+  lx = ((w & 1) << 3) | (l & 7);
+  ly = ((w >> 1) << 2) | (l >> 3);
+}
+
+// Sum 16 per-lane values across the warp with 16 shuffles: after the call lanes with an even index hold the
+// warp total of component ((lane>>4)&1)*8 + ((lane>>3)&1)*4 + ((lane>>2)&1)*2 + ((lane>>1)&1) in g[0].
+__device__ __forceinline__ void warp_transpose_reduce16(float (&g)[16], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const float send = b4 ? g[i] : g[i + 8];
+    const float keep = b4 ? g[i + 8] : g[i];
+    g[i] = keep + __shfl_xor_sync(FULL, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float send = b3 ? g[i] : g[i + 4];
+    const float keep = b3 ? g[i + 4] : g[i];
+    g[i] = keep + __shfl_xor_sync(FULL, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const float send = b2 ? g[i] : g[i + 2];
+    const float keep = b2 ? g[i + 2] : g[i];
+    g[i] = keep + __shfl_xor_sync(FULL, send, 4);
+  }
+  {
+    const float send = b1 ? g[0] : g[1];
+    const float keep = b1 ? g[1] : g[0];
+    g[0] = keep + __shfl_xor_sync(FULL, send, 2);
+  }
+  g[0] += __shfl_xor_sync(FULL, g[0], 1);
+}
+
+__global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
+    const float* __restrict__ bg, const SurfelRec* __restrict__ rec, const float* __restrict__ final_Ts,
+    const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
+    const float* __restrict__ dL_dothers, float* __restrict__ grad_rec) {
+  __shared__ float4 s_q0[BWD_BATCH], s_q1[BWD_BATCH], s_q2[BWD_BATCH], s_q3[BWD_BATCH], s_q4[BWD_BATCH];
+  __shared__ uint32_t s_id[BWD_BATCH];
+  __shared__ float s_acc[BWD_BATCH * ACC_STRIDE];
+  __shared__ uint32_t s_max[TILE_PIX / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int lx, ly;
+  pixel_of_thread_b(tid, lx, ly);
+  const uint32_t pix_x = blockIdx.x * TILE_X + lx, pix_y = blockIdx.y * TILE_Y + ly;
+  const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
+  const uint32_t pix_id = W * pix_y + pix_x;
+  const size_t HW = (size_t)H * W;
+  const float2 pixf = {(float)pix_x + 0.5f, (float)pix_y + 0.5f};
+  const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
+
+  const float T_final = inside ? final_Ts[pix_id] : 0;
+  float T = T_final;
+  const uint32_t last_contributor = inside ? n_contrib[pix_id] : 0;
+  const int median_contributor = inside ? (int)n_contrib[pix_id + HW] : 0;
+
+  // deepest list position any pixel of this tile consumed
+  {
+    const uint32_t m = __reduce_max_sync(FULL, last_contributor);
+    if (lane == 0) s_max[warp] = m;
+  }
+  for (int i = tid; i < BWD_BATCH * ACC_STRIDE; i += TILE_PIX) s_acc[i] = 0.f;
+  __syncthreads();
+  uint32_t len = 0;
+#pragma unroll
+  for (int i = 0; i < TILE_PIX / 32; i++) len = max(len, s_max[i]);
+  len = min(len, range.y - range.x);
+  if (len == 0) return;
+
+  float dL_dpixel[3] = {0.f, 0.f, 0.f}, dL_dnormal2D[3] = {0.f, 0.f, 0.f};
+  float dL_ddepth = 0.f, dL_daccum = 0.f, dL_dreg = 0.f, dL_dmedian_depth = 0.f, dL_dmax_dweight = 0.f;
+  if (inside) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) dL_dpixel[ch] = dL_dpixels[ch * HW + pix_id];
+    dL_ddepth = dL_dothers[0 * HW + pix_id];
+    dL_daccum = dL_dothers[1 * HW + pix_id];
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) dL_dnormal2D[ch] = dL_dothers[(2 + ch) * HW + pix_id];
+    dL_dmedian_depth = dL_dothers[5 * HW + pix_id];
+    dL_dreg = dL_dothers[6 * HW + pix_id];
+    dL_dmax_dweight = dL_dothers[7 * HW + pix_id];
+  }
+  const float final_D = inside ? final_Ts[pix_id + HW] : 0;
+  const float final_D2 = inside ? final_Ts[pix_id + 2 * HW] : 0;
+  const float final_A = 1 - T_final;
+  const float bg_dot_dpixel = bg[0] * dL_dpixel[0] + bg[1] * dL_dpixel[1] + bg[2] * dL_dpixel[2];
+
+  float accum_rec[3] = {0.f, 0.f, 0.f}, last_color[3] = {0.f, 0.f, 0.f};
+  float last_alpha = 0.f, last_depth = 0.f, last_normal[3] = {0.f, 0.f, 0.f};
+  float accum_depth_rec = 0.f, accum_alpha_rec = 0.f, accum_normal_rec[3] = {0.f, 0.f, 0.f};
+  float last_dL_dT = 0.f;
+
+  const int rounds = (len + BWD_BATCH - 1) / BWD_BATCH;
+  int remaining = (int)len;
+  for (int i = 0; i < rounds; i++, remaining -= BWD_BATCH) {
+    // stage the batch back to front: slot t holds list position len-1-(i*B+t)
+    const int n = min(BWD_BATCH, remaining);
+    if (tid < n) {
+      const uint32_t pos = len - 1 - (uint32_t)(i * BWD_BATCH + tid);
+      const uint32_t id = __ldg(&point_list[range.x + pos]);
+      s_id[tid] = id;
+      const float4* r4 = reinterpret_cast<const float4*>(rec + id);
+      s_q0[tid] = __ldg(r4 + 0);
+      s_q1[tid] = __ldg(r4 + 1);
+      s_q2[tid] = __ldg(r4 + 2);
+      s_q3[tid] = __ldg(r4 + 3);
+      s_q4[tid] = __ldg(r4 + 4);
+    }
+    __syncthreads();
+
+    for (int j = 0; j < n; j++) {
+      const uint32_t contributor = len - 1 - (uint32_t)(i * BWD_BATCH + j);   // 0-based list position
+      float g[16];
+#pragma unroll
+      for (int q = 0; q < 16; q++) g[q] = 0.f;
+      float gm0 = 0.f, gm1 = 0.f;
+      bool contrib = false, flat = false;
+      do {
+        if (!inside || contributor >= last_contributor) break;
+        const float4 a = s_q0[j], b = s_q1[j], c = s_q2[j];
+        const float3 Tu = {a.x, a.y, a.z}, Tv = {a.w, b.x, b.y}, Tw = {b.z, b.w, c.x};
+        const float3 k = {-Tu.x + pixf.x * Tw.x, -Tu.y + pixf.x * Tw.y, -Tu.z + pixf.x * Tw.z};
+        const float3 l = {-Tv.x + pixf.y * Tw.x, -Tv.y + pixf.y * Tw.y, -Tv.z + pixf.y * Tw.z};
+        const float3 p = {k.y * l.z - k.z * l.y, k.z * l.x - k.x * l.z, k.x * l.y - k.y * l.x};
+        if (p.z == 0.0f) break;
+        const float2 s = {p.x / p.z, p.y / p.z};
+        const float rho3d = (s.x * s.x + s.y * s.y);
+        const float2 d = {c.y - pixf.x, c.z - pixf.y};
+        const float rho2d = 2.0f * (d.x * d.x + d.y * d.y);
+        const float rho = fminf(rho3d, rho2d);
+        const float c_d = (rho3d <= rho2d) ? (s.x * Tw.x + s.y * Tw.y) + Tw.z : Tw.z;
+        if (c_d < 0.2f) break;
+        const float power = -0.5f * rho;
+        if (power > 0.0f) break;
+        const float G = expf(power);
+        const float opac = c.w;
+        const float alpha = fminf(0.99f, opac * G);
+        if (alpha < 1.0f / 255.0f) break;
+        const float4 nrm = s_q3[j];
+        const float4 col = s_q4[j];
+        const float normal[3] = {nrm.x, nrm.y, nrm.z};
+        const float color[3] = {col.x, col.y, col.z};
+
+        T = T / (1.f - alpha);
+        const float w = alpha * T;
+        float dL_dalpha = 0.0f;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+          accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
+          last_color[ch] = color[ch];
+          dL_dalpha += (color[ch] - accum_rec[ch]) * dL_dpixel[ch];
+          g[13 + ch] = w * dL_dpixel[ch];
+        }
+        float dL_dz = 0.0f, dL_dweight = 0.f;
+        // depth mapped to [0,1]; fp32 here (gradients are compared to 1e-4, not bit-wise)
+        const float m_d = (100.0f * c_d - 20.0f) / (99.8f * c_d);
+        const float dmd_dd = 20.0f / (99.8f * c_d * c_d);
+        if (contributor == (uint32_t)(median_contributor - 1)) {
+          dL_dz += dL_dmedian_depth;
+          dL_dweight += dL_dmax_dweight;
+        }
+        dL_dweight += (final_D2 + m_d * m_d * final_A - 2 * m_d * final_D) * dL_dreg;
+        dL_dalpha += dL_dweight - last_dL_dT;
+        last_dL_dT = dL_dweight * alpha + (1 - alpha) * last_dL_dT;
+        const float dL_dmd = 2.0f * (T * alpha) * (m_d * final_A - final_D) * dL_dreg;
+        dL_dz += dL_dmd * dmd_dd;
+
+        accum_depth_rec = last_alpha * last_depth + (1.f - last_alpha) * accum_depth_rec;
+        last_depth = c_d;
+        dL_dalpha += (c_d - accum_depth_rec) * dL_ddepth;
+        accum_alpha_rec = __fadd_rn(last_alpha, __fmul_rn(1.f - last_alpha, accum_alpha_rec));
+        dL_dalpha += (1 - accum_alpha_rec) * dL_daccum;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+          accum_normal_rec[ch] = last_alpha * last_normal[ch] + (1.f - last_alpha) * accum_normal_rec[ch];
+          last_normal[ch] = normal[ch];
+          dL_dalpha += (normal[ch] - accum_normal_rec[ch]) * dL_dnormal2D[ch];
+          g[9 + ch] = w * dL_dnormal2D[ch];
+        }
+        dL_dalpha *= T;
+        last_alpha = alpha;
+        dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+
+        const float dL_dG = opac * dL_dalpha;
+        dL_dz += w * dL_ddepth;
+
+        if (rho3d <= rho2d) {
+          const float2 dL_ds = {dL_dG * -G * s.x + dL_dz * Tw.x, dL_dG * -G * s.y + dL_dz * Tw.y};
+          const float dsx_pz = dL_ds.x / p.z, dsy_pz = dL_ds.y / p.z;
+          const float3 dL_dp = {dsx_pz, dsy_pz, -(dsx_pz * s.x + dsy_pz * s.y)};
+          const float3 dL_dk = {l.y * dL_dp.z - l.z * dL_dp.y, l.z * dL_dp.x - l.x * dL_dp.z, l.x * dL_dp.y - l.y * dL_dp.x};
+          const float3 dL_dl = {dL_dp.y * k.z - dL_dp.z * k.y, dL_dp.z * k.x - dL_dp.x * k.z, dL_dp.x * k.y - dL_dp.y * k.x};
+          g[0] = -dL_dk.x; g[1] = -dL_dk.y; g[2] = -dL_dk.z;
+          g[3] = -dL_dl.x; g[4] = -dL_dl.y; g[5] = -dL_dl.z;
+          g[6] = pixf.x * dL_dk.x + pixf.y * dL_dl.x + dL_dz * s.x;
+          g[7] = pixf.x * dL_dk.y + pixf.y * dL_dl.y + dL_dz * s.y;
+          g[8] = pixf.x * dL_dk.z + pixf.y * dL_dl.z + dL_dz;
+        } else {
+          // low-pass-filter branch: gradient goes to the 2-D centre and to Tw.z
+          const float dG_ddelx = -G * 2.0f * d.x;
+          const float dG_ddely = -G * 2.0f * d.y;
+          gm0 = dL_dG * dG_ddelx;
+          gm1 = dL_dG * dG_ddely;
+          g[8] = dL_dz;
+          flat = true;
+        }
+        g[12] = G * dL_dalpha;
+        contrib = true;
+      } while (0);
+
+      if (__any_sync(FULL, contrib)) {
+        warp_transpose_reduce16(g, lane);
+        if ((lane & 1) == 0) {
+          const int v = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+          const int slot = v < 9 ? v : v + 2;   // 0..8 transMat | 11..13 normal | 14 opacity | 15..17 colour
+          atomicAdd(&s_acc[j * ACC_STRIDE + slot], g[0]);
+        }
+        if (__any_sync(FULL, flat)) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            gm0 += __shfl_xor_sync(FULL, gm0, o);
+            gm1 += __shfl_xor_sync(FULL, gm1, o);
+          }
+          if (lane == 0) {
+            atomicAdd(&s_acc[j * ACC_STRIDE + G_M2D], gm0);
+            atomicAdd(&s_acc[j * ACC_STRIDE + G_M2D + 1], gm1);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // one global reduction per (tile, instance, component)
+    if (tid < n) {
+      float* dst = grad_rec + (size_t)s_id[tid] * GRAD_REC_FLOATS;
+#pragma unroll
+      for (int v = 0; v < 18; v++) {
+        const float val = s_acc[tid * ACC_STRIDE + v];
+        if (val != 0.f) {
+          atomicAdd(dst + v, val);
+          s_acc[tid * ACC_STRIDE + v] = 0.f;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+void launch_blend_bwd(const BwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
+                      const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, const float* dL_dothers,
+                      float* grad_rec, cudaStream_t s) {
+  dim3 grid(p.gx, p.gy, 1);
+  blend_bwd_kernel<<<grid, TILE_PIX, 0, s>>>(ranges, point_list, p.W, p.H, p.bg, rec, final_T, n_contrib, dL_dpix,
+                                            dL_dothers, grad_rec);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// per-surfel backward: AABB-centre term, homography -> (mean, scale, quaternion), normal, SH.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_sh_grad(const BwdParams& p, float* dL_dsh, float* dL_dsh_rest, int idx,
+                                              const float* g /*[48]*/) {
+  if (dL_dsh_rest == nullptr) {
+    float* base = dL_dsh + (size_t)idx * p.M * 3;
+    if (p.M == 16 && ((reinterpret_cast<uintptr_t>(dL_dsh) & 15) == 0)) {
+      float4* b4 = reinterpret_cast<float4*>(base);
+#pragma unroll
+      for (int i = 0; i < 12; i++) b4[i] = make_float4(g[4 * i], g[4 * i + 1], g[4 * i + 2], g[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 48; i++)
+        if (i < p.M * 3) base[i] = g[i];
+    }
+  } else {
+    float* dc = dL_dsh + (size_t)idx * 3;
+    dc[0] = g[0]; dc[1] = g[1]; dc[2] = g[2];
+    float* rest = dL_dsh_rest + (size_t)idx * (p.M - 1) * 3;
+#pragma unroll
+    for (int i = 3; i < 48; i++)
+      if (i < p.M * 3) rest[i - 3] = g[i];
+  }
+}
+
+__device__ __forceinline__ void load_sh_b(const BwdParams& p, int idx, int ncoef, float* sh) {
+  if (p.sh_rest == nullptr) {
+    const float* base = p.shs + (size_t)idx * p.M * 3;
+    if (p.M == 16 && ((reinterpret_cast<uintptr_t>(p.shs) & 15) == 0)) {
+      const float4* b4 = reinterpret_cast<const float4*>(base);
+      const int n4 = (ncoef * 3 + 3) / 4;
+#pragma unroll
+      for (int i = 0; i < 12; i++)
+        if (i < n4) {
+          float4 v = __ldg(b4 + i);
+          sh[4 * i] = v.x; sh[4 * i + 1] = v.y; sh[4 * i + 2] = v.z; sh[4 * i + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 48; i++)
+        if (i < ncoef * 3) sh[i] = __ldg(base + i);
+    }
+  } else {
+    const float* dc = p.shs + (size_t)idx * 3;
+    sh[0] = __ldg(dc); sh[1] = __ldg(dc + 1); sh[2] = __ldg(dc + 2);
+    const float* rest = p.sh_rest + (size_t)idx * (p.M - 1) * 3;
+#pragma unroll
+    for (int i = 3; i < 48; i++)
+      if (i < ncoef * 3) sh[i] = __ldg(rest + i - 3);
+  }
+}
+
+__global__ void __launch_bounds__(256) preprocess_bwd_kernel(
+    BwdParams p, const SurfelRec* __restrict__ rec, const uint8_t* __restrict__ clamped,
+    const int* __restrict__ radii, float* __restrict__ grad_rec, float* __restrict__ dL_dmeans2D,
+    float* __restrict__ dL_dcolors, float* __restrict__ dL_dopacity, float* __restrict__ dL_dmeans3D,
+    float* __restrict__ dL_dtransMat, float* __restrict__ dL_dsh, float* __restrict__ dL_dsh_rest,
+    float* __restrict__ dL_dscales, float* __restrict__ dL_drot) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.P) return;
+  const bool visible = radii[idx] > 0;
+
+  float gr[GRAD_REC_FLOATS];
+  v3 dmean3D = {0.f, 0.f, 0.f};
+  float2 dscale = {0.f, 0.f};
+  float4 drot = {0.f, 0.f, 0.f, 0.f};
+  float2 dm2d = {0.f, 0.f};
+  float gsh[48];
+#pragma unroll
+  for (int i = 0; i < 48; i++) gsh[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < GRAD_REC_FLOATS; i++) gr[i] = 0.f;
+
+  if (visible) {
+    float4* g4 = reinterpret_cast<float4*>(grad_rec + (size_t)idx * GRAD_REC_FLOATS);
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+      const float4 v = g4[i];
+      gr[4 * i] = v.x; gr[4 * i + 1] = v.y; gr[4 * i + 2] = v.z; gr[4 * i + 3] = v.w;
+      g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // leave the scratch clean for the next frame
+    }
+    const SurfelRec r = rec[idx];
+    const v3 Tu = {r.q0.x, r.q0.y, r.q0.z}, Tv = {r.q0.w, r.q1.x, r.q1.y}, Tw = {r.q1.z, r.q1.w, r.q2.x};
+
+    // (1) centre of the screen-space box -> homography rows
+    {
+      const v3 sgn = {1.0f, 1.0f, -1.0f};
+      const float gx2 = gr[G_M2D], gy2 = gr[G_M2D + 1];
+      const float d = dot3(sgn, Tw * Tw);
+      const v3 f = sgn * (1.0f / d);
+      const v3 dT0 = gx2 * f * Tw;
+      const v3 dT1 = gy2 * f * Tw;
+      v3 dT3 = gx2 * f * Tu + gy2 * f * Tv;
+      const v3 dL_df = (gx2 * Tu * Tw) + (gy2 * Tv * Tw);
+      const float dL_dd = dot3(dL_df, f) * (-1.0f / d);
+      const v3 dd_dT3 = sgn * Tw * 2.0f;
+      dT3 = dT3 + dL_dd * dd_dT3;
+      gr[0] += dT0.x; gr[1] += dT0.y; gr[2] += dT0.z;
+      gr[3] += dT1.x; gr[4] += dT1.y; gr[5] += dT1.z;
+      gr[6] += dT3.x; gr[7] += dT3.y; gr[8] += dT3.z;
+      // "projected 2-D gradient" the trainer uses for densification
+      const float z = Tw.z;
+      dm2d.x = gr[2] * z * (p.focal_x * p.tan_fovx);
+      dm2d.y = gr[5] * z * (p.focal_y * p.tan_fovy);
+    }
+
+    if (p.transMat_precomp == nullptr) {
+      // (2) homography rows -> surfel frame
+      const float* m = p.view;
+      const m3 Wm = view_rot(m);
+      const m3 Wt = transpose3(Wm);
+      const float fx = p.focal_x, fy = p.focal_y, cx = p.focal_x * p.tan_fovx, cy = p.focal_y * p.tan_fovy;
+      const float2 sc = reinterpret_cast<const float2*>(p.scales)[idx];
+      const float4 q = reinterpret_cast<const float4*>(p.rotations)[idx];
+      const m3 R = quat_to_rot(q);
+      const v3 pw = {p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]};
+      const v3 p_view = Wm * pw + v3{m[12], m[13], m[14]};
+      v3 dM[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) dM[k] = {fx * gr[k], fy * gr[3 + k], cx * gr[k] + cy * gr[3 + k] + gr[6 + k]};
+      const v3 dRS0 = Wt * dM[0], dRS1 = Wt * dM[1], dpw = Wt * dM[2];
+      v3 dtn = Wt * v3{gr[G_NRM], gr[G_NRM + 1], gr[G_NRM + 2]};
+      const v3 tn = Wm * R.c2;
+      const float cs = dot3(-tn, p_view);
+      dtn = dtn * (cs > 0 ? 1.f : -1.f);
+      const v3 c0 = dRS0 * sc.x, c1 = dRS1 * sc.y, c2 = dtn;   // columns of dL/dR
+      {
+        const float s = rsqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+        const float w = q.x * s, x = q.y * s, y = q.z * s, z = q.w * s;
+        drot.x = 2.f * (x * (c1.z - c2.y) + y * (c2.x - c0.z) + z * (c0.y - c1.x));
+        drot.y = 2.f * (-2.f * x * (c1.y + c2.z) + y * (c0.y + c1.x) + z * (c0.z + c2.x) + w * (c1.z - c2.y));
+        drot.z = 2.f * (x * (c0.y + c1.x) - 2.f * y * (c0.x + c2.z) + z * (c1.z + c2.y) + w * (c2.x - c0.z));
+        drot.w = 2.f * (x * (c0.z + c2.x) + y * (c1.z + c2.y) - 2.f * z * (c0.x + c1.y) + w * (c0.y - c1.x));
+      }
+      dscale = {dot3(dRS0, R.c0), dot3(dRS1, R.c1)};
+      dmean3D = dpw;
+    }
+
+    // (3) colour -> SH coefficients and view direction
+    if (p.shs != nullptr) {
+      const v3 pw = {p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]};
+      const v3 campos = {p.campos[0], p.campos[1], p.campos[2]};
+      const v3 dir_orig = pw - campos;
+      const v3 dir = dir_orig / sqrtf(dot3(dir_orig, dir_orig));
+      const int deg = p.D;
+      float sh[48];
+      load_sh_b(p, idx, (deg + 1) * (deg + 1), sh);
+      auto S = [&](int k) { return v3{sh[3 * k], sh[3 * k + 1], sh[3 * k + 2]}; };
+      const uint8_t cl = clamped[idx];
+      v3 gc = {gr[G_COL], gr[G_COL + 1], gr[G_COL + 2]};
+      gc.x *= (cl & 1) ? 0.f : 1.f;
+      gc.y *= (cl & 2) ? 0.f : 1.f;
+      gc.z *= (cl & 4) ? 0.f : 1.f;
+      auto put = [&](int k, float bsis) { gsh[3 * k] = bsis * gc.x; gsh[3 * k + 1] = bsis * gc.y; gsh[3 * k + 2] = bsis * gc.z; };
+      v3 dRGBdx = {0, 0, 0}, dRGBdy = {0, 0, 0}, dRGBdz = {0, 0, 0};
+      const float x = dir.x, y = dir.y, z = dir.z;
+      put(0, kSH_C0);
+      if (deg > 0) {
+        put(1, -kSH_C1 * y); put(2, kSH_C1 * z); put(3, -kSH_C1 * x);
+        dRGBdx = -kSH_C1 * S(3);
+        dRGBdy = -kSH_C1 * S(1);
+        dRGBdz = kSH_C1 * S(2);
+        if (deg > 1) {
+          const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+          put(4, kSH_C2[0] * xy); put(5, kSH_C2[1] * yz); put(6, kSH_C2[2] * (2.f * zz - xx - yy));
+          put(7, kSH_C2[3] * xz); put(8, kSH_C2[4] * (xx - yy));
+          dRGBdx = dRGBdx + kSH_C2[0] * y * S(4) + kSH_C2[2] * 2.f * -x * S(6) + kSH_C2[3] * z * S(7) + kSH_C2[4] * 2.f * x * S(8);
+          dRGBdy = dRGBdy + kSH_C2[0] * x * S(4) + kSH_C2[1] * z * S(5) + kSH_C2[2] * 2.f * -y * S(6) + kSH_C2[4] * 2.f * -y * S(8);
+          dRGBdz = dRGBdz + kSH_C2[1] * y * S(5) + kSH_C2[2] * 2.f * 2.f * z * S(6) + kSH_C2[3] * x * S(7);
+          if (deg > 2) {
+            put(9, kSH_C3[0] * y * (3.f * xx - yy)); put(10, kSH_C3[1] * xy * z);
+            put(11, kSH_C3[2] * y * (4.f * zz - xx - yy)); put(12, kSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy));
+            put(13, kSH_C3[4] * x * (4.f * zz - xx - yy)); put(14, kSH_C3[5] * z * (xx - yy));
+            put(15, kSH_C3[6] * x * (xx - 3.f * yy));
+            dRGBdx = dRGBdx + (kSH_C3[0] * S(9) * 3.f * 2.f * xy + kSH_C3[1] * S(10) * yz + kSH_C3[2] * S(11) * -2.f * xy +
+                               kSH_C3[3] * S(12) * -3.f * 2.f * xz + kSH_C3[4] * S(13) * (-3.f * xx + 4.f * zz - yy) +
+                               kSH_C3[5] * S(14) * 2.f * xz + kSH_C3[6] * S(15) * 3.f * (xx - yy));
+            dRGBdy = dRGBdy + (kSH_C3[0] * S(9) * 3.f * (xx - yy) + kSH_C3[1] * S(10) * xz +
+                               kSH_C3[2] * S(11) * (-3.f * yy + 4.f * zz - xx) + kSH_C3[3] * S(12) * -3.f * 2.f * yz +
+                               kSH_C3[4] * S(13) * -2.f * xy + kSH_C3[5] * S(14) * -2.f * yz + kSH_C3[6] * S(15) * -3.f * 2.f * xy);
+            dRGBdz = dRGBdz + (kSH_C3[1] * S(10) * xy + kSH_C3[2] * S(11) * 4.f * 2.f * yz +
+                               kSH_C3[3] * S(12) * 3.f * (2.f * zz - xx - yy) + kSH_C3[4] * S(13) * 4.f * 2.f * xz +
+                               kSH_C3[5] * S(14) * (xx - yy));
+          }
+        }
+      }
+      const v3 dL_ddir = {dot3(dRGBdx, gc), dot3(dRGBdy, gc), dot3(dRGBdz, gc)};
+      // derivative of v/|v|
+      const v3 v = dir_orig, dv = dL_ddir;
+      const float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
+      const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+      dmean3D.x += ((+sum2 - v.x * v.x) * dv.x - v.y * v.x * dv.y - v.z * v.x * dv.z) * invsum32;
+      dmean3D.y += (-v.x * v.y * dv.x + (sum2 - v.y * v.y) * dv.y - v.z * v.y * dv.z) * invsum32;
+      dmean3D.z += (-v.x * v.z * dv.x - v.y * v.z * dv.y + (sum2 - v.z * v.z) * dv.z) * invsum32;
+    }
+  }
+
+  if (dL_dmeans2D) { dL_dmeans2D[3 * (size_t)idx] = dm2d.x; dL_dmeans2D[3 * (size_t)idx + 1] = dm2d.y; dL_dmeans2D[3 * (size_t)idx + 2] = 0.f; }
+  if (dL_dcolors) { dL_dcolors[3 * (size_t)idx] = gr[G_COL]; dL_dcolors[3 * (size_t)idx + 1] = gr[G_COL + 1]; dL_dcolors[3 * (size_t)idx + 2] = gr[G_COL + 2]; }
+  if (dL_dopacity) dL_dopacity[idx] = gr[G_OPA];
+  if (dL_dmeans3D) { dL_dmeans3D[3 * (size_t)idx] = dmean3D.x; dL_dmeans3D[3 * (size_t)idx + 1] = dmean3D.y; dL_dmeans3D[3 * (size_t)idx + 2] = dmean3D.z; }
+  if (dL_dtransMat) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) dL_dtransMat[9 * (size_t)idx + i] = gr[i];
+  }
+  if (dL_dscales) reinterpret_cast<float2*>(dL_dscales)[idx] = dscale;
+  if (dL_drot) reinterpret_cast<float4*>(dL_drot)[idx] = drot;
+  if (dL_dsh && p.M > 0) store_sh_grad(p, dL_dsh, dL_dsh_rest, idx, gsh);
+}
+
+void launch_preprocess_bwd(const BwdParams& p, const SurfelRec* rec, const uint8_t* clamped, const int* radii,
+                           float* grad_rec, float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
+                           float* dL_dmeans3D, float* dL_dtransMat, float* dL_dsh, float* dL_dsh_rest,
+                           float* dL_dscales, float* dL_drot, cudaStream_t s) {
+  if (p.P == 0) return;
+  preprocess_bwd_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p, rec, clamped, radii, grad_rec, dL_dmeans2D, dL_dcolors,
+                                                         dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh, dL_dsh_rest,
+                                                         dL_dscales, dL_drot);
+}
+
+}  // namespace d2gs

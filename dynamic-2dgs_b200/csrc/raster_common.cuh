@@ -1,0 +1,172 @@
+// Shared definitions of the surfel rasterizer kernels (sm_100a).
+//
+// HBM layout (all offsets 256-B aligned inside the caller-owned workspaces):
+//   geometry workspace : SurfelRec[P]  (5 x float4 = 80 B, one contiguous record per surfel so the per-tile
+//                        gather of the blend kernels touches one or two 128-B lines per instance)
+//                        | clamped u8[P] (bit c set = colour channel c clamped at 0)
+//                        | tiles_touched u32[P] | point_offsets u32[P] | scan scratch
+//   image workspace    : ranges uint2[tiles] | final_T,dist1,dist2 f32[3*H*W] | n_contrib,median u32[2*H*W]
+//   binning workspace  : keys_unsorted u64[R] | keys_sorted u64[R] | values_unsorted u32[R] | point_list u32[R]
+//                        | radix-sort scratch
+//   grad scratch       : GradRec[P] (20 floats) accumulated by the blend backward, consumed+cleared per surfel
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace d2gs {
+
+constexpr int TILE_X = 16;
+constexpr int TILE_Y = 16;
+constexpr int TILE_PIX = TILE_X * TILE_Y;
+constexpr int NUM_CH = 3;
+#define D2GS_FILTER_SIZE 0.7071067811865476   // double literal, like the reference macro (auxiliary.h:20)
+#define D2GS_NEAR_PLANE 0.2
+#define D2GS_FAR_PLANE 100.0
+
+// spherical-harmonics constants
+__device__ const float kSH_C0 = 0.28209479177387814f;
+__device__ const float kSH_C1 = 0.4886025119029199f;
+__device__ const float kSH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                                 -1.0925484305920792f, 0.5462742152960396f};
+__device__ const float kSH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                                 0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                                                 -0.5900435899266435f};
+
+// Projected surfel record, 80 B.
+//  q0 = (Tu.x, Tu.y, Tu.z, Tv.x)   q1 = (Tv.y, Tv.z, Tw.x, Tw.y)   q2 = (Tw.z, mean2D.x, mean2D.y, opacity)
+//  q3 = (normal.x, normal.y, normal.z, depth)                      q4 = (r, g, b, 0)
+struct __align__(16) SurfelRec {
+  float4 q0, q1, q2, q3, q4;
+};
+static_assert(sizeof(SurfelRec) == 80, "SurfelRec must be 80 bytes");
+
+// Per-surfel raster gradients accumulated by the blend backward (80 B).
+//  [0..8] dL/dtransMat  [9..10] dL/dmean2D.xy  [11..13] dL/dnormal  [14] dL/dopacity  [15..17] dL/dcolor  [18..19] pad
+constexpr int GRAD_REC_FLOATS = 20;
+constexpr int G_T = 0, G_M2D = 9, G_NRM = 11, G_OPA = 14, G_COL = 15;
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+struct GeomLayout {
+  size_t rec, clamped, tiles_touched, point_offsets, scan_temp, total;
+  size_t scan_temp_bytes;
+};
+struct ImgLayout {
+  size_t ranges, final_T, n_contrib, total;
+};
+struct BinLayout {
+  size_t keys_unsorted, keys_sorted, vals_unsorted, point_list, sort_temp, total;
+  size_t sort_temp_bytes;
+};
+
+GeomLayout geom_layout(int P);
+ImgLayout img_layout(int W, int H);
+BinLayout bin_layout(int64_t R);
+
+struct RectU { uint32_t x0, y0, x1, y1; };
+
+// Tile rectangle of a surfel (reference: auxiliary.h:64-74).  Float arithmetic and the float->int truncation
+// are part of the contract: tile lists must be bit-exact.
+__device__ __forceinline__ RectU tile_rect(float px, float py, int max_radius, uint32_t gx, uint32_t gy) {
+  RectU r;
+  r.x0 = min(gx, (uint32_t)max(0, (int)((px - max_radius) / TILE_X)));
+  r.y0 = min(gy, (uint32_t)max(0, (int)((py - max_radius) / TILE_Y)));
+  r.x1 = min(gx, (uint32_t)max(0, (int)((px + max_radius + TILE_X - 1) / TILE_X)));
+  r.y1 = min(gy, (uint32_t)max(0, (int)((py + max_radius + TILE_Y - 1) / TILE_Y)));
+  return r;
+}
+
+// ---- minimal column-major 3-vector algebra; operators are component-wise so that the float-op DAG the
+// ---- compiler sees (and therefore its FMA contraction) is the one a generic vector library produces.
+struct v3 { float x, y, z; };
+__device__ __forceinline__ v3 operator+(v3 a, v3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ v3 operator-(v3 a, v3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ v3 operator-(v3 a) { return {-a.x, -a.y, -a.z}; }
+__device__ __forceinline__ v3 operator*(v3 a, v3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
+__device__ __forceinline__ v3 operator*(v3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ v3 operator*(float s, v3 a) { return {s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ v3 operator/(v3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+__device__ __forceinline__ float dot3(v3 a, v3 b) {
+  v3 t = a * b;
+  return t.x + t.y + t.z;
+}
+__device__ __forceinline__ v3 cross3(v3 a, v3 b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+struct m3 { v3 c0, c1, c2; };   // columns
+__device__ __forceinline__ v3 operator*(const m3& m, v3 v) {
+  return {m.c0.x * v.x + m.c1.x * v.y + m.c2.x * v.z, m.c0.y * v.x + m.c1.y * v.y + m.c2.y * v.z,
+          m.c0.z * v.x + m.c1.z * v.y + m.c2.z * v.z};
+}
+__device__ __forceinline__ m3 transpose3(const m3& m) {
+  return {{m.c0.x, m.c1.x, m.c2.x}, {m.c0.y, m.c1.y, m.c2.y}, {m.c0.z, m.c1.z, m.c2.z}};
+}
+// world->view rotation block of the (transposed, column-major indexed) view matrix
+__device__ __forceinline__ m3 view_rot(const float* v) {
+  return {{v[0], v[1], v[2]}, {v[4], v[5], v[6]}, {v[8], v[9], v[10]}};
+}
+// unit-quaternion (w,x,y,z) -> rotation, columns (reference: auxiliary.h:188-210)
+__device__ __forceinline__ m3 quat_to_rot(float4 q) {
+  float s = rsqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+  float w = q.x * s, x = q.y * s, y = q.z * s, z = q.w * s;
+  return {{1.f - 2.f * (y * y + z * z), 2.f * (x * y + w * z), 2.f * (x * z - w * y)},
+          {2.f * (x * y - w * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z + w * x)},
+          {2.f * (x * z + w * y), 2.f * (y * z - w * x), 1.f - 2.f * (x * x + y * y)}};
+}
+
+// ---- launch-side argument blocks ----------------------------------------------------------------------
+struct FwdParams {
+  int P, D, M, W, H;
+  const float* bg;
+  const float* means3D;
+  const float* shs;
+  const float* sh_rest;
+  const float* colors_precomp;
+  const float* opacities;
+  const float* scales;
+  const float* rotations;
+  const float* transMat_precomp;
+  const float* view;
+  const float* proj;
+  const float* campos;
+  float tan_fovx, tan_fovy, focal_x, focal_y;
+  int prefiltered;
+  uint32_t gx, gy;
+};
+
+void launch_preprocess_fwd(const FwdParams& p, SurfelRec* rec, uint8_t* clamped, int* radii, uint32_t* tiles_touched,
+                           cudaStream_t s);
+void launch_duplicate(int P, const SurfelRec* rec, const int* radii, const uint32_t* offsets, uint64_t* keys,
+                      uint32_t* vals, uint32_t gx, uint32_t gy, cudaStream_t s);
+void launch_ranges(int64_t R, const uint64_t* keys_sorted, uint2* ranges, cudaStream_t s);
+void launch_blend_fwd(const FwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
+                      float* final_T, uint32_t* n_contrib, float* out_color, float* out_others, cudaStream_t s);
+
+struct BwdParams {
+  int P, D, M, W, H;
+  const float* bg;
+  const float* means3D;
+  const float* shs;
+  const float* sh_rest;
+  const float* colors_precomp;
+  const float* scales;
+  const float* rotations;
+  const float* transMat_precomp;
+  const float* view;
+  const float* proj;
+  const float* campos;
+  float tan_fovx, tan_fovy, focal_x, focal_y;
+  uint32_t gx, gy;
+};
+void launch_blend_bwd(const BwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
+                      const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, const float* dL_dothers,
+                      float* grad_rec, cudaStream_t s);
+void launch_preprocess_bwd(const BwdParams& p, const SurfelRec* rec, const uint8_t* clamped, const int* radii,
+                           float* grad_rec, float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
+                           float* dL_dmeans3D, float* dL_dtransMat, float* dL_dsh, float* dL_dsh_rest,
+                           float* dL_dscales, float* dL_drot, cudaStream_t s);
+void launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s);
+
+}  // namespace d2gs

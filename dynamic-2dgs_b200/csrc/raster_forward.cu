@@ -1,0 +1,366 @@
+// Forward kernels of the surfel rasterizer for sm_100a:
+//   preprocess (per surfel) -> [scan] -> tile-instance emission -> [radix sort] -> tile ranges -> per-tile blend.
+// Behavioural contract: DSR/cuda_rasterizer/forward.cu:166-260 (preprocess), :265-463 (blend),
+// rasterizer_impl.cu:70-111 (instance emission), :116-138 (ranges).  Tile/sort indices must be bit-exact, so the
+// float expressions that feed integer decisions are written in the same association order as the reference's.
+#include "raster_common.cuh"
+
+namespace d2gs {
+
+// ------------------------------------------------------------------------------------------------------------
+// preprocess
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_sh(const FwdParams& p, int idx, int ncoef, float* sh /*[48]*/) {
+  if (p.sh_rest == nullptr) {
+    const float* base = p.shs + (size_t)idx * p.M * 3;
+    if (p.M == 16 && ((reinterpret_cast<uintptr_t>(p.shs) & 15) == 0)) {
+      const float4* b4 = reinterpret_cast<const float4*>(base);   // 192 B per surfel, 16-B aligned
+      const int n4 = (ncoef * 3 + 3) / 4;
+#pragma unroll
+      for (int i = 0; i < 12; i++) {
+        if (i < n4) {
+          float4 v = __ldg(b4 + i);
+          sh[4 * i] = v.x; sh[4 * i + 1] = v.y; sh[4 * i + 2] = v.z; sh[4 * i + 3] = v.w;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 48; i++)
+        if (i < ncoef * 3) sh[i] = __ldg(base + i);
+    }
+  } else {
+    const float* dc = p.shs + (size_t)idx * 3;
+    sh[0] = __ldg(dc); sh[1] = __ldg(dc + 1); sh[2] = __ldg(dc + 2);
+    const float* rest = p.sh_rest + (size_t)idx * (p.M - 1) * 3;
+#pragma unroll
+    for (int i = 3; i < 48; i++)
+      if (i < ncoef * 3) sh[i] = __ldg(rest + i - 3);
+  }
+}
+
+// SH basis evaluation, degree <= 3 (reference: forward.cu:20-71).  Returns the colour before "+0.5 / clamp".
+__device__ __forceinline__ v3 eval_sh(int deg, v3 dir, const float* sh) {
+  auto S = [&](int k) { return v3{sh[3 * k], sh[3 * k + 1], sh[3 * k + 2]}; };
+  v3 result = kSH_C0 * S(0);
+  if (deg > 0) {
+    float x = dir.x, y = dir.y, z = dir.z;
+    result = result - kSH_C1 * y * S(1) + kSH_C1 * z * S(2) - kSH_C1 * x * S(3);
+    if (deg > 1) {
+      float xx = x * x, yy = y * y, zz = z * z;
+      float xy = x * y, yz = y * z, xz = x * z;
+      result = result + kSH_C2[0] * xy * S(4) + kSH_C2[1] * yz * S(5) + kSH_C2[2] * (2.0f * zz - xx - yy) * S(6) +
+               kSH_C2[3] * xz * S(7) + kSH_C2[4] * (xx - yy) * S(8);
+      if (deg > 2) {
+        result = result + kSH_C3[0] * y * (3.0f * xx - yy) * S(9) + kSH_C3[1] * xy * z * S(10) +
+                 kSH_C3[2] * y * (4.0f * zz - xx - yy) * S(11) +
+                 kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * S(12) +
+                 kSH_C3[4] * x * (4.0f * zz - xx - yy) * S(13) + kSH_C3[5] * z * (xx - yy) * S(14) +
+                 kSH_C3[6] * x * (xx - 3.0f * yy) * S(15);
+      }
+    }
+  }
+  return result;
+}
+
+__global__ void __launch_bounds__(256) preprocess_fwd_kernel(FwdParams p, SurfelRec* __restrict__ rec,
+                                                             uint8_t* __restrict__ clamped, int* __restrict__ radii,
+                                                             uint32_t* __restrict__ tiles_touched) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.P) return;
+  radii[idx] = 0;
+  tiles_touched[idx] = 0;
+
+  const float* m = p.view;
+  const v3 pw = {p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]};
+  // near-plane cull (the only frustum test the reference keeps active)
+  const float depth = m[2] * pw.x + m[6] * pw.y + m[10] * pw.z + m[14];
+  if (depth <= 0.2f) {
+    if (p.prefiltered) {
+      printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+      __trap();
+    }
+    return;
+  }
+
+  float T[9];
+  v3 normal = {0.f, 0.f, 0.f};   // transMat_precomp path: the reference leaves this undefined; we define 0
+  if (p.transMat_precomp != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) T[i] = p.transMat_precomp[9 * (size_t)idx + i];
+  } else {
+    const float cx = float(p.W) / 2.0f, cy = float(p.H) / 2.0f;
+    const m3 Wm = view_rot(m);
+    const v3 cam = {m[12], m[13], m[14]};
+    const v3 p_view = Wm * pw + cam;
+    const float2 sc = reinterpret_cast<const float2*>(p.scales)[idx];
+    const float4 q = reinterpret_cast<const float4*>(p.rotations)[idx];
+    const m3 R = quat_to_rot(q);
+    const v3 M0 = Wm * (R.c0 * sc.x);
+    const v3 M1 = Wm * (R.c1 * sc.y);
+    const v3 M2 = p_view;
+    v3 tn = Wm * R.c2;
+    const float cs = dot3(-tn, p_view);
+    if (cs == 0.0f) return;   // exactly edge-on
+    const float mult = cs > 0 ? 1.f : -1.f;
+    tn = tn * mult;
+    // row k of the 3x3 homography: (fx*M_k.x + cx*M_k.z, fy*M_k.y + cy*M_k.z, M_k.z); the association
+    // order (product of focal first, then fused add of the principal-point term) is part of the contract.
+    T[0] = __fmaf_rn(cx, M0.z, __fmul_rn(p.focal_x, M0.x));
+    T[1] = __fmaf_rn(cx, M1.z, __fmul_rn(p.focal_x, M1.x));
+    T[2] = __fmaf_rn(cx, M2.z, __fmul_rn(p.focal_x, M2.x));
+    T[3] = __fmaf_rn(cy, M0.z, __fmul_rn(p.focal_y, M0.y));
+    T[4] = __fmaf_rn(cy, M1.z, __fmul_rn(p.focal_y, M1.y));
+    T[5] = __fmaf_rn(cy, M2.z, __fmul_rn(p.focal_y, M2.y));
+    T[6] = M0.z; T[7] = M1.z; T[8] = M2.z;
+    normal = tn;
+  }
+
+  // screen-space bounding box of the 1-sigma ellipse (forward.cu:133-163)
+  const v3 Tu = {T[0], T[1], T[2]}, Tv = {T[3], T[4], T[5]}, Tw = {T[6], T[7], T[8]};
+  const v3 sgn = {1.0f, 1.0f, -1.0f};
+  const float d = dot3(sgn, Tw * Tw);
+  if (d == 0.0f) return;
+  const v3 f = sgn * (1.0f / d);
+  const v3 pc = {dot3(f, Tu * Tw), dot3(f, Tv * Tw), dot3(f, Tw * Tw)};
+  const v3 h0 = pc * pc - v3{dot3(f, Tu * Tu), dot3(f, Tv * Tv), dot3(f, Tw * Tw)};
+  const float ex = sqrtf(fmaxf(0.0f, h0.x)), ey = sqrtf(fmaxf(0.0f, h0.y));
+  // radius = ceil(3 * max(extent, FilterSize)) evaluated in double because FilterSize is a double literal
+  const float radius = (float)ceil(3.f * fmax((double)fmaxf(ex, ey), D2GS_FILTER_SIZE));
+
+  const RectU r = tile_rect(pc.x, pc.y, (int)radius, p.gx, p.gy);
+  if ((r.x1 - r.x0) * (r.y1 - r.y0) == 0) return;
+
+  v3 rgb = {0.f, 0.f, 0.f};
+  if (p.colors_precomp == nullptr) {
+    const v3 campos = {p.campos[0], p.campos[1], p.campos[2]};
+    v3 dir = pw - campos;
+    dir = dir / sqrtf(dot3(dir, dir));
+    float sh[48];
+    const int ncoef = (p.D + 1) * (p.D + 1);
+    load_sh(p, idx, ncoef, sh);
+    v3 res = eval_sh(p.D, dir, sh);
+    res.x += 0.5f; res.y += 0.5f; res.z += 0.5f;
+    clamped[idx] = (uint8_t)((res.x < 0 ? 1 : 0) | (res.y < 0 ? 2 : 0) | (res.z < 0 ? 4 : 0));
+    rgb = {fmaxf(res.x, 0.0f), fmaxf(res.y, 0.0f), fmaxf(res.z, 0.0f)};
+  } else {
+    rgb = {p.colors_precomp[3 * (size_t)idx], p.colors_precomp[3 * (size_t)idx + 1], p.colors_precomp[3 * (size_t)idx + 2]};
+  }
+
+  radii[idx] = (int)radius;
+  tiles_touched[idx] = (r.y1 - r.y0) * (r.x1 - r.x0);
+  SurfelRec o;
+  o.q0 = make_float4(T[0], T[1], T[2], T[3]);
+  o.q1 = make_float4(T[4], T[5], T[6], T[7]);
+  o.q2 = make_float4(T[8], pc.x, pc.y, p.opacities[idx]);
+  o.q3 = make_float4(normal.x, normal.y, normal.z, depth);
+  o.q4 = make_float4(rgb.x, rgb.y, rgb.z, 0.f);
+  rec[idx] = o;
+}
+
+void launch_preprocess_fwd(const FwdParams& p, SurfelRec* rec, uint8_t* clamped, int* radii, uint32_t* tiles_touched,
+                           cudaStream_t s) {
+  if (p.P == 0) return;
+  preprocess_fwd_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p, rec, clamped, radii, tiles_touched);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// (surfel, tile) instance emission: key = tile id << 32 | depth bits, value = surfel id, row-major over the rect
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) duplicate_kernel(int P, const SurfelRec* __restrict__ rec,
+                                                        const int* __restrict__ radii,
+                                                        const uint32_t* __restrict__ offsets,
+                                                        uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                        uint32_t gx, uint32_t gy) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  const int rad = radii[idx];
+  if (rad <= 0) return;
+  uint32_t off = (idx == 0) ? 0 : offsets[idx - 1];
+  const float4 q2 = __ldg(&rec[idx].q2);
+  const float depth = __ldg(&rec[idx].q3.w);
+  const RectU r = tile_rect(q2.y, q2.z, rad, gx, gy);
+  const uint64_t dbits = (uint64_t)__float_as_uint(depth);
+  for (uint32_t y = r.y0; y < r.y1; y++) {
+    for (uint32_t x = r.x0; x < r.x1; x++) {
+      keys[off] = ((uint64_t)(y * gx + x) << 32) | dbits;
+      vals[off] = (uint32_t)idx;
+      off++;
+    }
+  }
+}
+
+void launch_duplicate(int P, const SurfelRec* rec, const int* radii, const uint32_t* offsets, uint64_t* keys,
+                      uint32_t* vals, uint32_t gx, uint32_t gy, cudaStream_t s) {
+  if (P == 0) return;
+  duplicate_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, rec, radii, offsets, keys, vals, gx, gy);
+}
+
+__global__ void __launch_bounds__(256) ranges_kernel(int64_t L, const uint64_t* __restrict__ keys,
+                                                     uint2* __restrict__ ranges) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= L) return;
+  const uint32_t cur = (uint32_t)(keys[idx] >> 32);
+  if (idx == 0) {
+    ranges[cur].x = 0;
+  } else {
+    const uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
+    if (cur != prev) {
+      ranges[prev].y = (uint32_t)idx;
+      ranges[cur].x = (uint32_t)idx;
+    }
+  }
+  if (idx == L - 1) ranges[cur].y = (uint32_t)L;
+}
+
+void launch_ranges(int64_t R, const uint64_t* keys_sorted, uint2* ranges, cudaStream_t s) {
+  if (R == 0) return;
+  ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(R, keys_sorted, ranges);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// per-tile front-to-back blend.  One CTA per 16x16 tile, one thread per pixel; each warp owns a compact
+// 8x4 pixel patch.  Instances are staged 256 at a time into shared memory as five float4 planes
+// (broadcast LDS.128 in the inner loop).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int BLEND_BATCH = 256;
+
+__device__ __forceinline__ void pixel_of_thread(int tid, int& lx, int& ly) {
+  const int w = tid >> 5, l = tid & 31;
+  lx = ((w & 1) << 3) | (l & 7);
+  ly = ((w >> 1) << 2) | (l >> 3);
+}
+
+__global__ void __launch_bounds__(TILE_PIX) blend_fwd_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
+    const SurfelRec* __restrict__ rec, const float* __restrict__ bg, float* __restrict__ final_T,
+    uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, float* __restrict__ out_others) {
+  __shared__ float4 s_q0[BLEND_BATCH], s_q1[BLEND_BATCH], s_q2[BLEND_BATCH], s_q3[BLEND_BATCH], s_q4[BLEND_BATCH];
+
+  const int tid = threadIdx.x;
+  int lx, ly;
+  pixel_of_thread(tid, lx, ly);
+  const uint32_t pix_x = blockIdx.x * TILE_X + lx, pix_y = blockIdx.y * TILE_Y + ly;
+  const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
+  const uint32_t pix_id = W * pix_y + pix_x;
+  const float2 pixf = {(float)pix_x + 0.5f, (float)pix_y + 0.5f};
+  bool done = !inside;
+
+  const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
+  const int rounds = (range.y - range.x + BLEND_BATCH - 1) / BLEND_BATCH;
+  int toDo = range.y - range.x;
+
+  float T = 1.0f;
+  uint32_t contributor = 0, last_contributor = 0;
+  float C[3] = {0.f, 0.f, 0.f};
+  float Dacc = 0.f, N[3] = {0.f, 0.f, 0.f};
+  float dist1 = 0.f, dist2 = 0.f, distortion = 0.f;
+  float median_depth = 0.f, median_weight = 0.f, median_contributor = -1.f;
+
+  for (int i = 0; i < rounds; i++, toDo -= BLEND_BATCH) {
+    if (__syncthreads_count(done) == TILE_PIX) break;
+    const int progress = i * BLEND_BATCH + tid;
+    if (range.x + progress < range.y) {
+      const uint32_t id = __ldg(&point_list[range.x + progress]);
+      const float4* r4 = reinterpret_cast<const float4*>(rec + id);
+      s_q0[tid] = __ldg(r4 + 0);
+      s_q1[tid] = __ldg(r4 + 1);
+      s_q2[tid] = __ldg(r4 + 2);
+      s_q3[tid] = __ldg(r4 + 3);
+      s_q4[tid] = __ldg(r4 + 4);
+    }
+    __syncthreads();
+
+    const int n = min(BLEND_BATCH, toDo);
+    for (int j = 0; !done && j < n; j++) {
+      contributor++;
+      const float4 a = s_q0[j], b = s_q1[j], c = s_q2[j];
+      const float3 Tu = {a.x, a.y, a.z}, Tv = {a.w, b.x, b.y}, Tw = {b.z, b.w, c.x};
+      // ray / splat intersection: two planes through the pixel, their cross product is the homogeneous hit point
+      const float3 k = {-Tu.x + pixf.x * Tw.x, -Tu.y + pixf.x * Tw.y, -Tu.z + pixf.x * Tw.z};
+      const float3 l = {-Tv.x + pixf.y * Tw.x, -Tv.y + pixf.y * Tw.y, -Tv.z + pixf.y * Tw.z};
+      const float3 p = {k.y * l.z - k.z * l.y, k.z * l.x - k.x * l.z, k.x * l.y - k.y * l.x};
+      if (p.z == 0.0f) continue;
+      const float2 s = {p.x / p.z, p.y / p.z};
+      const float rho3d = (s.x * s.x + s.y * s.y);
+      const float2 dd = {c.y - pixf.x, c.z - pixf.y};
+      // 1/FilterSize^2 * r^2 evaluated in double and rounded equals 2*r^2 in float exactly
+      const float rho2d = 2.0f * (dd.x * dd.x + dd.y * dd.y);
+      const float rho = fminf(rho3d, rho2d);
+      const float depth = (rho3d <= rho2d) ? (s.x * Tw.x + s.y * Tw.y) + Tw.z : Tw.z;
+      if (depth < 0.2f) continue;   // (double)depth < 0.2 <=> depth < 0.2f
+      const float power = -0.5f * rho;
+      if (power > 0.0f) continue;
+      const float alpha = fminf(0.99f, c.w * expf(power));
+      if (alpha < 1.0f / 255.0f) continue;
+      const float test_T = T * (1 - alpha);
+      if (test_T < 0.0001f) {
+        done = true;
+        continue;
+      }
+      const float w = alpha * T;
+      const float4 nrm = s_q3[j];
+      const float4 col = s_q4[j];
+      // distortion bookkeeping (depth mapped to [0,1] between the near and far planes)
+      const float A = 1 - T;
+      const float md = (float)((D2GS_FAR_PLANE * depth - D2GS_FAR_PLANE * D2GS_NEAR_PLANE) /
+                               ((D2GS_FAR_PLANE - D2GS_NEAR_PLANE) * depth));
+      const float error = md * md * A + dist2 - 2 * md * dist1;
+      distortion += error * alpha * T;
+      if (T > 0.5f) {
+        median_depth = depth;
+        median_weight = alpha * T;
+        median_contributor = contributor;
+      }
+      N[0] += nrm.x * alpha * T; N[1] += nrm.y * alpha * T; N[2] += nrm.z * alpha * T;
+      Dacc += depth * alpha * T;
+      dist1 += md * alpha * T;
+      dist2 += md * md * alpha * T;
+      C[0] += col.x * alpha * T; C[1] += col.y * alpha * T; C[2] += col.z * alpha * T;
+      (void)w;
+      T = test_T;
+      last_contributor = contributor;
+    }
+  }
+
+  if (inside) {
+    const size_t HW = (size_t)H * W;
+    final_T[pix_id] = T;
+    final_T[pix_id + HW] = dist1;
+    final_T[pix_id + 2 * HW] = dist2;
+    n_contrib[pix_id] = last_contributor;
+    n_contrib[pix_id + HW] = (uint32_t)median_contributor;   // -1 saturates to 0
+    out_color[0 * HW + pix_id] = C[0] + T * bg[0];
+    out_color[1 * HW + pix_id] = C[1] + T * bg[1];
+    out_color[2 * HW + pix_id] = C[2] + T * bg[2];
+    out_others[0 * HW + pix_id] = Dacc;
+    out_others[1 * HW + pix_id] = 1 - T;
+    out_others[2 * HW + pix_id] = N[0];
+    out_others[3 * HW + pix_id] = N[1];
+    out_others[4 * HW + pix_id] = N[2];
+    out_others[5 * HW + pix_id] = median_depth;
+    out_others[6 * HW + pix_id] = distortion;
+    out_others[7 * HW + pix_id] = median_weight;
+  }
+}
+
+void launch_blend_fwd(const FwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
+                      float* final_T, uint32_t* n_contrib, float* out_color, float* out_others, cudaStream_t s) {
+  dim3 grid(p.gx, p.gy, 1);
+  blend_fwd_kernel<<<grid, TILE_PIX, 0, s>>>(ranges, point_list, p.W, p.H, rec, p.bg, final_T, n_contrib, out_color,
+                                            out_others);
+}
+
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
+                                    uint8_t* __restrict__ present) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  const float z = view[2] * means3D[3 * idx] + view[6] * means3D[3 * idx + 1] + view[10] * means3D[3 * idx + 2] + view[14];
+  present[idx] = !(z <= 0.2f);
+}
+
+void launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s) {
+  if (P == 0) return;
+  mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, view, present);
+}
+
+}  // namespace d2gs

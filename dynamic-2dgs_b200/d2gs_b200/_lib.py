@@ -1,0 +1,143 @@
+"""ctypes binding of libd2gs.so (include/d2gs.h).
+
+The product path has NO fallback: if the CUDA library is missing or a call fails this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libd2gs.so")
+
+c_float_p = C.c_void_p  # raw device addresses are passed as integers
+
+
+class D2gsConfig(C.Structure):
+    _fields_ = [("num_channels", C.c_int), ("block_x", C.c_int), ("block_y", C.c_int), ("tight_bbox", C.c_int),
+                ("render_auxiliary", C.c_int), ("backface_cull", C.c_int), ("dual_visible", C.c_int),
+                ("detach_weight", C.c_int), ("near_plane", C.c_double), ("far_plane", C.c_double),
+                ("filter_size", C.c_double), ("sm_arch", C.c_int)]
+
+
+class RasterFwdArgs(C.Structure):
+    _fields_ = [("P", C.c_int), ("D", C.c_int), ("M", C.c_int), ("width", C.c_int), ("height", C.c_int),
+                ("background", C.c_void_p), ("means3D", C.c_void_p), ("shs", C.c_void_p), ("sh_rest", C.c_void_p),
+                ("colors_precomp", C.c_void_p), ("opacities", C.c_void_p), ("scales", C.c_void_p),
+                ("rotations", C.c_void_p), ("transMat_precomp", C.c_void_p), ("scale_modifier", C.c_float),
+                ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
+                ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("prefiltered", C.c_int), ("debug", C.c_int),
+                ("out_color", C.c_void_p), ("out_others", C.c_void_p), ("radii", C.c_void_p),
+                ("geom_buffer", C.c_void_p), ("geom_bytes", C.c_size_t),
+                ("img_buffer", C.c_void_p), ("img_bytes", C.c_size_t),
+                ("binning_buffer", C.c_void_p), ("binning_bytes", C.c_size_t),
+                ("resume", C.c_int),
+                ("num_rendered", C.POINTER(C.c_int64)), ("binning_required", C.POINTER(C.c_size_t))]
+
+
+class RasterBwdArgs(C.Structure):
+    _fields_ = [("P", C.c_int), ("D", C.c_int), ("M", C.c_int), ("width", C.c_int), ("height", C.c_int),
+                ("num_rendered", C.c_int64),
+                ("background", C.c_void_p), ("means3D", C.c_void_p), ("shs", C.c_void_p), ("sh_rest", C.c_void_p),
+                ("colors_precomp", C.c_void_p), ("scales", C.c_void_p), ("rotations", C.c_void_p),
+                ("transMat_precomp", C.c_void_p), ("scale_modifier", C.c_float),
+                ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
+                ("tan_fovx", C.c_float), ("tan_fovy", C.c_float),
+                ("radii", C.c_void_p), ("geom_buffer", C.c_void_p), ("binning_buffer", C.c_void_p),
+                ("img_buffer", C.c_void_p), ("dL_dout_color", C.c_void_p), ("dL_dout_others", C.c_void_p),
+                ("debug", C.c_int), ("grad_scratch", C.c_void_p),
+                ("dL_dmeans2D", C.c_void_p), ("dL_dcolors", C.c_void_p), ("dL_dopacity", C.c_void_p),
+                ("dL_dmeans3D", C.c_void_p), ("dL_dtransMat", C.c_void_p), ("dL_dsh", C.c_void_p),
+                ("dL_dsh_rest", C.c_void_p), ("dL_dscales", C.c_void_p), ("dL_drotations", C.c_void_p)]
+
+
+class RasterState(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("means2D", "depths", "transMat", "normal_opacity", "rgb", "clamped", "tiles_touched", "point_offsets",
+                 "keys_unsorted", "values_unsorted", "keys_sorted", "point_list", "ranges", "final_T", "n_contrib")]
+
+
+class DeformFwdArgs(C.Structure):
+    _fields_ = [("P", C.c_int), ("M", C.c_int), ("K", C.c_int), ("hyper_dim", C.c_int),
+                ("xyz", C.c_void_p), ("feature", C.c_void_p), ("feature_stride", C.c_int),
+                ("nodes", C.c_void_p), ("node_radius_log", C.c_void_p), ("node_weight_logit", C.c_void_p),
+                ("node_trans", C.c_void_p), ("node_rot", C.c_void_p), ("node_scale", C.c_void_p),
+                ("node_local_rot", C.c_void_p), ("motion_mask", C.c_void_p),
+                ("nn_idx", C.c_void_p), ("nn_dist", C.c_void_p), ("nn_weight", C.c_void_p),
+                ("d_xyz", C.c_void_p), ("d_rotation", C.c_void_p), ("d_scaling", C.c_void_p)]
+
+
+class DeformBwdArgs(C.Structure):
+    _fields_ = [("P", C.c_int), ("M", C.c_int), ("K", C.c_int), ("hyper_dim", C.c_int),
+                ("xyz", C.c_void_p), ("feature", C.c_void_p), ("feature_stride", C.c_int),
+                ("nodes", C.c_void_p), ("node_radius_log", C.c_void_p), ("node_weight_logit", C.c_void_p),
+                ("node_trans", C.c_void_p), ("node_rot", C.c_void_p), ("node_scale", C.c_void_p),
+                ("node_local_rot", C.c_void_p), ("motion_mask", C.c_void_p),
+                ("nn_idx", C.c_void_p), ("nn_dist", C.c_void_p), ("nn_weight", C.c_void_p),
+                ("dL_d_xyz", C.c_void_p), ("dL_d_rotation", C.c_void_p), ("dL_d_scaling", C.c_void_p),
+                ("dL_dnode_trans", C.c_void_p), ("dL_dnode_rot", C.c_void_p), ("dL_dnode_scale", C.c_void_p),
+                ("dL_dnode_local_rot", C.c_void_p), ("dL_dnodes", C.c_void_p), ("dL_dnode_radius_log", C.c_void_p),
+                ("dL_dnode_weight_logit", C.c_void_p), ("dL_dfeature", C.c_void_p), ("dL_dmotion_mask", C.c_void_p)]
+
+
+# every symbol include/d2gs.h declares; tests assert the shared library exports all of them
+EXPORTED_SYMBOLS = (
+    "d2gs_last_error", "d2gs_version", "d2gs_get_config", "d2gs_raster_workspace", "d2gs_raster_forward",
+    "d2gs_raster_backward", "d2gs_mark_visible", "d2gs_raster_export_state", "d2gs_deform_forward",
+    "d2gs_deform_backward",
+)
+
+D2GS_OK = 0
+D2GS_NEED_BINNING = 1
+
+_lib = None
+
+
+class D2gsError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libd2gs.so.  Raises (never falls back) when the CUDA extension is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise D2gsError(
+            f"{LIB_PATH} is missing: the sm_100a CUDA extension is not built. "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'` (or `make -C dynamic-2dgs_b200/csrc`). "
+            "There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.d2gs_last_error.restype = C.c_char_p
+    L.d2gs_version.restype = C.c_char_p
+    L.d2gs_get_config.argtypes = [C.POINTER(D2gsConfig)]
+    L.d2gs_raster_workspace.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_size_t),
+                                        C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    L.d2gs_raster_forward.argtypes = [C.POINTER(RasterFwdArgs), C.c_void_p]
+    L.d2gs_raster_backward.argtypes = [C.POINTER(RasterBwdArgs), C.c_void_p]
+    L.d2gs_mark_visible.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.d2gs_raster_export_state.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.POINTER(RasterState), C.c_void_p]
+    L.d2gs_deform_forward.argtypes = [C.POINTER(DeformFwdArgs), C.c_void_p]
+    L.d2gs_deform_backward.argtypes = [C.POINTER(DeformBwdArgs), C.c_void_p]
+    for name in EXPORTED_SYMBOLS:
+        getattr(L, name)
+    _lib = L
+    return L
+
+
+def check(code: int, what: str) -> None:
+    if code < 0:
+        raise D2gsError(f"{what} failed ({code}): {lib().d2gs_last_error().decode()}")
+
+
+def config() -> dict:
+    c = D2gsConfig()
+    check(lib().d2gs_get_config(C.byref(c)), "d2gs_get_config")
+    return {n: getattr(c, n) for n, _ in D2gsConfig._fields_}
+
+
+def workspace_sizes(P: int, W: int, H: int, R: int = 0):
+    g, i, b = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    check(lib().d2gs_raster_workspace(P, W, H, R, C.byref(g), C.byref(i), C.byref(b)), "d2gs_raster_workspace")
+    return g.value, i.value, b.value

@@ -1,0 +1,319 @@
+"""Autograd front-end of the B200 surfel rasterizer (calls libd2gs.so through the C ABI of include/d2gs.h).
+
+Mirrors ``_RasterizeGaussians`` of the reference op (DSR/diff_surfel_rasterization/__init__.py:44-156): same
+argument order, same outputs ``(color (3,H,W), radii (P) int32, allmap (8,H,W))``, same gradient slots, same
+debug-snapshot behaviour.  Extension over the reference: ``sh`` may be given as two tensors (DC block + rest)
+so the caller never concatenates 192 B per surfel per frame (gaussian_renderer/__init__.py:114,122).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+# (device index, P, W, H) -> last num_rendered; sizes the binning workspace so forward is one C call
+_R_HINT: dict = {}
+# (device index, P) -> zeroed (P,20) fp32 scratch the blend backward accumulates into (left zero by the library)
+_GRAD_SCRATCH: dict = {}
+_LAUNCH_COUNT = {"forward": 0, "backward": 0}
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _opt(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """The reference encodes "not provided" as an empty tensor (DSR/.../__init__.py:198-208)."""
+    if t is None or t.numel() == 0:
+        return None
+    return t
+
+
+def _prep(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def cpu_deep_copy_tuple(input_tuple):
+    return tuple(item.cpu().clone() if isinstance(item, torch.Tensor) else item for item in input_tuple)
+
+
+def grad_scratch(device: torch.device, P: int) -> torch.Tensor:
+    key = (device.index, P)
+    t = _GRAD_SCRATCH.get(key)
+    if t is None:
+        if len(_GRAD_SCRATCH) > 8:
+            _GRAD_SCRATCH.clear()
+        t = torch.zeros((max(P, 1), 20), dtype=torch.float32, device=device)
+        _GRAD_SCRATCH[key] = t
+    return t
+
+
+class RasterContext:
+    """Opaque forward state kept for backward (the reference's geomBuffer / binningBuffer / imgBuffer)."""
+    __slots__ = ("P", "D", "M", "W", "H", "num_rendered", "geom", "binning", "img")
+
+
+def raster_forward(bg, means3D, colors_precomp, opacities, scales, rotations, scale_modifier, transMat_precomp,
+                   viewmatrix, projmatrix, tanfovx, tanfovy, image_height, image_width, sh, sh_rest, degree, campos,
+                   prefiltered, debug):
+    """Equivalent of ``_C.rasterize_gaussians`` (DSR/rasterize_points.cu:39-141).
+
+    Returns (num_rendered, color, others, radii, ctx)."""
+    L = _lib.lib()
+    if means3D.dim() != 2 or means3D.shape[1] != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    if scales is not None and (scales.dim() != 2 or scales.shape[1] != 2):
+        raise RuntimeError("scales must have dimensions (num_points, 2)")
+    if rotations is not None and (rotations.dim() != 2 or rotations.shape[1] != 4):
+        raise RuntimeError("rotations must have dimensions (num_points, 4)")
+    dev = means3D.device
+    P, H, W = int(means3D.shape[0]), int(image_height), int(image_width)
+    M = 0
+    if sh is not None:
+        M = int(sh.shape[1]) + (int(sh_rest.shape[1]) if sh_rest is not None else 0)
+    f32 = dict(dtype=torch.float32, device=dev)
+    color = torch.empty((3, H, W), **f32)
+    others = torch.empty((8, H, W), **f32)
+    radii = torch.empty((P,), dtype=torch.int32, device=dev)
+    ctx = RasterContext()
+    ctx.P, ctx.D, ctx.M, ctx.W, ctx.H = P, int(degree), M, W, H
+    gbytes, ibytes, _ = _lib.workspace_sizes(P, W, H, 0)
+    ctx.geom = torch.empty((gbytes,), dtype=torch.uint8, device=dev)
+    ctx.img = torch.empty((ibytes,), dtype=torch.uint8, device=dev)
+    hint_key = (dev.index, P, W, H)
+    r_hint = _R_HINT.get(hint_key, 4 * P + 1024)
+    _, _, bbytes = _lib.workspace_sizes(P, W, H, int(r_hint * 1.25) + 1024)
+    ctx.binning = torch.empty((bbytes,), dtype=torch.uint8, device=dev)
+
+    num_rendered = C.c_int64(0)
+    required = C.c_size_t(0)
+    a = _lib.RasterFwdArgs()
+    a.P, a.D, a.M, a.width, a.height = P, int(degree), M, W, H
+    a.background = _ptr(bg); a.means3D = _ptr(means3D)
+    a.shs = _ptr(sh); a.sh_rest = _ptr(sh_rest); a.colors_precomp = _ptr(colors_precomp)
+    a.opacities = _ptr(opacities); a.scales = _ptr(scales); a.rotations = _ptr(rotations)
+    a.transMat_precomp = _ptr(transMat_precomp); a.scale_modifier = float(scale_modifier)
+    a.viewmatrix = _ptr(viewmatrix); a.projmatrix = _ptr(projmatrix); a.campos = _ptr(campos)
+    a.tan_fovx, a.tan_fovy = float(tanfovx), float(tanfovy)
+    a.prefiltered, a.debug = int(bool(prefiltered)), int(bool(debug))
+    a.out_color, a.out_others, a.radii = color.data_ptr(), others.data_ptr(), radii.data_ptr()
+    a.geom_buffer, a.geom_bytes = ctx.geom.data_ptr(), gbytes
+    a.img_buffer, a.img_bytes = ctx.img.data_ptr(), ibytes
+    a.binning_buffer, a.binning_bytes = ctx.binning.data_ptr(), bbytes
+    a.resume = 0
+    a.num_rendered = C.pointer(num_rendered)
+    a.binning_required = C.pointer(required)
+    stream = _stream_ptr(dev)
+    with torch.cuda.device(dev):
+        rc = L.d2gs_raster_forward(C.byref(a), stream)
+        if rc == _lib.D2GS_NEED_BINNING:
+            bbytes = int(required.value * 1.1) + 4096
+            ctx.binning = torch.empty((bbytes,), dtype=torch.uint8, device=dev)
+            a.binning_buffer, a.binning_bytes, a.resume = ctx.binning.data_ptr(), bbytes, 1
+            rc = L.d2gs_raster_forward(C.byref(a), stream)
+    _lib.check(rc, "d2gs_raster_forward")
+    if rc != _lib.D2GS_OK:
+        raise _lib.D2gsError(f"d2gs_raster_forward returned {rc}")
+    ctx.num_rendered = int(num_rendered.value)
+    _R_HINT[hint_key] = ctx.num_rendered
+    _LAUNCH_COUNT["forward"] += 1
+    return ctx.num_rendered, color, others, radii, ctx
+
+
+def raster_backward(bg, means3D, radii, colors_precomp, scales, rotations, scale_modifier, transMat_precomp, viewmatrix,
+                    projmatrix, tanfovx, tanfovy, dL_dout_color, dL_dout_others, sh, sh_rest, degree, campos, ctx,
+                    debug, want=None):
+    """Equivalent of ``_C.rasterize_gaussians_backward`` (DSR/rasterize_points.cu:143-240).
+
+    Returns dict with dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh, dL_dsh_rest,
+    dL_dscales, dL_drotations (entries not requested through ``want`` are None)."""
+    L = _lib.lib()
+    dev = means3D.device
+    P, M = ctx.P, ctx.M
+    f32 = dict(dtype=torch.float32, device=dev)
+    want = want or {}
+    w = lambda k: want.get(k, True)
+    g = dict.fromkeys(("dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dtransMat", "dL_dsh",
+                       "dL_dsh_rest", "dL_dscales", "dL_drotations"))
+    if w("dL_dmeans2D"): g["dL_dmeans2D"] = torch.empty((P, 3), **f32)
+    if w("dL_dcolors"): g["dL_dcolors"] = torch.empty((P, 3), **f32)
+    if w("dL_dopacity"): g["dL_dopacity"] = torch.empty((P, 1), **f32)
+    if w("dL_dmeans3D"): g["dL_dmeans3D"] = torch.empty((P, 3), **f32)
+    if w("dL_dtransMat"): g["dL_dtransMat"] = torch.empty((P, 9), **f32)
+    if sh is not None and w("dL_dsh"):
+        if sh_rest is not None:
+            g["dL_dsh"] = torch.empty((P, 1, 3), **f32)
+            g["dL_dsh_rest"] = torch.empty((P, M - 1, 3), **f32)
+        else:
+            g["dL_dsh"] = torch.empty((P, M, 3), **f32)
+    elif w("dL_dsh"):
+        g["dL_dsh"] = torch.zeros((P, 0, 3), **f32)
+    if w("dL_dscales"): g["dL_dscales"] = torch.empty((P, 2), **f32)
+    if w("dL_drotations"): g["dL_drotations"] = torch.empty((P, 4), **f32)
+    if P == 0:
+        return g
+    if scales is None:   # transMat_precomp path: no surfel-frame gradients
+        for k in ("dL_dscales", "dL_drotations"):
+            if g[k] is not None: g[k].zero_()
+    a = _lib.RasterBwdArgs()
+    a.P, a.D, a.M, a.width, a.height = P, int(degree), M, ctx.W, ctx.H
+    a.num_rendered = ctx.num_rendered
+    a.background = _ptr(bg); a.means3D = _ptr(means3D); a.shs = _ptr(sh); a.sh_rest = _ptr(sh_rest)
+    a.colors_precomp = _ptr(colors_precomp); a.scales = _ptr(scales); a.rotations = _ptr(rotations)
+    a.transMat_precomp = _ptr(transMat_precomp); a.scale_modifier = float(scale_modifier)
+    a.viewmatrix = _ptr(viewmatrix); a.projmatrix = _ptr(projmatrix); a.campos = _ptr(campos)
+    a.tan_fovx, a.tan_fovy = float(tanfovx), float(tanfovy)
+    a.radii = radii.data_ptr()
+    a.geom_buffer, a.binning_buffer, a.img_buffer = ctx.geom.data_ptr(), ctx.binning.data_ptr(), ctx.img.data_ptr()
+    a.dL_dout_color, a.dL_dout_others = dL_dout_color.data_ptr(), dL_dout_others.data_ptr()
+    a.debug = int(bool(debug))
+    a.grad_scratch = grad_scratch(dev, P).data_ptr()
+    a.dL_dmeans2D = _ptr(g["dL_dmeans2D"]); a.dL_dcolors = _ptr(g["dL_dcolors"]); a.dL_dopacity = _ptr(g["dL_dopacity"])
+    a.dL_dmeans3D = _ptr(g["dL_dmeans3D"]); a.dL_dtransMat = _ptr(g["dL_dtransMat"])
+    a.dL_dsh = _ptr(g["dL_dsh"]) if sh is not None else None
+    a.dL_dsh_rest = _ptr(g["dL_dsh_rest"])
+    a.dL_dscales = _ptr(g["dL_dscales"]) if scales is not None else None
+    a.dL_drotations = _ptr(g["dL_drotations"]) if scales is not None else None
+    with torch.cuda.device(dev):
+        rc = L.d2gs_raster_backward(C.byref(a), _stream_ptr(dev))
+    if rc != 0:
+        _GRAD_SCRATCH.pop((dev.index, P), None)   # scratch may be dirty: never reuse it
+    _lib.check(rc, "d2gs_raster_backward")
+    _LAUNCH_COUNT["backward"] += 1
+    return g
+
+
+class _RasterizeSurfels(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, sh_rest, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings):
+        rs = raster_settings
+        sh_, shr_ = _prep(_opt(sh), "sh"), _prep(_opt(sh_rest), "sh_rest")
+        col_ = _prep(_opt(colors_precomp), "colors")
+        sc_, rot_ = _prep(_opt(scales), "scales"), _prep(_opt(rotations), "rotations")
+        cov_ = _prep(_opt(cov3Ds_precomp), "transMat_precomp")
+        m3 = _prep(means3D, "means3D")
+        op_ = _prep(opacities, "opacity")
+        bg = _prep(rs.bg, "background")
+        view, proj, campos = _prep(rs.viewmatrix, "viewmatrix"), _prep(rs.projmatrix, "projmatrix"), _prep(rs.campos, "campos")
+        args = (bg, m3, col_, op_, sc_, rot_, rs.scale_modifier, cov_, view, proj, rs.tanfovx, rs.tanfovy,
+                rs.image_height, rs.image_width, sh_, shr_, rs.sh_degree, campos, rs.prefiltered, rs.debug)
+        if rs.debug:
+            cpu_args = cpu_deep_copy_tuple(args)   # copy before anything can be corrupted
+            try:
+                num_rendered, color, others, radii, rctx = raster_forward(*args)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise ex
+        else:
+            num_rendered, color, others, radii, rctx = raster_forward(*args)
+        ctx.raster_settings = rs
+        ctx.num_rendered = num_rendered
+        ctx.rctx = rctx
+        ctx.prepped = (bg, view, proj, campos)
+        ctx.save_for_backward(col_, m3, sc_, rot_, cov_, radii, sh_, shr_)
+        ctx.mark_non_differentiable(radii)
+        return color, radii, others
+
+    @staticmethod
+    def backward(ctx, grad_out_color, grad_radii, grad_depth):
+        rs = ctx.raster_settings
+        col_, m3, sc_, rot_, cov_, radii, sh_, shr_ = ctx.saved_tensors
+        bg, view, proj, campos = ctx.prepped
+        rctx = ctx.rctx
+        dev = m3.device
+        if grad_out_color is None:
+            grad_out_color = torch.zeros((3, rctx.H, rctx.W), dtype=torch.float32, device=dev)
+        if grad_depth is None:
+            grad_depth = torch.zeros((8, rctx.H, rctx.W), dtype=torch.float32, device=dev)
+        grad_out_color = grad_out_color.float().contiguous()
+        grad_depth = grad_depth.float().contiguous()
+        need = ctx.needs_input_grad
+        want = {"dL_dmeans3D": need[0], "dL_dmeans2D": need[1], "dL_dsh": need[2] or need[3],
+                "dL_dcolors": need[4] and col_ is not None, "dL_dopacity": need[5], "dL_dscales": need[6] or need[7],
+                "dL_drotations": need[6] or need[7], "dL_dtransMat": need[8] and cov_ is not None}
+        args = (bg, m3, radii, col_, sc_, rot_, rs.scale_modifier, cov_, view, proj, rs.tanfovx, rs.tanfovy,
+                grad_out_color, grad_depth, sh_, shr_, rs.sh_degree, campos, rctx, rs.debug)
+        if rs.debug:
+            cpu_args = cpu_deep_copy_tuple(args[:-2])
+            try:
+                g = raster_backward(*args, want=want)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_bw.dump")
+                print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+                raise ex
+        else:
+            g = raster_backward(*args, want=want)
+        grad_sh, grad_sh_rest = g["dL_dsh"], g["dL_dsh_rest"]
+        if sh_ is None:
+            grad_sh = None
+        return (g["dL_dmeans3D"], g["dL_dmeans2D"], grad_sh, grad_sh_rest, g["dL_dcolors"], g["dL_dopacity"],
+                g["dL_dscales"] if sc_ is not None else None, g["dL_drotations"] if rot_ is not None else None,
+                g["dL_dtransMat"] if cov_ is not None else None, None)
+
+
+def rasterize_surfels(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                      raster_settings, sh_rest=None):
+    """Functional entry point; with ``sh_rest`` the SH coefficients are passed as (P,1,3) + (P,M-1,3)."""
+    return _RasterizeSurfels.apply(means3D, means2D, sh, sh_rest, colors_precomp, opacities, scales, rotations,
+                                   cov3Ds_precomp, raster_settings)
+
+
+def mark_visible(positions, viewmatrix, projmatrix):
+    """Equivalent of ``_C.mark_visible`` (DSR/rasterize_points.cu:242-261)."""
+    L = _lib.lib()
+    pos = _prep(positions, "means3D")
+    view, proj = _prep(viewmatrix, "viewmatrix"), _prep(projmatrix, "projmatrix")
+    P = int(pos.shape[0])
+    present = torch.zeros((P,), dtype=torch.bool, device=pos.device)
+    if P:
+        with torch.cuda.device(pos.device):
+            _lib.check(L.d2gs_mark_visible(P, pos.data_ptr(), view.data_ptr(), proj.data_ptr(), present.data_ptr(),
+                                           _stream_ptr(pos.device)), "d2gs_mark_visible")
+    return present
+
+
+def export_state(rctx: RasterContext) -> dict:
+    """Parity/debug: the intermediates the reference hides in its three byte buffers, as torch tensors."""
+    L = _lib.lib()
+    dev = rctx.geom.device
+    P, W, H, R = rctx.P, rctx.W, rctx.H, rctx.num_rendered
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    f32 = dict(dtype=torch.float32, device=dev)
+    out = dict(means2D=torch.zeros((P, 2), **f32), depths=torch.zeros((P,), **f32), transMat=torch.zeros((P, 9), **f32),
+               normal_opacity=torch.zeros((P, 4), **f32), rgb=torch.zeros((P, 3), **f32),
+               clamped=torch.zeros((P, 3), dtype=torch.uint8, device=dev),
+               tiles_touched=torch.zeros((P,), dtype=torch.int32, device=dev),
+               point_offsets=torch.zeros((P,), dtype=torch.int32, device=dev),
+               keys_unsorted=torch.zeros((R,), dtype=torch.int64, device=dev),
+               values_unsorted=torch.zeros((R,), dtype=torch.int32, device=dev),
+               keys_sorted=torch.zeros((R,), dtype=torch.int64, device=dev),
+               point_list=torch.zeros((R,), dtype=torch.int32, device=dev),
+               ranges=torch.zeros((tiles, 2), dtype=torch.int32, device=dev),
+               final_T=torch.zeros((3, H, W), **f32), n_contrib=torch.zeros((2, H, W), dtype=torch.int32, device=dev))
+    st = _lib.RasterState()
+    for k, v in out.items():
+        setattr(st, k, v.data_ptr() if v.numel() else None)
+    with torch.cuda.device(dev):
+        _lib.check(L.d2gs_raster_export_state(P, W, H, R, rctx.geom.data_ptr(), rctx.binning.data_ptr(),
+                                              rctx.img.data_ptr(), C.byref(st), _stream_ptr(dev)),
+                   "d2gs_raster_export_state")
+    return out
+
+
+def launch_counts() -> dict:
+    return dict(_LAUNCH_COUNT)

@@ -1,0 +1,238 @@
+/*
+ * d2gs.h — C ABI of the B200-native Dynamic-2DGS render hot path (libd2gs.so).
+ *
+ * Plain C: raw DEVICE pointers, sizes, a cudaStream_t passed as void*, int status codes.  No torch
+ * types.  Every entry point names the reference interface it replaces (paths relative to
+ * /root/reference; DSR = submodules/diff-surfel-rasterization).
+ *
+ * Conventions
+ *   - all tensors are contiguous float32 unless stated; "int" = int32
+ *   - a NULL data pointer means "not provided" (DSR/cuda_rasterizer/forward.cu:215,247)
+ *   - every call is asynchronous on `stream` except where noted
+ *   - return 0 on success; on failure a negative D2GS_ERR_* code, text via d2gs_last_error()
+ */
+#ifndef D2GS_H_
+#define D2GS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define D2GS_API __attribute__((visibility("default")))
+#else
+#define D2GS_API
+#endif
+
+#define D2GS_OK 0
+#define D2GS_ERR_INVALID_ARG (-1)
+#define D2GS_ERR_CUDA (-2)
+#define D2GS_ERR_WORKSPACE (-3)      /* a workspace buffer is too small; *_required fields are filled */
+#define D2GS_NEED_BINNING 1          /* forward stopped after the geometry stage: grow the binning buffer, call again with resume=1 */
+
+/* Compile-time configuration baked into the kernels; mirrors DSR/cuda_rasterizer/config.h:15-17 and
+ * auxiliary.h:20-37.  Exposed so parity tests can assert the two builds agree. */
+typedef struct D2gsConfig {
+  int num_channels;      /* 3 */
+  int block_x, block_y;  /* 16, 16 */
+  int tight_bbox;        /* 0 */
+  int render_auxiliary;  /* 1 */
+  int backface_cull;     /* 1 */
+  int dual_visible;      /* 1 */
+  int detach_weight;     /* 0 */
+  double near_plane;     /* 0.2 */
+  double far_plane;      /* 100.0 */
+  double filter_size;    /* 0.7071067811865476 */
+  int sm_arch;           /* 100 */
+} D2gsConfig;
+
+D2GS_API const char* d2gs_last_error(void);
+D2GS_API const char* d2gs_version(void);
+D2GS_API int d2gs_get_config(D2gsConfig* out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Rasterizer.  Replaces CudaRasterizer::Rasterizer::{forward,backward,markVisible}
+ * (DSR/cuda_rasterizer/rasterizer.h:24-87) and their torch wrappers RasterizeGaussiansCUDA /
+ * RasterizeGaussiansBackwardCUDA / markVisible (DSR/rasterize_points.h:18-68).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Workspace sizes.  Replaces the required<GeometryState/ImageState/BinningState>() queries
+ * (DSR/cuda_rasterizer/rasterizer_impl.h:64-72).  binning_bytes is for `num_rendered` instances. */
+D2GS_API int d2gs_raster_workspace(int P, int width, int height, int64_t num_rendered,
+                          size_t* geom_bytes, size_t* img_bytes, size_t* binning_bytes);
+
+typedef struct D2gsRasterFwdArgs {
+  /* sizes: P surfels, D = active SH degree, M = SH coefficients per surfel (0 when colours are given) */
+  int P, D, M, width, height;
+  const float* background;        /* (3) */
+  const float* means3D;           /* (P,3) */
+  const float* shs;               /* (P,M,3) or NULL; when sh_rest != NULL this is the DC block (P,1,3) */
+  const float* sh_rest;           /* (P,M-1,3) or NULL: split layout, avoids the per-frame cat of gaussian_renderer/__init__.py:114,122 */
+  const float* colors_precomp;    /* (P,3) or NULL */
+  const float* opacities;         /* (P) */
+  const float* scales;            /* (P,2) or NULL */
+  const float* rotations;         /* (P,4) (w,x,y,z) or NULL */
+  const float* transMat_precomp;  /* (P,9) or NULL */
+  float scale_modifier;           /* accepted and ignored, like the reference (forward.cu:95) */
+  const float* viewmatrix;        /* (4,4) transposed world->view */
+  const float* projmatrix;        /* (4,4) transposed full projection */
+  const float* campos;            /* (3) */
+  float tan_fovx, tan_fovy;
+  int prefiltered;
+  int debug;                      /* 1: synchronise + check after every stage (auxiliary.h:271-278) */
+  /* outputs */
+  float* out_color;               /* (3,H,W) */
+  float* out_others;              /* (8,H,W): depth, alpha, normal xyz, median depth, distortion, median weight */
+  int* radii;                     /* (P) */
+  /* workspaces (device). geometry+image buffers must be kept for backward; so must `binning`. */
+  void* geom_buffer;   size_t geom_bytes;
+  void* img_buffer;    size_t img_bytes;
+  void* binning_buffer; size_t binning_bytes;
+  int resume;                     /* 1: geometry stage already done by a call that returned D2GS_NEED_BINNING */
+  /* results on the host */
+  int64_t* num_rendered;          /* host: R, number of (surfel,tile) instances */
+  size_t* binning_required;       /* host: bytes needed for R instances */
+} D2gsRasterFwdArgs;
+
+/* Forward.  Synchronises `stream` once (the reference's blocking readback of num_rendered,
+ * rasterizer_impl.cu:281-282) to size the binning stage.  If binning_bytes is too small returns
+ * D2GS_NEED_BINNING with *binning_required set. */
+D2GS_API int d2gs_raster_forward(const D2gsRasterFwdArgs* args, void* stream);
+
+typedef struct D2gsRasterBwdArgs {
+  int P, D, M, width, height;
+  int64_t num_rendered;
+  const float* background;
+  const float* means3D;
+  const float* shs;
+  const float* sh_rest;
+  const float* colors_precomp;
+  const float* scales;
+  const float* rotations;
+  const float* transMat_precomp;
+  float scale_modifier;
+  const float* viewmatrix;
+  const float* projmatrix;
+  const float* campos;
+  float tan_fovx, tan_fovy;
+  const int* radii;
+  const void* geom_buffer;
+  const void* binning_buffer;
+  const void* img_buffer;
+  const float* dL_dout_color;   /* (3,H,W) */
+  const float* dL_dout_others;  /* (8,H,W) */
+  int debug;
+  /* scratch: (P,20) floats, zero on entry; left zero on exit (the per-surfel stage clears what it consumes) */
+  float* grad_scratch;
+  /* outputs; every element is written (no pre-zeroing needed), NULL = not wanted */
+  float* dL_dmeans2D;     /* (P,3): xy = the densification "projected gradient" (backward.cu:645-648) */
+  float* dL_dcolors;      /* (P,3) */
+  float* dL_dopacity;     /* (P,1) */
+  float* dL_dmeans3D;     /* (P,3) */
+  float* dL_dtransMat;    /* (P,9) */
+  float* dL_dsh;          /* (P,M,3), or the DC block (P,1,3) when dL_dsh_rest != NULL */
+  float* dL_dsh_rest;     /* (P,M-1,3) or NULL */
+  float* dL_dscales;      /* (P,2) */
+  float* dL_drotations;   /* (P,4) */
+} D2gsRasterBwdArgs;
+
+D2GS_API int d2gs_raster_backward(const D2gsRasterBwdArgs* args, void* stream);
+
+/* Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer_impl.cu:141-153). present: (P) bytes. */
+D2GS_API int d2gs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                      uint8_t* present, void* stream);
+
+/* Debug/parity access to the intermediates the reference keeps inside geomBuffer/binningBuffer/imgBuffer
+ * (rasterizer_impl.cu:155-194).  Copies into caller-provided DEVICE arrays (NULL = skip). */
+typedef struct D2gsRasterState {
+  float* means2D;         /* (P,2) */
+  float* depths;          /* (P) */
+  float* transMat;        /* (P,9) */
+  float* normal_opacity;  /* (P,4) */
+  float* rgb;             /* (P,3) */
+  uint8_t* clamped;       /* (P,3) */
+  uint32_t* tiles_touched;   /* (P) */
+  uint32_t* point_offsets;   /* (P) */
+  uint64_t* keys_unsorted;   /* (R) */
+  uint32_t* values_unsorted; /* (R) */
+  uint64_t* keys_sorted;     /* (R) */
+  uint32_t* point_list;      /* (R) */
+  uint32_t* ranges;          /* (tiles,2) */
+  float* final_T;            /* (3,H,W): T, dist1, dist2 */
+  uint32_t* n_contrib;       /* (2,H,W): last contributor, median contributor */
+} D2gsRasterState;
+
+D2GS_API int d2gs_raster_export_state(int P, int width, int height, int64_t num_rendered, const void* geom_buffer,
+                             const void* binning_buffer, const void* img_buffer, const D2gsRasterState* out,
+                             void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Node-controlled deformation: KNN weights + blend.  Replaces ControlNodeWarp.cal_nn_weight
+ * (utils/time_utils.py:934-967, incl. pytorch3d.ops.knn_points at :950) and the blend of
+ * ControlNodeWarp.forward (utils/time_utils.py:1145-1157,1190-1194), fused with the activations of
+ * render() (gaussian_renderer/__init__.py:83-99).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct D2gsDeformFwdArgs {
+  int P, M, K, hyper_dim;        /* K <= 8 */
+  const float* xyz;              /* (P,3) canonical surfel centres */
+  const float* feature;          /* (P,feature_stride) first hyper_dim columns are the hyper coordinates; NULL: 3-D query */
+  int feature_stride;
+  const float* nodes;            /* (M,3+hyper_dim) */
+  const float* node_radius_log;  /* (M) _node_radius */
+  const float* node_weight_logit;/* (M) _node_weight or NULL */
+  const float* node_trans;       /* (M,3) MLP output d_xyz */
+  const float* node_rot;         /* (M,4) MLP output d_rotation */
+  const float* node_scale;       /* (M,2) MLP output d_scaling */
+  const float* node_local_rot;   /* (M,4) MLP output local_rotation or NULL (local_frame off) */
+  const float* motion_mask;      /* (P) or NULL (= ones) */
+  /* outputs */
+  int64_t* nn_idx;               /* (P,K) ascending distance */
+  float* nn_dist;                /* (P,K) squared distances */
+  float* nn_weight;              /* (P,K) normalised */
+  float* d_xyz;                  /* (P,3) */
+  float* d_rotation;             /* (P,4) */
+  float* d_scaling;              /* (P,2) */
+} D2gsDeformFwdArgs;
+
+D2GS_API int d2gs_deform_forward(const D2gsDeformFwdArgs* args, void* stream);
+
+typedef struct D2gsDeformBwdArgs {
+  int P, M, K, hyper_dim;
+  const float* xyz;
+  const float* feature; int feature_stride;
+  const float* nodes;
+  const float* node_radius_log;
+  const float* node_weight_logit;
+  const float* node_trans;
+  const float* node_rot;
+  const float* node_scale;
+  const float* node_local_rot;
+  const float* motion_mask;
+  const int64_t* nn_idx;
+  const float* nn_dist;
+  const float* nn_weight;
+  const float* dL_d_xyz;         /* (P,3) */
+  const float* dL_d_rotation;    /* (P,4) */
+  const float* dL_d_scaling;     /* (P,2) */
+  /* outputs (accumulated with atomics: must be zero on entry) */
+  float* dL_dnode_trans;         /* (M,3) */
+  float* dL_dnode_rot;           /* (M,4) */
+  float* dL_dnode_scale;         /* (M,2) */
+  float* dL_dnode_local_rot;     /* (M,4) or NULL */
+  float* dL_dnodes;              /* (M,3+hyper_dim): only the hyper columns receive gradient */
+  float* dL_dnode_radius_log;    /* (M) */
+  float* dL_dnode_weight_logit;  /* (M) or NULL */
+  /* outputs (written) */
+  float* dL_dfeature;            /* (P,feature_stride) or NULL */
+  float* dL_dmotion_mask;        /* (P) or NULL */
+} D2gsDeformBwdArgs;
+
+D2GS_API int d2gs_deform_backward(const D2gsDeformBwdArgs* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D2GS_H_ */
