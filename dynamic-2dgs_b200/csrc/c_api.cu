@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/d2gs.h"
 #include "raster_common.cuh"
@@ -33,6 +34,25 @@ static int fail(int code, const std::string& msg) {
     if (e__ != cudaSuccess)                                                                      \
       return fail(D2GS_ERR_CUDA, std::string("stage ") + name + ": " + cudaGetErrorString(e__)); \
   } while (0)
+
+// ---- optional per-stage timing (CUDA events on the launch stream) ------------------------------------------
+enum Stage { ST_PRE = 0, ST_SCAN, ST_DUP, ST_SORT, ST_RANGES, ST_BLEND_F, ST_BLEND_B, ST_PRE_B, ST_DEF_F, ST_DEF_B };
+struct StageRec { int stage; cudaEvent_t a, b; };
+static bool g_profile = false;
+static std::vector<StageRec> g_recs;
+static std::vector<cudaEvent_t> g_free_events;
+
+static cudaEvent_t get_event() {
+  if (!g_free_events.empty()) { cudaEvent_t e = g_free_events.back(); g_free_events.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct StageTimer {
+  bool on; cudaStream_t s; StageRec r;
+  StageTimer(int stage, cudaStream_t stream) : on(g_profile), s(stream) {
+    if (on) { r.stage = stage; r.a = get_event(); r.b = get_event(); cudaEventRecord(r.a, s); }
+  }
+  ~StageTimer() { if (on) { cudaEventRecord(r.b, s); g_recs.push_back(r); } }
+};
 
 GeomLayout geom_layout(int P) {
   GeomLayout L{};
@@ -100,6 +120,25 @@ using namespace d2gs;
 extern "C" {
 
 const char* d2gs_last_error(void) { return g_last_error.c_str(); }
+
+int d2gs_profile_enable(int on) { g_profile = on != 0; return D2GS_OK; }
+
+int d2gs_profile_collect(double* total_ms, int64_t* launches) {
+  if (!total_ms || !launches) return fail(D2GS_ERR_INVALID_ARG, "null output");
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return fail(D2GS_ERR_CUDA, cudaGetErrorString(e));
+  for (const StageRec& r : g_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess && r.stage >= 0 && r.stage < D2GS_NUM_STAGES) {
+      total_ms[r.stage] += ms;
+      launches[r.stage] += 1;
+    }
+    g_free_events.push_back(r.a);
+    g_free_events.push_back(r.b);
+  }
+  g_recs.clear();
+  return D2GS_OK;
+}
 const char* d2gs_version(void) { return "d2gs-b200 0.1 (sm_100a)"; }
 
 int d2gs_get_config(D2gsConfig* c) {
@@ -168,10 +207,11 @@ int d2gs_raster_forward(const D2gsRasterFwdArgs* a, void* stream_) {
   p.gx = (W + TILE_X - 1) / TILE_X; p.gy = (H + TILE_Y - 1) / TILE_Y;
 
   if (!a->resume) {
-    launch_preprocess_fwd(p, rec, clamped, a->radii, tiles_touched, stream);
+    { StageTimer t(ST_PRE, stream); launch_preprocess_fwd(p, rec, clamped, a->radii, tiles_touched, stream); }
     D2GS_STAGE("preprocess", a->debug, stream);
     size_t tmp = GL.scan_temp_bytes;
-    D2GS_CUDA_OK(cub::DeviceScan::InclusiveSum(gb + GL.scan_temp, tmp, tiles_touched, point_offsets, P, stream));
+    { StageTimer t(ST_SCAN, stream);
+      D2GS_CUDA_OK(cub::DeviceScan::InclusiveSum(gb + GL.scan_temp, tmp, tiles_touched, point_offsets, P, stream)); }
     D2GS_STAGE("scan", a->debug, stream);
   }
   uint32_t R32 = 0;
@@ -189,19 +229,22 @@ int d2gs_raster_forward(const D2gsRasterFwdArgs* a, void* stream_) {
   uint32_t* vals_unsorted = (uint32_t*)(bb + BL.vals_unsorted);
   uint32_t* point_list = (uint32_t*)(bb + BL.point_list);
 
-  launch_duplicate(P, rec, a->radii, point_offsets, keys_unsorted, vals_unsorted, p.gx, p.gy, stream);
+  { StageTimer t(ST_DUP, stream); launch_duplicate(P, rec, a->radii, point_offsets, keys_unsorted, vals_unsorted, p.gx, p.gy, stream); }
   D2GS_STAGE("duplicate", a->debug, stream);
   if (R > 0) {
     const int bit = (int)higher_msb(p.gx * p.gy);
     size_t tmp = BL.sort_temp_bytes;
+    StageTimer t(ST_SORT, stream);
     D2GS_CUDA_OK(cub::DeviceRadixSort::SortPairs(bb + BL.sort_temp, tmp, keys_unsorted, keys_sorted, vals_unsorted,
                                                  point_list, (int)R, 0, 32 + bit, stream));
     D2GS_STAGE("sort", a->debug, stream);
   }
-  D2GS_CUDA_OK(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)p.gx * p.gy, stream));
-  launch_ranges(R, keys_sorted, ranges, stream);
+  { StageTimer t(ST_RANGES, stream);
+    D2GS_CUDA_OK(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)p.gx * p.gy, stream));
+    launch_ranges(R, keys_sorted, ranges, stream); }
   D2GS_STAGE("ranges", a->debug, stream);
-  launch_blend_fwd(p, ranges, point_list, rec, final_T, n_contrib, a->out_color, a->out_others, stream);
+  { StageTimer t(ST_BLEND_F, stream);
+    launch_blend_fwd(p, ranges, point_list, rec, final_T, n_contrib, a->out_color, a->out_others, stream); }
   D2GS_STAGE("blend", a->debug, stream);
   return D2GS_OK;
 }
@@ -239,13 +282,15 @@ int d2gs_raster_backward(const D2gsRasterBwdArgs* a, void* stream_) {
   p.gx = (W + TILE_X - 1) / TILE_X; p.gy = (H + TILE_Y - 1) / TILE_Y;
 
   if (a->num_rendered > 0) {
-    launch_blend_bwd(p, ranges, point_list, rec, final_T, n_contrib, a->dL_dout_color, a->dL_dout_others,
-                     a->grad_scratch, stream);
+    { StageTimer t(ST_BLEND_B, stream);
+      launch_blend_bwd(p, ranges, point_list, rec, final_T, n_contrib, a->dL_dout_color, a->dL_dout_others,
+                       a->grad_scratch, stream); }
     D2GS_STAGE("blend_bwd", a->debug, stream);
   }
-  launch_preprocess_bwd(p, rec, clamped, a->radii, a->grad_scratch, a->dL_dmeans2D, a->dL_dcolors, a->dL_dopacity,
-                        a->dL_dmeans3D, a->dL_dtransMat, a->dL_dsh, a->dL_dsh_rest, a->dL_dscales, a->dL_drotations,
-                        stream);
+  { StageTimer t(ST_PRE_B, stream);
+    launch_preprocess_bwd(p, rec, clamped, a->radii, a->grad_scratch, a->dL_dmeans2D, a->dL_dcolors, a->dL_dopacity,
+                          a->dL_dmeans3D, a->dL_dtransMat, a->dL_dsh, a->dL_dsh_rest, a->dL_dscales, a->dL_drotations,
+                          stream); }
   D2GS_STAGE("preprocess_bwd", a->debug, stream);
   return D2GS_OK;
 }
@@ -333,7 +378,8 @@ int d2gs_deform_forward(const D2gsDeformFwdArgs* a, void* stream) {
   h.mask = a->motion_mask; h.nn_idx = a->nn_idx; h.nn_dist = a->nn_dist; h.nn_weight = a->nn_weight;
   h.d_xyz = a->d_xyz; h.d_rot = a->d_rotation; h.d_scale = a->d_scaling;
   const char* err = nullptr;
-  if (deform_forward_launch(h, (cudaStream_t)stream, &err) != 0) return fail(D2GS_ERR_INVALID_ARG, err);
+  { StageTimer t(ST_DEF_F, (cudaStream_t)stream);
+    if (deform_forward_launch(h, (cudaStream_t)stream, &err) != 0) return fail(D2GS_ERR_INVALID_ARG, err); }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(D2GS_ERR_CUDA, cudaGetErrorString(e));
   return D2GS_OK;
@@ -357,7 +403,8 @@ int d2gs_deform_backward(const D2gsDeformBwdArgs* a, void* stream) {
   h.d_local_rot = a->dL_dnode_local_rot; h.d_nodes = a->dL_dnodes; h.d_radius_log = a->dL_dnode_radius_log;
   h.d_weight_logit = a->dL_dnode_weight_logit; h.d_feature = a->dL_dfeature; h.d_mask = a->dL_dmotion_mask;
   const char* err = nullptr;
-  if (deform_backward_launch(h, (cudaStream_t)stream, &err) != 0) return fail(D2GS_ERR_INVALID_ARG, err);
+  { StageTimer t(ST_DEF_B, (cudaStream_t)stream);
+    if (deform_backward_launch(h, (cudaStream_t)stream, &err) != 0) return fail(D2GS_ERR_INVALID_ARG, err); }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(D2GS_ERR_CUDA, cudaGetErrorString(e));
   return D2GS_OK;

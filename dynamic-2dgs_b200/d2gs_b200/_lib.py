@@ -82,7 +82,7 @@ class DeformBwdArgs(C.Structure):
 
 # every symbol include/d2gs.h declares; tests assert the shared library exports all of them
 EXPORTED_SYMBOLS = (
-    "d2gs_last_error", "d2gs_version", "d2gs_get_config", "d2gs_raster_workspace", "d2gs_raster_forward",
+    "d2gs_profile_enable", "d2gs_profile_collect", "d2gs_last_error", "d2gs_version", "d2gs_get_config", "d2gs_raster_workspace", "d2gs_raster_forward",
     "d2gs_raster_backward", "d2gs_mark_visible", "d2gs_raster_export_state", "d2gs_deform_forward",
     "d2gs_deform_backward",
 )
@@ -120,6 +120,8 @@ def lib():
                                            C.POINTER(RasterState), C.c_void_p]
     L.d2gs_deform_forward.argtypes = [C.POINTER(DeformFwdArgs), C.c_void_p]
     L.d2gs_deform_backward.argtypes = [C.POINTER(DeformBwdArgs), C.c_void_p]
+    L.d2gs_profile_enable.argtypes = [C.c_int]
+    L.d2gs_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     for name in EXPORTED_SYMBOLS:
         getattr(L, name)
     _lib = L
@@ -141,3 +143,20 @@ def workspace_sizes(P: int, W: int, H: int, R: int = 0):
     g, i, b = C.c_size_t(), C.c_size_t(), C.c_size_t()
     check(lib().d2gs_raster_workspace(P, W, H, R, C.byref(g), C.byref(i), C.byref(b)), "d2gs_raster_workspace")
     return g.value, i.value, b.value
+
+
+STAGE_NAMES = ("preprocess_fwd", "scan", "duplicate", "sort", "ranges", "blend_fwd", "blend_bwd", "preprocess_bwd",
+               "deform_fwd", "deform_bwd")
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().d2gs_profile_enable(int(on)), "d2gs_profile_enable")
+
+
+def profile_collect() -> dict:
+    """{stage: (total_ms, launches)} since the last collect; synchronises the device."""
+    n = len(STAGE_NAMES)
+    ms = (C.c_double * n)()
+    cnt = (C.c_int64 * n)()
+    check(lib().d2gs_profile_collect(ms, cnt), "d2gs_profile_collect")
+    return {STAGE_NAMES[i]: (ms[i], cnt[i]) for i in range(n)}

@@ -1,0 +1,177 @@
+"""Drop-in replacement for the reference's ``gaussian_renderer.render`` (gaussian_renderer/__init__.py:41-219):
+same signature, same returned dict, backed by the B200 rasterizer.
+
+Differences that do not change results:
+  * SH coefficients are handed to the rasterizer as the two parameter tensors (DC, rest) instead of a fresh
+    P x 16 x 3 concatenation every frame (:114,122) whenever the model exposes ``_features_dc/_features_rest``;
+  * the per-camera ray table of depth_to_normal (utils/point_utils.py:9-25: meshgrid + two 3x3 inverses rebuilt per
+    call) is cached per camera pose.
+"""
+import math
+
+import torch
+
+from diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+from d2gs_b200 import raster as _raster
+
+_RAY_CACHE = {}
+
+
+def standardize_quaternion(quaternions: torch.Tensor) -> torch.Tensor:
+    return torch.where(quaternions[..., 0:1] < 0, -quaternions, quaternions)
+
+
+def quaternion_raw_multiply(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    aw, ax, ay, az = torch.unbind(a, -1)
+    bw, bx, by, bz = torch.unbind(b, -1)
+    ow = aw * bw - ax * bx - ay * by - az * bz
+    ox = aw * bx + ax * bw + ay * bz - az * by
+    oy = aw * by - ax * bz + ay * bw + az * bx
+    oz = aw * bz + ax * by - ay * bx + az * bw
+    return torch.stack((ow, ox, oy, oz), -1)
+
+
+def quaternion_multiply(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    return standardize_quaternion(quaternion_raw_multiply(a, b))
+
+
+def _camera_rays(view):
+    """rays_d (H*W,3), rays_o (3): utils/point_utils.py:9-24, cached per camera pose."""
+    key = (view.world_view_transform.data_ptr(), int(view.image_width), int(view.image_height), float(view.FoVx), float(view.FoVy),
+           view.world_view_transform._version)
+    hit = _RAY_CACHE.get(key)
+    if hit is not None:
+        return hit
+    dev = view.world_view_transform.device
+    c2w = (view.world_view_transform.T).inverse()
+    W, H = int(view.image_width), int(view.image_height)
+    fx = W / (2 * math.tan(view.FoVx / 2.))
+    fy = H / (2 * math.tan(view.FoVy / 2.))
+    intrins = torch.tensor([[fx, 0., W / 2.], [0., fy, H / 2.], [0., 0., 1.0]]).float().to(dev)
+    grid_x, grid_y = torch.meshgrid(torch.arange(W), torch.arange(H), indexing='xy')
+    points = torch.stack([grid_x, grid_y, torch.ones_like(grid_x)], dim=-1).reshape(-1, 3).float().to(dev)
+    rays_d = points @ intrins.inverse().T @ c2w[:3, :3].T
+    rays_o = c2w[:3, 3]
+    if len(_RAY_CACHE) > 512:
+        _RAY_CACHE.clear()
+    _RAY_CACHE[key] = (rays_d, rays_o)
+    return rays_d, rays_o
+
+
+def depths_to_points(view, depthmap):
+    rays_d, rays_o = _camera_rays(view)
+    return depthmap.reshape(-1, 1) * rays_d + rays_o
+
+
+def depth_to_normal(view, depth):
+    """utils/point_utils.py:27-38."""
+    points = depths_to_points(view, depth).reshape(*depth.shape[1:], 3)
+    output = torch.zeros_like(points)
+    dx = points[2:, 1:-1] - points[:-2, 1:-1]
+    dy = points[1:-1, 2:] - points[1:-1, :-2]
+    normal_map = torch.nn.functional.normalize(torch.cross(dx, dy, dim=-1), dim=-1)
+    output[1:-1, 1:-1, :] = normal_map
+    return output, points
+
+
+def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, d_xyz, d_rotation, d_scaling, d_opacity=None, d_color=None,
+           scaling_modifier=1.0, override_color=None, random_bg_color=False, render_motion=False, detach_xyz=False,
+           detach_scale=False, detach_rot=False, detach_opacity=False, d_rot_as_res=True, scale_const=None,
+           d_rotation_bias=None, force_visible=False, depth_filtering=False):
+    """Render the scene (reference: gaussian_renderer/__init__.py:41-219).  Background tensor must be on the GPU."""
+    xyz = pc.get_xyz
+    screenspace_points = torch.zeros_like(xyz, dtype=xyz.dtype, requires_grad=True, device=xyz.device) + 0
+    try:
+        screenspace_points.retain_grad()
+    except Exception:
+        pass
+
+    tanfovx = math.tan(viewpoint_camera.FoVx * 0.5)
+    tanfovy = math.tan(viewpoint_camera.FoVy * 0.5)
+    bg = bg_color if not random_bg_color else torch.rand_like(bg_color)
+    raster_settings = GaussianRasterizationSettings(
+        image_height=int(viewpoint_camera.image_height), image_width=int(viewpoint_camera.image_width),
+        tanfovx=tanfovx, tanfovy=tanfovy, bg=bg, scale_modifier=scaling_modifier,
+        viewmatrix=viewpoint_camera.world_view_transform, projmatrix=viewpoint_camera.full_proj_transform,
+        sh_degree=pc.active_sh_degree, campos=viewpoint_camera.camera_center, prefiltered=False, debug=pipe.debug)
+
+    means3D = xyz + d_xyz
+    means2D = screenspace_points
+    if scale_const is not None:
+        opacity = torch.ones_like(pc.get_opacity)
+    else:
+        opacity = pc.get_opacity if d_opacity is None else pc.get_opacity + d_opacity
+
+    if pipe.compute_cov3D_python:
+        raise NotImplementedError("compute_cov3D_python is broken for 2-D scales in the reference (utils/general_utils.py:167)")
+    scales = pc.get_scaling + d_scaling
+    rotations = pc.get_rotation_bias(d_rotation)
+    if d_rotation_bias is not None:
+        rotations = quaternion_multiply(d_rotation_bias, rotations)
+
+    shs, sh_rest, colors_precomp = None, None, None
+    if render_motion:
+        colors_precomp = torch.zeros_like(xyz)
+        colors_precomp[..., :1] = pc.motion_mask
+        colors_precomp[..., -1:] = 1 - pc.motion_mask
+    else:
+        has_dc = d_color is not None and type(d_color) is not float
+        split = hasattr(pc, "_features_dc") and hasattr(pc, "_features_rest") and not pipe.convert_SHs_python
+        if split:
+            shs = pc._features_dc + d_color[:, None] if has_dc else pc._features_dc
+            sh_rest = pc._features_rest
+        else:
+            feats = pc.get_features
+            sh_features = torch.cat([feats[:, :1] + d_color[:, None], feats[:, 1:]], dim=1) if has_dc else feats
+            if pipe.convert_SHs_python:
+                from d2gs_b200.sh import eval_sh
+                shs_view = sh_features.transpose(1, 2).view(-1, 3, (pc.max_sh_degree + 1) ** 2)
+                dir_pp = (xyz - viewpoint_camera.camera_center.repeat(sh_features.shape[0], 1))
+                dir_pp_normalized = dir_pp / dir_pp.norm(dim=1, keepdim=True)
+                colors_precomp = torch.clamp_min(eval_sh(pc.active_sh_degree, shs_view, dir_pp_normalized) + 0.5, 0.0)
+            else:
+                shs = sh_features
+
+    if detach_xyz:
+        means3D = means3D.detach()
+    if detach_rot:
+        rotations = rotations.detach()
+    if detach_scale:
+        scales = scales.detach()
+    if detach_opacity:
+        opacity = opacity.detach()
+    if scale_const is not None:
+        scales = scale_const * torch.ones_like(scales)
+
+    rendered_image, radii, allmap = _raster.rasterize_surfels(means3D, means2D, shs, colors_precomp, opacity, scales,
+                                                              rotations, None, raster_settings, sh_rest=sh_rest)
+
+    rets = {"render": rendered_image, "viewspace_points": means2D, "visibility_filter": radii > 0, "radii": radii}
+
+    whitebackground = torch.tensor([1, 1, 1], dtype=torch.float32, device=xyz.device)
+    if depth_filtering:
+        if bg_color.equal(whitebackground):
+            mask = (1 - (torch.all(rendered_image >= 0.95, dim=0)).to(torch.int))
+        else:
+            mask = (1 - (torch.all(rendered_image <= 0.05, dim=0)).to(torch.int))
+    else:
+        mask = 1
+    render_alpha = allmap[1:2]
+    render_normal = allmap[2:5]
+    render_normal = (render_normal.permute(1, 2, 0) @ (viewpoint_camera.world_view_transform[:3, :3].T)).permute(2, 0, 1)
+    render_normal = render_normal * mask
+    render_depth_median = torch.nan_to_num(allmap[5:6], 0, 0)
+    render_depth_expected = torch.nan_to_num(allmap[0:1] / render_alpha, 0, 0)
+    render_dist = allmap[6:7] * mask
+    pipe.depth_ratio = 1
+    surf_depth = render_depth_expected * (1 - pipe.depth_ratio) + (pipe.depth_ratio) * render_depth_median
+    surf_depth = surf_depth * mask
+    surf_normal, surf_point = depth_to_normal(viewpoint_camera, surf_depth)
+    surf_normal = surf_normal.permute(2, 0, 1)
+    surf_point = surf_point.permute(2, 0, 1)
+    surf_normal = surf_normal * (render_alpha).detach()
+    surf_normal = surf_normal * mask
+
+    rets.update({'alpha': render_alpha, 'rend_normal': render_normal, 'rend_dist': render_dist, 'depth': surf_depth,
+                 'surf_normal': surf_normal, 'surf_point': surf_point, "bg_color": bg})
+    return rets

@@ -49,6 +49,14 @@ typedef struct D2gsConfig {
   int sm_arch;           /* 100 */
 } D2gsConfig;
 
+/* Per-stage device timing with CUDA events recorded on the launch stream (for bench.py's roofline line).
+ * Stages: 0 preprocess_fwd, 1 scan, 2 duplicate, 3 sort, 4 ranges, 5 blend_fwd, 6 blend_bwd, 7 preprocess_bwd,
+ *         8 deform_fwd, 9 deform_bwd.  d2gs_profile_collect synchronises the device, adds the elapsed times of all
+ * recorded launches to total_ms[stage] / launches[stage] (arrays of D2GS_NUM_STAGES) and clears the record. */
+#define D2GS_NUM_STAGES 10
+D2GS_API int d2gs_profile_enable(int on);
+D2GS_API int d2gs_profile_collect(double* total_ms, int64_t* launches);
+
 D2GS_API const char* d2gs_last_error(void);
 D2GS_API const char* d2gs_version(void);
 D2GS_API int d2gs_get_config(D2gsConfig* out);

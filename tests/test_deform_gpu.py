@@ -1,0 +1,160 @@
+"""GPU: fused KNN + weights + blend kernels (d2gs_deform_forward/backward) against the torch oracle
+(oracle/deform_oracle.py, explicit-distance KNN; pytorch3d is unpinned — see its header), and the drop-in
+render()/DeformModel.step() against the reference pipeline restated around the reference CUDA extension."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import util
+from oracle import deform_oracle as do
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(P, M, K, hyper, seed, local_frame=True, with_mask=False):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(P, 3, generator=g) * 0.5
+    feat = torch.randn(P, hyper + (1 if with_mask else 0), generator=g) * 0.02
+    nodes = torch.cat([torch.randn(M, 3, generator=g) * 0.5, 0.01 + 0.02 * torch.randn(M, hyper, generator=g)], 1)
+    rad = torch.full((M,), math.log(0.25)) + 0.1 * torch.randn(M, generator=g)
+    wl = 0.5 * torch.randn(M, 1, generator=g)
+    attrs = {"d_xyz": 0.1 * torch.randn(M, 3, generator=g), "d_rotation": 0.1 * torch.randn(M, 4, generator=g),
+             "d_scaling": 0.01 * torch.randn(M, 2, generator=g), "local_rotation": 0.2 * torch.randn(M, 4, generator=g)}
+    if not local_frame:
+        attrs.pop("local_rotation")
+    return x, feat, nodes, rad, wl, attrs
+
+
+@pytest.mark.parametrize("P,M,K,hyper,local_frame,with_mask", [(3000, 64, 4, 8, True, False), (2000, 128, 3, 8, False, True),
+                                                                (1500, 37, 1, 0, True, False), (4000, 512, 8, 2, True, True)])
+def test_node_blend_matches_oracle(P, M, K, hyper, local_frame, with_mask, cuda_device):
+    from d2gs_b200 import deform as dfm
+    dev = cuda_device
+    x, feat, nodes, rad, wl, attrs = _case(P, M, K, hyper, seed=P + M, local_frame=local_frame, with_mask=with_mask)
+    gx, gr, gs = torch.randn(P, 3), torch.randn(P, 4), torch.randn(P, 2)
+
+    def leaves(to):
+        mk = lambda t: t.clone().to(to).requires_grad_(True)
+        return dict(feat=mk(feat), nodes=mk(nodes), rad=mk(rad), wl=mk(wl), **{k: mk(v) for k, v in attrs.items()})
+
+    # oracle (CPU, torch autograd)
+    o = leaves("cpu")
+    mask_o = torch.sigmoid(o["feat"][:, -1:]) if with_mask else torch.ones(P, 1)
+    w, d, i = do.cal_nn_weight(x, o["feat"] if hyper else None, o["nodes"], o["rad"], o["wl"], K, hyper)
+    a_o = {k: o[k] for k in attrs}
+    out_o = do.blend(x, w, i, o["nodes"], a_o, mask_o, local_frame)
+    ((out_o["d_xyz"] * gx).sum() + (out_o["d_rotation"] * gr).sum() + (out_o["d_scaling"] * gs).sum()).backward()
+
+    # ours
+    m = leaves(dev)
+    mask_m = torch.sigmoid(m["feat"][:, -1:]) if with_mask else None
+    out = dfm.node_blend(x.to(dev), m["feat"] if hyper else None, m["nodes"], m["rad"], m["wl"].reshape(-1), m["d_xyz"], m["d_rotation"],
+                         m["d_scaling"], m.get("local_rotation"), mask_m, K, hyper)
+    ((out["d_xyz"] * gx.to(dev)).sum() + (out["d_rotation"] * gr.to(dev)).sum() + (out["d_scaling"] * gs.to(dev)).sum()).backward()
+    torch.cuda.synchronize()
+
+    same = (out["nn_idx"].cpu() == i)
+    assert same.float().mean() > 0.999, "KNN indices differ from the explicit-distance oracle"
+    rows = same.all(1)
+    assert torch.allclose(out["nn_dist"].cpu()[rows], d[rows].detach(), rtol=1e-5, atol=1e-7)
+    assert torch.allclose(out["nn_weight"].cpu()[rows], w[rows].detach(), rtol=1e-4, atol=1e-6)
+    for k in ("d_xyz", "d_rotation", "d_scaling"):
+        assert util.rel_err(out[k].detach().cpu().numpy()[rows], out_o[k].detach().numpy()[rows]) < 1e-5, k
+    if rows.all():
+        checks = [("nodes", 2e-4), ("rad", 2e-4), ("wl", 2e-4), ("d_xyz", 1e-5), ("d_rotation", 1e-5), ("d_scaling", 1e-5)]
+        if hyper:
+            checks.append(("feat", 2e-4))
+        if local_frame:
+            checks.append(("local_rotation", 1e-4))
+        for k, tol in checks:
+            a, b = m[k].grad.cpu().numpy(), o[k].grad.numpy()
+            assert util.rel_err(a, b) < tol, (k, util.rel_err(a, b))
+        assert not m["nodes"].grad[:, :3].any()      # node positions are detached in the reference
+
+
+def test_control_node_warp_forward_and_cal_nn_weight(cuda_device):
+    from d2gs_b200 import deform as dfm
+    dev = cuda_device
+    torch.manual_seed(3)
+    P, M, K = 5000, 96, 4
+    cn = dfm.ControlNodeWarp(is_blender=True, node_num=M, K=K, hyper_dim=8, local_frame=True).to(dev)
+    with torch.no_grad():
+        cn.nodes.copy_(torch.cat([torch.randn(M, 3) * 0.5, torch.full((M, 8), 1e-2)], 1))
+        cn._node_radius.fill_(math.log(0.2))
+        for h in (cn.network.gaussian_warp, cn.network.gaussian_scaling, cn.network.gaussian_rotation, cn.network.local_rotation):
+            h.weight.mul_(1e3)
+    x = (torch.randn(P, 3) * 0.5).to(dev)
+    feat = torch.full((P, 8), -1e-2, device=dev, requires_grad=True)
+    t = cn.expand_time(torch.tensor([0.37], device=dev))
+    out = cn(x, t, feat, torch.ones(P, 1, device=dev))
+    assert set(out) == {"d_xyz", "d_rotation", "d_scaling", "d_opacity", "d_color"} and out["d_opacity"] is None
+    p = {k[len("network."):]: v.detach().cpu() for k, v in cn.state_dict().items() if k.startswith("network.")}
+    ref = do.control_node_warp_forward(p, cn.nodes.detach().cpu(), cn._node_radius.detach().cpu(), cn._node_weight.detach().cpu(),
+                                       x.cpu(), t.cpu(), feat.detach().cpu(), torch.ones(P, 1), K, 8, local_frame=True)
+    rows = (ref["nn_idx"] == cn.cal_nn_weight(x, feature=feat)[2].cpu()).all(1)
+    assert rows.float().mean() > 0.999
+    for k in ("d_xyz", "d_rotation", "d_scaling"):
+        assert util.rel_err(out[k].detach().cpu().numpy()[rows], ref[k].numpy()[rows]) < 1e-4, k
+    (out["d_xyz"].sum() + out["d_rotation"].sum()).backward()
+    assert cn.network.linear[0].weight.grad is not None and feat.grad is not None and cn._node_radius.grad is not None
+    assert cn.reg_loss == 0.
+
+
+def test_render_dropin_matches_reference_pipeline(cuda_device):
+    """render() + deform through the public API == the reference op sequence around the reference CUDA extension."""
+    ref = util.load_reference_ext()
+    if ref is None:
+        pytest.skip("oracle/_ref not available")
+    from d2gs_b200 import deform as dfm, model as mdl, synthetic as syn
+    from gaussian_renderer import render
+    from oracle import reference_pipeline as rp
+    dev = cuda_device
+    cfg = syn.CONFIGS["T1"]
+    sc = syn.make_scene(cfg["P"], cfg["seed"], cfg["s_med"], n_nodes=cfg["n_nodes"], hyper_dim=8)
+    cam = mdl.ViewCamera(syn.fibonacci_cameras(8, cfg["W"], cfg["H"])[5], dev)
+    torch.manual_seed(0)
+    dm = dfm.DeformModel(deform_type="node", is_blender=True, K=4, hyper_dim=8, node_num=cfg["n_nodes"], local_frame=True)
+    with torch.no_grad():
+        dm.deform.nodes.copy_(torch.as_tensor(sc.nodes, device=dev))
+        dm.deform._node_radius.copy_(torch.as_tensor(sc.node_radius, device=dev))
+        for h in (dm.deform.network.gaussian_warp, dm.deform.network.gaussian_rotation, dm.deform.network.local_rotation):
+            h.weight.mul_(1e3)
+    bg = torch.tensor([0.2, 0.1, 0.4], device=dev)
+    keys = ("render", "alpha", "rend_normal", "rend_dist", "depth", "surf_normal")
+    g = torch.Generator().manual_seed(1)
+    wts = {k: None for k in keys}
+
+    def run(ours: bool):
+        pc = mdl.SurfelModel(sc, dev)
+        for p_ in dm.deform.parameters():
+            p_.grad = None
+        if ours:
+            d = dm.step(pc.get_xyz.detach(), dm.deform.expand_time(cam.fid), feature=pc.feature, motion_mask=pc.motion_mask)
+            out = render(cam, pc, mdl.PipelineParams(), bg, d["d_xyz"], d["d_rotation"], d["d_scaling"])
+        else:
+            net = {k[len("network."):]: v for k, v in dm.deform.named_parameters() if k.startswith("network.")}
+            d = rp.deform_reference(net, dm.deform.nodes, dm.deform._node_radius, dm.deform._node_weight, pc.get_xyz.detach(), cam.fid,
+                                    pc.feature, pc.motion_mask, 4, 8, local_frame=True, knn_mode="exact")
+            out = rp.render_reference(ref, cam, pc, bg, d["d_xyz"], d["d_rotation"], d["d_scaling"])
+        loss = 0
+        for k in keys:
+            if wts[k] is None:
+                wts[k] = torch.randn(out[k].shape, generator=g).to(dev)
+            loss = loss + (out[k] * wts[k]).sum()
+        loss.backward()
+        torch.cuda.synchronize()
+        grads = {n: p_.grad.detach().cpu().numpy().copy() for n, p_ in list(pc.named_parameters()) + list(dm.deform.named_parameters()) if p_.grad is not None}
+        return {k: v.detach().cpu().numpy() for k, v in out.items() if torch.is_tensor(v)}, grads, out["viewspace_points"].grad.cpu().numpy()
+
+    o_out, o_g, o_vs = run(True)
+    r_out, r_g, r_vs = run(False)
+    assert set(o_out) == set(r_out)
+    assert np.array_equal(o_out["radii"], r_out["radii"]) and np.array_equal(o_out["visibility_filter"], r_out["visibility_filter"])
+    for k in keys + ("surf_point",):
+        assert util.rel_err(o_out[k], r_out[k]) < 1e-4, k
+    assert util.rel_err(o_vs, r_vs) < 5e-4
+    assert set(o_g) == set(r_g), set(o_g) ^ set(r_g)
+    for n in o_g:
+        assert util.rel_err(o_g[n], r_g[n]) < 2e-3, (n, util.rel_err(o_g[n], r_g[n]))
