@@ -50,43 +50,74 @@ def log(*a):
 # clocks
 # ----------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons DURING the timed region, read through NVML in a background thread.
 
-    def __init__(self, gpu_index: int):
-        self.gpu, self.proc, self.lines = gpu_index, None, []
+    (Spawning `nvidia-smi -lms` next to the benchmark was measured to slow every CUDA launch of this process by ~3x
+    on these hosts — the tool re-enumerates the devices under a driver lock on each sample — so the same counters are
+    read in-process; `nvidia-smi` is only the fallback when pynvml is missing.)"""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, gpu_index: int, period_s: float = 0.25):
+        self.gpu, self.period, self.samples, self.stop_flag, self.thread = gpu_index, period_s, [], False, None
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu_index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((float(sm), int(rs)))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        if self.h is None:
+            return
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx = float(f[2])
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        if self.h is None:
+            return self._smi_once()
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        if not self.samples:
+            self._loop_once()
+        sm = [s for s, _ in self.samples]
+        bits = 0
+        for _, r in self.samples:
+            bits |= r
+        reasons = sorted(n for b, n in self.REASONS.items() if bits & b)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "samples": len(sm), "source": "nvml"}
+
+    def _loop_once(self):
+        self.stop_flag = True
+        try:
+            nv = self.nv
+            self.samples.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)), 0))
+        except Exception:
+            pass
+
+    def _smi_once(self) -> dict:
+        try:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits", "-i",
+                                  str(self.gpu)], capture_output=True, text=True, timeout=20).stdout.strip().split(",")
+            return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": [], "samples": 1, "source": "nvidia-smi (after the run)"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -260,6 +291,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="diagnosis only: do not sample clocks during the timed region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -317,24 +349,23 @@ def main():
         step_fn = step_reference
         impl_note = "unmodified reference CUDA rasterizer (oracle/_ref) inside the reference's eager-torch pipeline (oracle/reference_pipeline.py)"
 
+    from d2gs_b200 import dist as ddist
     params = list(wl.pc.raster_parameters()) + list(wl.deform_parameters())
     # flat gradient bucket: every .grad is a view into it, so the all-reduce needs no pack step
-    flat = torch.zeros(sum(p.numel() for p in params), device=device)
-    off = 0
-    for p in params:
-        p.grad = flat[off: off + p.numel()].view_as(p)
-        off += p.numel()
+    bucket = ddist.FlatGradBucket(params)
+    flat = bucket.flat
 
     def view_of(step):
-        return wl.cams[(step * world + rank) % N_VIEWS]
+        return wl.cams[ddist.view_for(step, rank, world, N_VIEWS)]
 
     def run_step(step, e2e=False):
         flat.zero_()
         cam = view_of(step)
         if e2e:
             # per-step inputs come from pinned host memory: camera matrices, time, target image
-            c = wl.cams_np[(step * world + rank) % N_VIEWS]
-            hc = host_cams[(step * world + rank) % N_VIEWS]
+            vi = ddist.view_for(step, rank, world, N_VIEWS)
+            c = wl.cams_np[vi]
+            hc = host_cams[vi]
             cam = e2e_cam
             cam.world_view_transform.copy_(hc[0], non_blocking=True)
             cam.full_proj_transform.copy_(hc[1], non_blocking=True)
@@ -347,7 +378,7 @@ def main():
             gt = wl.gt_dev
         loss = step_fn(wl, cam, gt)
         if dist is not None:
-            dist.all_reduce(flat)
+            bucket.all_reduce()
         if e2e:
             return float(loss.item())   # device -> host read of the step's result
         return loss
@@ -365,7 +396,7 @@ def main():
     def timed(n_steps, e2e, first_step):
         barrier()
         sampler = ClockSampler(local_rank)
-        if rank == 0:
+        if rank == 0 and not args.no_clocks:
             sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -374,7 +405,7 @@ def main():
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1)
-        clocks = sampler.stop() if rank == 0 else None
+        clocks = (sampler.stop() if not args.no_clocks else {"sm_mhz": None, "reasons": ["not sampled"]}) if rank == 0 else None
         if dist is not None:
             t = torch.tensor([ms], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -9,6 +9,7 @@
 #include "../../include/d2gs.h"
 #include "raster_common.cuh"
 #include "deform.cuh"
+#include "epilogue.cuh"
 
 namespace d2gs {
 
@@ -36,7 +37,7 @@ static int fail(int code, const std::string& msg) {
   } while (0)
 
 // ---- optional per-stage timing (CUDA events on the launch stream) ------------------------------------------
-enum Stage { ST_PRE = 0, ST_SCAN, ST_DUP, ST_SORT, ST_RANGES, ST_BLEND_F, ST_BLEND_B, ST_PRE_B, ST_DEF_F, ST_DEF_B };
+enum Stage { ST_PRE = 0, ST_SCAN, ST_DUP, ST_SORT, ST_RANGES, ST_BLEND_F, ST_BLEND_B, ST_PRE_B, ST_DEF_F, ST_DEF_B, ST_EPI_F, ST_EPI_B };
 struct StageRec { int stage; cudaEvent_t a, b; };
 static bool g_profile = false;
 static std::vector<StageRec> g_recs;
@@ -205,6 +206,9 @@ int d2gs_raster_forward(const D2gsRasterFwdArgs* a, void* stream_) {
   p.focal_x = W / (2.0f * a->tan_fovx);
   p.prefiltered = a->prefiltered;
   p.gx = (W + TILE_X - 1) / TILE_X; p.gy = (H + TILE_Y - 1) / TILE_Y;
+  p.raw = a->raw_params; p.d_means3D = a->d_means3D; p.d_scales = a->d_scales; p.d_rotations = a->d_rotations;
+  if (p.raw && (a->transMat_precomp || !a->scales || !a->rotations))
+    return fail(D2GS_ERR_INVALID_ARG, "raw-parameter mode needs scales and rotations (no transMat_precomp)");
 
   if (!a->resume) {
     { StageTimer t(ST_PRE, stream); launch_preprocess_fwd(p, rec, clamped, a->radii, tiles_touched, stream); }
@@ -280,6 +284,10 @@ int d2gs_raster_backward(const D2gsRasterBwdArgs* a, void* stream_) {
   p.focal_y = H / (2.0f * a->tan_fovy);
   p.focal_x = W / (2.0f * a->tan_fovx);
   p.gx = (W + TILE_X - 1) / TILE_X; p.gy = (H + TILE_Y - 1) / TILE_Y;
+  p.raw = a->raw_params; p.opacities = a->opacities; p.d_means3D = a->d_means3D; p.d_scales = a->d_scales;
+  p.d_rotations = a->d_rotations;
+  if (p.raw && (!a->opacities || !a->scales || !a->rotations))
+    return fail(D2GS_ERR_INVALID_ARG, "raw-parameter mode needs opacities, scales and rotations");
 
   if (a->num_rendered > 0) {
     { StageTimer t(ST_BLEND_B, stream);
@@ -290,7 +298,7 @@ int d2gs_raster_backward(const D2gsRasterBwdArgs* a, void* stream_) {
   { StageTimer t(ST_PRE_B, stream);
     launch_preprocess_bwd(p, rec, clamped, a->radii, a->grad_scratch, a->dL_dmeans2D, a->dL_dcolors, a->dL_dopacity,
                           a->dL_dmeans3D, a->dL_dtransMat, a->dL_dsh, a->dL_dsh_rest, a->dL_dscales, a->dL_drotations,
-                          stream); }
+                          p.raw ? a->dL_dscales_raw : nullptr, stream); }
   D2GS_STAGE("preprocess_bwd", a->debug, stream);
   return D2GS_OK;
 }
@@ -318,7 +326,7 @@ __global__ void export_geom_kernel(int P, const SurfelRec* rec, const uint8_t* c
   }
   if (o.normal_opacity) {
     float* t = o.normal_opacity + 4 * (size_t)i;
-    t[0] = r.q3.x; t[1] = r.q3.y; t[2] = r.q3.z; t[3] = r.q2.w;
+    t[0] = r.q3.x; t[1] = r.q3.y; t[2] = r.q3.z; t[3] = r.q4.w;
   }
   if (o.rgb) { o.rgb[3 * i] = r.q4.x; o.rgb[3 * i + 1] = r.q4.y; o.rgb[3 * i + 2] = r.q4.z; }
   if (o.clamped) {
@@ -405,6 +413,31 @@ int d2gs_deform_backward(const D2gsDeformBwdArgs* a, void* stream) {
   const char* err = nullptr;
   { StageTimer t(ST_DEF_B, (cudaStream_t)stream);
     if (deform_backward_launch(h, (cudaStream_t)stream, &err) != 0) return fail(D2GS_ERR_INVALID_ARG, err); }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(D2GS_ERR_CUDA, cudaGetErrorString(e));
+  return D2GS_OK;
+}
+
+int d2gs_epilogue_forward(const D2gsEpilogueArgs* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!a || a->width <= 0 || a->height <= 0) return fail(D2GS_ERR_INVALID_ARG, "bad args");
+  if (!a->allmap || !a->viewmatrix || !a->alpha || !a->rend_normal || !a->rend_dist || !a->depth || !a->surf_normal || !a->surf_point)
+    return fail(D2GS_ERR_INVALID_ARG, "missing buffers");
+  { StageTimer t(ST_EPI_F, stream);
+    launch_epilogue_fwd(a->width, a->height, a->allmap, a->viewmatrix, a->focal_x, a->focal_y, a->alpha, a->rend_normal,
+                        a->rend_dist, a->depth, a->surf_normal, a->surf_point, stream); }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(D2GS_ERR_CUDA, cudaGetErrorString(e));
+  return D2GS_OK;
+}
+
+int d2gs_epilogue_backward(const D2gsEpilogueArgs* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!a || a->width <= 0 || a->height <= 0) return fail(D2GS_ERR_INVALID_ARG, "bad args");
+  if (!a->allmap || !a->viewmatrix || !a->dL_dallmap) return fail(D2GS_ERR_INVALID_ARG, "missing buffers");
+  { StageTimer t(ST_EPI_B, stream);
+    launch_epilogue_bwd(a->width, a->height, a->allmap, a->viewmatrix, a->focal_x, a->focal_y, a->g_alpha, a->g_rend_normal,
+                        a->g_rend_dist, a->g_depth, a->g_surf_normal, a->g_surf_point, a->dL_dallmap, stream); }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(D2GS_ERR_CUDA, cudaGetErrorString(e));
   return D2GS_OK;

@@ -134,9 +134,7 @@ __global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
 
     for (int j = 0; j < n; j++) {
       const uint32_t contributor = len - 1 - (uint32_t)(i * BWD_BATCH + j);   // 0-based list position
-      float g[16];
-#pragma unroll
-      for (int q = 0; q < 16; q++) g[q] = 0.f;
+      float g[16];          // written only by contributing lanes; zero-filled lazily before a reduction
       float gm0 = 0.f, gm1 = 0.f;
       bool contrib = false, flat = false;
       do {
@@ -146,22 +144,23 @@ __global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
         const float3 k = {-Tu.x + pixf.x * Tw.x, -Tu.y + pixf.x * Tw.y, -Tu.z + pixf.x * Tw.z};
         const float3 l = {-Tv.x + pixf.y * Tw.x, -Tv.y + pixf.y * Tw.y, -Tv.z + pixf.y * Tw.z};
         const float3 p = {k.y * l.z - k.z * l.y, k.z * l.x - k.x * l.z, k.x * l.y - k.y * l.x};
+        const float2 d = {c.y - pixf.x, c.z - pixf.y};
+        const float rho2d = 2.0f * (d.x * d.x + d.y * d.y);
+        if (pair_rejected(p.x, p.y, p.z, rho2d, c.w)) break;   // alpha < 1/255 for certain
         if (p.z == 0.0f) break;
         const float2 s = {p.x / p.z, p.y / p.z};
         const float rho3d = (s.x * s.x + s.y * s.y);
-        const float2 d = {c.y - pixf.x, c.z - pixf.y};
-        const float rho2d = 2.0f * (d.x * d.x + d.y * d.y);
         const float rho = fminf(rho3d, rho2d);
         const float c_d = (rho3d <= rho2d) ? (s.x * Tw.x + s.y * Tw.y) + Tw.z : Tw.z;
         if (c_d < 0.2f) break;
         const float power = -0.5f * rho;
         if (power > 0.0f) break;
         const float G = expf(power);
-        const float opac = c.w;
+        const float4 col = s_q4[j];   // rgb + opacity
+        const float opac = col.w;
         const float alpha = fminf(0.99f, opac * G);
         if (alpha < 1.0f / 255.0f) break;
         const float4 nrm = s_q3[j];
-        const float4 col = s_q4[j];
         const float normal[3] = {nrm.x, nrm.y, nrm.z};
         const float color[3] = {col.x, col.y, col.z};
 
@@ -225,6 +224,8 @@ __global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
           const float dG_ddely = -G * 2.0f * d.y;
           gm0 = dL_dG * dG_ddelx;
           gm1 = dL_dG * dG_ddely;
+#pragma unroll
+          for (int q = 0; q < 8; q++) g[q] = 0.f;
           g[8] = dL_dz;
           flat = true;
         }
@@ -233,6 +234,10 @@ __global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
       } while (0);
 
       if (__any_sync(FULL, contrib)) {
+        if (!contrib) {
+#pragma unroll
+          for (int q = 0; q < 16; q++) g[q] = 0.f;
+        }
         warp_transpose_reduce16(g, lane);
         if ((lane & 1) == 0) {
           const int v = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
@@ -335,10 +340,14 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
     const int* __restrict__ radii, float* __restrict__ grad_rec, float* __restrict__ dL_dmeans2D,
     float* __restrict__ dL_dcolors, float* __restrict__ dL_dopacity, float* __restrict__ dL_dmeans3D,
     float* __restrict__ dL_dtransMat, float* __restrict__ dL_dsh, float* __restrict__ dL_dsh_rest,
-    float* __restrict__ dL_dscales, float* __restrict__ dL_drot) {
+    float* __restrict__ dL_dscales, float* __restrict__ dL_drot, float* __restrict__ dL_dscales_raw) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= p.P) return;
   const bool visible = radii[idx] > 0;
+  Activated act;
+  if (p.raw && visible) act = activate_surfel(idx, p.means3D, p.d_means3D, p.scales, p.d_scales, p.rotations, p.d_rotations, p.opacities);
+  float2 dscale_raw = {0.f, 0.f};
+  float dopacity = 0.f;
 
   float gr[GRAD_REC_FLOATS];
   v3 dmean3D = {0.f, 0.f, 0.f};
@@ -390,10 +399,10 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
       const m3 Wm = view_rot(m);
       const m3 Wt = transpose3(Wm);
       const float fx = p.focal_x, fy = p.focal_y, cx = p.focal_x * p.tan_fovx, cy = p.focal_y * p.tan_fovy;
-      const float2 sc = reinterpret_cast<const float2*>(p.scales)[idx];
-      const float4 q = reinterpret_cast<const float4*>(p.rotations)[idx];
+      const float2 sc = p.raw ? act.sc : reinterpret_cast<const float2*>(p.scales)[idx];
+      const float4 q = p.raw ? act.q : reinterpret_cast<const float4*>(p.rotations)[idx];
       const m3 R = quat_to_rot(q);
-      const v3 pw = {p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]};
+      const v3 pw = p.raw ? act.pw : v3{p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]};
       const v3 p_view = Wm * pw + v3{m[12], m[13], m[14]};
       v3 dM[3];
 #pragma unroll
@@ -414,11 +423,21 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
       }
       dscale = {dot3(dRS0, R.c0), dot3(dRS1, R.c1)};
       dmean3D = dpw;
+      if (p.raw) {
+        // chain through exp (scale), F.normalize (rotation: d/dv of v/|v|) — see activate_surfel
+        const float2 ls = reinterpret_cast<const float2*>(p.scales)[idx];
+        dscale_raw = {dscale.x * expf(ls.x), dscale.y * expf(ls.y)};
+        const float qg = act.q.x * drot.x + act.q.y * drot.y + act.q.z * drot.z + act.q.w * drot.w;
+        drot = {(drot.x - act.q.x * qg) / act.qnorm, (drot.y - act.q.y * qg) / act.qnorm,
+                (drot.z - act.q.z * qg) / act.qnorm, (drot.w - act.q.w * qg) / act.qnorm};
+      }
     }
+    dopacity = gr[G_OPA];
+    if (p.raw) dopacity *= act.opacity * (1.0f - act.opacity);
 
     // (3) colour -> SH coefficients and view direction
     if (p.shs != nullptr) {
-      const v3 pw = {p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]};
+      const v3 pw = p.raw ? act.pw : v3{p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]};
       const v3 campos = {p.campos[0], p.campos[1], p.campos[2]};
       const v3 dir_orig = pw - campos;
       const v3 dir = dir_orig / sqrtf(dot3(dir_orig, dir_orig));
@@ -477,13 +496,14 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
 
   if (dL_dmeans2D) { dL_dmeans2D[3 * (size_t)idx] = dm2d.x; dL_dmeans2D[3 * (size_t)idx + 1] = dm2d.y; dL_dmeans2D[3 * (size_t)idx + 2] = 0.f; }
   if (dL_dcolors) { dL_dcolors[3 * (size_t)idx] = gr[G_COL]; dL_dcolors[3 * (size_t)idx + 1] = gr[G_COL + 1]; dL_dcolors[3 * (size_t)idx + 2] = gr[G_COL + 2]; }
-  if (dL_dopacity) dL_dopacity[idx] = gr[G_OPA];
+  if (dL_dopacity) dL_dopacity[idx] = dopacity;
   if (dL_dmeans3D) { dL_dmeans3D[3 * (size_t)idx] = dmean3D.x; dL_dmeans3D[3 * (size_t)idx + 1] = dmean3D.y; dL_dmeans3D[3 * (size_t)idx + 2] = dmean3D.z; }
   if (dL_dtransMat) {
 #pragma unroll
     for (int i = 0; i < 9; i++) dL_dtransMat[9 * (size_t)idx + i] = gr[i];
   }
   if (dL_dscales) reinterpret_cast<float2*>(dL_dscales)[idx] = dscale;
+  if (dL_dscales_raw) reinterpret_cast<float2*>(dL_dscales_raw)[idx] = dscale_raw;
   if (dL_drot) reinterpret_cast<float4*>(dL_drot)[idx] = drot;
   if (dL_dsh && p.M > 0) store_sh_grad(p, dL_dsh, dL_dsh_rest, idx, gsh);
 }
@@ -491,11 +511,11 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
 void launch_preprocess_bwd(const BwdParams& p, const SurfelRec* rec, const uint8_t* clamped, const int* radii,
                            float* grad_rec, float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
                            float* dL_dmeans3D, float* dL_dtransMat, float* dL_dsh, float* dL_dsh_rest,
-                           float* dL_dscales, float* dL_drot, cudaStream_t s) {
+                           float* dL_dscales, float* dL_drot, float* dL_dscales_raw, cudaStream_t s) {
   if (p.P == 0) return;
   preprocess_bwd_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p, rec, clamped, radii, grad_rec, dL_dmeans2D, dL_dcolors,
                                                          dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh, dL_dsh_rest,
-                                                         dL_dscales, dL_drot);
+                                                         dL_dscales, dL_drot, dL_dscales_raw);
 }
 
 }  // namespace d2gs

@@ -35,8 +35,10 @@ __device__ const float kSH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0
                                                  -0.5900435899266435f};
 
 // Projected surfel record, 80 B.
-//  q0 = (Tu.x, Tu.y, Tu.z, Tv.x)   q1 = (Tv.y, Tv.z, Tw.x, Tw.y)   q2 = (Tw.z, mean2D.x, mean2D.y, opacity)
-//  q3 = (normal.x, normal.y, normal.z, depth)                      q4 = (r, g, b, 0)
+//  q0 = (Tu.x, Tu.y, Tu.z, Tv.x)   q1 = (Tv.y, Tv.z, Tw.x, Tw.y)   q2 = (Tw.z, mean2D.x, mean2D.y, tau)
+//  q3 = (normal.x, normal.y, normal.z, depth)                      q4 = (r, g, b, opacity)
+//  tau = 2*ln(255*opacity) + 1e-4: a pixel whose Mahalanobis term exceeds tau has alpha < 1/255 with margin, so the
+//  blend kernels can drop it after ~20 instructions (q0..q2 only) with exactly the reference's outcome.
 struct __align__(16) SurfelRec {
   float4 q0, q1, q2, q3, q4;
 };
@@ -66,6 +68,15 @@ ImgLayout img_layout(int W, int H);
 BinLayout bin_layout(int64_t R);
 
 struct RectU { uint32_t x0, y0, x1, y1; };
+
+// Conservative rejection of a (pixel, surfel) pair from the homogeneous hit point p and the screen distance:
+// true only if BOTH the ray-splat term (|p.xy|^2 / p.z^2) and the low-pass term (rho2d) are safely above tau,
+// i.e. min(rho3d, rho2d) > tau => opacity*exp(-rho/2) < 1/255.  Non-finite inputs never reject (slow path decides).
+__device__ __forceinline__ bool pair_rejected(float px, float py, float pz, float rho2d, float tau) {
+  const float m2 = px * px + py * py;
+  const float z2 = pz * pz;
+  return (rho2d > tau) && (m2 > tau * z2) && (m2 < 3.0e38f);
+}
 
 // Tile rectangle of a surfel (reference: auxiliary.h:64-74).  Float arithmetic and the float->int truncation
 // are part of the contract: tile lists must be bit-exact.
@@ -134,7 +145,35 @@ struct FwdParams {
   float tan_fovx, tan_fovy, focal_x, focal_y;
   int prefiltered;
   uint32_t gx, gy;
+  int raw;                 // raw-parameter mode: activations + deltas applied in-kernel
+  const float* d_means3D;
+  const float* d_scales;
+  const float* d_rotations;
 };
+
+// Activated surfel parameters from the raw ones, op for op what the eager glue computes
+// (exp / sigmoid / F.normalize with eps 1e-12, IEEE division): see DESIGN.md "raw-parameter mode".
+struct Activated { v3 pw; float2 sc; float4 q; float opacity; float qnorm; };
+__device__ __forceinline__ Activated activate_surfel(int idx, const float* means3D, const float* d_means3D,
+                                                     const float* scales, const float* d_scales, const float* rotations,
+                                                     const float* d_rotations, const float* opacities) {
+  Activated a;
+  a.pw = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+  if (d_means3D) { a.pw.x += d_means3D[3 * idx]; a.pw.y += d_means3D[3 * idx + 1]; a.pw.z += d_means3D[3 * idx + 2]; }
+  const float2 ls = reinterpret_cast<const float2*>(scales)[idx];
+  a.sc = {expf(ls.x), expf(ls.y)};
+  if (d_scales) { a.sc.x += d_scales[2 * idx]; a.sc.y += d_scales[2 * idx + 1]; }
+  float4 r = reinterpret_cast<const float4*>(rotations)[idx];
+  if (d_rotations) {
+    const float4 dr = reinterpret_cast<const float4*>(d_rotations)[idx];
+    r.x += dr.x; r.y += dr.y; r.z += dr.z; r.w += dr.w;
+  }
+  const float n = sqrtf(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r.x, r.x), __fmul_rn(r.y, r.y)), __fmul_rn(r.z, r.z)), __fmul_rn(r.w, r.w)));
+  a.qnorm = fmaxf(n, 1e-12f);
+  a.q = {r.x / a.qnorm, r.y / a.qnorm, r.z / a.qnorm, r.w / a.qnorm};
+  a.opacity = opacities ? 1.0f / (1.0f + expf(-opacities[idx])) : 0.f;
+  return a;
+}
 
 void launch_preprocess_fwd(const FwdParams& p, SurfelRec* rec, uint8_t* clamped, int* radii, uint32_t* tiles_touched,
                            cudaStream_t s);
@@ -159,6 +198,11 @@ struct BwdParams {
   const float* campos;
   float tan_fovx, tan_fovy, focal_x, focal_y;
   uint32_t gx, gy;
+  int raw;
+  const float* opacities;
+  const float* d_means3D;
+  const float* d_scales;
+  const float* d_rotations;
 };
 void launch_blend_bwd(const BwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
                       const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, const float* dL_dothers,
@@ -166,7 +210,7 @@ void launch_blend_bwd(const BwdParams& p, const uint2* ranges, const uint32_t* p
 void launch_preprocess_bwd(const BwdParams& p, const SurfelRec* rec, const uint8_t* clamped, const int* radii,
                            float* grad_rec, float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
                            float* dL_dmeans3D, float* dL_dtransMat, float* dL_dsh, float* dL_dsh_rest,
-                           float* dL_dscales, float* dL_drot, cudaStream_t s);
+                           float* dL_dscales, float* dL_drot, float* dL_dscales_raw, cudaStream_t s);
 void launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s);
 
 }  // namespace d2gs

@@ -71,7 +71,9 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(FwdParams p, Surfel
   tiles_touched[idx] = 0;
 
   const float* m = p.view;
-  const v3 pw = {p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]};
+  Activated act;
+  if (p.raw) act = activate_surfel(idx, p.means3D, p.d_means3D, p.scales, p.d_scales, p.rotations, p.d_rotations, p.opacities);
+  const v3 pw = p.raw ? act.pw : v3{p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]};
   // near-plane cull (the only frustum test the reference keeps active)
   const float depth = m[2] * pw.x + m[6] * pw.y + m[10] * pw.z + m[14];
   if (depth <= 0.2f) {
@@ -92,8 +94,8 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(FwdParams p, Surfel
     const m3 Wm = view_rot(m);
     const v3 cam = {m[12], m[13], m[14]};
     const v3 p_view = Wm * pw + cam;
-    const float2 sc = reinterpret_cast<const float2*>(p.scales)[idx];
-    const float4 q = reinterpret_cast<const float4*>(p.rotations)[idx];
+    const float2 sc = p.raw ? act.sc : reinterpret_cast<const float2*>(p.scales)[idx];
+    const float4 q = p.raw ? act.q : reinterpret_cast<const float4*>(p.rotations)[idx];
     const m3 R = quat_to_rot(q);
     const v3 M0 = Wm * (R.c0 * sc.x);
     const v3 M1 = Wm * (R.c1 * sc.y);
@@ -151,9 +153,10 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(FwdParams p, Surfel
   SurfelRec o;
   o.q0 = make_float4(T[0], T[1], T[2], T[3]);
   o.q1 = make_float4(T[4], T[5], T[6], T[7]);
-  o.q2 = make_float4(T[8], pc.x, pc.y, p.opacities[idx]);
+  const float opacity = p.raw ? act.opacity : p.opacities[idx];
+  o.q2 = make_float4(T[8], pc.x, pc.y, 2.0f * logf(255.0f * opacity) + 1e-4f);
   o.q3 = make_float4(normal.x, normal.y, normal.z, depth);
-  o.q4 = make_float4(rgb.x, rgb.y, rgb.z, 0.f);
+  o.q4 = make_float4(rgb.x, rgb.y, rgb.z, opacity);
   rec[idx] = o;
 }
 
@@ -279,18 +282,20 @@ __global__ void __launch_bounds__(TILE_PIX) blend_fwd_kernel(
       const float3 k = {-Tu.x + pixf.x * Tw.x, -Tu.y + pixf.x * Tw.y, -Tu.z + pixf.x * Tw.z};
       const float3 l = {-Tv.x + pixf.y * Tw.x, -Tv.y + pixf.y * Tw.y, -Tv.z + pixf.y * Tw.z};
       const float3 p = {k.y * l.z - k.z * l.y, k.z * l.x - k.x * l.z, k.x * l.y - k.y * l.x};
-      if (p.z == 0.0f) continue;
-      const float2 s = {p.x / p.z, p.y / p.z};
-      const float rho3d = (s.x * s.x + s.y * s.y);
       const float2 dd = {c.y - pixf.x, c.z - pixf.y};
       // 1/FilterSize^2 * r^2 evaluated in double and rounded equals 2*r^2 in float exactly
       const float rho2d = 2.0f * (dd.x * dd.x + dd.y * dd.y);
+      if (pair_rejected(p.x, p.y, p.z, rho2d, c.w)) continue;   // alpha < 1/255 for certain
+      if (p.z == 0.0f) continue;
+      const float2 s = {p.x / p.z, p.y / p.z};
+      const float rho3d = (s.x * s.x + s.y * s.y);
       const float rho = fminf(rho3d, rho2d);
       const float depth = (rho3d <= rho2d) ? (s.x * Tw.x + s.y * Tw.y) + Tw.z : Tw.z;
       if (depth < 0.2f) continue;   // (double)depth < 0.2 <=> depth < 0.2f
       const float power = -0.5f * rho;
       if (power > 0.0f) continue;
-      const float alpha = fminf(0.99f, c.w * expf(power));
+      const float4 col = s_q4[j];   // rgb + opacity
+      const float alpha = fminf(0.99f, col.w * expf(power));
       if (alpha < 1.0f / 255.0f) continue;
       const float test_T = T * (1 - alpha);
       if (test_T < 0.0001f) {
@@ -299,7 +304,6 @@ __global__ void __launch_bounds__(TILE_PIX) blend_fwd_kernel(
       }
       const float w = alpha * T;
       const float4 nrm = s_q3[j];
-      const float4 col = s_q4[j];
       // distortion bookkeeping (depth mapped to [0,1] between the near and far planes)
       const float A = 1 - T;
       const float md = (float)((D2GS_FAR_PLANE * depth - D2GS_FAR_PLANE * D2GS_NEAR_PLANE) /

@@ -32,7 +32,8 @@ class RasterFwdArgs(C.Structure):
                 ("img_buffer", C.c_void_p), ("img_bytes", C.c_size_t),
                 ("binning_buffer", C.c_void_p), ("binning_bytes", C.c_size_t),
                 ("resume", C.c_int),
-                ("num_rendered", C.POINTER(C.c_int64)), ("binning_required", C.POINTER(C.c_size_t))]
+                ("num_rendered", C.POINTER(C.c_int64)), ("binning_required", C.POINTER(C.c_size_t)),
+                ("raw_params", C.c_int), ("d_means3D", C.c_void_p), ("d_scales", C.c_void_p), ("d_rotations", C.c_void_p)]
 
 
 class RasterBwdArgs(C.Structure):
@@ -48,7 +49,9 @@ class RasterBwdArgs(C.Structure):
                 ("debug", C.c_int), ("grad_scratch", C.c_void_p),
                 ("dL_dmeans2D", C.c_void_p), ("dL_dcolors", C.c_void_p), ("dL_dopacity", C.c_void_p),
                 ("dL_dmeans3D", C.c_void_p), ("dL_dtransMat", C.c_void_p), ("dL_dsh", C.c_void_p),
-                ("dL_dsh_rest", C.c_void_p), ("dL_dscales", C.c_void_p), ("dL_drotations", C.c_void_p)]
+                ("dL_dsh_rest", C.c_void_p), ("dL_dscales", C.c_void_p), ("dL_drotations", C.c_void_p),
+                ("raw_params", C.c_int), ("opacities", C.c_void_p), ("d_means3D", C.c_void_p), ("d_scales", C.c_void_p),
+                ("d_rotations", C.c_void_p), ("dL_dscales_raw", C.c_void_p)]
 
 
 class RasterState(C.Structure):
@@ -80,11 +83,20 @@ class DeformBwdArgs(C.Structure):
                 ("dL_dnode_weight_logit", C.c_void_p), ("dL_dfeature", C.c_void_p), ("dL_dmotion_mask", C.c_void_p)]
 
 
+class EpilogueArgs(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("allmap", C.c_void_p), ("viewmatrix", C.c_void_p),
+                ("focal_x", C.c_float), ("focal_y", C.c_float),
+                ("alpha", C.c_void_p), ("rend_normal", C.c_void_p), ("rend_dist", C.c_void_p), ("depth", C.c_void_p),
+                ("surf_normal", C.c_void_p), ("surf_point", C.c_void_p),
+                ("g_alpha", C.c_void_p), ("g_rend_normal", C.c_void_p), ("g_rend_dist", C.c_void_p), ("g_depth", C.c_void_p),
+                ("g_surf_normal", C.c_void_p), ("g_surf_point", C.c_void_p), ("dL_dallmap", C.c_void_p)]
+
+
 # every symbol include/d2gs.h declares; tests assert the shared library exports all of them
 EXPORTED_SYMBOLS = (
     "d2gs_profile_enable", "d2gs_profile_collect", "d2gs_last_error", "d2gs_version", "d2gs_get_config", "d2gs_raster_workspace", "d2gs_raster_forward",
     "d2gs_raster_backward", "d2gs_mark_visible", "d2gs_raster_export_state", "d2gs_deform_forward",
-    "d2gs_deform_backward",
+    "d2gs_deform_backward", "d2gs_epilogue_forward", "d2gs_epilogue_backward",
 )
 
 D2GS_OK = 0
@@ -120,6 +132,8 @@ def lib():
                                            C.POINTER(RasterState), C.c_void_p]
     L.d2gs_deform_forward.argtypes = [C.POINTER(DeformFwdArgs), C.c_void_p]
     L.d2gs_deform_backward.argtypes = [C.POINTER(DeformBwdArgs), C.c_void_p]
+    L.d2gs_epilogue_forward.argtypes = [C.POINTER(EpilogueArgs), C.c_void_p]
+    L.d2gs_epilogue_backward.argtypes = [C.POINTER(EpilogueArgs), C.c_void_p]
     L.d2gs_profile_enable.argtypes = [C.c_int]
     L.d2gs_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     for name in EXPORTED_SYMBOLS:
@@ -146,7 +160,7 @@ def workspace_sizes(P: int, W: int, H: int, R: int = 0):
 
 
 STAGE_NAMES = ("preprocess_fwd", "scan", "duplicate", "sort", "ranges", "blend_fwd", "blend_bwd", "preprocess_bwd",
-               "deform_fwd", "deform_bwd")
+               "deform_fwd", "deform_bwd", "epilogue_fwd", "epilogue_bwd")
 
 
 def profile_enable(on: bool) -> None:

@@ -68,7 +68,7 @@ class RasterContext:
 
 def raster_forward(bg, means3D, colors_precomp, opacities, scales, rotations, scale_modifier, transMat_precomp,
                    viewmatrix, projmatrix, tanfovx, tanfovy, image_height, image_width, sh, sh_rest, degree, campos,
-                   prefiltered, debug):
+                   prefiltered, debug, raw_params=False, d_means3D=None, d_scales=None, d_rotations=None):
     """Equivalent of ``_C.rasterize_gaussians`` (DSR/rasterize_points.cu:39-141).
 
     Returns (num_rendered, color, others, radii, ctx)."""
@@ -114,6 +114,8 @@ def raster_forward(bg, means3D, colors_precomp, opacities, scales, rotations, sc
     a.img_buffer, a.img_bytes = ctx.img.data_ptr(), ibytes
     a.binning_buffer, a.binning_bytes = ctx.binning.data_ptr(), bbytes
     a.resume = 0
+    a.raw_params = int(bool(raw_params))
+    a.d_means3D, a.d_scales, a.d_rotations = _ptr(d_means3D), _ptr(d_scales), _ptr(d_rotations)
     a.num_rendered = C.pointer(num_rendered)
     a.binning_required = C.pointer(required)
     stream = _stream_ptr(dev)
@@ -135,7 +137,7 @@ def raster_forward(bg, means3D, colors_precomp, opacities, scales, rotations, sc
 
 def raster_backward(bg, means3D, radii, colors_precomp, scales, rotations, scale_modifier, transMat_precomp, viewmatrix,
                     projmatrix, tanfovx, tanfovy, dL_dout_color, dL_dout_others, sh, sh_rest, degree, campos, ctx,
-                    debug, want=None):
+                    debug, want=None, raw_params=False, opacities=None, d_means3D=None, d_scales=None, d_rotations=None):
     """Equivalent of ``_C.rasterize_gaussians_backward`` (DSR/rasterize_points.cu:143-240).
 
     Returns dict with dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh, dL_dsh_rest,
@@ -147,7 +149,9 @@ def raster_backward(bg, means3D, radii, colors_precomp, scales, rotations, scale
     want = want or {}
     w = lambda k: want.get(k, True)
     g = dict.fromkeys(("dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dtransMat", "dL_dsh",
-                       "dL_dsh_rest", "dL_dscales", "dL_drotations"))
+                       "dL_dsh_rest", "dL_dscales", "dL_drotations", "dL_dscales_raw"))
+    if raw_params:
+        g["dL_dscales_raw"] = torch.empty((P, 2), **f32)
     if w("dL_dmeans2D"): g["dL_dmeans2D"] = torch.empty((P, 3), **f32)
     if w("dL_dcolors"): g["dL_dcolors"] = torch.empty((P, 3), **f32)
     if w("dL_dopacity"): g["dL_dopacity"] = torch.empty((P, 1), **f32)
@@ -187,6 +191,9 @@ def raster_backward(bg, means3D, radii, colors_precomp, scales, rotations, scale
     a.dL_dsh_rest = _ptr(g["dL_dsh_rest"])
     a.dL_dscales = _ptr(g["dL_dscales"]) if scales is not None else None
     a.dL_drotations = _ptr(g["dL_drotations"]) if scales is not None else None
+    a.raw_params = int(bool(raw_params))
+    a.opacities, a.d_means3D, a.d_scales, a.d_rotations = _ptr(opacities), _ptr(d_means3D), _ptr(d_scales), _ptr(d_rotations)
+    a.dL_dscales_raw = _ptr(g["dL_dscales_raw"])
     with torch.cuda.device(dev):
         rc = L.d2gs_raster_backward(C.byref(a), _stream_ptr(dev))
     if rc != 0:
@@ -264,6 +271,63 @@ class _RasterizeSurfels(torch.autograd.Function):
         return (g["dL_dmeans3D"], g["dL_dmeans2D"], grad_sh, grad_sh_rest, g["dL_dcolors"], g["dL_dopacity"],
                 g["dL_dscales"] if sc_ is not None else None, g["dL_drotations"] if rot_ is not None else None,
                 g["dL_dtransMat"] if cov_ is not None else None, None)
+
+
+class _RasterizeSurfelsRaw(torch.autograd.Function):
+    """Rasterizer fused with the activations and deformation deltas of render() (raw-parameter mode of the C ABI).
+
+    inputs: xyz, d_xyz, log-scales, d_scaling, raw quaternions, d_rotation, opacity logits (deltas may be None /
+    python scalars 0.0), SH as (DC, rest).  Semantics == rasterize(xyz+d_xyz, exp(s)+d_s, normalize(q+d_q), sigmoid(o))."""
+
+    @staticmethod
+    def forward(ctx, xyz, d_xyz, scaling, d_scaling, rotation, d_rotation, opacity, means2D, sh, sh_rest, colors_precomp,
+                raster_settings):
+        rs = raster_settings
+        t = lambda v, n: _prep(v, n) if torch.is_tensor(v) else None
+        xyz_, sc_, rot_, op_ = _prep(xyz, "xyz"), _prep(scaling, "scaling"), _prep(rotation, "rotation"), _prep(opacity, "opacity")
+        dx_, ds_, dr_ = t(d_xyz, "d_xyz"), t(d_scaling, "d_scaling"), t(d_rotation, "d_rotation")
+        for v, like, n in ((dx_, xyz_, "d_xyz"), (ds_, sc_, "d_scaling"), (dr_, rot_, "d_rotation")):
+            if v is not None and v.shape != like.shape:
+                raise RuntimeError(f"{n} must have the shape of the parameter it offsets, got {tuple(v.shape)}")
+        sh_, shr_, col_ = _prep(_opt(sh), "sh"), _prep(_opt(sh_rest), "sh_rest"), _prep(_opt(colors_precomp), "colors")
+        bg = _prep(rs.bg, "background")
+        view, proj, campos = _prep(rs.viewmatrix, "viewmatrix"), _prep(rs.projmatrix, "projmatrix"), _prep(rs.campos, "campos")
+        num_rendered, color, others, radii, rctx = raster_forward(
+            bg, xyz_, col_, op_, sc_, rot_, rs.scale_modifier, None, view, proj, rs.tanfovx, rs.tanfovy, rs.image_height,
+            rs.image_width, sh_, shr_, rs.sh_degree, campos, rs.prefiltered, rs.debug, raw_params=True, d_means3D=dx_,
+            d_scales=ds_, d_rotations=dr_)
+        ctx.raster_settings, ctx.rctx, ctx.prepped = rs, rctx, (bg, view, proj, campos)
+        ctx.has_delta = (dx_ is not None, ds_ is not None, dr_ is not None)
+        ctx.save_for_backward(xyz_, sc_, rot_, op_, dx_, ds_, dr_, radii, sh_, shr_, col_)
+        ctx.mark_non_differentiable(radii)
+        return color, radii, others
+
+    @staticmethod
+    def backward(ctx, grad_out_color, grad_radii, grad_depth):
+        rs = ctx.raster_settings
+        xyz_, sc_, rot_, op_, dx_, ds_, dr_, radii, sh_, shr_, col_ = ctx.saved_tensors
+        bg, view, proj, campos = ctx.prepped
+        rctx = ctx.rctx
+        dev = xyz_.device
+        if grad_out_color is None:
+            grad_out_color = torch.zeros((3, rctx.H, rctx.W), dtype=torch.float32, device=dev)
+        if grad_depth is None:
+            grad_depth = torch.zeros((8, rctx.H, rctx.W), dtype=torch.float32, device=dev)
+        want = {"dL_dtransMat": False, "dL_dcolors": col_ is not None}
+        g = raster_backward(bg, xyz_, radii, col_, sc_, rot_, rs.scale_modifier, None, view, proj, rs.tanfovx, rs.tanfovy,
+                            grad_out_color.float().contiguous(), grad_depth.float().contiguous(), sh_, shr_, rs.sh_degree,
+                            campos, rctx, rs.debug, want=want, raw_params=True, opacities=op_, d_means3D=dx_, d_scales=ds_,
+                            d_rotations=dr_)
+        hd = ctx.has_delta
+        return (g["dL_dmeans3D"], g["dL_dmeans3D"] if hd[0] else None, g["dL_dscales_raw"], g["dL_dscales"] if hd[1] else None,
+                g["dL_drotations"], g["dL_drotations"] if hd[2] else None, g["dL_dopacity"], g["dL_dmeans2D"],
+                g["dL_dsh"] if sh_ is not None else None, g["dL_dsh_rest"], g["dL_dcolors"], None)
+
+
+def rasterize_surfels_raw(xyz, d_xyz, scaling, d_scaling, rotation, d_rotation, opacity, means2D, sh, sh_rest,
+                          colors_precomp, raster_settings):
+    return _RasterizeSurfelsRaw.apply(xyz, d_xyz, scaling, d_scaling, rotation, d_rotation, opacity, means2D, sh, sh_rest,
+                                      colors_precomp, raster_settings)
 
 
 def rasterize_surfels(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,

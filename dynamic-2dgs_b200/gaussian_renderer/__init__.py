@@ -13,6 +13,7 @@ import torch
 
 from diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
 from d2gs_b200 import raster as _raster
+from d2gs_b200 import epilogue as _epilogue
 
 _RAY_CACHE = {}
 
@@ -48,8 +49,8 @@ def _camera_rays(view):
     fx = W / (2 * math.tan(view.FoVx / 2.))
     fy = H / (2 * math.tan(view.FoVy / 2.))
     intrins = torch.tensor([[fx, 0., W / 2.], [0., fy, H / 2.], [0., 0., 1.0]]).float().to(dev)
-    grid_x, grid_y = torch.meshgrid(torch.arange(W), torch.arange(H), indexing='xy')
-    points = torch.stack([grid_x, grid_y, torch.ones_like(grid_x)], dim=-1).reshape(-1, 3).float().to(dev)
+    grid_x, grid_y = torch.meshgrid(torch.arange(W, device=dev), torch.arange(H, device=dev), indexing='xy')
+    points = torch.stack([grid_x, grid_y, torch.ones_like(grid_x)], dim=-1).reshape(-1, 3).float()
     rays_d = points @ intrins.inverse().T @ c2w[:3, :3].T
     rays_o = c2w[:3, 3]
     if len(_RAY_CACHE) > 512:
@@ -95,20 +96,12 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, d_xyz, d_rotation
         viewmatrix=viewpoint_camera.world_view_transform, projmatrix=viewpoint_camera.full_proj_transform,
         sh_degree=pc.active_sh_degree, campos=viewpoint_camera.camera_center, prefiltered=False, debug=pipe.debug)
 
-    means3D = xyz + d_xyz
     means2D = screenspace_points
-    if scale_const is not None:
-        opacity = torch.ones_like(pc.get_opacity)
-    else:
-        opacity = pc.get_opacity if d_opacity is None else pc.get_opacity + d_opacity
 
     if pipe.compute_cov3D_python:
         raise NotImplementedError("compute_cov3D_python is broken for 2-D scales in the reference (utils/general_utils.py:167)")
-    scales = pc.get_scaling + d_scaling
-    rotations = pc.get_rotation_bias(d_rotation)
-    if d_rotation_bias is not None:
-        rotations = quaternion_multiply(d_rotation_bias, rotations)
 
+    # ---- colour inputs -----------------------------------------------------------------------------------------
     shs, sh_rest, colors_precomp = None, None, None
     if render_motion:
         colors_precomp = torch.zeros_like(xyz)
@@ -132,45 +125,75 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, d_xyz, d_rotation
             else:
                 shs = sh_features
 
-    if detach_xyz:
-        means3D = means3D.detach()
-    if detach_rot:
-        rotations = rotations.detach()
-    if detach_scale:
-        scales = scales.detach()
-    if detach_opacity:
-        opacity = opacity.detach()
-    if scale_const is not None:
-        scales = scale_const * torch.ones_like(scales)
+    # ---- geometry inputs: fused path (activations + deltas inside the per-surfel kernel) when the model exposes the
+    # ---- reference's raw parameters with its standard activations; otherwise the reference's eager op sequence.
+    def _delta_ok(d, like):
+        return (not torch.is_tensor(d) and d == 0) or (torch.is_tensor(d) and d.shape == like.shape)
 
-    rendered_image, radii, allmap = _raster.rasterize_surfels(means3D, means2D, shs, colors_precomp, opacity, scales,
-                                                              rotations, None, raster_settings, sh_rest=sh_rest)
+    fused = (all(hasattr(pc, n) for n in ("_scaling", "_rotation", "_opacity"))
+             and getattr(pc, "scaling_activation", torch.exp) is torch.exp
+             and getattr(pc, "opacity_activation", torch.sigmoid) is torch.sigmoid
+             and getattr(pc, "rotation_activation", torch.nn.functional.normalize) is torch.nn.functional.normalize
+             and scale_const is None and d_opacity is None and d_rotation_bias is None
+             and _delta_ok(d_xyz, xyz) and _delta_ok(d_scaling, pc._scaling) and _delta_ok(d_rotation, pc._rotation)
+             and pc._scaling.dim() == 2 and pc._scaling.shape[1] == 2 and not getattr(pc, "all_the_same", False))
+    if fused:
+        det = lambda t, flag: (t.detach() if flag and torch.is_tensor(t) else t)
+        tz = lambda d: d if torch.is_tensor(d) else None
+        rendered_image, radii, allmap = _raster.rasterize_surfels_raw(
+            det(xyz, detach_xyz), det(tz(d_xyz), detach_xyz), det(pc._scaling, detach_scale), det(tz(d_scaling), detach_scale),
+            det(pc._rotation, detach_rot), det(tz(d_rotation), detach_rot), det(pc._opacity, detach_opacity), means2D,
+            shs, sh_rest, colors_precomp, raster_settings)
+    else:
+        means3D = xyz + d_xyz
+        if scale_const is not None:
+            opacity = torch.ones_like(pc.get_opacity)
+        else:
+            opacity = pc.get_opacity if d_opacity is None else pc.get_opacity + d_opacity
+        scales = pc.get_scaling + d_scaling
+        rotations = pc.get_rotation_bias(d_rotation)
+        if d_rotation_bias is not None:
+            rotations = quaternion_multiply(d_rotation_bias, rotations)
+        if detach_xyz:
+            means3D = means3D.detach()
+        if detach_rot:
+            rotations = rotations.detach()
+        if detach_scale:
+            scales = scales.detach()
+        if detach_opacity:
+            opacity = opacity.detach()
+        if scale_const is not None:
+            scales = scale_const * torch.ones_like(scales)
+        rendered_image, radii, allmap = _raster.rasterize_surfels(means3D, means2D, shs, colors_precomp, opacity, scales,
+                                                                  rotations, None, raster_settings, sh_rest=sh_rest)
 
     rets = {"render": rendered_image, "viewspace_points": means2D, "visibility_filter": radii > 0, "radii": radii}
 
-    whitebackground = torch.tensor([1, 1, 1], dtype=torch.float32, device=xyz.device)
-    if depth_filtering:
+    if not depth_filtering:
+        # fused image-space epilogue: one kernel forward / one backward (d2gs_b200/epilogue.py)
+        render_alpha, render_normal, render_dist, surf_depth, surf_normal, surf_point = _epilogue.render_epilogue(allmap, viewpoint_camera)
+        pipe.depth_ratio = 1
+    else:
+        whitebackground = torch.tensor([1, 1, 1], dtype=torch.float32, device=xyz.device)
         if bg_color.equal(whitebackground):
             mask = (1 - (torch.all(rendered_image >= 0.95, dim=0)).to(torch.int))
         else:
             mask = (1 - (torch.all(rendered_image <= 0.05, dim=0)).to(torch.int))
-    else:
-        mask = 1
-    render_alpha = allmap[1:2]
-    render_normal = allmap[2:5]
-    render_normal = (render_normal.permute(1, 2, 0) @ (viewpoint_camera.world_view_transform[:3, :3].T)).permute(2, 0, 1)
-    render_normal = render_normal * mask
-    render_depth_median = torch.nan_to_num(allmap[5:6], 0, 0)
-    render_depth_expected = torch.nan_to_num(allmap[0:1] / render_alpha, 0, 0)
-    render_dist = allmap[6:7] * mask
-    pipe.depth_ratio = 1
-    surf_depth = render_depth_expected * (1 - pipe.depth_ratio) + (pipe.depth_ratio) * render_depth_median
-    surf_depth = surf_depth * mask
-    surf_normal, surf_point = depth_to_normal(viewpoint_camera, surf_depth)
-    surf_normal = surf_normal.permute(2, 0, 1)
-    surf_point = surf_point.permute(2, 0, 1)
-    surf_normal = surf_normal * (render_alpha).detach()
-    surf_normal = surf_normal * mask
+        render_alpha = allmap[1:2]
+        render_normal = allmap[2:5]
+        render_normal = (render_normal.permute(1, 2, 0) @ (viewpoint_camera.world_view_transform[:3, :3].T)).permute(2, 0, 1)
+        render_normal = render_normal * mask
+        render_depth_median = torch.nan_to_num(allmap[5:6], 0, 0)
+        render_depth_expected = torch.nan_to_num(allmap[0:1] / render_alpha, 0, 0)
+        render_dist = allmap[6:7] * mask
+        pipe.depth_ratio = 1
+        surf_depth = render_depth_expected * (1 - pipe.depth_ratio) + (pipe.depth_ratio) * render_depth_median
+        surf_depth = surf_depth * mask
+        surf_normal, surf_point = depth_to_normal(viewpoint_camera, surf_depth)
+        surf_normal = surf_normal.permute(2, 0, 1)
+        surf_point = surf_point.permute(2, 0, 1)
+        surf_normal = surf_normal * (render_alpha).detach()
+        surf_normal = surf_normal * mask
 
     rets.update({'alpha': render_alpha, 'rend_normal': render_normal, 'rend_dist': render_dist, 'depth': surf_depth,
                  'surf_normal': surf_normal, 'surf_point': surf_point, "bg_color": bg})

@@ -51,9 +51,9 @@ typedef struct D2gsConfig {
 
 /* Per-stage device timing with CUDA events recorded on the launch stream (for bench.py's roofline line).
  * Stages: 0 preprocess_fwd, 1 scan, 2 duplicate, 3 sort, 4 ranges, 5 blend_fwd, 6 blend_bwd, 7 preprocess_bwd,
- *         8 deform_fwd, 9 deform_bwd.  d2gs_profile_collect synchronises the device, adds the elapsed times of all
+ *         8 deform_fwd, 9 deform_bwd, 10 epilogue_fwd, 11 epilogue_bwd.  d2gs_profile_collect synchronises the device, adds the elapsed times of all
  * recorded launches to total_ms[stage] / launches[stage] (arrays of D2GS_NUM_STAGES) and clears the record. */
-#define D2GS_NUM_STAGES 10
+#define D2GS_NUM_STAGES 12
 D2GS_API int d2gs_profile_enable(int on);
 D2GS_API int d2gs_profile_collect(double* total_ms, int64_t* launches);
 
@@ -103,6 +103,14 @@ typedef struct D2gsRasterFwdArgs {
   /* results on the host */
   int64_t* num_rendered;          /* host: R, number of (surfel,tile) instances */
   size_t* binning_required;       /* host: bytes needed for R instances */
+  /* Raw-parameter mode (raw_params = 1): the activations and deformation deltas of render()
+   * (gaussian_renderer/__init__.py:83-99, scene/gaussian_model.py:67-75,101-124) are applied inside the per-surfel
+   * kernel instead of by ~10 eager ops:  means3D += d_means3D;  scales = exp(scales) + d_scales;
+   * rotations = normalize(rotations + d_rotations);  opacities = sigmoid(opacities).   Deltas may be NULL (= 0). */
+  int raw_params;
+  const float* d_means3D;         /* (P,3) or NULL */
+  const float* d_scales;          /* (P,2) or NULL */
+  const float* d_rotations;       /* (P,4) or NULL */
 } D2gsRasterFwdArgs;
 
 /* Forward.  Synchronises `stream` once (the reference's blocking readback of num_rendered,
@@ -145,6 +153,16 @@ typedef struct D2gsRasterBwdArgs {
   float* dL_dsh_rest;     /* (P,M-1,3) or NULL */
   float* dL_dscales;      /* (P,2) */
   float* dL_drotations;   /* (P,4) */
+  /* Raw-parameter mode (must match the forward call).  Then: opacities = the logits given to forward;
+   * dL_dmeans3D is the gradient of xyz AND d_means3D; dL_dscales the gradient of d_scales (and of the activated
+   * scale); dL_dscales_raw that of the log-scales; dL_drotations the gradient of rotations AND d_rotations (through
+   * the normalisation); dL_dopacity the gradient of the opacity logits. */
+  int raw_params;
+  const float* opacities;
+  const float* d_means3D;
+  const float* d_scales;
+  const float* d_rotations;
+  float* dL_dscales_raw;  /* (P,2) */
 } D2gsRasterBwdArgs;
 
 D2GS_API int d2gs_raster_backward(const D2gsRasterBwdArgs* args, void* stream);
@@ -176,6 +194,31 @@ typedef struct D2gsRasterState {
 D2GS_API int d2gs_raster_export_state(int P, int width, int height, int64_t num_rendered, const void* geom_buffer,
                              const void* binning_buffer, const void* img_buffer, const D2gsRasterState* out,
                              void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Image-space epilogue of render(): replaces gaussian_renderer/__init__.py:172-207 and depth_to_normal /
+ * depths_to_points (utils/point_utils.py:9-38).  All planes are (c,H,W) float32 on the device.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct D2gsEpilogueArgs {
+  int width, height;
+  const float* allmap;        /* (8,H,W) rasterizer output */
+  const float* viewmatrix;    /* (4,4) transposed world->view */
+  float focal_x, focal_y;     /* W / (2 tan(FoVx/2)), H / (2 tan(FoVy/2)) */
+  /* forward outputs */
+  float* alpha;               /* (1,H,W) */
+  float* rend_normal;         /* (3,H,W) world space */
+  float* rend_dist;           /* (1,H,W) */
+  float* depth;               /* (1,H,W) median depth, nan_to_num'd */
+  float* surf_normal;         /* (3,H,W) normal of the depth map x alpha */
+  float* surf_point;          /* (3,H,W) unprojected depth */
+  /* backward: upstream gradients (NULL = zero) and the result */
+  const float* g_alpha; const float* g_rend_normal; const float* g_rend_dist; const float* g_depth;
+  const float* g_surf_normal; const float* g_surf_point;
+  float* dL_dallmap;          /* (8,H,W), fully written */
+} D2gsEpilogueArgs;
+
+D2GS_API int d2gs_epilogue_forward(const D2gsEpilogueArgs* args, void* stream);
+D2GS_API int d2gs_epilogue_backward(const D2gsEpilogueArgs* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Node-controlled deformation: KNN weights + blend.  Replaces ControlNodeWarp.cal_nn_weight

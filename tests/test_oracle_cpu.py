@@ -34,7 +34,11 @@ def test_oracle_matches_reference_golden(path):
         assert np.array_equal(st.ranges, g["ranges"])
         same_list = st.point_list == g["point_list"]
         assert same_list.mean() > 0.999   # equal-depth ties cannot occur; ulp-level depth flips can
-        assert (st.n_contrib == g["n_contrib"]).mean() > 0.999
+        assert (st.n_contrib[0] == g["n_contrib"][0]).mean() > 0.999
+        # the median contributor of a pixel nothing contributed to is (uint32)(-1.0f) in the reference: undefined
+        # behaviour in C++, observed as garbage on sm_100 — compare only where a contributor exists
+        has = g["n_contrib"][0] > 0
+        assert (st.n_contrib[1][has] == g["n_contrib"][1][has]).mean() > 0.999
     vis = g["radii"] > 0
     np.testing.assert_allclose(st.means2D[vis], g["means2D"][vis], rtol=1e-4, atol=1e-3)
     np.testing.assert_allclose(st.depths[vis], g["depths"][vis], rtol=1e-5, atol=1e-6)

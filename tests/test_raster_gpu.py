@@ -70,6 +70,15 @@ def np_(t):
     return t.detach().cpu().numpy()
 
 
+def _assert_n_contrib_equal(ours, ref):
+    """last contributor: bit-exact.  median contributor: bit-exact wherever it is defined — for a pixel nothing
+    contributed to the reference stores (uint32)(-1.0f), undefined behaviour that yields garbage on sm_100 (we store 0)."""
+    assert np.array_equal(ours[0], ref[0])
+    has = ref[0] > 0
+    assert np.array_equal(ours[1][has], ref[1][has])
+    assert not ours[1][~has].any()
+
+
 @pytest.mark.skipif(not GOLDEN, reason="golden fixtures not recorded yet")
 @pytest.mark.parametrize("path", GOLDEN)
 def test_against_reference_golden(path, cuda_device):
@@ -87,7 +96,7 @@ def test_against_reference_golden(path, cuda_device):
     assert np.array_equal(st["keys_sorted"].view(np.uint64), g["keys_sorted"])
     assert np.array_equal(st["point_list"].view(np.uint32), g["point_list"])
     assert np.array_equal(st["ranges"].view(np.uint32), g["ranges"])
-    assert np.array_equal(st["n_contrib"].view(np.uint32), g["n_contrib"])
+    _assert_n_contrib_equal(st["n_contrib"].view(np.uint32), g["n_contrib"])
     vis = g["radii"] > 0
     assert np.array_equal(st["depths"][vis].view(np.uint32), g["depths"][vis].view(np.uint32))   # sort keys
     assert np.array_equal(st["clamped"][vis], g["clamped"][vis])
@@ -125,7 +134,7 @@ def test_against_reference_extension_live(cfg, s_med, bg, cuda_device):
     assert np.array_equal(st["keys_sorted"].view(np.uint64), g["keys_sorted"])
     assert np.array_equal(st["point_list"].view(np.uint32), g["point_list"])
     assert np.array_equal(st["ranges"].view(np.uint32), g["ranges"])
-    assert np.array_equal(st["n_contrib"].view(np.uint32), g["n_contrib"])
+    _assert_n_contrib_equal(st["n_contrib"].view(np.uint32), g["n_contrib"])
     np.testing.assert_allclose(np_(o["color"]), g["out_color"], rtol=FWD_TOL, atol=1e-6)
     np.testing.assert_allclose(np_(o["allmap"]), g["out_others"], rtol=FWD_TOL, atol=1e-5)
     ins = o["ins"]
