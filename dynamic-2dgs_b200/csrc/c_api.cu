@@ -10,6 +10,7 @@
 #include "raster_common.cuh"
 #include "deform.cuh"
 #include "epilogue.cuh"
+#include "mlp.cuh"
 
 namespace d2gs {
 
@@ -37,9 +38,10 @@ static int fail(int code, const std::string& msg) {
   } while (0)
 
 // ---- optional per-stage timing (CUDA events on the launch stream) ------------------------------------------
-enum Stage { ST_PRE = 0, ST_SCAN, ST_DUP, ST_SORT, ST_RANGES, ST_BLEND_F, ST_BLEND_B, ST_PRE_B, ST_DEF_F, ST_DEF_B, ST_EPI_F, ST_EPI_B };
+enum Stage { ST_PRE = 0, ST_SCAN, ST_DUP, ST_SORT, ST_RANGES, ST_BLEND_F, ST_BLEND_B, ST_PRE_B, ST_DEF_F, ST_DEF_B, ST_EPI_F, ST_EPI_B, ST_MLP_F, ST_MLP_B };
 struct StageRec { int stage; cudaEvent_t a, b; };
 static bool g_profile = false;
+static int g_cull = 1;   // warp-level cull boxes in the blend kernels (tests switch it off to prove it changes nothing)
 static std::vector<StageRec> g_recs;
 static std::vector<cudaEvent_t> g_free_events;
 
@@ -123,6 +125,12 @@ extern "C" {
 const char* d2gs_last_error(void) { return g_last_error.c_str(); }
 
 int d2gs_profile_enable(int on) { g_profile = on != 0; return D2GS_OK; }
+
+int d2gs_set_option(const char* name, int value) {
+  if (!name) return fail(D2GS_ERR_INVALID_ARG, "null option name");
+  if (std::strcmp(name, "cull") == 0) { g_cull = value != 0; return D2GS_OK; }
+  return fail(D2GS_ERR_INVALID_ARG, std::string("unknown option ") + name);
+}
 
 int d2gs_profile_collect(double* total_ms, int64_t* launches) {
   if (!total_ms || !launches) return fail(D2GS_ERR_INVALID_ARG, "null output");
@@ -248,7 +256,7 @@ int d2gs_raster_forward(const D2gsRasterFwdArgs* a, void* stream_) {
     launch_ranges(R, keys_sorted, ranges, stream); }
   D2GS_STAGE("ranges", a->debug, stream);
   { StageTimer t(ST_BLEND_F, stream);
-    launch_blend_fwd(p, ranges, point_list, rec, final_T, n_contrib, a->out_color, a->out_others, stream); }
+    launch_blend_fwd(p, ranges, point_list, rec, final_T, n_contrib, a->out_color, a->out_others, g_cull, stream); }
   D2GS_STAGE("blend", a->debug, stream);
   return D2GS_OK;
 }
@@ -292,7 +300,7 @@ int d2gs_raster_backward(const D2gsRasterBwdArgs* a, void* stream_) {
   if (a->num_rendered > 0) {
     { StageTimer t(ST_BLEND_B, stream);
       launch_blend_bwd(p, ranges, point_list, rec, final_T, n_contrib, a->dL_dout_color, a->dL_dout_others,
-                       a->grad_scratch, stream); }
+                       a->grad_scratch, g_cull, stream); }
     D2GS_STAGE("blend_bwd", a->debug, stream);
   }
   { StageTimer t(ST_PRE_B, stream);
@@ -438,6 +446,135 @@ int d2gs_epilogue_backward(const D2gsEpilogueArgs* a, void* stream_) {
   { StageTimer t(ST_EPI_B, stream);
     launch_epilogue_bwd(a->width, a->height, a->allmap, a->viewmatrix, a->focal_x, a->focal_y, a->g_alpha, a->g_rend_normal,
                         a->g_rend_dist, a->g_depth, a->g_surf_normal, a->g_surf_point, a->dL_dallmap, stream); }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(D2GS_ERR_CUDA, cudaGetErrorString(e));
+  return D2GS_OK;
+}
+
+}  // extern "C"
+
+namespace d2gs {
+struct MlpPlan {
+  MlpLayers L;
+  int Et, Tt, in0, NH, has_timenet;
+  size_t wt_floats, off_te, off_th, off_inp, off_h, off_G, off_Gt1, off_gt, total_bytes;
+};
+static bool mlp_plan(const D2gsMlpArgs* a, int rows, int is_blender, int NH, MlpPlan& P) {
+  P.has_timenet = is_blender ? 1 : 0;
+  P.Et = is_blender ? 13 : 21;
+  P.Tt = is_blender ? 30 : P.Et;
+  P.in0 = 63 + P.Tt;
+  P.NH = NH;
+  int c = 0;
+  size_t off = 0;
+  auto add = [&](const float* W, const float* b, int N, int K) {
+    MlpLayer& l = P.L.layer[c++];
+    l.W = W; l.b = b; l.N = N; l.K = K; l.NP = (N + 3) & ~3; l.wt_off = off;
+    off += (size_t)K * l.NP;
+  };
+  if (is_blender) {
+    add(a ? a->timenet0_w : nullptr, a ? a->timenet0_b : nullptr, 256, P.Et);
+    add(a ? a->timenet2_w : nullptr, a ? a->timenet2_b : nullptr, 30, 256);
+  }
+  for (int l = 0; l < 8; l++) add(a ? a->linear_w[l] : nullptr, a ? a->linear_b[l] : nullptr, 256, l == 0 ? P.in0 : (l == 5 ? P.in0 + 256 : 256));
+  add(a ? a->heads_w : nullptr, a ? a->heads_b : nullptr, NH, 256);
+  P.L.count = c;
+  P.wt_floats = off;
+  size_t o = align_up(4 * off);
+  const size_t R = (size_t)rows;
+  P.off_te = o;  o = align_up(o + 4 * R * 32);
+  P.off_th = o;  o = align_up(o + 4 * R * 256);
+  P.off_inp = o; o = align_up(o + 4 * R * 96);
+  P.off_h = o;   o = align_up(o + 4 * R * 256 * 8);
+  P.off_G = o;   o = align_up(o + 4 * R * 256 * 8);
+  P.off_Gt1 = o; o = align_up(o + 4 * R * 256);
+  P.off_gt = o;  o = align_up(o + 4 * R * 32);
+  P.total_bytes = o + 256;
+  return NH >= 1 && NH <= 16 && rows >= 0;
+}
+}  // namespace d2gs
+
+extern "C" {
+
+int d2gs_mlp_workspace(int rows, int is_blender, int num_out, size_t* bytes) {
+  MlpPlan P;
+  if (!bytes || !mlp_plan(nullptr, rows, is_blender, num_out, P)) return fail(D2GS_ERR_INVALID_ARG, "bad mlp sizes");
+  *bytes = P.total_bytes;
+  return D2GS_OK;
+}
+
+const float* d2gs_mlp_hidden(int rows, int is_blender, int num_out, const void* workspace) {
+  MlpPlan P;
+  if (!workspace || !mlp_plan(nullptr, rows, is_blender, num_out, P)) return nullptr;
+  return (const float*)(aligned_base(workspace) + P.off_h) + (size_t)7 * rows * 256;
+}
+
+int d2gs_mlp_forward(const D2gsMlpArgs* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!a) return fail(D2GS_ERR_INVALID_ARG, "null args");
+  MlpPlan P;
+  if (!mlp_plan(a, a->rows, a->is_blender, a->num_out, P)) return fail(D2GS_ERR_INVALID_ARG, "bad mlp sizes");
+  if (a->rows == 0) return D2GS_OK;
+  if (!a->x || !a->t || !a->out || !a->heads_w || !a->workspace) return fail(D2GS_ERR_INVALID_ARG, "missing buffers");
+  for (int i = 0; i < P.L.count; i++)
+    if (!P.L.layer[i].W || !P.L.layer[i].b) return fail(D2GS_ERR_INVALID_ARG, "missing weights");
+  if (a->workspace_bytes < P.total_bytes) return fail(D2GS_ERR_WORKSPACE, "mlp workspace too small");
+  char* ws = aligned_base(a->workspace);
+  P.L.wt = (float*)ws;
+  MlpFwd f{};
+  f.layers = P.L; f.rows = a->rows; f.Et = P.Et; f.Tt = P.Tt; f.NH = P.NH; f.has_timenet = P.has_timenet;
+  f.t_stride = a->t_stride; f.x = a->x; f.t = a->t; f.out = a->out;
+  f.save_inp = (float*)(ws + P.off_inp); f.save_te = (float*)(ws + P.off_te); f.save_th = (float*)(ws + P.off_th);
+  f.save_h = (float*)(ws + P.off_h);
+  { StageTimer t(ST_MLP_F, stream);
+    mlp_launch_transpose(P.L, stream);
+    mlp_launch_forward(f, stream); }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(D2GS_ERR_CUDA, cudaGetErrorString(e));
+  return D2GS_OK;
+}
+
+int d2gs_mlp_backward(const D2gsMlpArgs* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!a) return fail(D2GS_ERR_INVALID_ARG, "null args");
+  MlpPlan P;
+  if (!mlp_plan(a, a->rows, a->is_blender, a->num_out, P)) return fail(D2GS_ERR_INVALID_ARG, "bad mlp sizes");
+  if (a->rows == 0) return D2GS_OK;
+  if (!a->g_out || !a->workspace || !a->g_heads_w || !a->g_heads_b) return fail(D2GS_ERR_INVALID_ARG, "missing buffers");
+  if (a->workspace_bytes < P.total_bytes) return fail(D2GS_ERR_WORKSPACE, "mlp workspace too small");
+  char* ws = aligned_base(a->workspace);
+  P.L.wt = (float*)ws;
+  const int rows = a->rows;
+  float* save_inp = (float*)(ws + P.off_inp); float* save_te = (float*)(ws + P.off_te);
+  float* save_th = (float*)(ws + P.off_th); float* save_h = (float*)(ws + P.off_h);
+  float* G = (float*)(ws + P.off_G); float* Gt1 = (float*)(ws + P.off_Gt1); float* gt = (float*)(ws + P.off_gt);
+  MlpBwd b{};
+  b.layers = P.L; b.rows = rows; b.Et = P.Et; b.Tt = P.Tt; b.NH = P.NH; b.has_timenet = P.has_timenet;
+  b.g_out = a->g_out; b.save_th = save_th; b.save_h = save_h; b.G = G; b.G_t1 = Gt1; b.g_tfeat = gt;
+  MlpWJobs J{};
+  int c = 0;
+  auto job = [&](const float* Gp, int ldG, int N, const float* A, int ldA, int Ka, const float* B, int ldB, int Kb, float* dW,
+                 float* db) {
+    MlpWJob& j = J.job[c++];
+    j.G = Gp; j.ldG = ldG; j.N = N; j.A = A; j.ldA = ldA; j.Ka = Ka; j.B = B; j.ldB = ldB; j.Kb = Kb; j.dW = dW; j.db = db;
+    j.tiles = ((N + 63) / 64) * ((Ka + Kb + 63) / 64);
+  };
+  if (P.has_timenet) {
+    if (!a->g_timenet0_w || !a->g_timenet2_w) return fail(D2GS_ERR_INVALID_ARG, "missing timenet gradient buffers");
+    job(Gt1, 256, 256, save_te, 32, P.Et, nullptr, 0, 0, a->g_timenet0_w, a->g_timenet0_b);
+    job(gt, 32, 30, save_th, 256, 256, nullptr, 0, 0, a->g_timenet2_w, a->g_timenet2_b);
+  }
+  for (int l = 0; l < 8; l++) {
+    if (!a->g_linear_w[l]) return fail(D2GS_ERR_INVALID_ARG, "missing trunk gradient buffers");
+    const float* Gl = G + (size_t)l * rows * 256;
+    if (l == 0) job(Gl, 256, 256, save_inp, 96, P.in0, nullptr, 0, 0, a->g_linear_w[l], a->g_linear_b[l]);
+    else if (l == 5) job(Gl, 256, 256, save_inp, 96, P.in0, save_h + (size_t)4 * rows * 256, 256, 256, a->g_linear_w[l], a->g_linear_b[l]);
+    else job(Gl, 256, 256, save_h + (size_t)(l - 1) * rows * 256, 256, 256, nullptr, 0, 0, a->g_linear_w[l], a->g_linear_b[l]);
+  }
+  job(a->g_out, P.NH, P.NH, save_h + (size_t)7 * rows * 256, 256, 256, nullptr, 0, 0, a->g_heads_w, a->g_heads_b);
+  J.count = c;
+  { StageTimer t(ST_MLP_B, stream);
+    mlp_launch_backward(b, J, stream); }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(D2GS_ERR_CUDA, cudaGetErrorString(e));
   return D2GS_OK;

@@ -13,9 +13,14 @@
 
 namespace d2gs {
 
-constexpr int BWD_BATCH = 256;
+constexpr int BWD_BATCH = 128;   // instances staged per round
+constexpr int NWARP = TILE_PIX / 32;
 constexpr int ACC_STRIDE = 19;   // 18 components, odd stride keeps the flush free of bank conflicts
 constexpr unsigned FULL = 0xffffffffu;
+// dynamic shared memory of blend_bwd_kernel
+constexpr size_t BWD_SMEM_Q = sizeof(float4) * REC_QUADS * BWD_BATCH;                  // staged records
+constexpr size_t BWD_SMEM_ACC = sizeof(float) * NWARP * BWD_BATCH * ACC_STRIDE;        // per-warp private accumulators
+constexpr size_t BWD_SMEM_BYTES = BWD_SMEM_Q + BWD_SMEM_ACC + sizeof(uint32_t) * (BWD_BATCH + NWARP);
 
 __device__ __forceinline__ void pixel_of_thread_b(int tid, int& lx, int& ly) {
   const int w = tid >> 5, l = tid & 31;
@@ -57,11 +62,12 @@ __global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
     const float* __restrict__ bg, const SurfelRec* __restrict__ rec, const float* __restrict__ final_Ts,
     const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
-    const float* __restrict__ dL_dothers, float* __restrict__ grad_rec) {
-  __shared__ float4 s_q0[BWD_BATCH], s_q1[BWD_BATCH], s_q2[BWD_BATCH], s_q3[BWD_BATCH], s_q4[BWD_BATCH];
-  __shared__ uint32_t s_id[BWD_BATCH];
-  __shared__ float s_acc[BWD_BATCH * ACC_STRIDE];
-  __shared__ uint32_t s_max[TILE_PIX / 32];
+    const float* __restrict__ dL_dothers, float* __restrict__ grad_rec, int cull) {
+  extern __shared__ __align__(16) unsigned char bwd_smem[];
+  float4(*s_q)[BWD_BATCH] = reinterpret_cast<float4(*)[BWD_BATCH]>(bwd_smem);
+  float* s_acc = reinterpret_cast<float*>(bwd_smem + BWD_SMEM_Q);        // [warp][slot][ACC_STRIDE]
+  uint32_t* s_id = reinterpret_cast<uint32_t*>(bwd_smem + BWD_SMEM_Q + BWD_SMEM_ACC);
+  uint32_t* s_max = s_id + BWD_BATCH;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int lx, ly;
@@ -72,6 +78,12 @@ __global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
   const size_t HW = (size_t)H * W;
   const float2 pixf = {(float)pix_x + 0.5f, (float)pix_y + 0.5f};
   const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
+  const float pcx0 = (float)(blockIdx.x * TILE_X + ((warp & 1) << 3)) + 0.5f, pcx1 = pcx0 + 7.0f;
+  const float pcy0 = (float)(blockIdx.y * TILE_Y + ((warp >> 1) << 2)) + 0.5f, pcy1 = pcy0 + 3.0f;
+  const uint32_t sb0 = smem_addr(&s_q[0][0]);
+  constexpr uint32_t QS = 16u * BWD_BATCH;   // bytes per staged quad plane
+  const uint32_t sb1 = sb0 + QS, sb2 = sb0 + 2 * QS, sb3 = sb0 + 3 * QS, sb4 = sb0 + 4 * QS, sb5 = sb0 + 5 * QS;
+  float* my_acc = s_acc + (size_t)warp * BWD_BATCH * ACC_STRIDE;
 
   const float T_final = inside ? final_Ts[pix_id] : 0;
   float T = T_final;
@@ -83,7 +95,7 @@ __global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
     const uint32_t m = __reduce_max_sync(FULL, last_contributor);
     if (lane == 0) s_max[warp] = m;
   }
-  for (int i = tid; i < BWD_BATCH * ACC_STRIDE; i += TILE_PIX) s_acc[i] = 0.f;
+  for (int i = tid; i < NWARP * BWD_BATCH * ACC_STRIDE; i += TILE_PIX) s_acc[i] = 0.f;
   __syncthreads();
   uint32_t len = 0;
 #pragma unroll
@@ -124,22 +136,24 @@ __global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
       const uint32_t id = __ldg(&point_list[range.x + pos]);
       s_id[tid] = id;
       const float4* r4 = reinterpret_cast<const float4*>(rec + id);
-      s_q0[tid] = __ldg(r4 + 0);
-      s_q1[tid] = __ldg(r4 + 1);
-      s_q2[tid] = __ldg(r4 + 2);
-      s_q3[tid] = __ldg(r4 + 3);
-      s_q4[tid] = __ldg(r4 + 4);
+#pragma unroll
+      for (int q = 0; q < REC_QUADS; q++) s_q[q][tid] = __ldg(r4 + q);
     }
     __syncthreads();
 
     for (int j = 0; j < n; j++) {
       const uint32_t contributor = len - 1 - (uint32_t)(i * BWD_BATCH + j);   // 0-based list position
+      const uint32_t off = (uint32_t)j << 4;
+      if (cull) {   // uniform per warp: no pixel of this 8x4 patch can pass the prefilter
+        const float4 bb = lds128(sb5 + off);
+        if (bb.z < pcx0 || bb.x > pcx1 || bb.w < pcy0 || bb.y > pcy1) continue;
+      }
       float g[16];          // written only by contributing lanes; zero-filled lazily before a reduction
       float gm0 = 0.f, gm1 = 0.f;
       bool contrib = false, flat = false;
       do {
         if (!inside || contributor >= last_contributor) break;
-        const float4 a = s_q0[j], b = s_q1[j], c = s_q2[j];
+        const float4 a = lds128(sb0 + off), b = lds128(sb1 + off), c = lds128(sb2 + off);
         const float3 Tu = {a.x, a.y, a.z}, Tv = {a.w, b.x, b.y}, Tw = {b.z, b.w, c.x};
         const float3 k = {-Tu.x + pixf.x * Tw.x, -Tu.y + pixf.x * Tw.y, -Tu.z + pixf.x * Tw.z};
         const float3 l = {-Tv.x + pixf.y * Tw.x, -Tv.y + pixf.y * Tw.y, -Tv.z + pixf.y * Tw.z};
@@ -156,15 +170,16 @@ __global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
         const float power = -0.5f * rho;
         if (power > 0.0f) break;
         const float G = expf(power);
-        const float4 col = s_q4[j];   // rgb + opacity
+        const float4 col = lds128(sb4 + off);   // rgb + opacity
         const float opac = col.w;
         const float alpha = fminf(0.99f, opac * G);
         if (alpha < 1.0f / 255.0f) break;
-        const float4 nrm = s_q3[j];
+        const float4 nrm = lds128(sb3 + off);
         const float normal[3] = {nrm.x, nrm.y, nrm.z};
         const float color[3] = {col.x, col.y, col.z};
 
-        T = T / (1.f - alpha);
+        const float inv_1ma = __fdividef(1.0f, 1.f - alpha);   // gradients are compared to 1e-4: 2-ulp reciprocal
+        T = T * inv_1ma;
         const float w = alpha * T;
         float dL_dalpha = 0.0f;
 #pragma unroll
@@ -176,8 +191,9 @@ __global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
         }
         float dL_dz = 0.0f, dL_dweight = 0.f;
         // depth mapped to [0,1]; fp32 here (gradients are compared to 1e-4, not bit-wise)
-        const float m_d = (100.0f * c_d - 20.0f) / (99.8f * c_d);
-        const float dmd_dd = 20.0f / (99.8f * c_d * c_d);
+        const float inv_d = __fdividef(1.0f, c_d);
+        const float m_d = (1.0f - 0.2f * inv_d) * 1.002004008016032f;       // same fp32 form as the forward
+        const float dmd_dd = 0.2004008016032064f * inv_d * inv_d;            // near*far/(far-near) / d^2
         if (contributor == (uint32_t)(median_contributor - 1)) {
           dL_dz += dL_dmedian_depth;
           dL_dweight += dL_dmax_dweight;
@@ -202,14 +218,15 @@ __global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
         }
         dL_dalpha *= T;
         last_alpha = alpha;
-        dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+        dL_dalpha += (-T_final * inv_1ma) * bg_dot_dpixel;
 
         const float dL_dG = opac * dL_dalpha;
         dL_dz += w * dL_ddepth;
 
         if (rho3d <= rho2d) {
           const float2 dL_ds = {dL_dG * -G * s.x + dL_dz * Tw.x, dL_dG * -G * s.y + dL_dz * Tw.y};
-          const float dsx_pz = dL_ds.x / p.z, dsy_pz = dL_ds.y / p.z;
+          const float inv_pz = __fdividef(1.0f, p.z);
+          const float dsx_pz = dL_ds.x * inv_pz, dsy_pz = dL_ds.y * inv_pz;
           const float3 dL_dp = {dsx_pz, dsy_pz, -(dsx_pz * s.x + dsy_pz * s.y)};
           const float3 dL_dk = {l.y * dL_dp.z - l.z * dL_dp.y, l.z * dL_dp.x - l.x * dL_dp.z, l.x * dL_dp.y - l.y * dL_dp.x};
           const float3 dL_dl = {dL_dp.y * k.z - dL_dp.z * k.y, dL_dp.z * k.x - dL_dp.x * k.z, dL_dp.x * k.y - dL_dp.y * k.x};
@@ -242,7 +259,7 @@ __global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
         if ((lane & 1) == 0) {
           const int v = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
           const int slot = v < 9 ? v : v + 2;   // 0..8 transMat | 11..13 normal | 14 opacity | 15..17 colour
-          atomicAdd(&s_acc[j * ACC_STRIDE + slot], g[0]);
+          my_acc[j * ACC_STRIDE + slot] += g[0];   // slot private to this warp: plain read-modify-write
         }
         if (__any_sync(FULL, flat)) {
 #pragma unroll
@@ -251,22 +268,30 @@ __global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
             gm1 += __shfl_xor_sync(FULL, gm1, o);
           }
           if (lane == 0) {
-            atomicAdd(&s_acc[j * ACC_STRIDE + G_M2D], gm0);
-            atomicAdd(&s_acc[j * ACC_STRIDE + G_M2D + 1], gm1);
+            my_acc[j * ACC_STRIDE + G_M2D] += gm0;
+            my_acc[j * ACC_STRIDE + G_M2D + 1] += gm1;
           }
         }
       }
     }
     __syncthreads();
-    // one global reduction per (tile, instance, component)
-    if (tid < n) {
-      float* dst = grad_rec + (size_t)s_id[tid] * GRAD_REC_FLOATS;
+    // fold the 8 warp-private accumulators and issue one global reduction per (tile, instance, component);
+    // two threads per instance, nine components each
+    {
+      const int slot = tid >> 1, half = tid & 1;
+      if (slot < n) {
+        float* dst = grad_rec + (size_t)s_id[slot] * GRAD_REC_FLOATS;
 #pragma unroll
-      for (int v = 0; v < 18; v++) {
-        const float val = s_acc[tid * ACC_STRIDE + v];
-        if (val != 0.f) {
-          atomicAdd(dst + v, val);
-          s_acc[tid * ACC_STRIDE + v] = 0.f;
+        for (int q = 0; q < 9; q++) {
+          const int v = half * 9 + q;
+          float val = 0.f;
+#pragma unroll
+          for (int w8 = 0; w8 < NWARP; w8++) {
+            float* a = s_acc + ((size_t)w8 * BWD_BATCH + slot) * ACC_STRIDE + v;
+            const float x = *a;
+            if (x != 0.f) { val += x; *a = 0.f; }
+          }
+          if (val != 0.f) atomicAdd(dst + v, val);
         }
       }
     }
@@ -276,10 +301,15 @@ __global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
 
 void launch_blend_bwd(const BwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
                       const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, const float* dL_dothers,
-                      float* grad_rec, cudaStream_t s) {
+                      float* grad_rec, int cull, cudaStream_t s) {
   dim3 grid(p.gx, p.gy, 1);
-  blend_bwd_kernel<<<grid, TILE_PIX, 0, s>>>(ranges, point_list, p.W, p.H, p.bg, rec, final_T, n_contrib, dL_dpix,
-                                            dL_dothers, grad_rec);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES);
+    configured = true;
+  }
+  blend_bwd_kernel<<<grid, TILE_PIX, BWD_SMEM_BYTES, s>>>(ranges, point_list, p.W, p.H, p.bg, rec, final_T, n_contrib, dL_dpix,
+                                            dL_dothers, grad_rec, cull);
 }
 
 // ------------------------------------------------------------------------------------------------------------

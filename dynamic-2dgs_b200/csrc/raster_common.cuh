@@ -37,12 +37,14 @@ __device__ const float kSH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0
 // Projected surfel record, 80 B.
 //  q0 = (Tu.x, Tu.y, Tu.z, Tv.x)   q1 = (Tv.y, Tv.z, Tw.x, Tw.y)   q2 = (Tw.z, mean2D.x, mean2D.y, tau)
 //  q3 = (normal.x, normal.y, normal.z, depth)                      q4 = (r, g, b, opacity)
+//  q5 = (x0, y0, x1, y1): screen box outside which every pixel centre is certainly rejected (see cull_box)
 //  tau = 2*ln(255*opacity) + 1e-4: a pixel whose Mahalanobis term exceeds tau has alpha < 1/255 with margin, so the
 //  blend kernels can drop it after ~20 instructions (q0..q2 only) with exactly the reference's outcome.
 struct __align__(16) SurfelRec {
-  float4 q0, q1, q2, q3, q4;
+  float4 q0, q1, q2, q3, q4, q5;
 };
-static_assert(sizeof(SurfelRec) == 80, "SurfelRec must be 80 bytes");
+static_assert(sizeof(SurfelRec) == 96, "SurfelRec must be 96 bytes");
+constexpr int REC_QUADS = 6;
 
 // Per-surfel raster gradients accumulated by the blend backward (80 B).
 //  [0..8] dL/dtransMat  [9..10] dL/dmean2D.xy  [11..13] dL/dnormal  [14] dL/dopacity  [15..17] dL/dcolor  [18..19] pad
@@ -76,6 +78,53 @@ __device__ __forceinline__ bool pair_rejected(float px, float py, float pz, floa
   const float m2 = px * px + py * py;
   const float z2 = pz * pz;
   return (rho2d > tau) && (m2 > tau * z2) && (m2 < 3.0e38f);
+}
+
+// Conservative screen-space box of the pixels that can survive pair_rejected(): the union of
+//   (a) the disc |pix - mean2D|^2 <= tau/2 of the low-pass term, and
+//   (b) the image of the splat-plane disc u^2+v^2 <= tau.  A pixel column x touches that disc iff the line
+//       (Tu - x*Tw).(u,v,1) = 0 comes within sqrt(tau) of the origin, i.e.  A x^2 - 2 B x + C <= 0  with
+//       g = (tau, tau, -1), A = g.(Tw*Tw), B = g.(Tu*Tw), C = g.(Tu*Tu)   (tau = 1 gives the reference's 1-sigma box).
+// tau is inflated by 1e-3 relative + 1e-3 absolute over the prefilter threshold and the box by 1e-4 relative + 0.01 px, far
+// above fp32 evaluation error; when the disc reaches the camera plane (A >= 0 up to a guard band) the box is infinite.
+// A NaN anywhere yields a box that never culls.
+__device__ __forceinline__ float4 cull_box(const float* T, float mx, float my, float tau_prefilter) {
+  const float inf = __int_as_float(0x7f800000);
+  if (!(tau_prefilter > 0.f)) {
+    // opacity < 1/255: the prefilter already rejects every pair (tau <= 0); NaN keeps the box open
+    return (tau_prefilter <= 0.f) ? make_float4(inf, inf, -inf, -inf) : make_float4(-inf, -inf, inf, inf);
+  }
+  const float tau = tau_prefilter * 1.001f + 1e-3f;
+  const float r2 = sqrtf(0.5f * tau) + 0.01f;
+  float x0 = mx - r2, x1 = mx + r2, y0 = my - r2, y1 = my + r2;
+  const float Axy = T[6] * T[6] + T[7] * T[7];
+  const float A = tau * Axy - T[8] * T[8];
+  if (!(A < -1e-3f * (T[8] * T[8]))) return make_float4(-inf, -inf, inf, inf);
+  const float Bx = tau * (T[0] * T[6] + T[1] * T[7]) - T[2] * T[8];
+  const float Cx = tau * (T[0] * T[0] + T[1] * T[1]) - T[2] * T[2];
+  const float By = tau * (T[3] * T[6] + T[4] * T[7]) - T[5] * T[8];
+  const float Cy = tau * (T[3] * T[3] + T[4] * T[4]) - T[5] * T[5];
+  const float ia = 1.0f / A;
+  const float cxm = Bx * ia, cym = By * ia;
+  const float ex = sqrtf(fmaxf(0.f, Bx * Bx - A * Cx)) * fabsf(ia), ey = sqrtf(fmaxf(0.f, By * By - A * Cy)) * fabsf(ia);
+  const float mxg = 1e-4f * (fabsf(cxm) + ex) + 0.01f, myg = 1e-4f * (fabsf(cym) + ey) + 0.01f;
+  x0 = fminf(x0, cxm - ex - mxg); x1 = fmaxf(x1, cxm + ex + mxg);
+  y0 = fminf(y0, cym - ey - myg); y1 = fmaxf(y1, cym + ey + myg);
+  if (!(x0 == x0 && x1 == x1 && y0 == y0 && y1 == y1)) return make_float4(-inf, -inf, inf, inf);
+  return make_float4(x0, y0, x1, y1);
+}
+
+// 32-bit shared-window address, made opaque (volatile asm) so the compiler keeps it in a register instead of
+// re-deriving it from the CTA id in front of every load of the inner loop.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  uint32_t a;
+  asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(a) : "l"(p));
+  return a;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
 }
 
 // Tile rectangle of a surfel (reference: auxiliary.h:64-74).  Float arithmetic and the float->int truncation
@@ -181,7 +230,7 @@ void launch_duplicate(int P, const SurfelRec* rec, const int* radii, const uint3
                       uint32_t* vals, uint32_t gx, uint32_t gy, cudaStream_t s);
 void launch_ranges(int64_t R, const uint64_t* keys_sorted, uint2* ranges, cudaStream_t s);
 void launch_blend_fwd(const FwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
-                      float* final_T, uint32_t* n_contrib, float* out_color, float* out_others, cudaStream_t s);
+                      float* final_T, uint32_t* n_contrib, float* out_color, float* out_others, int cull, cudaStream_t s);
 
 struct BwdParams {
   int P, D, M, W, H;
@@ -206,7 +255,7 @@ struct BwdParams {
 };
 void launch_blend_bwd(const BwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
                       const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, const float* dL_dothers,
-                      float* grad_rec, cudaStream_t s);
+                      float* grad_rec, int cull, cudaStream_t s);
 void launch_preprocess_bwd(const BwdParams& p, const SurfelRec* rec, const uint8_t* clamped, const int* radii,
                            float* grad_rec, float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
                            float* dL_dmeans3D, float* dL_dtransMat, float* dL_dsh, float* dL_dsh_rest,

@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(FwdParams p, Surfel
   o.q2 = make_float4(T[8], pc.x, pc.y, 2.0f * logf(255.0f * opacity) + 1e-4f);
   o.q3 = make_float4(normal.x, normal.y, normal.z, depth);
   o.q4 = make_float4(rgb.x, rgb.y, rgb.z, opacity);
+  o.q5 = cull_box(T, pc.x, pc.y, o.q2.w);
   rec[idx] = o;
 }
 
@@ -233,11 +234,14 @@ __device__ __forceinline__ void pixel_of_thread(int tid, int& lx, int& ly) {
   ly = ((w >> 1) << 2) | (l >> 3);
 }
 
+// One CTA per 16x16 tile, one thread per pixel, each warp a compact 8x4 patch.  Per staged instance a warp first tests
+// the instance's cull box against its patch (uniform branch, one broadcast LDS.128), then each lane runs the exact
+// prefilter (q0..q2) and only survivors pay for the divisions / exp / accumulation.
 __global__ void __launch_bounds__(TILE_PIX) blend_fwd_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
     const SurfelRec* __restrict__ rec, const float* __restrict__ bg, float* __restrict__ final_T,
-    uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, float* __restrict__ out_others) {
-  __shared__ float4 s_q0[BLEND_BATCH], s_q1[BLEND_BATCH], s_q2[BLEND_BATCH], s_q3[BLEND_BATCH], s_q4[BLEND_BATCH];
+    uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, float* __restrict__ out_others, int cull) {
+  __shared__ float4 s_q[REC_QUADS][BLEND_BATCH];
 
   const int tid = threadIdx.x;
   int lx, ly;
@@ -247,17 +251,24 @@ __global__ void __launch_bounds__(TILE_PIX) blend_fwd_kernel(
   const uint32_t pix_id = W * pix_y + pix_x;
   const float2 pixf = {(float)pix_x + 0.5f, (float)pix_y + 0.5f};
   bool done = !inside;
+  // pixel-centre bounds of this warp's patch
+  const int wq = tid >> 5;
+  const float pcx0 = (float)(blockIdx.x * TILE_X + ((wq & 1) << 3)) + 0.5f, pcx1 = pcx0 + 7.0f;
+  const float pcy0 = (float)(blockIdx.y * TILE_Y + ((wq >> 1) << 2)) + 0.5f, pcy1 = pcy0 + 3.0f;
 
   const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
   const int rounds = (range.y - range.x + BLEND_BATCH - 1) / BLEND_BATCH;
   int toDo = range.y - range.x;
+  const uint32_t sb0 = smem_addr(&s_q[0][0]);
+  constexpr uint32_t QS = 16u * 256u;   // bytes per staged quad plane
+  const uint32_t sb1 = sb0 + QS, sb2 = sb0 + 2 * QS, sb3 = sb0 + 3 * QS, sb4 = sb0 + 4 * QS, sb5 = sb0 + 5 * QS;
 
   float T = 1.0f;
-  uint32_t contributor = 0, last_contributor = 0;
+  uint32_t last_contributor = 0, median_contributor = 0;
   float C[3] = {0.f, 0.f, 0.f};
   float Dacc = 0.f, N[3] = {0.f, 0.f, 0.f};
   float dist1 = 0.f, dist2 = 0.f, distortion = 0.f;
-  float median_depth = 0.f, median_weight = 0.f, median_contributor = -1.f;
+  float median_depth = 0.f, median_weight = 0.f;
 
   for (int i = 0; i < rounds; i++, toDo -= BLEND_BATCH) {
     if (__syncthreads_count(done) == TILE_PIX) break;
@@ -265,18 +276,21 @@ __global__ void __launch_bounds__(TILE_PIX) blend_fwd_kernel(
     if (range.x + progress < range.y) {
       const uint32_t id = __ldg(&point_list[range.x + progress]);
       const float4* r4 = reinterpret_cast<const float4*>(rec + id);
-      s_q0[tid] = __ldg(r4 + 0);
-      s_q1[tid] = __ldg(r4 + 1);
-      s_q2[tid] = __ldg(r4 + 2);
-      s_q3[tid] = __ldg(r4 + 3);
-      s_q4[tid] = __ldg(r4 + 4);
+#pragma unroll
+      for (int q = 0; q < REC_QUADS; q++) s_q[q][tid] = __ldg(r4 + q);
     }
     __syncthreads();
 
     const int n = min(BLEND_BATCH, toDo);
-    for (int j = 0; !done && j < n; j++) {
-      contributor++;
-      const float4 a = s_q0[j], b = s_q1[j], c = s_q2[j];
+    const uint32_t cbase = (uint32_t)(i * BLEND_BATCH) + 1u;
+    for (int j = 0; j < n; j++) {
+      if (done) break;
+      const uint32_t off = (uint32_t)j << 4;
+      if (cull) {
+        const float4 bb = lds128(sb5 + off);
+        if (bb.z < pcx0 || bb.x > pcx1 || bb.w < pcy0 || bb.y > pcy1) continue;   // whole patch certainly rejected
+      }
+      const float4 a = lds128(sb0 + off), b = lds128(sb1 + off), c = lds128(sb2 + off);
       const float3 Tu = {a.x, a.y, a.z}, Tv = {a.w, b.x, b.y}, Tw = {b.z, b.w, c.x};
       // ray / splat intersection: two planes through the pixel, their cross product is the homogeneous hit point
       const float3 k = {-Tu.x + pixf.x * Tw.x, -Tu.y + pixf.x * Tw.y, -Tu.z + pixf.x * Tw.z};
@@ -294,7 +308,7 @@ __global__ void __launch_bounds__(TILE_PIX) blend_fwd_kernel(
       if (depth < 0.2f) continue;   // (double)depth < 0.2 <=> depth < 0.2f
       const float power = -0.5f * rho;
       if (power > 0.0f) continue;
-      const float4 col = s_q4[j];   // rgb + opacity
+      const float4 col = lds128(sb4 + off);   // rgb + opacity
       const float alpha = fminf(0.99f, col.w * expf(power));
       if (alpha < 1.0f / 255.0f) continue;
       const float test_T = T * (1 - alpha);
@@ -302,12 +316,12 @@ __global__ void __launch_bounds__(TILE_PIX) blend_fwd_kernel(
         done = true;
         continue;
       }
-      const float w = alpha * T;
-      const float4 nrm = s_q3[j];
-      // distortion bookkeeping (depth mapped to [0,1] between the near and far planes)
+      const uint32_t contributor = cbase + (uint32_t)j;
+      const float4 nrm = lds128(sb3 + off);
+      // distortion bookkeeping: depth mapped to [0,1] between the near and far planes,
+      // (far*d - far*near) / ((far-near)*d) == (1 - near/d) * far/(far-near), evaluated in fp32
       const float A = 1 - T;
-      const float md = (float)((D2GS_FAR_PLANE * depth - D2GS_FAR_PLANE * D2GS_NEAR_PLANE) /
-                               ((D2GS_FAR_PLANE - D2GS_NEAR_PLANE) * depth));
+      const float md = (1.0f - 0.2f / depth) * 1.002004008016032f;
       const float error = md * md * A + dist2 - 2 * md * dist1;
       distortion += error * alpha * T;
       if (T > 0.5f) {
@@ -320,7 +334,6 @@ __global__ void __launch_bounds__(TILE_PIX) blend_fwd_kernel(
       dist1 += md * alpha * T;
       dist2 += md * md * alpha * T;
       C[0] += col.x * alpha * T; C[1] += col.y * alpha * T; C[2] += col.z * alpha * T;
-      (void)w;
       T = test_T;
       last_contributor = contributor;
     }
@@ -332,7 +345,7 @@ __global__ void __launch_bounds__(TILE_PIX) blend_fwd_kernel(
     final_T[pix_id + HW] = dist1;
     final_T[pix_id + 2 * HW] = dist2;
     n_contrib[pix_id] = last_contributor;
-    n_contrib[pix_id + HW] = (uint32_t)median_contributor;   // -1 saturates to 0
+    n_contrib[pix_id + HW] = median_contributor;   // 0 when nothing contributed (the reference converts -1.0f: undefined)
     out_color[0 * HW + pix_id] = C[0] + T * bg[0];
     out_color[1 * HW + pix_id] = C[1] + T * bg[1];
     out_color[2 * HW + pix_id] = C[2] + T * bg[2];
@@ -348,10 +361,10 @@ __global__ void __launch_bounds__(TILE_PIX) blend_fwd_kernel(
 }
 
 void launch_blend_fwd(const FwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
-                      float* final_T, uint32_t* n_contrib, float* out_color, float* out_others, cudaStream_t s) {
+                      float* final_T, uint32_t* n_contrib, float* out_color, float* out_others, int cull, cudaStream_t s) {
   dim3 grid(p.gx, p.gy, 1);
   blend_fwd_kernel<<<grid, TILE_PIX, 0, s>>>(ranges, point_list, p.W, p.H, rec, p.bg, final_T, n_contrib, out_color,
-                                            out_others);
+                                            out_others, cull);
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,

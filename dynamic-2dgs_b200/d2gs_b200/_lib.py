@@ -92,11 +92,22 @@ class EpilogueArgs(C.Structure):
                 ("g_surf_normal", C.c_void_p), ("g_surf_point", C.c_void_p), ("dL_dallmap", C.c_void_p)]
 
 
+class MlpArgs(C.Structure):
+    _fields_ = [("rows", C.c_int), ("is_blender", C.c_int), ("num_out", C.c_int), ("x", C.c_void_p), ("t", C.c_void_p),
+                ("t_stride", C.c_int),
+                ("timenet0_w", C.c_void_p), ("timenet0_b", C.c_void_p), ("timenet2_w", C.c_void_p), ("timenet2_b", C.c_void_p),
+                ("linear_w", C.c_void_p * 8), ("linear_b", C.c_void_p * 8), ("heads_w", C.c_void_p), ("heads_b", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("out", C.c_void_p), ("g_out", C.c_void_p),
+                ("g_timenet0_w", C.c_void_p), ("g_timenet0_b", C.c_void_p), ("g_timenet2_w", C.c_void_p), ("g_timenet2_b", C.c_void_p),
+                ("g_linear_w", C.c_void_p * 8), ("g_linear_b", C.c_void_p * 8), ("g_heads_w", C.c_void_p), ("g_heads_b", C.c_void_p)]
+
+
 # every symbol include/d2gs.h declares; tests assert the shared library exports all of them
 EXPORTED_SYMBOLS = (
-    "d2gs_profile_enable", "d2gs_profile_collect", "d2gs_last_error", "d2gs_version", "d2gs_get_config", "d2gs_raster_workspace", "d2gs_raster_forward",
+    "d2gs_set_option", "d2gs_profile_enable", "d2gs_profile_collect", "d2gs_last_error", "d2gs_version", "d2gs_get_config", "d2gs_raster_workspace", "d2gs_raster_forward",
     "d2gs_raster_backward", "d2gs_mark_visible", "d2gs_raster_export_state", "d2gs_deform_forward",
     "d2gs_deform_backward", "d2gs_epilogue_forward", "d2gs_epilogue_backward",
+    "d2gs_mlp_workspace", "d2gs_mlp_forward", "d2gs_mlp_backward", "d2gs_mlp_hidden",
 )
 
 D2GS_OK = 0
@@ -134,6 +145,12 @@ def lib():
     L.d2gs_deform_backward.argtypes = [C.POINTER(DeformBwdArgs), C.c_void_p]
     L.d2gs_epilogue_forward.argtypes = [C.POINTER(EpilogueArgs), C.c_void_p]
     L.d2gs_epilogue_backward.argtypes = [C.POINTER(EpilogueArgs), C.c_void_p]
+    L.d2gs_mlp_workspace.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+    L.d2gs_mlp_forward.argtypes = [C.POINTER(MlpArgs), C.c_void_p]
+    L.d2gs_mlp_backward.argtypes = [C.POINTER(MlpArgs), C.c_void_p]
+    L.d2gs_mlp_hidden.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.d2gs_mlp_hidden.restype = C.c_void_p
+    L.d2gs_set_option.argtypes = [C.c_char_p, C.c_int]
     L.d2gs_profile_enable.argtypes = [C.c_int]
     L.d2gs_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     for name in EXPORTED_SYMBOLS:
@@ -160,7 +177,7 @@ def workspace_sizes(P: int, W: int, H: int, R: int = 0):
 
 
 STAGE_NAMES = ("preprocess_fwd", "scan", "duplicate", "sort", "ranges", "blend_fwd", "blend_bwd", "preprocess_bwd",
-               "deform_fwd", "deform_bwd", "epilogue_fwd", "epilogue_bwd")
+               "deform_fwd", "deform_bwd", "epilogue_fwd", "epilogue_bwd", "mlp_fwd", "mlp_bwd")
 
 
 def profile_enable(on: bool) -> None:
@@ -174,3 +191,7 @@ def profile_collect() -> dict:
     cnt = (C.c_int64 * n)()
     check(lib().d2gs_profile_collect(ms, cnt), "d2gs_profile_collect")
     return {STAGE_NAMES[i]: (ms[i], cnt[i]) for i in range(n)}
+
+
+def set_option(name: str, value: int) -> None:
+    check(lib().d2gs_set_option(name.encode(), int(value)), "d2gs_set_option")

@@ -128,6 +128,82 @@ def node_blend(xyz, feature, nodes, node_radius_log, node_weight_logit, node_tra
 
 
 # --------------------------------------------------------------------------------------------------------------
+# fused MLP (libd2gs.so: d2gs_mlp_forward/backward)
+# --------------------------------------------------------------------------------------------------------------
+class _FusedMLP(torch.autograd.Function):
+    """(x, t, is_blender, num_out, *weights) -> (out (rows,num_out), hidden (rows,256)).
+
+    weights = [timenet.0.w, timenet.0.b, timenet.2.w, timenet.2.b] (is_blender only) + 8 x (linear.w, linear.b)
+              + [heads_w (num_out,256), heads_b (num_out)]."""
+
+    @staticmethod
+    def forward(ctx, x, t, is_blender, num_out, *weights):
+        L = _lib.lib()
+        dev = x.device
+        x_ = x.detach().float().contiguous()
+        t_ = t.detach().float()
+        rows = int(x_.shape[0])
+        t2 = t_.reshape(rows, -1) if t_.numel() == rows else t_.expand(rows, 1)
+        t_stride = int(t2.stride(0))
+        if t_stride not in (0, 1):
+            t2 = t2.contiguous(); t_stride = 1
+        ws_bytes = C.c_size_t(0)
+        _lib.check(L.d2gs_mlp_workspace(rows, int(is_blender), int(num_out), C.byref(ws_bytes)), "d2gs_mlp_workspace")
+        ws = torch.empty((ws_bytes.value,), dtype=torch.uint8, device=dev)
+        out = torch.empty((rows, num_out), dtype=torch.float32, device=dev)
+        w = [p_.detach().float().contiguous() for p_ in weights]
+        a = _FusedMLP._args(rows, is_blender, num_out, x_, t2, t_stride, w, ws)
+        a.out = out.data_ptr()
+        with torch.cuda.device(dev):
+            _lib.check(L.d2gs_mlp_forward(C.byref(a), _stream(dev)), "d2gs_mlp_forward")
+            hp = L.d2gs_mlp_hidden(rows, int(is_blender), int(num_out), ws.data_ptr())
+        off = hp - ws.data_ptr()
+        hidden = ws[off: off + rows * 256 * 4].view(torch.float32).view(rows, 256)
+        ctx.cfg = (rows, bool(is_blender), int(num_out), t_stride)
+        ctx.save_for_backward(x_, t2, ws, *w)
+        ctx.mark_non_differentiable(hidden)
+        return out, hidden
+
+    @staticmethod
+    def _args(rows, is_blender, num_out, x_, t2, t_stride, w, ws):
+        a = _lib.MlpArgs()
+        a.rows, a.is_blender, a.num_out = rows, int(is_blender), int(num_out)
+        a.x, a.t, a.t_stride = x_.data_ptr(), t2.data_ptr(), t_stride
+        i = 0
+        if is_blender:
+            a.timenet0_w, a.timenet0_b, a.timenet2_w, a.timenet2_b = (w[j].data_ptr() for j in range(4))
+            i = 4
+        for l in range(8):
+            a.linear_w[l] = w[i + 2 * l].data_ptr()
+            a.linear_b[l] = w[i + 2 * l + 1].data_ptr()
+        a.heads_w, a.heads_b = w[i + 16].data_ptr(), w[i + 17].data_ptr()
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        return a
+
+    @staticmethod
+    def backward(ctx, g_out, g_hidden):
+        L = _lib.lib()
+        rows, is_blender, num_out, t_stride = ctx.cfg
+        x_, t2, ws, *w = ctx.saved_tensors
+        dev = x_.device
+        g_out = torch.zeros((rows, num_out), dtype=torch.float32, device=dev) if g_out is None else g_out.float().contiguous()
+        grads = [torch.empty_like(p_) for p_ in w]
+        a = _FusedMLP._args(rows, is_blender, num_out, x_, t2, t_stride, w, ws)
+        a.g_out = g_out.data_ptr()
+        i = 0
+        if is_blender:
+            a.g_timenet0_w, a.g_timenet0_b, a.g_timenet2_w, a.g_timenet2_b = (grads[j].data_ptr() for j in range(4))
+            i = 4
+        for l in range(8):
+            a.g_linear_w[l] = grads[i + 2 * l].data_ptr()
+            a.g_linear_b[l] = grads[i + 2 * l + 1].data_ptr()
+        a.g_heads_w, a.g_heads_b = grads[i + 16].data_ptr(), grads[i + 17].data_ptr()
+        with torch.cuda.device(dev):
+            _lib.check(L.d2gs_mlp_backward(C.byref(a), _stream(dev)), "d2gs_mlp_backward")
+        return (None, None, None, None, *grads)
+
+
+# --------------------------------------------------------------------------------------------------------------
 # embedder + MLP (same parameter names as the reference so deform.pth round-trips)
 # --------------------------------------------------------------------------------------------------------------
 class Embedder:
@@ -206,7 +282,41 @@ class DeformNetwork(nn.Module):
     def trainable_parameters(self):
         return [{'params': list(self.parameters()), 'name': 'mlp'}]
 
+    use_fused = True   # set False to force the eager torch layers (tests compare the two)
+
+    def _fusable(self, x, t) -> bool:
+        return (self.use_fused and x.is_cuda and self.D == 8 and self.W == 256 and self.skips == [4] and x.dim() == 2 and x.shape[1] == 3
+                and isinstance(self.embed_fn, Embedder) and self.embed_fn.multires == 10 and t.shape[-1] == 1
+                and (t.numel() == x.shape[0] or t.numel() == 1))
+
+    def _forward_fused(self, x, t):
+        heads = [self.gaussian_warp, self.gaussian_scaling, self.gaussian_rotation]
+        if self.local_frame:
+            heads.append(self.local_rotation)
+        if self.pred_opacity:
+            heads.append(self.gaussian_opacity)
+        hw = torch.cat([h.weight for h in heads], 0)
+        hb = torch.cat([h.bias for h in heads], 0)
+        ws = []
+        if self.is_blender:
+            ws += [self.timenet[0].weight, self.timenet[0].bias, self.timenet[2].weight, self.timenet[2].bias]
+        for l in self.linear:
+            ws += [l.weight, l.bias]
+        out, hidden = _FusedMLP.apply(x, t, self.is_blender, int(hw.shape[0]), *ws, hw, hb)
+        scaling = out[:, 3:5]
+        if self.max_d_scale > 0:
+            scaling = torch.tanh(scaling) * math.log(self.max_d_scale)
+        ret = {'d_xyz': out[:, 0:3], 'd_rotation': out[:, 5:9], 'd_scaling': scaling, 'hidden': hidden, 'd_opacity': None, 'd_color': None}
+        c = 9
+        if self.local_frame:
+            ret['local_rotation'] = out[:, c:c + 4]; c += 4
+        if self.pred_opacity:
+            ret['d_opacity'] = out[:, c:c + 1]
+        return ret
+
     def forward(self, x, t, **kwargs):
+        if self._fusable(x, t):
+            return self._forward_fused(x, t)
         t_emb = self.embed_time_fn(t)
         if self.is_blender:
             t_emb = self.timenet(t_emb)

@@ -51,9 +51,11 @@ typedef struct D2gsConfig {
 
 /* Per-stage device timing with CUDA events recorded on the launch stream (for bench.py's roofline line).
  * Stages: 0 preprocess_fwd, 1 scan, 2 duplicate, 3 sort, 4 ranges, 5 blend_fwd, 6 blend_bwd, 7 preprocess_bwd,
- *         8 deform_fwd, 9 deform_bwd, 10 epilogue_fwd, 11 epilogue_bwd.  d2gs_profile_collect synchronises the device, adds the elapsed times of all
+ *         8 deform_fwd, 9 deform_bwd, 10 epilogue_fwd, 11 epilogue_bwd, 12 mlp_fwd, 13 mlp_bwd.  d2gs_profile_collect synchronises the device, adds the elapsed times of all
  * recorded launches to total_ms[stage] / launches[stage] (arrays of D2GS_NUM_STAGES) and clears the record. */
-#define D2GS_NUM_STAGES 12
+#define D2GS_NUM_STAGES 14
+/* Runtime switches.  "cull" (default 1): warp-level cull boxes in the blend kernels; results are identical either way. */
+D2GS_API int d2gs_set_option(const char* name, int value);
 D2GS_API int d2gs_profile_enable(int on);
 D2GS_API int d2gs_profile_collect(double* total_ms, int64_t* launches);
 
@@ -219,6 +221,41 @@ typedef struct D2gsEpilogueArgs {
 
 D2GS_API int d2gs_epilogue_forward(const D2gsEpilogueArgs* args, void* stream);
 D2GS_API int d2gs_epilogue_backward(const D2gsEpilogueArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Deformation MLP, fused.  Replaces DeformNetwork.forward (utils/time_utils.py:410-453: embedders :208-256,
+ * timenet :344-346, 8x256 trunk with the skip concat :348-352,416-420, heads :363-371,422-452) and its autograd
+ * backward.  Fixed architecture of the reference: D=8, W=256, multires=10, skip after layer 4; is_blender selects the
+ * 6-frequency time embedding + timenet (13->256->30) or the 10-frequency embedding fed directly (21).
+ * Head rows are concatenated by the caller: [gaussian_warp 3 | gaussian_scaling 2 | gaussian_rotation 4 |
+ * local_rotation 4 (optional) | gaussian_opacity 1 (optional)] -> num_out <= 16.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct D2gsMlpArgs {
+  int rows;                 /* number of evaluated points (control nodes, or nodes x times) */
+  int is_blender;
+  int num_out;
+  const float* x;           /* (rows,3) */
+  const float* t;           /* time per row; element i at t[i * t_stride] (t_stride 0: one time for all rows) */
+  int t_stride;
+  const float* timenet0_w; const float* timenet0_b;   /* (256,13) (256)  — NULL unless is_blender */
+  const float* timenet2_w; const float* timenet2_b;   /* (30,256) (30) */
+  const float* linear_w[8]; const float* linear_b[8]; /* (256,in) (256) */
+  const float* heads_w; const float* heads_b;         /* (num_out,256) (num_out) */
+  void* workspace; size_t workspace_bytes;            /* from d2gs_mlp_workspace; forward fills it, backward reads it */
+  /* forward output */
+  float* out;               /* (rows,num_out) */
+  /* backward */
+  const float* g_out;       /* (rows,num_out) */
+  float* g_timenet0_w; float* g_timenet0_b; float* g_timenet2_w; float* g_timenet2_b;
+  float* g_linear_w[8]; float* g_linear_b[8];
+  float* g_heads_w; float* g_heads_b;                 /* all fully written */
+} D2gsMlpArgs;
+
+D2GS_API int d2gs_mlp_workspace(int rows, int is_blender, int num_out, size_t* bytes);
+D2GS_API int d2gs_mlp_forward(const D2gsMlpArgs* args, void* stream);
+D2GS_API int d2gs_mlp_backward(const D2gsMlpArgs* args, void* stream);
+/* hidden activations of the last trunk layer (rows,256) inside a workspace filled by d2gs_mlp_forward */
+D2GS_API const float* d2gs_mlp_hidden(int rows, int is_blender, int num_out, const void* workspace);
 
 /* ------------------------------------------------------------------------------------------------
  * Node-controlled deformation: KNN weights + blend.  Replaces ControlNodeWarp.cal_nn_weight

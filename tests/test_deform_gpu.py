@@ -71,11 +71,50 @@ def test_node_blend_matches_oracle(P, M, K, hyper, local_frame, with_mask, cuda_
         for k, tol in checks:
             a = m[k].grad.cpu().numpy() if m[k].grad is not None else np.zeros(tuple(m[k].shape), np.float32)
             b = o[k].grad.numpy() if o[k].grad is not None else np.zeros(tuple(o[k].shape), np.float32)
-            if not b.any():
-                assert not a.any(), k
+            if np.abs(b).max() < 1e-5:      # mathematically zero (e.g. K=1: the single weight is normalised to 1)
+                assert np.abs(a).max() < 1e-4, k
             else:
                 assert util.rel_err(a, b) < tol, (k, util.rel_err(a, b))
         assert not m["nodes"].grad[:, :3].any()      # node positions are detached in the reference
+
+
+@pytest.mark.parametrize("rows,is_blender,local_frame,pred_opacity", [(512, True, True, False), (37, True, False, False),
+                                                                       (300, False, True, True), (1, True, True, False)])
+def test_fused_mlp_matches_eager_layers(rows, is_blender, local_frame, pred_opacity, cuda_device):
+    """d2gs_mlp_forward/backward (one fused kernel each way) == the nn.Linear/ReLU/cat sequence of
+    DeformNetwork.forward (utils/time_utils.py:410-453) in fp32, outputs and every parameter gradient."""
+    from d2gs_b200 import deform as dfm
+    dev = cuda_device
+    torch.manual_seed(rows)
+    net = dfm.DeformNetwork(is_blender=is_blender, local_frame=local_frame, pred_opacity=pred_opacity).to(dev)
+    with torch.no_grad():
+        for h in (net.gaussian_warp, net.gaussian_scaling, net.gaussian_rotation):
+            h.weight.mul_(1e3); h.bias.normal_(0, 0.01)
+        for l in net.linear:
+            l.bias.normal_(0, 0.05)
+    x = torch.randn(rows, 3, device=dev) * 0.7
+    t_same = torch.tensor([0.37], device=dev).unsqueeze(0).expand(rows, -1)      # expand_time(): stride-0 rows
+    t_rows = torch.rand(rows, 1, device=dev)
+    for t in (t_same, t_rows):
+        res = {}
+        for fused in (False, True):
+            net.use_fused = fused
+            net.zero_grad(set_to_none=True)
+            out = net(x, t)
+            keys = [k for k in ("d_xyz", "d_rotation", "d_scaling", "local_rotation", "d_opacity") if out.get(k) is not None]
+            g = torch.Generator().manual_seed(1)
+            loss = sum((out[k] * torch.randn(out[k].shape, generator=g).to(dev)).sum() for k in keys)
+            loss.backward()
+            torch.cuda.synchronize()
+            res[fused] = ({k: out[k].detach().cpu().numpy() for k in keys + ["hidden"]},
+                          {n: p.grad.detach().cpu().numpy().copy() for n, p in net.named_parameters()})
+        for k in res[False][0]:
+            assert res[True][0][k].shape == res[False][0][k].shape, k
+            assert util.rel_err(res[True][0][k], res[False][0][k]) < 2e-5, (k, util.rel_err(res[True][0][k], res[False][0][k]))
+        assert set(res[True][1]) == set(res[False][1])
+        for n in res[False][1]:
+            assert util.rel_err(res[True][1][n], res[False][1][n]) < 1e-4, (n, util.rel_err(res[True][1][n], res[False][1][n]))
+    net.use_fused = True
 
 
 def test_control_node_warp_forward_and_cal_nn_weight(cuda_device):
@@ -155,7 +194,10 @@ def test_render_dropin_matches_reference_pipeline(cuda_device):
     o_out, o_g, o_vs = run(True)
     r_out, r_g, r_vs = run(False)
     assert set(o_out) == set(r_out)
-    assert np.array_equal(o_out["radii"], r_out["radii"]) and np.array_equal(o_out["visibility_filter"], r_out["visibility_filter"])
+    # the deformation deltas agree to ~1e-6 (different fp32 summation order than the eager blend), so a handful of
+    # radii may flip by one pixel; the rasterizer itself is bit-exact on identical inputs (test_raster_gpu.py)
+    assert (o_out["radii"] != r_out["radii"]).mean() < 2e-3
+    assert (o_out["visibility_filter"] != r_out["visibility_filter"]).mean() < 2e-3
     for k in keys + ("surf_point",):
         assert util.rel_err(o_out[k], r_out[k]) < 1e-4, k
     assert util.rel_err(o_vs, r_vs) < 5e-4

@@ -221,6 +221,35 @@ def test_split_sh_colors_precomp_transmat_paths(cuda_device):
     assert gT is not None and gT.shape == (act["means3D"].shape[0], 9) and gT.abs().sum() > 0
 
 
+@pytest.mark.parametrize("cfg,s_med,cam_pos", [("T1", None, None), ("T1", 0.05, None), ("T1", 0.02, (0.3, 0.2, 0.1)), ("T0", 0.15, (0.0, 0.9, 0.0))])
+def test_warp_cull_boxes_change_nothing(cfg, s_med, cam_pos, cuda_device):
+    """The blend kernels skip (warp patch, surfel) pairs whose conservative cull box misses the patch; with the switch
+    off every pair goes through the exact per-pixel tests.  Images, n_contrib and final_T must be bit-identical, also
+    with large splats and with the camera INSIDE the object (splats crossing the camera plane -> infinite boxes)."""
+    from d2gs_b200 import _lib, raster, synthetic as syn
+    act, kw = util.raster_inputs(cfg, s_med=s_med)
+    if cam_pos is not None:
+        c = syn.look_at_camera(cam_pos, kw["image_width"], kw["image_height"], target=(0.0, 0.0, 0.0))
+        kw.update(viewmatrix=c.world_view_transform, projmatrix=c.full_proj_transform, campos=c.camera_center)
+    gc, go = util.upstream_grads(kw["image_height"], kw["image_width"], seed=8)
+    res = {}
+    try:
+        for cull in (1, 0):
+            _lib.set_option("cull", cull)
+            o = run_ours(act, kw, cuda_device, gc, go)
+            st = raster.export_state(o["ctx"])
+            res[cull] = (o, st)
+    finally:
+        _lib.set_option("cull", 1)
+    (a, sa), (b, sb) = res[1], res[0]
+    assert a["ctx"].num_rendered == b["ctx"].num_rendered > 0
+    assert torch.equal(a["color"], b["color"]) and torch.equal(a["allmap"], b["allmap"])
+    assert torch.equal(sa["n_contrib"], sb["n_contrib"]) and torch.equal(sa["final_T"], sb["final_T"])
+    for k in ("means3D", "shs", "scales", "rotations", "opacities"):
+        assert util.rel_err(np_(a["ins"][k].grad), np_(b["ins"][k].grad)) < 2e-5, k
+    assert float(a["allmap"][1].max()) > 0.5      # the view actually shows the object
+
+
 def test_debug_mode_and_repeatability(cuda_device):
     act, kw = util.raster_inputs("T0")
     gc, go = util.upstream_grads(kw["image_height"], kw["image_width"], seed=4)
