@@ -270,11 +270,13 @@ def stage_bytes(P, R, HW, n_pass):
         "preprocess_fwd": 232 * P + 80 * P,
         "duplicate": 12 * R + 16 * P,
         "sort": 24 * R * n_pass,
-        "blend_fwd": 80 * R + 64 * HW,
-        "blend_bwd": 80 * R + 64 * HW + 76 * P,
+        "blend_fwd": 96 * R + 64 * HW,            # 96-B projected record (incl. cull box) per instance + 16 planes
+        "blend_bwd": 96 * R + 64 * HW + 80 * P,   # + the 80-B per-surfel gradient record
         "preprocess_bwd": (232 + 76 + 36 + 3) * P + 244 * P,
         "deform_fwd": (12 + 32) * P + 36 * P,
         "deform_bwd": (12 + 32) * P + 36 * P + 32 * P,
+        "epilogue_fwd": (32 + 56) * HW,
+        "epilogue_bwd": (32 + 56) * HW,
     }
 
 
@@ -483,8 +485,10 @@ def main():
                                      "frac": frame_bytes(P, R, HW, wl.use_deform) / (ms / args.steps * 1e-3) / 1e9 / hbm_peak},
                            "stages_ms": {k: (v[0] / v[1] if v[1] else None) for k, v in stage.items()}}
         out["num_rendered"] = R
-        mine_kernels = ("preprocess_fwd", "duplicate", "ranges", "blend_fwd", "blend_bwd", "preprocess_bwd", "deform_fwd", "deform_bwd")
-        out["gpu_launches"] = int(sum(stage[k][1] for k in mine_kernels))
+        # hand-written kernels launched per stage call (CUB scan/sort launches are library code and not counted)
+        mine_kernels = {"preprocess_fwd": 1, "duplicate": 1, "ranges": 1, "blend_fwd": 1, "blend_bwd": 1, "preprocess_bwd": 1,
+                        "deform_fwd": 1, "deform_bwd": 1, "epilogue_fwd": 1, "epilogue_bwd": 1, "mlp_fwd": 2, "mlp_bwd": 2}
+        out["gpu_launches"] = int(sum(stage[k][1] * n for k, n in mine_kernels.items() if k in stage))
         if world == 1 and not args.no_cpu_baseline:
             try:
                 out["cpu_baseline"] = cpu_baseline(args.config)

@@ -41,6 +41,7 @@ static int fail(int code, const std::string& msg) {
 enum Stage { ST_PRE = 0, ST_SCAN, ST_DUP, ST_SORT, ST_RANGES, ST_BLEND_F, ST_BLEND_B, ST_PRE_B, ST_DEF_F, ST_DEF_B, ST_EPI_F, ST_EPI_B, ST_MLP_F, ST_MLP_B };
 struct StageRec { int stage; cudaEvent_t a, b; };
 static bool g_profile = false;
+int g_deform_bwd_smem = 1;  // node-gradient accumulation of deform_bwd: 1 = per-CTA shared accumulators, 0 = global reductions
 static int g_cull = 1;   // warp-level cull boxes in the blend kernels (tests switch it off to prove it changes nothing)
 static std::vector<StageRec> g_recs;
 static std::vector<cudaEvent_t> g_free_events;
@@ -129,6 +130,7 @@ int d2gs_profile_enable(int on) { g_profile = on != 0; return D2GS_OK; }
 int d2gs_set_option(const char* name, int value) {
   if (!name) return fail(D2GS_ERR_INVALID_ARG, "null option name");
   if (std::strcmp(name, "cull") == 0) { g_cull = value != 0; return D2GS_OK; }
+  if (std::strcmp(name, "deform_bwd_smem") == 0) { g_deform_bwd_smem = value != 0; return D2GS_OK; }
   return fail(D2GS_ERR_INVALID_ARG, std::string("unknown option ") + name);
 }
 

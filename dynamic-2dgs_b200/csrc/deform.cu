@@ -9,6 +9,7 @@
 
 namespace d2gs {
 
+extern int g_deform_bwd_smem;
 constexpr int MAX_K = 8;
 constexpr int MAX_D = 3 + 16;   // 3 spatial + up to 16 hyper coordinates
 
@@ -56,25 +57,36 @@ struct DeformFwdP {
 // warp whose lanes insert at different nodes does not serialise a sorted-insertion ladder (measured 3.5x faster than the
 // insertion sort it replaces at M=512).  Ties: a candidate must be strictly closer than the current worst to enter, and
 // the worst among equal distances is the one with the larger index, so lower node indices win like a stable sort.
-template <int K>
+// Distances are evaluated for TWO nodes per instruction with the packed fp32 pipe of sm_100 (FADD2 / FFMA2): node pairs
+// are interleaved in shared memory as [pair][dim][2]; each packed lane still accumulates its node's squared distance
+// sequentially over the coordinates, so the value is bit-identical to the scalar loop.
+template <int K, int NQ>   // NQ = round_up(D, 4) / 4 coordinate quads
 __global__ void __launch_bounds__(256) deform_fwd_kernel(DeformFwdP a) {
-  extern __shared__ float4 s_nodes4[];   // M rows of DP = round_up(D,4) floats (zero padded): broadcast LDS.128 in the scan
+  extern __shared__ float4 s_nodes4[];   // [ceil(M/2)][4*NQ dims][2 nodes] floats: one LDS.128 = 2 dims x 2 nodes
   float* s_nodes = reinterpret_cast<float*>(s_nodes4);
+  constexpr int DP = 4 * NQ;
   const int D = a.D;
-  const int DP = (D + 3) & ~3;
   const int nstride = 3 + a.hyper;
-  for (int t = threadIdx.x; t < a.M * DP; t += blockDim.x) {
-    const int m = t / DP, d = t - m * DP;
-    s_nodes[t] = d < D ? a.nodes[(size_t)m * nstride + d] : 0.f;
+  const int MP = (a.M + 1) & ~1;
+  for (int t = threadIdx.x; t < MP * DP; t += blockDim.x) {
+    const int pr = t / (2 * DP), r = t - pr * 2 * DP, d = r >> 1, which = r & 1;
+    const int m = 2 * pr + which;
+    float v = 0.f;
+    if (d < D) v = (m < a.M) ? a.nodes[(size_t)m * nstride + d] : 1e30f;   // padding node: infinitely far
+    s_nodes[t] = v;
   }
   __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.P) return;
 
-  float q[MAX_D + 1];
-  q[0] = a.xyz[3 * (size_t)i]; q[1] = a.xyz[3 * (size_t)i + 1]; q[2] = a.xyz[3 * (size_t)i + 2];
+  float2 q2[DP];   // query coordinate d duplicated in both packed lanes
 #pragma unroll
-  for (int d = 3; d < MAX_D + 1; d++) q[d] = (d < D) ? a.feature[(size_t)i * a.fstride + (d - 3)] : 0.f;
+  for (int d = 0; d < DP; d++) {
+    float v = 0.f;
+    if (d < 3) v = a.xyz[3 * (size_t)i + d];
+    else if (d < D) v = a.feature[(size_t)i * a.fstride + (d - 3)];
+    q2[d] = make_float2(v, v);
+  }
 
   float bd[K];
   int bi[K];
@@ -82,21 +94,7 @@ __global__ void __launch_bounds__(256) deform_fwd_kernel(DeformFwdP a) {
   for (int k = 0; k < K; k++) { bd[k] = INFINITY; bi[k] = 0x7fffffff - k; }
   float wd = INFINITY;   // current worst (largest (dist, idx)) of the set and its slot
   int ws = 0;
-  const int nq = DP >> 2;
-  for (int m = 0; m < a.M; m++) {
-    const float4* n4 = s_nodes4 + m * nq;
-    float dist = 0.f;
-#pragma unroll
-    for (int c = 0; c < (MAX_D + 1) / 4; c++) {
-      if (c < nq) {
-        const float4 v = n4[c];
-        // sequential accumulation over the coordinates (zero padding adds exact zeros)
-        float df = q[4 * c] - v.x;     dist = fmaf(df, df, dist);
-        df = q[4 * c + 1] - v.y;       dist = fmaf(df, df, dist);
-        df = q[4 * c + 2] - v.z;       dist = fmaf(df, df, dist);
-        df = q[4 * c + 3] - v.w;       dist = fmaf(df, df, dist);
-      }
-    }
+  auto offer = [&](float dist, int m) {
     if (dist < wd) {
 #pragma unroll
       for (int k = 0; k < K; k++) {
@@ -114,6 +112,21 @@ __global__ void __launch_bounds__(256) deform_fwd_kernel(DeformFwdP a) {
         ws = worse ? k : ws;
       }
     }
+  };
+  const int npairs = MP >> 1;
+  for (int pr = 0; pr < npairs; pr++) {
+    const float4* n4 = s_nodes4 + pr * (DP / 2);
+    float2 dist = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < DP / 2; c++) {
+      const float4 v = n4[c];   // (dim 2c: node A, node B), (dim 2c+1: node A, node B)
+      float2 df = __fadd2_rn(q2[2 * c], make_float2(-v.x, -v.y));
+      dist = __ffma2_rn(df, df, dist);
+      df = __fadd2_rn(q2[2 * c + 1], make_float2(-v.z, -v.w));
+      dist = __ffma2_rn(df, df, dist);
+    }
+    offer(dist.x, 2 * pr);
+    offer(dist.y, 2 * pr + 1);
   }
   // order the K survivors by (distance, index): tiny odd-even transposition network
 #pragma unroll
@@ -140,7 +153,7 @@ __global__ void __launch_bounds__(256) deform_fwd_kernel(DeformFwdP a) {
     w[k] = wk;
     wsum += wk;
   }
-  const float x0 = q[0], x1 = q[1], x2 = q[2];
+  const float x0 = q2[0].x, x1 = q2[1].x, x2 = q2[2].x;
   float t0 = 0.f, t1 = 0.f, t2 = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, s0 = 0.f, s1 = 0.f;
 #pragma unroll
   for (int k = 0; k < K; k++) {
@@ -152,7 +165,8 @@ __global__ void __launch_bounds__(256) deform_fwd_kernel(DeformFwdP a) {
                      __ldg(a.local_rot + 4 * m + 3)};
       float R[9];
       quat_to_matrix_raw(lq, R);
-      const float n0 = s_nodes[m * DP], n1 = s_nodes[m * DP + 1], n2 = s_nodes[m * DP + 2];
+      const int nb = (m >> 1) * 2 * DP + (m & 1);
+      const float n0 = s_nodes[nb], n1 = s_nodes[nb + 2], n2 = s_nodes[nb + 4];
       const float e0 = x0 - n0, e1 = x1 - n1, e2 = x2 - n2;
       const float A0 = (R[0] * e0 + R[1] * e1 + R[2] * e2) + n0 + tr0;
       const float A1 = (R[3] * e0 + R[4] * e1 + R[5] * e2) + n1 + tr1;
@@ -350,19 +364,35 @@ int deform_forward_launch(const DeformFwdHost& h, cudaStream_t s, const char** e
   a.trans = h.trans; a.rot = h.rot; a.scale = h.scale; a.local_rot = h.local_rot; a.mask = h.mask;
   a.nn_idx = h.nn_idx; a.nn_dist = h.nn_dist; a.nn_weight = h.nn_weight;
   a.d_xyz = h.d_xyz; a.d_rot = h.d_rot; a.d_scale = h.d_scale;
-  const size_t smem = sizeof(float) * (size_t)a.M * ((a.D + 3) & ~3);
+  const int nq = (a.D + 3) / 4;
+  const size_t smem = sizeof(float) * (size_t)((a.M + 1) & ~1) * 4 * nq;
   if (smem > 200 * 1024) { *err = "node table exceeds shared memory (M*(3+hyper) floats > 200 KB)"; return -1; }
   const int grid = (h.P + 255) / 256;
-#define D2GS_KNN_CASE(KK)                                                                                   \
-  case KK:                                                                                                 \
-    cudaFuncSetAttribute(deform_fwd_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-    deform_fwd_kernel<KK><<<grid, 256, smem, s>>>(a);                                                       \
-    break;
-  switch (h.K) {
-    D2GS_KNN_CASE(1) D2GS_KNN_CASE(2) D2GS_KNN_CASE(3) D2GS_KNN_CASE(4)
-    D2GS_KNN_CASE(5) D2GS_KNN_CASE(6) D2GS_KNN_CASE(7) D2GS_KNN_CASE(8)
+#define D2GS_KNN_LAUNCH(KK, QQ)                                                                                  \
+  do {                                                                                                          \
+    cudaFuncSetAttribute(deform_fwd_kernel<KK, QQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+    deform_fwd_kernel<KK, QQ><<<grid, 256, smem, s>>>(a);                                                        \
+  } while (0)
+#define D2GS_KNN_Q(KK)                                                                     \
+  switch (nq) {                                                                           \
+    case 1: D2GS_KNN_LAUNCH(KK, 1); break;                                                \
+    case 2: D2GS_KNN_LAUNCH(KK, 2); break;                                                \
+    case 3: D2GS_KNN_LAUNCH(KK, 3); break;                                                \
+    case 4: D2GS_KNN_LAUNCH(KK, 4); break;                                                \
+    default: D2GS_KNN_LAUNCH(KK, 5); break;                                               \
   }
-#undef D2GS_KNN_CASE
+  switch (h.K) {
+    case 1: D2GS_KNN_Q(1) break;
+    case 2: D2GS_KNN_Q(2) break;
+    case 3: D2GS_KNN_Q(3) break;
+    case 4: D2GS_KNN_Q(4) break;
+    case 5: D2GS_KNN_Q(5) break;
+    case 6: D2GS_KNN_Q(6) break;
+    case 7: D2GS_KNN_Q(7) break;
+    default: D2GS_KNN_Q(8) break;
+  }
+#undef D2GS_KNN_Q
+#undef D2GS_KNN_LAUNCH
   return 0;
 }
 
@@ -381,7 +411,7 @@ int deform_backward_launch(const DeformBwdHost& h, cudaStream_t s, const char** 
   if (h.hyper < 0 || h.hyper > MAX_D - 3) { *err = "hyper_dim must be <= 16"; return -1; }
   if (h.P == 0) return 0;
   const size_t smem = sizeof(float) * (size_t)h.M * (NG_FIXED + h.hyper);
-  a.use_smem = smem <= 200 * 1024;
+  a.use_smem = g_deform_bwd_smem && smem <= 200 * 1024;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -48,71 +48,72 @@ __global__ void __launch_bounds__(256) mlp_transpose_kernel(MlpLayers L) {
 // forward
 // ---------------------------------------------------------------------------------------------------------------
 // out[n] (for the CTA's ROWS rows) = bias[n] + sum_k in[k] * Wt[k][n];   in: shared [K][ROWS]
+// Thread (kg, nq) = (tid >> 6, tid & 63) owns outputs 4nq..4nq+3 for the k with k % 4 == kg: one coalesced LDG.128 of
+// W^T and one broadcast LDS.128 of the activations feed 16 FMAs; the four k-groups are summed through shared memory.
+__device__ __forceinline__ float4 ldg128(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ void fma16(float4 (&acc)[4], const float4 wv, const float4 xv) {
+  acc[0].x = fmaf(wv.x, xv.x, acc[0].x); acc[0].y = fmaf(wv.x, xv.y, acc[0].y); acc[0].z = fmaf(wv.x, xv.z, acc[0].z); acc[0].w = fmaf(wv.x, xv.w, acc[0].w);
+  acc[1].x = fmaf(wv.y, xv.x, acc[1].x); acc[1].y = fmaf(wv.y, xv.y, acc[1].y); acc[1].z = fmaf(wv.y, xv.z, acc[1].z); acc[1].w = fmaf(wv.y, xv.w, acc[1].w);
+  acc[2].x = fmaf(wv.z, xv.x, acc[2].x); acc[2].y = fmaf(wv.z, xv.y, acc[2].y); acc[2].z = fmaf(wv.z, xv.z, acc[2].z); acc[2].w = fmaf(wv.z, xv.w, acc[2].w);
+  acc[3].x = fmaf(wv.w, xv.x, acc[3].x); acc[3].y = fmaf(wv.w, xv.y, acc[3].y); acc[3].z = fmaf(wv.w, xv.z, acc[3].z); acc[3].w = fmaf(wv.w, xv.w, acc[3].w);
+}
+
 template <bool RELU>
 __device__ __forceinline__ void dense(const float* __restrict__ wt, int NP, const float* __restrict__ bias, int N,
-                                      const float4* s_in_a, int Ka, const float4* s_in_b, int Kb, float4* s_out,
+                                      const float4* s_in, int K, float4* s_red /*[4][256]*/, float4* s_out,
                                       float* g_out, int ld_out, int row0, int rows, int tid) {
-  for (int n = tid; n < N; n += 256) {
-    const float b = bias ? __ldg(bias + n) : 0.f;
-    float a0 = b, a1 = b, a2 = b, a3 = b;
-    const float* w = wt + n;
-    int k = 0;
+  const int kg = tid >> 6, nq = tid & 63;
+  float4 acc[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (4 * nq < NP) {
+    const float* w = wt + 4 * nq;
+    int k = kg;
 #pragma unroll 1
-    for (; k + 8 <= Ka; k += 8) {
-      float wv[8];
-#pragma unroll
-      for (int u = 0; u < 8; u++) wv[u] = __ldg(w + (size_t)(k + u) * NP);
-#pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const float4 x = s_in_a[k + u];
-        a0 = fmaf(wv[u], x.x, a0); a1 = fmaf(wv[u], x.y, a1); a2 = fmaf(wv[u], x.z, a2); a3 = fmaf(wv[u], x.w, a3);
-      }
+    for (; k + 12 < K; k += 16) {
+      const float4 w0 = ldg128(w + (size_t)k * NP), w1 = ldg128(w + (size_t)(k + 4) * NP),
+                   w2 = ldg128(w + (size_t)(k + 8) * NP), w3 = ldg128(w + (size_t)(k + 12) * NP);
+      const float4 x0 = s_in[k], x1 = s_in[k + 4], x2 = s_in[k + 8], x3 = s_in[k + 12];
+      fma16(acc, w0, x0); fma16(acc, w1, x1); fma16(acc, w2, x2); fma16(acc, w3, x3);
     }
-    for (; k < Ka; k++) {
-      const float wv = __ldg(w + (size_t)k * NP);
-      const float4 x = s_in_a[k];
-      a0 = fmaf(wv, x.x, a0); a1 = fmaf(wv, x.y, a1); a2 = fmaf(wv, x.z, a2); a3 = fmaf(wv, x.w, a3);
-    }
-    if (Kb > 0) {
-      const float* w2 = w + (size_t)Ka * NP;
-      int kk = 0;
-#pragma unroll 1
-      for (; kk + 8 <= Kb; kk += 8) {
-        float wv[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) wv[u] = __ldg(w2 + (size_t)(kk + u) * NP);
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-          const float4 x = s_in_b[kk + u];
-          a0 = fmaf(wv[u], x.x, a0); a1 = fmaf(wv[u], x.y, a1); a2 = fmaf(wv[u], x.z, a2); a3 = fmaf(wv[u], x.w, a3);
-        }
-      }
-      for (; kk < Kb; kk++) {
-        const float wv = __ldg(w2 + (size_t)kk * NP);
-        const float4 x = s_in_b[kk];
-        a0 = fmaf(wv, x.x, a0); a1 = fmaf(wv, x.y, a1); a2 = fmaf(wv, x.z, a2); a3 = fmaf(wv, x.w, a3);
-      }
-    }
-    if (RELU) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
-    if (s_out) s_out[n] = make_float4(a0, a1, a2, a3);
-    if (g_out) {
-      if (rows > 0) g_out[(size_t)(row0 + 0) * ld_out + n] = a0;
-      if (rows > 1) g_out[(size_t)(row0 + 1) * ld_out + n] = a1;
-      if (rows > 2) g_out[(size_t)(row0 + 2) * ld_out + n] = a2;
-      if (rows > 3) g_out[(size_t)(row0 + 3) * ld_out + n] = a3;
+    for (; k < K; k += 4) {
+      const float4 w0 = ldg128(w + (size_t)k * NP);
+      const float4 x0 = s_in[k];
+      fma16(acc, w0, x0);
     }
   }
+#pragma unroll
+  for (int j = 0; j < 4; j++) s_red[kg * MW + 4 * nq + j] = acc[j];
+  __syncthreads();
+  if (tid < N) {
+    const float b = bias ? __ldg(bias + tid) : 0.f;
+    const float4 p0 = s_red[tid], p1 = s_red[MW + tid], p2 = s_red[2 * MW + tid], p3 = s_red[3 * MW + tid];
+    float a0 = b + ((p0.x + p1.x) + (p2.x + p3.x)), a1 = b + ((p0.y + p1.y) + (p2.y + p3.y));
+    float a2 = b + ((p0.z + p1.z) + (p2.z + p3.z)), a3 = b + ((p0.w + p1.w) + (p2.w + p3.w));
+    if (RELU) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+    if (s_out) s_out[tid] = make_float4(a0, a1, a2, a3);
+    if (g_out) {
+      if (rows > 0) g_out[(size_t)(row0 + 0) * ld_out + tid] = a0;
+      if (rows > 1) g_out[(size_t)(row0 + 1) * ld_out + tid] = a1;
+      if (rows > 2) g_out[(size_t)(row0 + 2) * ld_out + tid] = a2;
+      if (rows > 3) g_out[(size_t)(row0 + 3) * ld_out + tid] = a3;
+    }
+  }
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(256) mlp_fwd_kernel(MlpFwd a) {
-  __shared__ float4 s_inp[INP_LD];       // [x_emb (63), t feature (Tt)]
-  __shared__ float4 s_te[32];            // time embedding (Et <= 21)
-  __shared__ float4 s_h[2][MW];          // ping-pong hidden / timenet hidden
+  __shared__ float4 s_x[2][INP_LD + MW];  // each buffer: [x_emb (63) | time feature (Tt)] at 0..in0-1, hidden at in0..in0+255
+  __shared__ float4 s_te[32];             // time embedding (Et <= 21)
+  __shared__ float4 s_th[MW];             // timenet hidden
+  __shared__ float4 s_red[4 * MW];        // partial sums of the four k-groups
   const int tid = threadIdx.x;
   const int row0 = blockIdx.x * ROWS;
   const int rows = min(ROWS, a.rows - row0);
   const MlpLayers& L = a.layers;
   const int Et = a.Et, Tt = a.Tt;
+  const int in0 = EX + Tt;
 
   // positional embeddings: [v, sin(2^0 v), cos(2^0 v), ..., sin(2^(F-1) v), cos(2^(F-1) v)] per input dimension block
   for (int e = tid; e < EX + Et; e += 256) {
@@ -136,10 +137,10 @@ __global__ void __launch_bounds__(256) mlp_fwd_kernel(MlpFwd a) {
       v[r] = val;
     }
     const float4 p = make_float4(v[0], v[1], v[2], v[3]);
-    if (e < EX) s_inp[e] = p;
+    if (e < EX) { s_x[0][e] = p; s_x[1][e] = p; }
     else {
       s_te[e - EX] = p;
-      if (!a.has_timenet) s_inp[e] = p;
+      if (!a.has_timenet) { s_x[0][e] = p; s_x[1][e] = p; }
     }
     if (a.save_inp) {
 #pragma unroll
@@ -154,27 +155,24 @@ __global__ void __launch_bounds__(256) mlp_fwd_kernel(MlpFwd a) {
   int li = 0;
   if (a.has_timenet) {
     const MlpLayer& t1 = L.layer[li++];
-    dense<true>(L.wt + t1.wt_off, t1.NP, t1.b, t1.N, s_te, t1.K, nullptr, 0, s_h[0], a.save_th, MW, row0, rows, tid);
-    __syncthreads();
+    dense<true>(L.wt + t1.wt_off, t1.NP, t1.b, t1.N, s_te, t1.K, s_red, s_th, a.save_th, MW, row0, rows, tid);
     const MlpLayer& t2 = L.layer[li++];
-    dense<false>(L.wt + t2.wt_off, t2.NP, t2.b, t2.N, s_h[0], t2.K, nullptr, 0, s_inp + EX, a.save_inp ? a.save_inp + EX : nullptr,
+    dense<false>(L.wt + t2.wt_off, t2.NP, t2.b, t2.N, s_th, t2.K, s_red, s_x[0] + EX, a.save_inp ? a.save_inp + EX : nullptr,
                  INP_LD, row0, rows, tid);
+    if (tid < Tt) s_x[1][EX + tid] = s_x[0][EX + tid];
     __syncthreads();
   }
-  const int in0 = EX + Tt;
-  int cur = 0;
+  int cur = 0;   // layer l writes its hidden block into s_x[cur] + in0 and reads from s_x[cur ^ 1]
   for (int l = 0; l < MD; l++) {
     const MlpLayer& ly = L.layer[li++];
     float* save = a.save_h ? a.save_h + (size_t)l * a.rows * MW : nullptr;
-    if (l == 0) dense<true>(L.wt + ly.wt_off, ly.NP, ly.b, ly.N, s_inp, in0, nullptr, 0, s_h[cur], save, MW, row0, rows, tid);
-    else if (l == SKIP + 1) dense<true>(L.wt + ly.wt_off, ly.NP, ly.b, ly.N, s_inp, in0, s_h[cur ^ 1], MW, s_h[cur], save, MW, row0, rows, tid);
-    else dense<true>(L.wt + ly.wt_off, ly.NP, ly.b, ly.N, s_h[cur ^ 1], MW, nullptr, 0, s_h[cur], save, MW, row0, rows, tid);
-    __syncthreads();
+    const float4* in = (l == 0 || l == SKIP + 1) ? s_x[cur ^ 1] : s_x[cur ^ 1] + in0;   // skip layer reads [x, t, h] contiguously
+    dense<true>(L.wt + ly.wt_off, ly.NP, ly.b, ly.N, in, ly.K, s_red, s_x[cur] + in0, save, MW, row0, rows, tid);
     cur ^= 1;
   }
   // heads: concatenated outputs [warp 3 | scaling 2 | rotation 4 | local 4 | opacity 1] -> (rows, NH)
   const MlpLayer& hd = L.layer[li];
-  dense<false>(L.wt + hd.wt_off, hd.NP, hd.b, hd.N, s_h[cur ^ 1], MW, nullptr, 0, nullptr, a.out, a.NH, row0, rows, tid);
+  dense<false>(L.wt + hd.wt_off, hd.NP, hd.b, hd.N, s_x[cur ^ 1] + in0, MW, s_red, nullptr, a.out, a.NH, row0, rows, tid);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -221,10 +219,42 @@ __device__ __forceinline__ float4 relu_mask(float4 g, float4 h) {
   return make_float4(h.x > 0.f ? g.x : 0.f, h.y > 0.f ? g.y : 0.f, h.z > 0.f ? g.z : 0.f, h.w > 0.f ? g.w : 0.f);
 }
 
+// K == 256 fast path: thread (ng, kq) = (tid >> 6, tid & 63) owns inputs 4kq..4kq+3 for the n with n % 4 == ng (one
+// LDG.128 of a W row + one broadcast LDS.128 of G feed 16 FMAs); the four n-groups are summed through shared memory and
+// thread tid returns g_in[tid].
+__device__ __forceinline__ float4 back_dense_k256(const float* __restrict__ W, int N, const float4* s_g, float4* s_red, int tid) {
+  const int ng = tid >> 6, kq = tid & 63;
+  float4 acc[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* w = W + 4 * kq;
+  int n = ng;
+#pragma unroll 1
+  for (; n + 12 < N; n += 16) {
+    const float4 w0 = ldg128(w + (size_t)n * MW), w1 = ldg128(w + (size_t)(n + 4) * MW), w2 = ldg128(w + (size_t)(n + 8) * MW),
+                 w3 = ldg128(w + (size_t)(n + 12) * MW);
+    const float4 g0 = s_g[n], g1 = s_g[n + 4], g2 = s_g[n + 8], g3 = s_g[n + 12];
+    fma16(acc, w0, g0); fma16(acc, w1, g1); fma16(acc, w2, g2); fma16(acc, w3, g3);
+  }
+  for (; n < N; n += 4) {
+    const float4 w0 = ldg128(w + (size_t)n * MW);
+    const float4 g0 = s_g[n];
+    fma16(acc, w0, g0);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) s_red[ng * MW + 4 * kq + j] = acc[j];
+  __syncthreads();
+  const float4 p0 = s_red[tid], p1 = s_red[MW + tid], p2 = s_red[2 * MW + tid], p3 = s_red[3 * MW + tid];
+  __syncthreads();
+  return make_float4((p0.x + p1.x) + (p2.x + p3.x), (p0.y + p1.y) + (p2.y + p3.y), (p0.z + p1.z) + (p2.z + p3.z),
+                     (p0.w + p1.w) + (p2.w + p3.w));
+}
+
 __global__ void __launch_bounds__(256) mlp_bwd_act_kernel(MlpBwd a) {
   __shared__ float4 s_g[2][MW];      // pre-activation gradient of the current layer (ping-pong)
   __shared__ float4 s_gh[16];        // head gradients
   __shared__ float4 s_gt[32];        // gradient of the time feature (Tt <= 30)
+  __shared__ float4 s_red[4 * MW];
   const int tid = threadIdx.x;
   const int row0 = blockIdx.x * ROWS;
   const int rows = min(ROWS, a.rows - row0);
@@ -238,7 +268,7 @@ __global__ void __launch_bounds__(256) mlp_bwd_act_kernel(MlpBwd a) {
   const MlpLayer& hd = L.layer[first_trunk + MD];
   int cur = 0;
   {
-    float4 g = back_dense(hd.W, MW, hd.N, s_gh, tid);
+    float4 g = back_dense_k256(hd.W, hd.N, s_gh, s_red, tid);
     const float4 h = load_rows(a.save_h + (size_t)(MD - 1) * a.rows * MW, MW, row0, rows, tid);
     g = relu_mask(g, h);
     s_g[cur][tid] = g;
@@ -248,14 +278,15 @@ __global__ void __launch_bounds__(256) mlp_bwd_act_kernel(MlpBwd a) {
   for (int l = MD - 1; l >= 1; l--) {
     const MlpLayer& ly = L.layer[first_trunk + l];     // input of layer l is h_{l-1} (plus [x,t] for l == SKIP+1)
     const int K = ly.K;
-    const int hoff = (l == SKIP + 1) ? in0 : 0;       // column offset of the h block inside the layer input
-    float4 g = back_dense(ly.W, K, MW, s_g[cur], hoff + tid);
+    float4 g;
+    if (l == SKIP + 1) {                               // K = in0 + 256: rows are not 16-B aligned, scalar loads
+      g = back_dense(ly.W, K, MW, s_g[cur], in0 + tid);
+      if (tid < Tt) s_gt[tid] = back_dense(ly.W, K, MW, s_g[cur], EX + tid);   // time feature through the skip input
+    } else {
+      g = back_dense_k256(ly.W, MW, s_g[cur], s_red, tid);
+    }
     const float4 h = load_rows(a.save_h + (size_t)(l - 1) * a.rows * MW, MW, row0, rows, tid);
     g = relu_mask(g, h);
-    if (l == SKIP + 1 && tid < Tt) {   // gradient into the time feature through the skip input
-      const float4 gt = back_dense(ly.W, K, MW, s_g[cur], EX + tid);
-      s_gt[tid] = gt;
-    }
     s_g[cur ^ 1][tid] = g;
     store_rows(a.G + (size_t)(l - 1) * a.rows * MW, MW, row0, rows, tid, g);
     __syncthreads();
@@ -274,7 +305,7 @@ __global__ void __launch_bounds__(256) mlp_bwd_act_kernel(MlpBwd a) {
   if (a.has_timenet) {
     if (tid < Tt) store_rows(a.g_tfeat, 32, row0, rows, tid, s_gt[tid]);
     const MlpLayer& t2 = L.layer[1];
-    float4 g = back_dense(t2.W, MW, t2.N, s_gt, tid);
+    float4 g = back_dense_k256(t2.W, t2.N, s_gt, s_red, tid);
     const float4 h = load_rows(a.save_th, MW, row0, rows, tid);
     g = relu_mask(g, h);
     store_rows(a.G_t1, MW, row0, rows, tid, g);

@@ -13,14 +13,16 @@
 
 namespace d2gs {
 
-constexpr int BWD_BATCH = 128;   // instances staged per round
+constexpr int BWD_BATCH = 80;   // instances staged per round
 constexpr int NWARP = TILE_PIX / 32;
 constexpr int ACC_STRIDE = 19;   // 18 components, odd stride keeps the flush free of bank conflicts
 constexpr unsigned FULL = 0xffffffffu;
 // dynamic shared memory of blend_bwd_kernel
-constexpr size_t BWD_SMEM_Q = sizeof(float4) * REC_QUADS * BWD_BATCH;                  // staged records
+constexpr int BWD_WORDS = (BWD_BATCH + 31) / 32;
+constexpr size_t BWD_SMEM_Q1 = sizeof(float4) * REC_QUADS * BWD_BATCH;                 // one staging buffer
+constexpr size_t BWD_SMEM_Q = 2 * BWD_SMEM_Q1;                                         // double buffered (cp.async)
 constexpr size_t BWD_SMEM_ACC = sizeof(float) * NWARP * BWD_BATCH * ACC_STRIDE;        // per-warp private accumulators
-constexpr size_t BWD_SMEM_BYTES = BWD_SMEM_Q + BWD_SMEM_ACC + sizeof(uint32_t) * (BWD_BATCH + NWARP);
+constexpr size_t BWD_SMEM_BYTES = BWD_SMEM_Q + BWD_SMEM_ACC + sizeof(uint32_t) * (2 * BWD_BATCH + NWARP);
 
 __device__ __forceinline__ void pixel_of_thread_b(int tid, int& lx, int& ly) {
   const int w = tid >> 5, l = tid & 31;
@@ -58,16 +60,15 @@ __device__ __forceinline__ void warp_transpose_reduce16(float (&g)[16], int lane
   g[0] += __shfl_xor_sync(FULL, g[0], 1);
 }
 
-__global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
+__global__ void __launch_bounds__(TILE_PIX, 3) blend_bwd_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
     const float* __restrict__ bg, const SurfelRec* __restrict__ rec, const float* __restrict__ final_Ts,
     const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
     const float* __restrict__ dL_dothers, float* __restrict__ grad_rec, int cull) {
   extern __shared__ __align__(16) unsigned char bwd_smem[];
-  float4(*s_q)[BWD_BATCH] = reinterpret_cast<float4(*)[BWD_BATCH]>(bwd_smem);
   float* s_acc = reinterpret_cast<float*>(bwd_smem + BWD_SMEM_Q);        // [warp][slot][ACC_STRIDE]
-  uint32_t* s_id = reinterpret_cast<uint32_t*>(bwd_smem + BWD_SMEM_Q + BWD_SMEM_ACC);
-  uint32_t* s_max = s_id + BWD_BATCH;
+  uint32_t* s_id = reinterpret_cast<uint32_t*>(bwd_smem + BWD_SMEM_Q + BWD_SMEM_ACC);   // [2][BWD_BATCH]
+  uint32_t* s_max = s_id + 2 * BWD_BATCH;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int lx, ly;
@@ -80,9 +81,8 @@ __global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
   const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
   const float pcx0 = (float)(blockIdx.x * TILE_X + ((warp & 1) << 3)) + 0.5f, pcx1 = pcx0 + 7.0f;
   const float pcy0 = (float)(blockIdx.y * TILE_Y + ((warp >> 1) << 2)) + 0.5f, pcy1 = pcy0 + 3.0f;
-  const uint32_t sb0 = smem_addr(&s_q[0][0]);
+  const uint32_t sq_base = smem_addr(bwd_smem);
   constexpr uint32_t QS = 16u * BWD_BATCH;   // bytes per staged quad plane
-  const uint32_t sb1 = sb0 + QS, sb2 = sb0 + 2 * QS, sb3 = sb0 + 3 * QS, sb4 = sb0 + 4 * QS, sb5 = sb0 + 5 * QS;
   float* my_acc = s_acc + (size_t)warp * BWD_BATCH * ACC_STRIDE;
 
   const float T_final = inside ? final_Ts[pix_id] : 0;
@@ -127,27 +127,62 @@ __global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
   float last_dL_dT = 0.f;
 
   const int rounds = (len + BWD_BATCH - 1) / BWD_BATCH;
+  // instance id of this thread's slot in batch bi (back to front: slot t holds list position len-1-(bi*B+t))
+  auto slot_id = [&](int bi) -> uint32_t {
+    const int nb = min(BWD_BATCH, (int)len - bi * BWD_BATCH);
+    return (bi < rounds && tid < nb) ? __ldg(&point_list[range.x + (len - 1 - (uint32_t)(bi * BWD_BATCH + tid))]) : 0xffffffffu;
+  };
+  // stage batch bi into buffer buf with cp.async; `id` was fetched one iteration earlier so no load latency is exposed
+  auto stage = [&](int bi, int buf, uint32_t id) {
+    if (id != 0xffffffffu) {
+      s_id[buf * BWD_BATCH + tid] = id;
+      const float4* r4 = reinterpret_cast<const float4*>(rec + id);
+      const uint32_t dst = sq_base + (uint32_t)buf * (uint32_t)BWD_SMEM_Q1 + ((uint32_t)tid << 4);
+#pragma unroll
+      for (int q = 0; q < REC_QUADS; q++) cp_async16(dst + q * QS, r4 + q);
+    }
+    cp_async_commit();
+  };
+  stage(0, 0, slot_id(0));
+  uint32_t pre_id = slot_id(1);
   int remaining = (int)len;
   for (int i = 0; i < rounds; i++, remaining -= BWD_BATCH) {
-    // stage the batch back to front: slot t holds list position len-1-(i*B+t)
     const int n = min(BWD_BATCH, remaining);
-    if (tid < n) {
-      const uint32_t pos = len - 1 - (uint32_t)(i * BWD_BATCH + tid);
-      const uint32_t id = __ldg(&point_list[range.x + pos]);
-      s_id[tid] = id;
-      const float4* r4 = reinterpret_cast<const float4*>(rec + id);
-#pragma unroll
-      for (int q = 0; q < REC_QUADS; q++) s_q[q][tid] = __ldg(r4 + q);
+    const int buf = i & 1;
+    // buffer buf^1 was last read in batch i-1, which every warp left before the flush barrier of that batch
+    if (i + 1 < rounds) {
+      stage(i + 1, buf ^ 1, pre_id);
+      pre_id = slot_id(i + 2);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
+    const uint32_t sb0 = sq_base + (uint32_t)buf * (uint32_t)BWD_SMEM_Q1;
+    const uint32_t sb1 = sb0 + QS, sb2 = sb0 + 2 * QS, sb3 = sb0 + 3 * QS, sb4 = sb0 + 4 * QS, sb5 = sb0 + 5 * QS;
+    const uint32_t* cur_id = s_id + buf * BWD_BATCH;
 
-    for (int j = 0; j < n; j++) {
+    // Warp-level compaction (see blend_fwd_kernel): survivors of the cull-box test as a bit mask, visited in staged
+    // (back-to-front) order.
+    uint32_t keepmask[BWD_WORDS];
+#pragma unroll
+    for (int w = 0; w < BWD_WORDS; w++) {
+      const int jj = w * 32 + lane;
+      bool keep = jj < n;
+      if (keep && cull) {
+        const float4 bb = lds128(sb5 + ((uint32_t)jj << 4));
+        keep = !(bb.z < pcx0 || bb.x > pcx1 || bb.w < pcy0 || bb.y > pcy1);
+      }
+      keepmask[w] = __ballot_sync(FULL, keep);
+    }
+#pragma unroll
+    for (int w = 0; w < BWD_WORDS; w++) {
+      uint32_t m = keepmask[w];
+      while (m != 0u) {
+      const int j = w * 32 + (__ffs(m) - 1);
+      m &= m - 1u;
       const uint32_t contributor = len - 1 - (uint32_t)(i * BWD_BATCH + j);   // 0-based list position
       const uint32_t off = (uint32_t)j << 4;
-      if (cull) {   // uniform per warp: no pixel of this 8x4 patch can pass the prefilter
-        const float4 bb = lds128(sb5 + off);
-        if (bb.z < pcx0 || bb.x > pcx1 || bb.w < pcy0 || bb.y > pcy1) continue;
-      }
       float g[16];          // written only by contributing lanes; zero-filled lazily before a reduction
       float gm0 = 0.f, gm1 = 0.f;
       bool contrib = false, flat = false;
@@ -273,6 +308,7 @@ __global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
           }
         }
       }
+      }
     }
     __syncthreads();
     // fold the 8 warp-private accumulators and issue one global reduction per (tile, instance, component);
@@ -280,7 +316,7 @@ __global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
     {
       const int slot = tid >> 1, half = tid & 1;
       if (slot < n) {
-        float* dst = grad_rec + (size_t)s_id[slot] * GRAD_REC_FLOATS;
+        float* dst = grad_rec + (size_t)cur_id[slot] * GRAD_REC_FLOATS;
 #pragma unroll
         for (int q = 0; q < 9; q++) {
           const int v = half * 9 + q;
@@ -315,57 +351,54 @@ void launch_blend_bwd(const BwdParams& p, const uint2* ranges, const uint32_t* p
 // ------------------------------------------------------------------------------------------------------------
 // per-surfel backward: AABB-centre term, homography -> (mean, scale, quaternion), normal, SH.
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_sh_grad(const BwdParams& p, float* dL_dsh, float* dL_dsh_rest, int idx,
-                                              const float* g /*[48]*/) {
-  if (dL_dsh_rest == nullptr) {
-    float* base = dL_dsh + (size_t)idx * p.M * 3;
-    if (p.M == 16 && ((reinterpret_cast<uintptr_t>(dL_dsh) & 15) == 0)) {
-      float4* b4 = reinterpret_cast<float4*>(base);
+// SH coefficients 4c..4c+3 of surfel idx (12 floats) in any of the three layouts: packed (P,16,3) with 16-B aligned
+// rows (3 x LDG.128), generic packed (P,M,3), or split DC (P,1,3) + rest (P,M-1,3).  Coefficients >= ncoef read as 0.
+__device__ __forceinline__ void load_sh_chunk(const BwdParams& p, int idx, int c, int ncoef, float* sv /*[12]*/) {
+  if (p.sh_rest == nullptr && p.M == 16 && ((reinterpret_cast<uintptr_t>(p.shs) & 15) == 0)) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.shs + (size_t)idx * 48) + 3 * c;
+    if (4 * c < ncoef) {
 #pragma unroll
-      for (int i = 0; i < 12; i++) b4[i] = make_float4(g[4 * i], g[4 * i + 1], g[4 * i + 2], g[4 * i + 3]);
+      for (int i = 0; i < 3; i++) {
+        const float4 v = __ldg(b4 + i);
+        sv[4 * i] = v.x; sv[4 * i + 1] = v.y; sv[4 * i + 2] = v.z; sv[4 * i + 3] = v.w;
+      }
     } else {
 #pragma unroll
-      for (int i = 0; i < 48; i++)
-        if (i < p.M * 3) base[i] = g[i];
+      for (int i = 0; i < 12; i++) sv[i] = 0.f;
     }
-  } else {
-    float* dc = dL_dsh + (size_t)idx * 3;
-    dc[0] = g[0]; dc[1] = g[1]; dc[2] = g[2];
-    float* rest = dL_dsh_rest + (size_t)idx * (p.M - 1) * 3;
+    return;
+  }
 #pragma unroll
-    for (int i = 3; i < 48; i++)
-      if (i < p.M * 3) rest[i - 3] = g[i];
+  for (int i = 0; i < 12; i++) {
+    const int f = 12 * c + i;   // flat float index inside the surfel's SH block
+    float v = 0.f;
+    if (f < ncoef * 3) {
+      if (p.sh_rest == nullptr) v = __ldg(p.shs + (size_t)idx * p.M * 3 + f);
+      else v = (f < 3) ? __ldg(p.shs + (size_t)idx * 3 + f) : __ldg(p.sh_rest + (size_t)idx * (p.M - 1) * 3 + (f - 3));
+    }
+    sv[i] = v;
+  }
+}
+__device__ __forceinline__ void store_sh_chunk(const BwdParams& p, float* dL_dsh, float* dL_dsh_rest, int idx, int c,
+                                               const float* g /*[12]*/) {
+  if (dL_dsh == nullptr) return;
+  if (dL_dsh_rest == nullptr && p.M == 16 && ((reinterpret_cast<uintptr_t>(dL_dsh) & 15) == 0)) {
+    float4* b4 = reinterpret_cast<float4*>(dL_dsh + (size_t)idx * 48) + 3 * c;
+#pragma unroll
+    for (int i = 0; i < 3; i++) b4[i] = make_float4(g[4 * i], g[4 * i + 1], g[4 * i + 2], g[4 * i + 3]);
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    const int f = 12 * c + i;
+    if (f >= p.M * 3) continue;
+    if (dL_dsh_rest == nullptr) dL_dsh[(size_t)idx * p.M * 3 + f] = g[i];
+    else if (f < 3) dL_dsh[(size_t)idx * 3 + f] = g[i];
+    else dL_dsh_rest[(size_t)idx * (p.M - 1) * 3 + (f - 3)] = g[i];
   }
 }
 
-__device__ __forceinline__ void load_sh_b(const BwdParams& p, int idx, int ncoef, float* sh) {
-  if (p.sh_rest == nullptr) {
-    const float* base = p.shs + (size_t)idx * p.M * 3;
-    if (p.M == 16 && ((reinterpret_cast<uintptr_t>(p.shs) & 15) == 0)) {
-      const float4* b4 = reinterpret_cast<const float4*>(base);
-      const int n4 = (ncoef * 3 + 3) / 4;
-#pragma unroll
-      for (int i = 0; i < 12; i++)
-        if (i < n4) {
-          float4 v = __ldg(b4 + i);
-          sh[4 * i] = v.x; sh[4 * i + 1] = v.y; sh[4 * i + 2] = v.z; sh[4 * i + 3] = v.w;
-        }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 48; i++)
-        if (i < ncoef * 3) sh[i] = __ldg(base + i);
-    }
-  } else {
-    const float* dc = p.shs + (size_t)idx * 3;
-    sh[0] = __ldg(dc); sh[1] = __ldg(dc + 1); sh[2] = __ldg(dc + 2);
-    const float* rest = p.sh_rest + (size_t)idx * (p.M - 1) * 3;
-#pragma unroll
-    for (int i = 3; i < 48; i++)
-      if (i < ncoef * 3) sh[i] = __ldg(rest + i - 3);
-  }
-}
-
-__global__ void __launch_bounds__(256) preprocess_bwd_kernel(
+__global__ void __launch_bounds__(256, 3) preprocess_bwd_kernel(
     BwdParams p, const SurfelRec* __restrict__ rec, const uint8_t* __restrict__ clamped,
     const int* __restrict__ radii, float* __restrict__ grad_rec, float* __restrict__ dL_dmeans2D,
     float* __restrict__ dL_dcolors, float* __restrict__ dL_dopacity, float* __restrict__ dL_dmeans3D,
@@ -384,9 +417,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
   float2 dscale = {0.f, 0.f};
   float4 drot = {0.f, 0.f, 0.f, 0.f};
   float2 dm2d = {0.f, 0.f};
-  float gsh[48];
-#pragma unroll
-  for (int i = 0; i < 48; i++) gsh[i] = 0.f;
+  bool sh_written = false;
 #pragma unroll
   for (int i = 0; i < GRAD_REC_FLOATS; i++) gr[i] = 0.f;
 
@@ -472,48 +503,54 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
       const v3 dir_orig = pw - campos;
       const v3 dir = dir_orig / sqrtf(dot3(dir_orig, dir_orig));
       const int deg = p.D;
-      float sh[48];
-      load_sh_b(p, idx, (deg + 1) * (deg + 1), sh);
-      auto S = [&](int k) { return v3{sh[3 * k], sh[3 * k + 1], sh[3 * k + 2]}; };
       const uint8_t cl = clamped[idx];
       v3 gc = {gr[G_COL], gr[G_COL + 1], gr[G_COL + 2]};
       gc.x *= (cl & 1) ? 0.f : 1.f;
       gc.y *= (cl & 2) ? 0.f : 1.f;
       gc.z *= (cl & 4) ? 0.f : 1.f;
-      auto put = [&](int k, float bsis) { gsh[3 * k] = bsis * gc.x; gsh[3 * k + 1] = bsis * gc.y; gsh[3 * k + 2] = bsis * gc.z; };
-      v3 dRGBdx = {0, 0, 0}, dRGBdy = {0, 0, 0}, dRGBdz = {0, 0, 0};
+      // Streamed in chunks of 4 coefficients (3 x float4 in, 3 x float4 out) so that no 48-float array stays live:
+      //   dL/dsh_k = b_k(dir) * gc,   dL/ddir += grad b_k(dir) * (sh_k . gc)
+      // with b_k the real SH basis of the forward pass and grad b_k its analytic derivative w.r.t. the unit direction.
       const float x = dir.x, y = dir.y, z = dir.z;
-      put(0, kSH_C0);
-      if (deg > 0) {
-        put(1, -kSH_C1 * y); put(2, kSH_C1 * z); put(3, -kSH_C1 * x);
-        dRGBdx = -kSH_C1 * S(3);
-        dRGBdy = -kSH_C1 * S(1);
-        dRGBdz = kSH_C1 * S(2);
-        if (deg > 1) {
-          const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-          put(4, kSH_C2[0] * xy); put(5, kSH_C2[1] * yz); put(6, kSH_C2[2] * (2.f * zz - xx - yy));
-          put(7, kSH_C2[3] * xz); put(8, kSH_C2[4] * (xx - yy));
-          dRGBdx = dRGBdx + kSH_C2[0] * y * S(4) + kSH_C2[2] * 2.f * -x * S(6) + kSH_C2[3] * z * S(7) + kSH_C2[4] * 2.f * x * S(8);
-          dRGBdy = dRGBdy + kSH_C2[0] * x * S(4) + kSH_C2[1] * z * S(5) + kSH_C2[2] * 2.f * -y * S(6) + kSH_C2[4] * 2.f * -y * S(8);
-          dRGBdz = dRGBdz + kSH_C2[1] * y * S(5) + kSH_C2[2] * 2.f * 2.f * z * S(6) + kSH_C2[3] * x * S(7);
-          if (deg > 2) {
-            put(9, kSH_C3[0] * y * (3.f * xx - yy)); put(10, kSH_C3[1] * xy * z);
-            put(11, kSH_C3[2] * y * (4.f * zz - xx - yy)); put(12, kSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy));
-            put(13, kSH_C3[4] * x * (4.f * zz - xx - yy)); put(14, kSH_C3[5] * z * (xx - yy));
-            put(15, kSH_C3[6] * x * (xx - 3.f * yy));
-            dRGBdx = dRGBdx + (kSH_C3[0] * S(9) * 3.f * 2.f * xy + kSH_C3[1] * S(10) * yz + kSH_C3[2] * S(11) * -2.f * xy +
-                               kSH_C3[3] * S(12) * -3.f * 2.f * xz + kSH_C3[4] * S(13) * (-3.f * xx + 4.f * zz - yy) +
-                               kSH_C3[5] * S(14) * 2.f * xz + kSH_C3[6] * S(15) * 3.f * (xx - yy));
-            dRGBdy = dRGBdy + (kSH_C3[0] * S(9) * 3.f * (xx - yy) + kSH_C3[1] * S(10) * xz +
-                               kSH_C3[2] * S(11) * (-3.f * yy + 4.f * zz - xx) + kSH_C3[3] * S(12) * -3.f * 2.f * yz +
-                               kSH_C3[4] * S(13) * -2.f * xy + kSH_C3[5] * S(14) * -2.f * yz + kSH_C3[6] * S(15) * -3.f * 2.f * xy);
-            dRGBdz = dRGBdz + (kSH_C3[1] * S(10) * xy + kSH_C3[2] * S(11) * 4.f * 2.f * yz +
-                               kSH_C3[3] * S(12) * 3.f * (2.f * zz - xx - yy) + kSH_C3[4] * S(13) * 4.f * 2.f * xz +
-                               kSH_C3[5] * S(14) * (xx - yy));
+      const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+      v3 dL_ddir = {0.f, 0.f, 0.f};
+      const int ncoef = (deg + 1) * (deg + 1);
+      sh_written = true;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        float sv[12], go[12];
+        load_sh_chunk(p, idx, c, ncoef, sv);
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          const int k = 4 * c + t;
+          float bk, bx, by, bz;
+          switch (k) {   // compile-time after unrolling
+            case 0: bk = kSH_C0; bx = 0.f; by = 0.f; bz = 0.f; break;
+            case 1: bk = -kSH_C1 * y; bx = 0.f; by = -kSH_C1; bz = 0.f; break;
+            case 2: bk = kSH_C1 * z; bx = 0.f; by = 0.f; bz = kSH_C1; break;
+            case 3: bk = -kSH_C1 * x; bx = -kSH_C1; by = 0.f; bz = 0.f; break;
+            case 4: bk = kSH_C2[0] * xy; bx = kSH_C2[0] * y; by = kSH_C2[0] * x; bz = 0.f; break;
+            case 5: bk = kSH_C2[1] * yz; bx = 0.f; by = kSH_C2[1] * z; bz = kSH_C2[1] * y; break;
+            case 6: bk = kSH_C2[2] * (2.f * zz - xx - yy); bx = kSH_C2[2] * -2.f * x; by = kSH_C2[2] * -2.f * y; bz = kSH_C2[2] * 4.f * z; break;
+            case 7: bk = kSH_C2[3] * xz; bx = kSH_C2[3] * z; by = 0.f; bz = kSH_C2[3] * x; break;
+            case 8: bk = kSH_C2[4] * (xx - yy); bx = kSH_C2[4] * 2.f * x; by = kSH_C2[4] * -2.f * y; bz = 0.f; break;
+            case 9: bk = kSH_C3[0] * y * (3.f * xx - yy); bx = kSH_C3[0] * 6.f * xy; by = kSH_C3[0] * 3.f * (xx - yy); bz = 0.f; break;
+            case 10: bk = kSH_C3[1] * xy * z; bx = kSH_C3[1] * yz; by = kSH_C3[1] * xz; bz = kSH_C3[1] * xy; break;
+            case 11: bk = kSH_C3[2] * y * (4.f * zz - xx - yy); bx = kSH_C3[2] * -2.f * xy; by = kSH_C3[2] * (-3.f * yy + 4.f * zz - xx); bz = kSH_C3[2] * 8.f * yz; break;
+            case 12: bk = kSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy); bx = kSH_C3[3] * -6.f * xz; by = kSH_C3[3] * -6.f * yz; bz = kSH_C3[3] * 3.f * (2.f * zz - xx - yy); break;
+            case 13: bk = kSH_C3[4] * x * (4.f * zz - xx - yy); bx = kSH_C3[4] * (-3.f * xx + 4.f * zz - yy); by = kSH_C3[4] * -2.f * xy; bz = kSH_C3[4] * 8.f * xz; break;
+            case 14: bk = kSH_C3[5] * z * (xx - yy); bx = kSH_C3[5] * 2.f * xz; by = kSH_C3[5] * -2.f * yz; bz = kSH_C3[5] * (xx - yy); break;
+            default: bk = kSH_C3[6] * x * (xx - 3.f * yy); bx = kSH_C3[6] * 3.f * (xx - yy); by = kSH_C3[6] * -6.f * xy; bz = 0.f; break;
+          }
+          const bool on = k < ncoef;
+          go[3 * t] = on ? bk * gc.x : 0.f; go[3 * t + 1] = on ? bk * gc.y : 0.f; go[3 * t + 2] = on ? bk * gc.z : 0.f;
+          if (on) {
+            const float sg = sv[3 * t] * gc.x + sv[3 * t + 1] * gc.y + sv[3 * t + 2] * gc.z;
+            dL_ddir.x += bx * sg; dL_ddir.y += by * sg; dL_ddir.z += bz * sg;
           }
         }
+        store_sh_chunk(p, dL_dsh, dL_dsh_rest, idx, c, go);
       }
-      const v3 dL_ddir = {dot3(dRGBdx, gc), dot3(dRGBdy, gc), dot3(dRGBdz, gc)};
       // derivative of v/|v|
       const v3 v = dir_orig, dv = dL_ddir;
       const float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
@@ -535,7 +572,13 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
   if (dL_dscales) reinterpret_cast<float2*>(dL_dscales)[idx] = dscale;
   if (dL_dscales_raw) reinterpret_cast<float2*>(dL_dscales_raw)[idx] = dscale_raw;
   if (dL_drot) reinterpret_cast<float4*>(dL_drot)[idx] = drot;
-  if (dL_dsh && p.M > 0) store_sh_grad(p, dL_dsh, dL_dsh_rest, idx, gsh);
+  if (dL_dsh && p.M > 0 && !sh_written) {   // culled surfel: the gradient row is zero
+    float zero12[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) zero12[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; c++) store_sh_chunk(p, dL_dsh, dL_dsh_rest, idx, c, zero12);
+  }
 }
 
 void launch_preprocess_bwd(const BwdParams& p, const SurfelRec* rec, const uint8_t* clamped, const int* radii,

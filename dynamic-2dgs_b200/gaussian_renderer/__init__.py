@@ -18,22 +18,15 @@ from d2gs_b200 import epilogue as _epilogue
 _RAY_CACHE = {}
 
 
-def standardize_quaternion(quaternions: torch.Tensor) -> torch.Tensor:
-    return torch.where(quaternions[..., 0:1] < 0, -quaternions, quaternions)
-
-
-def quaternion_raw_multiply(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    aw, ax, ay, az = torch.unbind(a, -1)
-    bw, bx, by, bz = torch.unbind(b, -1)
-    ow = aw * bw - ax * bx - ay * by - az * bz
-    ox = aw * bx + ax * bw + ay * bz - az * by
-    oy = aw * by - ax * bz + ay * bw + az * bx
-    oz = aw * bz + ax * by - ay * bx + az * bw
-    return torch.stack((ow, ox, oy, oz), -1)
-
-
 def quaternion_multiply(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    return standardize_quaternion(quaternion_raw_multiply(a, b))
+    """Hamilton product a*b of (w,x,y,z) quaternions, returned with a non-negative real part
+    (used only by the editing branch that passes ``d_rotation_bias``)."""
+    aw, av = a[..., :1], a[..., 1:]
+    bw, bv = b[..., :1], b[..., 1:]
+    w = aw * bw - (av * bv).sum(-1, keepdim=True)
+    v = aw * bv + bw * av + torch.cross(av, bv, dim=-1)
+    q = torch.cat([w, v], -1)
+    return torch.where(q[..., :1] < 0, -q, q)
 
 
 def _camera_rays(view):

@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_render_gpu.py tests/test_deform_gpu.py::test_render_dropin_matches_reference_pipeline -q -m gpu -x --tb=short 2>&1 | grep -vE "^E\s+\[|^E\s+[0-9\.\-e, ]+\]|DESIRED|ACTUAL" > gpurun_out/fail1.log 2>&1
-timeout 600 python -m pytest tests/test_render_gpu.py::test_fused_epilogue_equals_eager tests/test_deform_gpu.py::test_render_dropin_matches_reference_pipeline -q -m gpu --tb=short 2>&1 | grep -vE "^E\s+\[|^E\s+[0-9\.\-e, ]+\]" > gpurun_out/fail2.log 2>&1
-python bench.py --steps 40 --warmup 8 --no-cpu-baseline > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; tail -3 gpurun_out/bench_ours.err; grep -o '"ms_per_step": [0-9.]*' gpurun_out/bench_ours.json | head -2;  grep -o '"stages_ms": {[^}]*}' gpurun_out/bench_ours.json
+timeout 1500 python -m pytest tests -q -m gpu --tb=short 2>&1 | grep -vE "^E\s+\[|^E\s+[0-9\.\-e, ]+\]|^E\s+\+|array\(" | tail -15 | cut -c1-250
+python bench.py --steps 60 --warmup 8 > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; tail -3 gpurun_out/bench_ours.err; cat gpurun_out/bench_ours.json
+python bench.py --impl reference --steps 30 --warmup 5 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -3 gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json | cut -c1-400
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_r1d.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_b.log 2>&1; tail -1 gpurun_out/ncu_b.log | cut -c1-200
