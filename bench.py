@@ -353,15 +353,15 @@ def main():
 
     from d2gs_b200 import dist as ddist
     params = list(wl.pc.raster_parameters()) + list(wl.deform_parameters())
-    # flat gradient bucket: every .grad is a view into it, so the all-reduce needs no pack step
-    bucket = ddist.FlatGradBucket(params)
-    flat = bucket.flat
+    # flat gradient bucket: our backward kernels write parameter gradients straight into it (dist.claim), the reference arm's
+    # autograd accumulates into pre-attached views; either way the all-reduce needs no pack step
+    bucket = ddist.FlatGradBucket(params, direct=(args.impl != "reference"))
 
     def view_of(step):
         return wl.cams[ddist.view_for(step, rank, world, N_VIEWS)]
 
     def run_step(step, e2e=False):
-        flat.zero_()
+        bucket.zero()
         cam = view_of(step)
         if e2e:
             # per-step inputs come from pinned host memory: camera matrices, time, target image
@@ -379,8 +379,7 @@ def main():
         else:
             gt = wl.gt_dev
         loss = step_fn(wl, cam, gt)
-        if dist is not None:
-            bucket.all_reduce()
+        bucket.all_reduce()      # finalize + (N > 1) ONE NCCL all-reduce over the flat buffer
         if e2e:
             return float(loss.item())   # device -> host read of the step's result
         return loss

@@ -185,6 +185,11 @@ int d2gs_raster_forward(const D2gsRasterFwdArgs* a, void* stream_) {
   }
   if (!a->means3D || !a->opacities || !a->viewmatrix || !a->projmatrix || !a->campos || !a->background || !a->radii)
     return fail(D2GS_ERR_INVALID_ARG, "missing inputs");
+  {
+    const void* v16[] = {a->shs, a->sh_rest, a->rotations, a->d_rotations};
+    for (const void* q : v16)
+      if (q && ((uintptr_t)q & 15)) return fail(D2GS_ERR_INVALID_ARG, "SH / rotation tables must be 16-byte aligned");
+  }
   if ((a->shs == nullptr) == (a->colors_precomp == nullptr))
     return fail(D2GS_ERR_INVALID_ARG, "provide exactly one of SHs or precomputed colours");
   if (((a->scales == nullptr) || (a->rotations == nullptr)) == (a->transMat_precomp == nullptr))
@@ -272,6 +277,12 @@ int d2gs_raster_backward(const D2gsRasterBwdArgs* a, void* stream_) {
   if (!a->geom_buffer || !a->img_buffer || !a->binning_buffer || !a->grad_scratch || !a->radii ||
       !a->dL_dout_color || !a->dL_dout_others)
     return fail(D2GS_ERR_INVALID_ARG, "missing buffers");
+  {  // the per-surfel kernels use 16-byte vector loads/stores on these tables
+    const void* v16[] = {a->shs, a->sh_rest, a->rotations, a->d_rotations, a->dL_dsh, a->dL_dsh_rest, a->dL_drotations,
+                         a->grad_scratch};
+    for (const void* q : v16)
+      if (q && ((uintptr_t)q & 15)) return fail(D2GS_ERR_INVALID_ARG, "SH / rotation tables and their gradients must be 16-byte aligned");
+  }
   const GeomLayout GL = geom_layout(P);
   const ImgLayout IL = img_layout(W, H);
   const BinLayout BL = bin_layout(a->num_rendered);
@@ -395,6 +406,7 @@ int d2gs_deform_forward(const D2gsDeformFwdArgs* a, void* stream) {
   h.trans = a->node_trans; h.rot = a->node_rot; h.scale = a->node_scale; h.local_rot = a->node_local_rot;
   h.mask = a->motion_mask; h.nn_idx = a->nn_idx; h.nn_dist = a->nn_dist; h.nn_weight = a->nn_weight;
   h.d_xyz = a->d_xyz; h.d_rot = a->d_rotation; h.d_scale = a->d_scaling;
+  h.attr_stride = a->node_attr_stride;
   const char* err = nullptr;
   { StageTimer t(ST_DEF_F, (cudaStream_t)stream);
     if (deform_forward_launch(h, (cudaStream_t)stream, &err) != 0) return fail(D2GS_ERR_INVALID_ARG, err); }
@@ -420,6 +432,7 @@ int d2gs_deform_backward(const D2gsDeformBwdArgs* a, void* stream) {
   h.d_trans = a->dL_dnode_trans; h.d_rot = a->dL_dnode_rot; h.d_scale = a->dL_dnode_scale;
   h.d_local_rot = a->dL_dnode_local_rot; h.d_nodes = a->dL_dnodes; h.d_radius_log = a->dL_dnode_radius_log;
   h.d_weight_logit = a->dL_dnode_weight_logit; h.d_feature = a->dL_dfeature; h.d_mask = a->dL_dmotion_mask;
+  h.attr_stride = a->node_attr_stride;
   const char* err = nullptr;
   { StageTimer t(ST_DEF_B, (cudaStream_t)stream);
     if (deform_backward_launch(h, (cudaStream_t)stream, &err) != 0) return fail(D2GS_ERR_INVALID_ARG, err); }

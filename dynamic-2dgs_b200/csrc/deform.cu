@@ -51,6 +51,7 @@ struct DeformFwdP {
   const float* mask;
   int64_t* nn_idx; float* nn_dist; float* nn_weight;
   float* d_xyz; float* d_rot; float* d_scale;
+  int st_t, st_r, st_s, st_l;   // row strides of the node attribute tables (3,4,2,4 or the packed MLP output width)
 };
 
 // K nearest control nodes by an unordered "replace the current worst" set: every step is a predicated select, so a
@@ -159,10 +160,10 @@ __global__ void __launch_bounds__(256) deform_fwd_kernel(DeformFwdP a) {
   for (int k = 0; k < K; k++) {
     const int m = bi[k];
     const float wk = w[k] / wsum;
-    const float tr0 = __ldg(a.trans + 3 * m), tr1 = __ldg(a.trans + 3 * m + 1), tr2 = __ldg(a.trans + 3 * m + 2);
+    const float tr0 = __ldg(a.trans + a.st_t * m), tr1 = __ldg(a.trans + a.st_t * m + 1), tr2 = __ldg(a.trans + a.st_t * m + 2);
     if (a.local_rot) {
-      float lq[4] = {__ldg(a.local_rot + 4 * m) + 1.0f, __ldg(a.local_rot + 4 * m + 1), __ldg(a.local_rot + 4 * m + 2),
-                     __ldg(a.local_rot + 4 * m + 3)};
+      float lq[4] = {__ldg(a.local_rot + a.st_l * m) + 1.0f, __ldg(a.local_rot + a.st_l * m + 1), __ldg(a.local_rot + a.st_l * m + 2),
+                     __ldg(a.local_rot + a.st_l * m + 3)};
       float R[9];
       quat_to_matrix_raw(lq, R);
       const int nb = (m >> 1) * 2 * DP + (m & 1);
@@ -175,9 +176,9 @@ __global__ void __launch_bounds__(256) deform_fwd_kernel(DeformFwdP a) {
     } else {
       t0 += tr0 * wk; t1 += tr1 * wk; t2 += tr2 * wk;
     }
-    r0 += __ldg(a.rot + 4 * m) * wk; r1 += __ldg(a.rot + 4 * m + 1) * wk;
-    r2 += __ldg(a.rot + 4 * m + 2) * wk; r3 += __ldg(a.rot + 4 * m + 3) * wk;
-    s0 += __ldg(a.scale + 2 * m) * wk; s1 += __ldg(a.scale + 2 * m + 1) * wk;
+    r0 += __ldg(a.rot + a.st_r * m) * wk; r1 += __ldg(a.rot + a.st_r * m + 1) * wk;
+    r2 += __ldg(a.rot + a.st_r * m + 2) * wk; r3 += __ldg(a.rot + a.st_r * m + 3) * wk;
+    s0 += __ldg(a.scale + a.st_s * m) * wk; s1 += __ldg(a.scale + a.st_s * m + 1) * wk;
     if (a.nn_idx) a.nn_idx[(size_t)i * K + k] = m;
     if (a.nn_dist) a.nn_dist[(size_t)i * K + k] = bd[k];
     if (a.nn_weight) a.nn_weight[(size_t)i * K + k] = wk;
@@ -202,6 +203,7 @@ struct DeformBwdP {
   float* d_weight_logit;
   float* d_feature; float* d_mask;
   int use_smem;   // 1: per-CTA shared accumulators for the node gradients
+  int st_t, st_r, st_s, st_l;
 };
 
 // per-node gradient row inside the accumulator: [0..2] trans [3..6] rot [7..8] scale [9..12] local_rot
@@ -218,10 +220,10 @@ __global__ void __launch_bounds__(256) deform_bwd_kernel(DeformBwdP a) {
   }
   auto add = [&](int m, int c, float v) {
     if (a.use_smem) { atomicAdd(&s_acc[m * NG + c], v); return; }
-    if (c < 3) atomicAdd(a.d_trans + 3 * m + c, v);
-    else if (c < 7) atomicAdd(a.d_rot + 4 * m + (c - 3), v);
-    else if (c < 9) atomicAdd(a.d_scale + 2 * m + (c - 7), v);
-    else if (c < 13) { if (a.d_local_rot) atomicAdd(a.d_local_rot + 4 * m + (c - 9), v); }
+    if (c < 3) atomicAdd(a.d_trans + a.st_t * m + c, v);
+    else if (c < 7) atomicAdd(a.d_rot + a.st_r * m + (c - 3), v);
+    else if (c < 9) atomicAdd(a.d_scale + a.st_s * m + (c - 7), v);
+    else if (c < 13) { if (a.d_local_rot) atomicAdd(a.d_local_rot + a.st_l * m + (c - 9), v); }
     else if (c == 13) atomicAdd(a.d_radius_log + m, v);
     else if (c == 14) { if (a.d_weight_logit) atomicAdd(a.d_weight_logit + m, v); }
     else atomicAdd(a.d_nodes + (size_t)m * nstride + 3 + (c - NG_FIXED), v);
@@ -251,11 +253,11 @@ __global__ void __launch_bounds__(256) deform_bwd_kernel(DeformBwdP a) {
         const int m = (int)a.nn_idx[(size_t)i * K + k];
         const float w = a.nn_weight[(size_t)i * K + k];
         idx[k] = m; wk[k] = w;
-        const float tr0 = __ldg(a.trans + 3 * m), tr1 = __ldg(a.trans + 3 * m + 1), tr2 = __ldg(a.trans + 3 * m + 2);
+        const float tr0 = __ldg(a.trans + a.st_t * m), tr1 = __ldg(a.trans + a.st_t * m + 1), tr2 = __ldg(a.trans + a.st_t * m + 2);
         float A0 = tr0, A1 = tr1, A2 = tr2;
         if (a.local_rot) {
-          float lq[4] = {__ldg(a.local_rot + 4 * m) + 1.0f, __ldg(a.local_rot + 4 * m + 1), __ldg(a.local_rot + 4 * m + 2),
-                         __ldg(a.local_rot + 4 * m + 3)};
+          float lq[4] = {__ldg(a.local_rot + a.st_l * m) + 1.0f, __ldg(a.local_rot + a.st_l * m + 1), __ldg(a.local_rot + a.st_l * m + 2),
+                         __ldg(a.local_rot + a.st_l * m + 3)};
           float R[9];
           quat_to_matrix_raw(lq, R);
           const float n0 = __ldg(a.nodes + (size_t)m * nstride), n1 = __ldg(a.nodes + (size_t)m * nstride + 1),
@@ -271,9 +273,9 @@ __global__ void __launch_bounds__(256) deform_bwd_kernel(DeformBwdP a) {
           quat_to_matrix_raw_vjp(lq, dR, dq);
           add(m, 9, dq[0]); add(m, 10, dq[1]); add(m, 11, dq[2]); add(m, 12, dq[3]);
         }
-        const float rr0 = __ldg(a.rot + 4 * m), rr1 = __ldg(a.rot + 4 * m + 1), rr2 = __ldg(a.rot + 4 * m + 2),
-                    rr3 = __ldg(a.rot + 4 * m + 3);
-        const float ss0 = __ldg(a.scale + 2 * m), ss1 = __ldg(a.scale + 2 * m + 1);
+        const float rr0 = __ldg(a.rot + a.st_r * m), rr1 = __ldg(a.rot + a.st_r * m + 1), rr2 = __ldg(a.rot + a.st_r * m + 2),
+                    rr3 = __ldg(a.rot + a.st_r * m + 3);
+        const float ss0 = __ldg(a.scale + a.st_s * m), ss1 = __ldg(a.scale + a.st_s * m + 1);
         add(m, 0, w * Gx0); add(m, 1, w * Gx1); add(m, 2, w * Gx2);
         add(m, 3, w * Gr0); add(m, 4, w * Gr1); add(m, 5, w * Gr2); add(m, 6, w * Gr3);
         add(m, 7, w * Gs0); add(m, 8, w * Gs1);
@@ -340,10 +342,10 @@ __global__ void __launch_bounds__(256) deform_bwd_kernel(DeformBwdP a) {
       const float v = s_acc[t];
       if (v == 0.f) continue;
       const int m = t / NG, c = t - m * NG;
-      if (c < 3) atomicAdd(a.d_trans + 3 * m + c, v);
-      else if (c < 7) atomicAdd(a.d_rot + 4 * m + (c - 3), v);
-      else if (c < 9) atomicAdd(a.d_scale + 2 * m + (c - 7), v);
-      else if (c < 13) { if (a.d_local_rot) atomicAdd(a.d_local_rot + 4 * m + (c - 9), v); }
+      if (c < 3) atomicAdd(a.d_trans + a.st_t * m + c, v);
+      else if (c < 7) atomicAdd(a.d_rot + a.st_r * m + (c - 3), v);
+      else if (c < 9) atomicAdd(a.d_scale + a.st_s * m + (c - 7), v);
+      else if (c < 13) { if (a.d_local_rot) atomicAdd(a.d_local_rot + a.st_l * m + (c - 9), v); }
       else if (c == 13) atomicAdd(a.d_radius_log + m, v);
       else if (c == 14) { if (a.d_weight_logit) atomicAdd(a.d_weight_logit + m, v); }
       else atomicAdd(a.d_nodes + (size_t)m * nstride + 3 + (c - NG_FIXED), v);
@@ -364,6 +366,8 @@ int deform_forward_launch(const DeformFwdHost& h, cudaStream_t s, const char** e
   a.trans = h.trans; a.rot = h.rot; a.scale = h.scale; a.local_rot = h.local_rot; a.mask = h.mask;
   a.nn_idx = h.nn_idx; a.nn_dist = h.nn_dist; a.nn_weight = h.nn_weight;
   a.d_xyz = h.d_xyz; a.d_rot = h.d_rot; a.d_scale = h.d_scale;
+  a.st_t = h.attr_stride > 0 ? h.attr_stride : 3; a.st_r = h.attr_stride > 0 ? h.attr_stride : 4;
+  a.st_s = h.attr_stride > 0 ? h.attr_stride : 2; a.st_l = h.attr_stride > 0 ? h.attr_stride : 4;
   const int nq = (a.D + 3) / 4;
   const size_t smem = sizeof(float) * (size_t)((a.M + 1) & ~1) * 4 * nq;
   if (smem > 200 * 1024) { *err = "node table exceeds shared memory (M*(3+hyper) floats > 200 KB)"; return -1; }
@@ -407,6 +411,8 @@ int deform_backward_launch(const DeformBwdHost& h, cudaStream_t s, const char** 
   a.d_trans = h.d_trans; a.d_rot = h.d_rot; a.d_scale = h.d_scale; a.d_local_rot = h.d_local_rot;
   a.d_nodes = h.d_nodes; a.d_radius_log = h.d_radius_log; a.d_weight_logit = h.d_weight_logit;
   a.d_feature = h.d_feature; a.d_mask = h.d_mask;
+  a.st_t = h.attr_stride > 0 ? h.attr_stride : 3; a.st_r = h.attr_stride > 0 ? h.attr_stride : 4;
+  a.st_s = h.attr_stride > 0 ? h.attr_stride : 2; a.st_l = h.attr_stride > 0 ? h.attr_stride : 4;
   if (h.K < 1 || h.K > MAX_K) { *err = "K must be in [1, 8]"; return -1; }
   if (h.hyper < 0 || h.hyper > MAX_D - 3) { *err = "hyper_dim must be <= 16"; return -1; }
   if (h.P == 0) return 0;

@@ -12,6 +12,7 @@ struct DeformFwdHost {
   const float* trans; const float* rot; const float* scale; const float* local_rot; const float* mask;
   int64_t* nn_idx; float* nn_dist; float* nn_weight;
   float* d_xyz; float* d_rot; float* d_scale;
+  int attr_stride;      // > 0: trans/rot/scale/local_rot are columns of one (M, attr_stride) matrix
 };
 
 struct DeformBwdHost {
@@ -23,6 +24,7 @@ struct DeformBwdHost {
   const float* g_xyz; const float* g_rot; const float* g_scale;
   float* d_trans; float* d_rot; float* d_scale; float* d_local_rot; float* d_nodes; float* d_radius_log;
   float* d_weight_logit; float* d_feature; float* d_mask;
+  int attr_stride;
 };
 
 int deform_forward_launch(const DeformFwdHost& h, cudaStream_t s, const char** err);

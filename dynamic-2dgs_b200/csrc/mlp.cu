@@ -316,9 +316,10 @@ __global__ void __launch_bounds__(256) mlp_bwd_act_kernel(MlpBwd a) {
 // backward, weight gradients: dW[n][k] = sum_r G[r][n] * in[r][k],  db[n] = sum_r G[r][n]
 // one CTA per (job, 64x64 tile); 256 threads, 4x4 outputs each; rows streamed 16 at a time through shared memory
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int WROWS = 64;   // rows reduced per shared-memory chunk (32 independent loads per thread in flight)
 __global__ void __launch_bounds__(256) mlp_bwd_w_kernel(MlpWJobs J, int rows) {
-  __shared__ float sG[16][64 + 4];
-  __shared__ float sA[16][64 + 4];
+  __shared__ float sG[WROWS][64 + 4];
+  __shared__ float sA[WROWS][64 + 4];
   int b = blockIdx.x, j = 0;
   while (j < J.count && b >= J.job[j].tiles) { b -= J.job[j].tiles; j++; }
   if (j >= J.count) return;
@@ -333,43 +334,47 @@ __global__ void __launch_bounds__(256) mlp_bwd_w_kernel(MlpWJobs J, int rows) {
 #pragma unroll
     for (int q = 0; q < 4; q++) acc[i][q] = 0.f;
   float bacc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int r0 = 0; r0 < rows; r0 += 16) {
-    for (int e = tid; e < 16 * 64; e += 256) {
-      const int r = e >> 6, c = e & 63;
-      const int rr = r0 + r;
-      const int n = n0 + c, k = k0 + c;
-      sG[r][c] = (rr < rows && n < jb.N) ? jb.G[(size_t)rr * jb.ldG + n] : 0.f;
-      float v = 0.f;
-      if (rr < rows && k < Ktot) v = (k < jb.Ka) ? jb.A[(size_t)rr * jb.ldA + k] : jb.B[(size_t)rr * jb.ldB + (k - jb.Ka)];
-      sA[r][c] = v;
+  const int c = tid & 63, rq = tid >> 6;          // this thread stages column c of rows rq, rq+4, ...
+  const int n = n0 + c, k = k0 + c;
+  const bool n_ok = n < jb.N, k_ok = k < Ktot;
+  const float* gcol = jb.G + n;
+  const float* acol = (k < jb.Ka) ? jb.A + k : jb.B + (k - jb.Ka);
+  const int lda = (k < jb.Ka) ? jb.ldA : jb.ldB;
+  for (int r0 = 0; r0 < rows; r0 += WROWS) {
+    float gv[WROWS / 4], av[WROWS / 4];
+#pragma unroll
+    for (int u = 0; u < WROWS / 4; u++) {
+      const int rr = r0 + rq + 4 * u;
+      gv[u] = (n_ok && rr < rows) ? __ldg(gcol + (size_t)rr * jb.ldG) : 0.f;
+      av[u] = (k_ok && rr < rows) ? __ldg(acol + (size_t)rr * lda) : 0.f;
     }
+#pragma unroll
+    for (int u = 0; u < WROWS / 4; u++) { sG[rq + 4 * u][c] = gv[u]; sA[rq + 4 * u][c] = av[u]; }
     __syncthreads();
-#pragma unroll
-    for (int r = 0; r < 16; r++) {
-      float g[4], x[4];
-#pragma unroll
-      for (int i = 0; i < 4; i++) g[i] = sG[r][tn * 4 + i];
-#pragma unroll
-      for (int q = 0; q < 4; q++) x[q] = sA[r][tkx * 4 + q];
+#pragma unroll 8
+    for (int r = 0; r < WROWS; r++) {
+      const float4 g4 = *reinterpret_cast<const float4*>(&sG[r][tn * 4]);
+      const float4 x4 = *reinterpret_cast<const float4*>(&sA[r][tkx * 4]);
+      const float g[4] = {g4.x, g4.y, g4.z, g4.w}, x[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
       for (int i = 0; i < 4; i++) {
 #pragma unroll
         for (int q = 0; q < 4; q++) acc[i][q] = fmaf(g[i], x[q], acc[i][q]);
-        if (k0 == 0 && tkx == 0) bacc[i] += g[i];
       }
+      if (k0 == 0 && tkx == 0) { bacc[0] += g[0]; bacc[1] += g[1]; bacc[2] += g[2]; bacc[3] += g[3]; }
     }
     __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 4; i++) {
-    const int n = n0 + tn * 4 + i;
-    if (n >= jb.N) continue;
+    const int nn = n0 + tn * 4 + i;
+    if (nn >= jb.N) continue;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-      const int k = k0 + tkx * 4 + q;
-      if (k < Ktot) jb.dW[(size_t)n * Ktot + k] = acc[i][q];
+      const int kk = k0 + tkx * 4 + q;
+      if (kk < Ktot) jb.dW[(size_t)nn * Ktot + kk] = acc[i][q];
     }
-    if (k0 == 0 && tkx == 0 && jb.db) jb.db[n] = bacc[i];
+    if (k0 == 0 && tkx == 0 && jb.db) jb.db[nn] = bacc[i];
   }
 }
 

@@ -67,7 +67,7 @@ class DeformFwdArgs(C.Structure):
                 ("node_trans", C.c_void_p), ("node_rot", C.c_void_p), ("node_scale", C.c_void_p),
                 ("node_local_rot", C.c_void_p), ("motion_mask", C.c_void_p),
                 ("nn_idx", C.c_void_p), ("nn_dist", C.c_void_p), ("nn_weight", C.c_void_p),
-                ("d_xyz", C.c_void_p), ("d_rotation", C.c_void_p), ("d_scaling", C.c_void_p)]
+                ("d_xyz", C.c_void_p), ("d_rotation", C.c_void_p), ("d_scaling", C.c_void_p), ("node_attr_stride", C.c_int)]
 
 
 class DeformBwdArgs(C.Structure):
@@ -80,7 +80,8 @@ class DeformBwdArgs(C.Structure):
                 ("dL_d_xyz", C.c_void_p), ("dL_d_rotation", C.c_void_p), ("dL_d_scaling", C.c_void_p),
                 ("dL_dnode_trans", C.c_void_p), ("dL_dnode_rot", C.c_void_p), ("dL_dnode_scale", C.c_void_p),
                 ("dL_dnode_local_rot", C.c_void_p), ("dL_dnodes", C.c_void_p), ("dL_dnode_radius_log", C.c_void_p),
-                ("dL_dnode_weight_logit", C.c_void_p), ("dL_dfeature", C.c_void_p), ("dL_dmotion_mask", C.c_void_p)]
+                ("dL_dnode_weight_logit", C.c_void_p), ("dL_dfeature", C.c_void_p), ("dL_dmotion_mask", C.c_void_p),
+                ("node_attr_stride", C.c_int)]
 
 
 class EpilogueArgs(C.Structure):

@@ -37,86 +37,163 @@ def _stream(dev):
     return torch.cuda.current_stream(dev).cuda_stream
 
 
+def _f32(t):
+    return None if t is None else t.detach().float().contiguous()
+
+
+def _blend_forward(ctx, xyz, feature, nodes, node_radius_log, node_weight_logit, attr_ptrs, attr_stride, motion_mask, K, hyper_dim):
+    """Shared forward of the two autograd Functions below.  attr_ptrs = device pointers of (trans, rot, scale, local_rot)."""
+    L = _lib.lib()
+    dev = xyz.device
+    if not xyz.is_cuda:
+        raise RuntimeError("xyz must be a CUDA tensor (the deformation blend has no CPU path)")
+    xyz_, feat_, nodes_ = _f32(xyz), _f32(feature), _f32(nodes)
+    rad_, wl_ = _f32(node_radius_log), _f32(node_weight_logit)
+    mask_ = None
+    if torch.is_tensor(motion_mask):
+        mask_ = _f32(motion_mask).reshape(-1)
+        if mask_.numel() == 1:
+            mask_ = mask_.expand(xyz_.shape[0]).contiguous()
+    P, M = int(xyz_.shape[0]), int(nodes_.shape[0])
+    use_hyper = hyper_dim > 0 and feat_ is not None
+    a = _lib.DeformFwdArgs()
+    a.P, a.M, a.K, a.hyper_dim = P, M, int(K), int(nodes_.shape[1] - 3)
+    a.xyz = _p(xyz_)
+    a.feature = _p(feat_) if use_hyper else None
+    a.feature_stride = int(feat_.shape[1]) if use_hyper else 0
+    a.nodes, a.node_radius_log, a.node_weight_logit = _p(nodes_), _p(rad_), _p(wl_)
+    a.node_trans, a.node_rot, a.node_scale, a.node_local_rot = attr_ptrs
+    a.node_attr_stride = attr_stride
+    a.motion_mask = _p(mask_)
+    nn_idx = torch.empty((P, K), dtype=torch.int64, device=dev)
+    nn_dist = torch.empty((P, K), dtype=torch.float32, device=dev)
+    nn_weight = torch.empty((P, K), dtype=torch.float32, device=dev)
+    d_xyz = torch.empty((P, 3), dtype=torch.float32, device=dev)
+    d_rot = torch.empty((P, 4), dtype=torch.float32, device=dev)
+    d_scale = torch.empty((P, 2), dtype=torch.float32, device=dev)
+    a.nn_idx, a.nn_dist, a.nn_weight = _p(nn_idx), _p(nn_dist), _p(nn_weight)
+    a.d_xyz, a.d_rotation, a.d_scaling = _p(d_xyz), _p(d_rot), _p(d_scale)
+    with torch.cuda.device(dev):
+        _lib.check(L.d2gs_deform_forward(C.byref(a), _stream(dev)), "d2gs_deform_forward")
+    ctx.K, ctx.use_hyper = int(K), use_hyper
+    ctx.mask_shape = motion_mask.shape if torch.is_tensor(motion_mask) else None
+    ctx.mark_non_differentiable(nn_idx)
+    return (xyz_, feat_, nodes_, rad_, wl_, mask_, nn_idx, nn_dist, nn_weight), (d_xyz, d_rot, d_scale, nn_weight, nn_dist, nn_idx)
+
+
+def _blend_backward(ctx, common, attr_ptrs, d_attr_ptrs, attr_stride, g_xyz, g_rot, g_scale):
+    """Shared backward.  Node-level outputs are accumulated with atomics: d_attr_ptrs must point at zeroed memory.
+    Parameter gradients go straight into the gradient bucket when one has claimed the parameter (dist.claim)."""
+    from . import dist as _dist
+    L = _lib.lib()
+    xyz_, feat_, nodes_, rad_, wl_, mask_, nn_idx, nn_dist, nn_weight = common
+    dev = xyz_.device
+    P, M, K = int(xyz_.shape[0]), int(nodes_.shape[0]), ctx.K
+    zeros = lambda shape: torch.zeros(shape, dtype=torch.float32, device=dev)
+    g_xyz = zeros((P, 3)) if g_xyz is None else g_xyz.float().contiguous()
+    g_rot = zeros((P, 4)) if g_rot is None else g_rot.float().contiguous()
+    g_scale = zeros((P, 2)) if g_scale is None else g_scale.float().contiguous()
+    n_nodes, n_wl = nodes_.numel(), (wl_.numel() if wl_ is not None else 0)
+    d_nodes, d_rad = _dist.claim(nodes_, zeroed=True), _dist.claim(rad_, zeroed=True)
+    d_wl = _dist.claim(wl_, zeroed=True) if wl_ is not None else None
+    if d_nodes is None or d_rad is None or (wl_ is not None and d_wl is None):
+        flat = zeros((n_nodes + M + n_wl,))          # one fill for the three accumulated parameter gradients
+        d_nodes = flat[:n_nodes].view_as(nodes_) if d_nodes is None else d_nodes
+        d_rad = flat[n_nodes:n_nodes + M].view_as(rad_) if d_rad is None else d_rad
+        if wl_ is not None and d_wl is None:
+            d_wl = flat[n_nodes + M:].view_as(wl_)
+    want_feat = feat_ is not None and ctx.use_hyper
+    d_feat = None
+    if want_feat:
+        d_feat = _dist.claim(feat_, zeroed=False)
+        if d_feat is None:
+            d_feat = torch.empty_like(feat_)
+    d_mask = torch.empty((P,), dtype=torch.float32, device=dev) if mask_ is not None else None
+    a = _lib.DeformBwdArgs()
+    a.P, a.M, a.K, a.hyper_dim = P, M, K, int(nodes_.shape[1] - 3)
+    a.xyz = _p(xyz_)
+    a.feature = _p(feat_) if ctx.use_hyper else None
+    a.feature_stride = int(feat_.shape[1]) if ctx.use_hyper else 0
+    a.nodes, a.node_radius_log, a.node_weight_logit = _p(nodes_), _p(rad_), _p(wl_)
+    a.node_trans, a.node_rot, a.node_scale, a.node_local_rot = attr_ptrs
+    a.node_attr_stride = attr_stride
+    a.motion_mask = _p(mask_)
+    a.nn_idx, a.nn_dist, a.nn_weight = _p(nn_idx), _p(nn_dist), _p(nn_weight)
+    a.dL_d_xyz, a.dL_d_rotation, a.dL_d_scaling = _p(g_xyz), _p(g_rot), _p(g_scale)
+    a.dL_dnode_trans, a.dL_dnode_rot, a.dL_dnode_scale, a.dL_dnode_local_rot = d_attr_ptrs
+    a.dL_dnodes, a.dL_dnode_radius_log, a.dL_dnode_weight_logit = _p(d_nodes), _p(d_rad), _p(d_wl)
+    a.dL_dfeature, a.dL_dmotion_mask = _p(d_feat), _p(d_mask)
+    with torch.cuda.device(dev):
+        _lib.check(L.d2gs_deform_backward(C.byref(a), _stream(dev)), "d2gs_deform_backward")
+    if d_mask is not None and ctx.mask_shape is not None:
+        d_mask = d_mask.sum().reshape(ctx.mask_shape) if math.prod(ctx.mask_shape) == 1 else d_mask.reshape(ctx.mask_shape)
+    return d_feat, d_nodes, d_rad, d_wl, d_mask
+
+
 class _NodeBlend(torch.autograd.Function):
     """(xyz, feature, nodes, log-radius, weight-logit, node outputs, mask) -> (d_xyz, d_rotation, d_scaling)."""
 
     @staticmethod
     def forward(ctx, xyz, feature, nodes, node_radius_log, node_weight_logit, node_trans, node_rot, node_scale,
                 node_local_rot, motion_mask, K, hyper_dim):
-        L = _lib.lib()
-        dev = xyz.device
-        if not xyz.is_cuda:
-            raise RuntimeError("xyz must be a CUDA tensor (the deformation blend has no CPU path)")
-        f32 = lambda t: None if t is None else t.detach().float().contiguous()
-        xyz_, feat_, nodes_ = f32(xyz), f32(feature), f32(nodes)
-        rad_, wl_ = f32(node_radius_log), f32(node_weight_logit)
-        tr_, rt_, sc_, lr_ = f32(node_trans), f32(node_rot), f32(node_scale), f32(node_local_rot)
-        mask_ = None
-        if torch.is_tensor(motion_mask):
-            mask_ = f32(motion_mask).reshape(-1)
-            if mask_.numel() == 1:
-                mask_ = mask_.expand(xyz_.shape[0]).contiguous()
-        P, M = int(xyz_.shape[0]), int(nodes_.shape[0])
-        use_hyper = hyper_dim > 0 and feat_ is not None
-        a = _lib.DeformFwdArgs()
-        a.P, a.M, a.K, a.hyper_dim = P, M, int(K), int(nodes_.shape[1] - 3)
-        a.xyz = _p(xyz_)
-        a.feature = _p(feat_) if use_hyper else None
-        a.feature_stride = int(feat_.shape[1]) if use_hyper else 0
-        a.nodes, a.node_radius_log, a.node_weight_logit = _p(nodes_), _p(rad_), _p(wl_)
-        a.node_trans, a.node_rot, a.node_scale, a.node_local_rot = _p(tr_), _p(rt_), _p(sc_), _p(lr_)
-        a.motion_mask = _p(mask_)
-        nn_idx = torch.empty((P, K), dtype=torch.int64, device=dev)
-        nn_dist = torch.empty((P, K), dtype=torch.float32, device=dev)
-        nn_weight = torch.empty((P, K), dtype=torch.float32, device=dev)
-        d_xyz = torch.empty((P, 3), dtype=torch.float32, device=dev)
-        d_rot = torch.empty((P, 4), dtype=torch.float32, device=dev)
-        d_scale = torch.empty((P, 2), dtype=torch.float32, device=dev)
-        a.nn_idx, a.nn_dist, a.nn_weight = _p(nn_idx), _p(nn_dist), _p(nn_weight)
-        a.d_xyz, a.d_rotation, a.d_scaling = _p(d_xyz), _p(d_rot), _p(d_scale)
-        with torch.cuda.device(dev):
-            _lib.check(L.d2gs_deform_forward(C.byref(a), _stream(dev)), "d2gs_deform_forward")
-        ctx.K, ctx.use_hyper = int(K), use_hyper
-        ctx.mask_shape = motion_mask.shape if torch.is_tensor(motion_mask) else None
-        ctx.save_for_backward(xyz_, feat_, nodes_, rad_, wl_, tr_, rt_, sc_, lr_, mask_, nn_idx, nn_dist, nn_weight)
-        ctx.mark_non_differentiable(nn_idx)
-        return d_xyz, d_rot, d_scale, nn_weight, nn_dist, nn_idx
+        tr_, rt_, sc_, lr_ = _f32(node_trans), _f32(node_rot), _f32(node_scale), _f32(node_local_rot)
+        common, outs = _blend_forward(ctx, xyz, feature, nodes, node_radius_log, node_weight_logit,
+                                      (_p(tr_), _p(rt_), _p(sc_), _p(lr_)), 0, motion_mask, K, hyper_dim)
+        ctx.has = [t is not None for t in common]
+        ctx.save_for_backward(tr_, rt_, sc_, lr_, *[t for t in common if t is not None])
+        return outs
 
     @staticmethod
     def backward(ctx, g_xyz, g_rot, g_scale, g_w, g_d, g_i):
-        L = _lib.lib()
-        xyz_, feat_, nodes_, rad_, wl_, tr_, rt_, sc_, lr_, mask_, nn_idx, nn_dist, nn_weight = ctx.saved_tensors
-        dev = xyz_.device
-        P, M, K = int(xyz_.shape[0]), int(nodes_.shape[0]), ctx.K
-        z = lambda t: torch.zeros_like(t)
-        g_xyz = z(tr_.new_empty((P, 3))) if g_xyz is None else g_xyz.float().contiguous()
-        g_rot = z(tr_.new_empty((P, 4))) if g_rot is None else g_rot.float().contiguous()
-        g_scale = z(tr_.new_empty((P, 2))) if g_scale is None else g_scale.float().contiguous()
-        d_trans, d_rot, d_scale = z(tr_), z(rt_), z(sc_)
-        d_lr = z(lr_) if lr_ is not None else None
-        d_nodes, d_rad = z(nodes_), z(rad_)
-        d_wl = z(wl_) if wl_ is not None else None
-        d_feat = torch.empty_like(feat_) if (feat_ is not None and ctx.use_hyper) else None
-        d_mask = torch.empty((P,), dtype=torch.float32, device=dev) if mask_ is not None else None
-        a = _lib.DeformBwdArgs()
-        a.P, a.M, a.K, a.hyper_dim = P, M, K, int(nodes_.shape[1] - 3)
-        a.xyz = _p(xyz_)
-        a.feature = _p(feat_) if ctx.use_hyper else None
-        a.feature_stride = int(feat_.shape[1]) if ctx.use_hyper else 0
-        a.nodes, a.node_radius_log, a.node_weight_logit = _p(nodes_), _p(rad_), _p(wl_)
-        a.node_trans, a.node_rot, a.node_scale, a.node_local_rot = _p(tr_), _p(rt_), _p(sc_), _p(lr_)
-        a.motion_mask = _p(mask_)
-        a.nn_idx, a.nn_dist, a.nn_weight = _p(nn_idx), _p(nn_dist), _p(nn_weight)
-        a.dL_d_xyz, a.dL_d_rotation, a.dL_d_scaling = _p(g_xyz), _p(g_rot), _p(g_scale)
-        a.dL_dnode_trans, a.dL_dnode_rot, a.dL_dnode_scale, a.dL_dnode_local_rot = _p(d_trans), _p(d_rot), _p(d_scale), _p(d_lr)
-        a.dL_dnodes, a.dL_dnode_radius_log, a.dL_dnode_weight_logit = _p(d_nodes), _p(d_rad), _p(d_wl)
-        a.dL_dfeature, a.dL_dmotion_mask = _p(d_feat), _p(d_mask)
-        with torch.cuda.device(dev):
-            _lib.check(L.d2gs_deform_backward(C.byref(a), _stream(dev)), "d2gs_deform_backward")
-        if d_mask is not None and ctx.mask_shape is not None:
-            d_mask = d_mask.sum().reshape(ctx.mask_shape) if math.prod(ctx.mask_shape) == 1 else d_mask.reshape(ctx.mask_shape)
+        tr_, rt_, sc_, lr_, *rest = ctx.saved_tensors
+        it = iter(rest)
+        common = tuple(next(it) if h else None for h in ctx.has)
+        M = int(tr_.shape[0])
+        ncol = 9 + (4 if lr_ is not None else 0)
+        flat = torch.zeros((M * ncol,), dtype=torch.float32, device=tr_.device)   # one fill for all node-level gradients
+        d_trans, d_rot = flat[:3 * M].view(M, 3), flat[3 * M:7 * M].view(M, 4)
+        d_scale = flat[7 * M:9 * M].view(M, 2)
+        d_lr = flat[9 * M:].view(M, 4) if lr_ is not None else None
+        d_feat, d_nodes, d_rad, d_wl, d_mask = _blend_backward(
+            ctx, common, (_p(tr_), _p(rt_), _p(sc_), _p(lr_)), (_p(d_trans), _p(d_rot), _p(d_scale), _p(d_lr)), 0,
+            g_xyz, g_rot, g_scale)
         # xyz is detached by the reference (time_utils.py:1136), node xyz columns too (:947,1151)
         return (None, d_feat, d_nodes, d_rad, d_wl, d_trans, d_rot, d_scale, d_lr, d_mask, None, None)
+
+
+class _NodeBlendPacked(torch.autograd.Function):
+    """Same op, with the per-node MLP outputs given as ONE (M, S) matrix (the fused MLP's head output) and the column of
+    each attribute: no slicing copies forward, one (M, S) gradient matrix backward.  cols = (trans, rot, scale, local_rot | -1)."""
+
+    @staticmethod
+    def forward(ctx, xyz, feature, nodes, node_radius_log, node_weight_logit, attrs, motion_mask, K, hyper_dim, cols):
+        at_ = _f32(attrs)
+        S = int(at_.shape[1])
+        base = at_.data_ptr()
+        ptrs = tuple((base + 4 * c) if c >= 0 else None for c in cols)
+        common, outs = _blend_forward(ctx, xyz, feature, nodes, node_radius_log, node_weight_logit, ptrs, S, motion_mask, K, hyper_dim)
+        ctx.cols = tuple(cols)
+        ctx.has = [t is not None for t in common]
+        ctx.save_for_backward(at_, *[t for t in common if t is not None])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_xyz, g_rot, g_scale, g_w, g_d, g_i):
+        at_, *rest = ctx.saved_tensors
+        it = iter(rest)
+        common = tuple(next(it) if h else None for h in ctx.has)
+        S = int(at_.shape[1])
+        d_attrs = torch.zeros_like(at_)
+        ptrs = tuple((at_.data_ptr() + 4 * c) if c >= 0 else None for c in ctx.cols)
+        d_ptrs = tuple((d_attrs.data_ptr() + 4 * c) if c >= 0 else None for c in ctx.cols)
+        d_feat, d_nodes, d_rad, d_wl, d_mask = _blend_backward(ctx, common, ptrs, d_ptrs, S, g_xyz, g_rot, g_scale)
+        return (None, d_feat, d_nodes, d_rad, d_wl, d_attrs, d_mask, None, None, None)
+
+
+def node_blend_packed(xyz, feature, nodes, node_radius_log, node_weight_logit, attrs, cols, motion_mask, K: int, hyper_dim: int):
+    d_xyz, d_rot, d_scale, w, d, i = _NodeBlendPacked.apply(xyz, feature, nodes, node_radius_log, node_weight_logit, attrs,
+                                                            motion_mask, K, hyper_dim, tuple(cols))
+    return {"d_xyz": d_xyz, "d_rotation": d_rot, "d_scaling": d_scale, "nn_weight": w, "nn_dist": d, "nn_index": i, "nn_idx": i}
 
 
 def node_blend(xyz, feature, nodes, node_radius_log, node_weight_logit, node_trans, node_rot, node_scale,
@@ -187,7 +264,9 @@ class _FusedMLP(torch.autograd.Function):
         x_, t2, ws, *w = ctx.saved_tensors
         dev = x_.device
         g_out = torch.zeros((rows, num_out), dtype=torch.float32, device=dev) if g_out is None else g_out.float().contiguous()
-        grads = [torch.empty_like(p_) for p_ in w]
+        from .dist import claim
+        grads = [claim(p_, False) for p_ in w]      # parameters owned by a gradient bucket are written in place
+        grads = [torch.empty_like(p_) if g_ is None else g_ for p_, g_ in zip(w, grads)]
         a = _FusedMLP._args(rows, is_blender, num_out, x_, t2, t_stride, w, ws)
         a.g_out = g_out.data_ptr()
         i = 0
@@ -290,6 +369,7 @@ class DeformNetwork(nn.Module):
                 and (t.numel() == x.shape[0] or t.numel() == 1))
 
     def _forward_fused(self, x, t):
+        self._packed = None
         heads = [self.gaussian_warp, self.gaussian_scaling, self.gaussian_rotation]
         if self.local_frame:
             heads.append(self.local_rotation)
@@ -310,6 +390,9 @@ class DeformNetwork(nn.Module):
         c = 9
         if self.local_frame:
             ret['local_rotation'] = out[:, c:c + 4]; c += 4
+        if self.max_d_scale <= 0:
+            # the un-sliced head matrix + column map, so ControlNodeWarp can blend without slicing copies
+            self._packed = (out, (0, 5, 3, 9 if self.local_frame else -1))
         if self.pred_opacity:
             ret['d_opacity'] = out[:, c:c + 1]
         return ret
@@ -515,12 +598,20 @@ class ControlNodeWarp(nn.Module):
         if t.dim() == 0:
             t = self.expand_time(t)
         x = x.detach()
+        net = self.network
+        if hasattr(net, '_packed'):
+            net._packed = None
         node_attrs = self.node_deform(t=t, **kwargs)
-        out = node_blend(x, feature, self.nodes, self._node_radius,
-                         self._node_weight.reshape(-1) if self.with_node_weight else None,
-                         node_attrs['d_xyz'], node_attrs['d_rotation'], node_attrs['d_scaling'],
-                         node_attrs.get('local_rotation') if self.local_frame else None,
-                         motion_mask if torch.is_tensor(motion_mask) else None, self.K, self.hyper_dim)
+        packed = getattr(net, '_packed', None)
+        wl = self._node_weight.reshape(-1) if self.with_node_weight else None
+        mm = motion_mask if torch.is_tensor(motion_mask) else None
+        if packed is not None and t.dim() == 2 and packed[0].shape[0] == self.nodes.shape[0]:
+            net._packed = None
+            out = node_blend_packed(x, feature, self.nodes, self._node_radius, wl, packed[0], packed[1], mm, self.K, self.hyper_dim)
+        else:
+            out = node_blend(x, feature, self.nodes, self._node_radius, wl,
+                             node_attrs['d_xyz'], node_attrs['d_rotation'], node_attrs['d_scaling'],
+                             node_attrs.get('local_rotation') if self.local_frame else None, mm, self.K, self.hyper_dim)
         ret = {'d_xyz': out['d_xyz'], 'd_rotation': out['d_rotation'], 'd_scaling': out['d_scaling'],
                'd_opacity': None, 'd_color': None}
         if self.pred_opacity:

@@ -2,7 +2,7 @@
 
 The path shards by camera view: every rank holds a full replica of the surfel parameters and the deformation
 network, renders its own views, and the only exchange is the parameter gradient — ONE all-reduce per step over a flat
-bucket every ``.grad`` is a view of (no pack/unpack), plus the small densification statistics the trainer keeps
+bucket the backward kernels write into directly (no AccumulateGrad kernels, no pack/unpack), plus the small densification statistics the trainer keeps
 (scene/gaussian_model.py:484-486, train_gui.py:389-391).  One process per GPU, ``torch.distributed`` (NCCL over
 NVLink on the B200 box, gloo in the CPU tests).  The reference has no multi-GPU support at all.
 """
@@ -24,30 +24,112 @@ def views_of_rank(rank: int, world: int, n_views: int) -> List[int]:
     return list(range(rank, n_views, world))
 
 
+class _Slot:
+    __slots__ = ("view", "claimed", "dirty", "large")
+
+    def __init__(self, view, large):
+        self.view, self.claimed, self.dirty, self.large = view, False, False, large
+
+
+_SLOTS = {}   # data_ptr of a parameter -> _Slot of the bucket that owns it
+
+
+def claim(t: Optional[torch.Tensor], zeroed: bool) -> Optional[torch.Tensor]:
+    """Called by the backward wrappers (raster.py, deform.py) with the tensor they saved for a parameter: returns that
+    parameter's slice of the gradient bucket, shaped like ``t``, so the CUDA backward writes the gradient where the
+    all-reduce will read it (autograd then adopts the returned view as ``.grad`` without an accumulate kernel).
+    ``zeroed``: the kernel accumulates with atomics and needs zeros.  Returns None when no bucket owns the tensor or
+    the slot was already handed out this step (a parameter used twice: autograd sums out of place and
+    ``FlatGradBucket.finalize`` copies the sum back)."""
+    if t is None or not _SLOTS:
+        return None
+    s = _SLOTS.get(t.data_ptr())
+    if s is None or s.claimed or s.view.numel() != t.numel() or not t.is_contiguous() or s.view.device != t.device:
+        return None
+    if zeroed and s.dirty:
+        s.view.zero_()
+    s.claimed, s.dirty = True, True
+    return s.view.view(t.shape)
+
+
 class FlatGradBucket:
-    """All parameter gradients as views of one contiguous fp32 buffer.
+    """All parameter gradients as slices of one contiguous fp32 buffer, reduced with ONE collective.
 
-    After ``attach()`` autograd accumulates straight into the bucket (``.grad`` is pre-set to a view, so
-    AccumulateGrad adds in place); ``all_reduce()`` is then a single collective over the whole buffer."""
+    ``direct=True`` (default): ``.grad`` starts every step as None and the backward kernels write into the bucket
+    through ``claim()``; autograd adopts those views, so a step costs no AccumulateGrad kernels and no pack.
+    Small slots (< ``large_numel`` elements) sit first and are cleared by one fill per step; large slots (the per-surfel
+    tables) are fully overwritten by the rasterizer backward and only cleared when a step does not claim them.
+    ``direct=False``: ``.grad`` is pre-set to the views and autograd accumulates in place."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
-        self.params = [p for p in params if p.requires_grad]
-        assert self.params, "no trainable parameters"
+    ALIGN = 64   # floats
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], direct: bool = True, large_numel: int = 1 << 20):
+        ps = [p for p in params if p.requires_grad]
+        assert ps, "no trainable parameters"
+        self.params = [p for p in ps if p.numel() < large_numel] + [p for p in ps if p.numel() >= large_numel]
         dev = self.params[0].device
-        self.numel = sum(p.numel() for p in self.params)
+        # every slot starts on a 256-byte boundary, like a tensor from the CUDA caching allocator: the backward kernels
+        # store gradients with 16-byte vector instructions
+        pad = lambda n: (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.numel = sum(pad(p.numel()) for p in self.params)
+        self.n_small = sum(pad(p.numel()) for p in self.params if p.numel() < large_numel)
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self.direct = direct
+        self.slots: List[_Slot] = []
+        off = 0
+        for p in self.params:
+            self.slots.append(_Slot(self.flat[off: off + p.numel()].view_as(p), p.numel() >= large_numel))
+            off += pad(p.numel())
         self.attach()
 
     def attach(self) -> None:
-        off = 0
+        for p, s in zip(self.params, self.slots):
+            if self.direct:
+                _SLOTS[p.data_ptr()] = s
+                p.grad = None
+            else:
+                p.grad = s.view
+
+    def detach(self) -> None:
         for p in self.params:
-            p.grad = self.flat[off: off + p.numel()].view_as(p)
-            off += p.numel()
+            _SLOTS.pop(p.data_ptr(), None)
 
     def zero(self) -> None:
-        self.flat.zero_()
+        """Start of a step."""
+        if not self.direct:
+            self.flat.zero_()
+            return
+        if self.n_small:
+            self.flat[: self.n_small].zero_()
+        for p, s in zip(self.params, self.slots):
+            p.grad = None
+            s.claimed = False
+            if not s.large:
+                s.dirty = False
+
+    begin_step = zero
+
+    def finalize(self) -> None:
+        """After backward: every ``.grad`` is its bucket slice and the slice holds this step's gradient."""
+        if not self.direct:
+            return
+        for p, s in zip(self.params, self.slots):
+            g = p.grad
+            if g is None:
+                if s.dirty and not s.claimed:
+                    s.view.zero_()
+                    s.dirty = False
+                elif s.claimed:            # handed out but never returned to autograd: not a gradient
+                    s.view.zero_()
+                    s.dirty = False
+                p.grad = s.view
+            elif g.data_ptr() != s.view.data_ptr():
+                s.view.copy_(g)
+                s.dirty = True
+                p.grad = s.view
 
     def all_reduce(self, group=None, average: bool = False) -> None:
+        self.finalize()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
             if average:

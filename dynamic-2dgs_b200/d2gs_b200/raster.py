@@ -8,6 +8,7 @@ so the caller never concatenates 192 B per surfel per frame (gaussian_renderer/_
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import Optional
 
 import torch
@@ -137,8 +138,10 @@ def raster_forward(bg, means3D, colors_precomp, opacities, scales, rotations, sc
 
 def raster_backward(bg, means3D, radii, colors_precomp, scales, rotations, scale_modifier, transMat_precomp, viewmatrix,
                     projmatrix, tanfovx, tanfovy, dL_dout_color, dL_dout_others, sh, sh_rest, degree, campos, ctx,
-                    debug, want=None, raw_params=False, opacities=None, d_means3D=None, d_scales=None, d_rotations=None):
+                    debug, want=None, raw_params=False, opacities=None, d_means3D=None, d_scales=None, d_rotations=None, out=None):
     """Equivalent of ``_C.rasterize_gaussians_backward`` (DSR/rasterize_points.cu:143-240).
+
+    ``out``: optional dict of preallocated gradient tensors (e.g. slices of a gradient bucket); every element is written.
 
     Returns dict with dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh, dL_dsh_rest,
     dL_dscales, dL_drotations (entries not requested through ``want`` are None)."""
@@ -150,23 +153,32 @@ def raster_backward(bg, means3D, radii, colors_precomp, scales, rotations, scale
     w = lambda k: want.get(k, True)
     g = dict.fromkeys(("dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dtransMat", "dL_dsh",
                        "dL_dsh_rest", "dL_dscales", "dL_drotations", "dL_dscales_raw"))
+    out = out or {}
+
+    def buf(k, shape):
+        t = out.get(k)
+        if t is not None:
+            assert t.is_contiguous() and t.dtype == torch.float32 and t.numel() == math.prod(shape), k
+            return t.view(shape)
+        return torch.empty(shape, **f32)
+
     if raw_params:
-        g["dL_dscales_raw"] = torch.empty((P, 2), **f32)
-    if w("dL_dmeans2D"): g["dL_dmeans2D"] = torch.empty((P, 3), **f32)
-    if w("dL_dcolors"): g["dL_dcolors"] = torch.empty((P, 3), **f32)
-    if w("dL_dopacity"): g["dL_dopacity"] = torch.empty((P, 1), **f32)
-    if w("dL_dmeans3D"): g["dL_dmeans3D"] = torch.empty((P, 3), **f32)
-    if w("dL_dtransMat"): g["dL_dtransMat"] = torch.empty((P, 9), **f32)
+        g["dL_dscales_raw"] = buf("dL_dscales_raw", (P, 2))
+    if w("dL_dmeans2D"): g["dL_dmeans2D"] = buf("dL_dmeans2D", (P, 3))
+    if w("dL_dcolors"): g["dL_dcolors"] = buf("dL_dcolors", (P, 3))
+    if w("dL_dopacity"): g["dL_dopacity"] = buf("dL_dopacity", (P, 1))
+    if w("dL_dmeans3D"): g["dL_dmeans3D"] = buf("dL_dmeans3D", (P, 3))
+    if w("dL_dtransMat"): g["dL_dtransMat"] = buf("dL_dtransMat", (P, 9))
     if sh is not None and w("dL_dsh"):
         if sh_rest is not None:
-            g["dL_dsh"] = torch.empty((P, 1, 3), **f32)
-            g["dL_dsh_rest"] = torch.empty((P, M - 1, 3), **f32)
+            g["dL_dsh"] = buf("dL_dsh", (P, 1, 3))
+            g["dL_dsh_rest"] = buf("dL_dsh_rest", (P, M - 1, 3))
         else:
-            g["dL_dsh"] = torch.empty((P, M, 3), **f32)
+            g["dL_dsh"] = buf("dL_dsh", (P, M, 3))
     elif w("dL_dsh"):
         g["dL_dsh"] = torch.zeros((P, 0, 3), **f32)
-    if w("dL_dscales"): g["dL_dscales"] = torch.empty((P, 2), **f32)
-    if w("dL_drotations"): g["dL_drotations"] = torch.empty((P, 4), **f32)
+    if w("dL_dscales"): g["dL_dscales"] = buf("dL_dscales", (P, 2))
+    if w("dL_drotations"): g["dL_drotations"] = buf("dL_drotations", (P, 4))
     if P == 0:
         return g
     if scales is None:   # transMat_precomp path: no surfel-frame gradients
@@ -314,13 +326,18 @@ class _RasterizeSurfelsRaw(torch.autograd.Function):
         if grad_depth is None:
             grad_depth = torch.zeros((8, rctx.H, rctx.W), dtype=torch.float32, device=dev)
         want = {"dL_dtransMat": False, "dL_dcolors": col_ is not None}
+        # parameter gradients are written straight into the gradient bucket when one owns the parameter (dist.claim)
+        from .dist import claim
+        out = {"dL_dmeans3D": claim(xyz_, False), "dL_dscales_raw": claim(sc_, False), "dL_drotations": claim(rot_, False),
+               "dL_dopacity": claim(op_, False), "dL_dsh": claim(sh_, False), "dL_dsh_rest": claim(shr_, False)}
         g = raster_backward(bg, xyz_, radii, col_, sc_, rot_, rs.scale_modifier, None, view, proj, rs.tanfovx, rs.tanfovy,
                             grad_out_color.float().contiguous(), grad_depth.float().contiguous(), sh_, shr_, rs.sh_degree,
                             campos, rctx, rs.debug, want=want, raw_params=True, opacities=op_, d_means3D=dx_, d_scales=ds_,
-                            d_rotations=dr_)
+                            d_rotations=dr_, out=out)
         hd = ctx.has_delta
-        return (g["dL_dmeans3D"], g["dL_dmeans3D"] if hd[0] else None, g["dL_dscales_raw"], g["dL_dscales"] if hd[1] else None,
-                g["dL_drotations"], g["dL_drotations"] if hd[2] else None, g["dL_dopacity"], g["dL_dmeans2D"],
+        alias = lambda t: t.view_as(t)   # a second tensor object on the same memory, so autograd can adopt the first as .grad
+        return (g["dL_dmeans3D"], alias(g["dL_dmeans3D"]) if hd[0] else None, g["dL_dscales_raw"], g["dL_dscales"] if hd[1] else None,
+                g["dL_drotations"], alias(g["dL_drotations"]) if hd[2] else None, g["dL_dopacity"], g["dL_dmeans2D"],
                 g["dL_dsh"] if sh_ is not None else None, g["dL_dsh_rest"], g["dL_dcolors"], None)
 
 

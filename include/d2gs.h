@@ -283,6 +283,8 @@ typedef struct D2gsDeformFwdArgs {
   float* d_xyz;                  /* (P,3) */
   float* d_rotation;             /* (P,4) */
   float* d_scaling;              /* (P,2) */
+  int node_attr_stride;          /* 0: node_trans/rot/scale/local_rot are separate packed tables; > 0: they are columns
+                                    of ONE (M,node_attr_stride) row-major matrix (the MLP head output), no slicing copies */
 } D2gsDeformFwdArgs;
 
 D2GS_API int d2gs_deform_forward(const D2gsDeformFwdArgs* args, void* stream);
@@ -316,6 +318,7 @@ typedef struct D2gsDeformBwdArgs {
   /* outputs (written) */
   float* dL_dfeature;            /* (P,feature_stride) or NULL */
   float* dL_dmotion_mask;        /* (P) or NULL */
+  int node_attr_stride;          /* as in D2gsDeformFwdArgs; applies to node_* and dL_dnode_{trans,rot,scale,local_rot} */
 } D2gsDeformBwdArgs;
 
 D2GS_API int d2gs_deform_backward(const D2gsDeformBwdArgs* args, void* stream);

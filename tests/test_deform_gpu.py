@@ -3,6 +3,8 @@
 render()/DeformModel.step() against the reference pipeline restated around the reference CUDA extension."""
 import math
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -177,10 +179,17 @@ def test_render_dropin_matches_reference_pipeline(cuda_device):
     g = torch.Generator().manual_seed(1)
     wts = {k: None for k in keys}
 
-    def run(ours: bool):
+    adopted = []
+
+    def run(ours: bool, bucketed: bool = False, perturb: float = 0.0):
         pc = mdl.SurfelModel(sc, dev)
         for p_ in dm.deform.parameters():
             p_.grad = None
+        bucket = None
+        if bucketed:
+            from d2gs_b200 import dist as ddist
+            bucket = ddist.FlatGradBucket(list(pc.parameters()) + list(dm.deform.parameters()), large_numel=1 << 14)
+            bucket.zero()
         if ours:
             d = dm.step(pc.get_xyz.detach(), dm.deform.expand_time(cam.fid), feature=pc.feature, motion_mask=pc.motion_mask)
             out = render(cam, pc, mdl.PipelineParams(), bg, d["d_xyz"], d["d_rotation"], d["d_scaling"])
@@ -188,6 +197,9 @@ def test_render_dropin_matches_reference_pipeline(cuda_device):
             net = {k[len("network."):]: v for k, v in dm.deform.named_parameters() if k.startswith("network.")}
             d = rp.deform_reference(net, dm.deform.nodes, dm.deform._node_radius, dm.deform._node_weight, pc.get_xyz.detach(), cam.fid,
                                     pc.feature, pc.motion_mask, 4, 8, local_frame=True, knn_mode="exact")
+            if perturb:
+                gp = torch.Generator().manual_seed(7)
+                d = {k: d[k] * (1.0 + perturb * torch.randn(d[k].shape, generator=gp).to(dev)) for k in ("d_xyz", "d_rotation", "d_scaling")}
             out = rp.render_reference(ref, cam, pc, bg, d["d_xyz"], d["d_rotation"], d["d_scaling"])
         loss = 0
         for k in keys:
@@ -198,7 +210,19 @@ def test_render_dropin_matches_reference_pipeline(cuda_device):
             loss = loss + (out[k] * wts[k]).sum()
         loss.backward()
         torch.cuda.synchronize()
-        grads = {n: p_.grad.detach().cpu().numpy().copy() for n, p_ in list(pc.named_parameters()) + list(dm.deform.named_parameters()) if p_.grad is not None}
+        named = list(pc.named_parameters()) + list(dm.deform.named_parameters())
+        if bucket is not None:
+            lo, hi = bucket.flat.data_ptr(), bucket.flat.data_ptr() + bucket.nbytes()
+            adopted.extend(n for n, p_ in named if p_.grad is not None and lo <= p_.grad.data_ptr() < hi)
+            had_grad = {n for n, p_ in named if p_.grad is not None}
+            bucket.all_reduce()
+            assert all(lo <= p_.grad.data_ptr() < hi for p_ in bucket.params)
+            grads = {n: p_.grad.detach().cpu().numpy().copy() for n, p_ in named if n in had_grad}
+            bucket.detach()
+            for p_ in bucket.params:
+                p_.grad = None
+        else:
+            grads = {n: p_.grad.detach().cpu().numpy().copy() for n, p_ in named if p_.grad is not None}
         return {k: v.detach().cpu().numpy() for k, v in out.items() if torch.is_tensor(v)}, grads, out["viewspace_points"].grad.cpu().numpy()
 
     o_out, o_g, o_vs = run(True)
@@ -215,5 +239,32 @@ def test_render_dropin_matches_reference_pipeline(cuda_device):
         assert util.rel_err(o_out[k], r_out[k]) < tol, (k, util.rel_err(o_out[k], r_out[k]))
     assert util.rel_err(o_vs, r_vs) < 5e-2      # densification statistic: a sum of large cancelling terms, sensitive to the 1e-6 deform differences
     assert set(o_g) == set(r_g), set(o_g) ^ set(r_g)
+    # Noise floor: our fused deformation and the eager one differ by ~1e-6 relative in d_xyz / d_rotation / d_scaling
+    # (fp32 summation order).  That flips the radius or visibility of up to 0.2 % of the surfels (asserted above) and the
+    # gradients respond discontinuously, so the yardstick is the reference pipeline run against ITSELF with its own
+    # deformation outputs perturbed by 1e-6: our deviation must stay within a few of those floors.
+    # (`feature` additionally has an analytically ~zero gradient here - all nodes share one radius, so the normalised
+    # weights are invariant to the common shift of the K distances - hence the absolute term.)
+    _, p_g, _ = run(False, perturb=1e-6)
+    scale = max(float(np.linalg.norm(v)) for v in r_g.values())
+    report = {}
     for n in o_g:
-        assert util.rel_err(o_g[n], r_g[n]) < 5e-3, (n, util.rel_err(o_g[n], r_g[n]))
+        err = float(np.linalg.norm(o_g[n].astype(np.float64) - r_g[n]))
+        floor = float(np.linalg.norm(p_g[n].astype(np.float64) - r_g[n]))
+        report[n] = (err, floor, float(np.linalg.norm(r_g[n])))
+    if os.environ.get("D2GS_TEST_REPORT"):
+        import json
+        with open(os.environ["D2GS_TEST_REPORT"], "w") as fh:
+            json.dump(report, fh, indent=1)
+    bad = {n: v for n, v in report.items() if v[0] > 2e-3 * v[2] + 4.0 * v[1] + 1e-6 * scale}
+    assert not bad, (bad, scale)
+
+    # gradient bucket, direct mode: the backward kernels write the parameter gradients into bucket slices which autograd
+    # adopts as .grad (no AccumulateGrad kernels); same numbers as the bucket-less run up to atomic ordering
+    b_out, b_g, _ = run(True, bucketed=True)
+    assert {"_xyz", "_features_rest", "_scaling", "_rotation", "_opacity", "nodes", "_node_radius", "network.linear.0.weight",
+            "network.linear.7.bias"} <= set(adopted), sorted(adopted)
+    assert set(b_g) == set(o_g)
+    for n in o_g:
+        err = float(np.linalg.norm(b_g[n].astype(np.float64) - o_g[n]))
+        assert err <= 1e-4 * float(np.linalg.norm(o_g[n])) + 1e-6 * scale, (n, err)

@@ -34,16 +34,16 @@ def _worker(rank, world, port, n_views, steps, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     params = _model()
-    bucket = ddist.FlatGradBucket(params)
-    assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in params)
+    bucket = ddist.FlatGradBucket(params, direct=bool(out.get("direct", True)))
     seen = []
     for s in range(steps):
         bucket.zero()
         v = ddist.view_for(s, rank, world, n_views)
         seen.append(v)
         _fake_render_loss(params, v).backward()
-        assert all(p.grad.data_ptr() == q for p, q in zip(params, out["ptrs"])) if out.get("ptrs") else True
         bucket.all_reduce()
+        lo, hi = bucket.flat.data_ptr(), bucket.flat.data_ptr() + bucket.nbytes()
+        assert all(lo <= p.grad.data_ptr() < hi for p in params)      # every .grad is a slice of the bucket
     gn = torch.full((50, 1), float(rank + 1)); vis = torch.arange(50) % (rank + 2) == 0
     radii = torch.arange(50, dtype=torch.int32) * (1 if rank == 0 else -1) + (0 if rank == 0 else 60)
     acc, cnt, rmax = ddist.reduce_densification_stats(gn, vis, radii)
@@ -62,17 +62,19 @@ def test_view_sharding_is_a_partition():
             assert sorted(sum(shards, [])) == list(range(n_views))
 
 
-def test_flat_bucket_allreduce_equals_sum_over_views(tmp_path):
+@pytest.mark.parametrize("direct", [True, False])
+def test_flat_bucket_allreduce_equals_sum_over_views(tmp_path, direct):
     world, n_views, steps = 2, 6, 3
     path = str(tmp_path / "r0.pt")
-    mp.spawn(_worker, args=(world, _free_port(), n_views, steps, {"path": path}), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n_views, steps, {"path": path, "direct": direct}), nprocs=world, join=True)
     got = torch.load(path)
     # single-process reference: gradient of the LAST step's views summed over ranks
     params = _model()
     last_views = [ddist.view_for(steps - 1, r, world, n_views) for r in range(world)]
     total = sum(_fake_render_loss(params, v) for v in last_views)
     total.backward()
-    ref = torch.cat([p.grad.reshape(-1) for p in params])
+    pad = lambda g: torch.cat([g.reshape(-1), torch.zeros(-g.numel() % ddist.FlatGradBucket.ALIGN)])      # slots are 256-B aligned
+    ref = torch.cat([pad(p.grad) for p in params])
     assert torch.allclose(got["flat"], ref, rtol=1e-6, atol=1e-6)
     assert got["seen"] == [ddist.view_for(s, 0, world, n_views) for s in range(steps)]
     # densification statistics: SUM of masked norms / counts, MAX of radii
@@ -83,10 +85,59 @@ def test_flat_bucket_allreduce_equals_sum_over_views(tmp_path):
 
 def test_bucket_single_process_noop():
     params = _model()
-    b = ddist.FlatGradBucket(params)
+    b = ddist.FlatGradBucket(params, direct=False)
     _fake_render_loss(params, 2).backward()
     before = b.flat.clone()
     b.all_reduce()          # no process group: must be a no-op
-    assert torch.equal(before, b.flat) and b.nbytes() == 4 * sum(p.numel() for p in params)
+    assert torch.equal(before, b.flat) and b.nbytes() >= 4 * sum(p.numel() for p in params)
     b.zero()
     assert not any(p.grad.any() for p in params)
+
+
+class _ClaimingSquare(torch.autograd.Function):
+    """Stand-in for the CUDA backward wrappers: writes the parameter gradient into the slot the bucket hands out."""
+
+    @staticmethod
+    def forward(ctx, w):
+        ctx.save_for_backward(w.detach())
+        return (w * w).sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        (w,) = ctx.saved_tensors
+        out = ddist.claim(w, zeroed=False)
+        if out is None:
+            out = torch.empty_like(w)
+        torch.mul(w, 2.0 * g, out=out)
+        return out
+
+
+def test_direct_bucket_adopts_kernel_written_gradients():
+    torch.manual_seed(0)
+    big = torch.nn.Parameter(torch.randn(40, 3))
+    small = torch.nn.Parameter(torch.randn(5))
+    unused = torch.nn.Parameter(torch.randn(4))
+    b = ddist.FlatGradBucket([big, small, unused], large_numel=100)
+    assert b.params[0] is small and b.params[-1] is big            # small slots first, large ones last
+    try:
+        for step in range(3):
+            b.zero()
+            assert big.grad is None and small.grad is None
+            loss = _ClaimingSquare.apply(big) + _ClaimingSquare.apply(small)
+            if step == 1:
+                loss = loss + _ClaimingSquare.apply(small) + big.sum()      # parameters used twice: autograd sums out of place
+            if step == 2:
+                loss = _ClaimingSquare.apply(small)                          # the large slot is not written this step
+            loss.backward()
+            if step == 0:      # autograd adopted the views: no accumulate, no copy
+                assert big.grad.data_ptr() == b.slots[-1].view.data_ptr() and small.grad.data_ptr() == b.slots[0].view.data_ptr()
+            b.all_reduce()
+            lo, hi = b.flat.data_ptr(), b.flat.data_ptr() + b.nbytes()
+            assert all(lo <= p.grad.data_ptr() < hi for p in (big, small, unused))
+            eb = {0: 2 * big.data, 1: 2 * big.data + 1, 2: torch.zeros_like(big)}[step]
+            es = {0: 2 * small.data, 1: 4 * small.data, 2: 2 * small.data}[step]
+            assert torch.allclose(big.grad, eb) and torch.allclose(small.grad, es) and not unused.grad.any()
+            assert all(s_.view.data_ptr() % 256 == b.flat.data_ptr() % 256 for s_ in b.slots)
+            assert float(b.flat.sum()) == pytest.approx(float(small.grad.sum() + big.grad.sum()), rel=1e-5, abs=1e-5)
+    finally:
+        b.detach()
