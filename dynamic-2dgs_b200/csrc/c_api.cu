@@ -533,6 +533,8 @@ int d2gs_mlp_forward(const D2gsMlpArgs* a, void* stream_) {
   if (!a->x || !a->t || !a->out || !a->heads_w || !a->workspace) return fail(D2GS_ERR_INVALID_ARG, "missing buffers");
   for (int i = 0; i < P.L.count; i++)
     if (!P.L.layer[i].W || !P.L.layer[i].b) return fail(D2GS_ERR_INVALID_ARG, "missing weights");
+  for (int i = 0; i < P.L.count; i++)   // the backward streams W with 16-byte-granular bulk copies
+    if ((uintptr_t)P.L.layer[i].W & 15) return fail(D2GS_ERR_INVALID_ARG, "weight matrices must be 16-byte aligned");
   if (a->workspace_bytes < P.total_bytes) return fail(D2GS_ERR_WORKSPACE, "mlp workspace too small");
   char* ws = aligned_base(a->workspace);
   P.L.wt = (float*)ws;

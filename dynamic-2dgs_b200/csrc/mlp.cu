@@ -45,11 +45,89 @@ __global__ void __launch_bounds__(256) mlp_transpose_kernel(MlpLayers L) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// weight streaming: TMA bulk copies (cp.async.bulk, global -> shared) completing on mbarriers
+// ---------------------------------------------------------------------------------------------------------------
+// Every CTA needs all 2.1 MB of weights once per pass.  A ninth warp (one elected lane) streams them through a ring of
+// shared-memory stages with 1-D bulk copies; the eight consumer warps wait on the stage's "full" mbarrier, run their
+// FMAs out of shared memory and release the stage through its "empty" mbarrier.  The producer runs ahead across layer
+// boundaries, so the next layer's first chunks land while the current layer is reduced and stored.  The copy engine
+// keeps the L2 -> SM pipe busy regardless of what the math warps are doing (the LDG version of this kernel was bound
+// by load latency: 8 warps x 4 LDG.128 in flight per SM).
+constexpr int CONSUMERS = 256;               // 8 math warps
+constexpr int MLP_THREADS = CONSUMERS + 32;  // + 1 producer warp
+constexpr int STAGES = 3;
+constexpr int KCH = 32;                      // forward: k-rows of W^T per chunk (32 x NP floats <= 32 KB)
+constexpr int NCH = 32;                      // backward: n-rows of W per chunk (32 x K floats <= 44672 B at K = 349)
+constexpr int FWD_STAGE_BYTES = KCH * MW * 4;
+constexpr int BWD_STAGE_BYTES = 44800;       // >= 32 * 349 * 4, multiple of 128
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok, spins = 0;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 28)) __trap();   // a lost arrival must fail loudly, never hang the device
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory"); }
+
+struct Ring {
+  uint32_t stage0, stage_bytes, full0, empty0;   // shared-window addresses
+  int g;                                         // running chunk counter (same sequence on both sides)
+  __device__ __forceinline__ uint32_t stage(int st) const { return stage0 + (uint32_t)st * stage_bytes; }
+  __device__ __forceinline__ uint32_t full(int st) const { return full0 + 8u * st; }
+  __device__ __forceinline__ uint32_t empty(int st) const { return empty0 + 8u * st; }
+};
+__device__ __forceinline__ void ring_setup(Ring& r, unsigned char* stages, uint32_t stage_bytes, uint64_t* bars, int tid) {
+  r.stage0 = smem_addr(stages); r.stage_bytes = stage_bytes;
+  r.full0 = smem_addr(bars); r.empty0 = smem_addr(bars + STAGES); r.g = 0;
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; i++) { mbar_init(r.full(i), 1); mbar_init(r.empty(i), CONSUMERS / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+}
+// producer side: one chunk
+__device__ __forceinline__ void ring_push(Ring& r, const void* src, uint32_t bytes) {
+  const int st = r.g % STAGES; const uint32_t par = (uint32_t)(r.g / STAGES) & 1u;
+  mbar_wait(r.empty(st), par ^ 1u);
+  mbar_expect_tx(r.full(st), bytes);
+  bulk_g2s(r.stage(st), src, bytes, r.full(st));
+  r.g++;
+}
+// consumer side: returns the stage index once its bytes have landed; release with ring_pop
+__device__ __forceinline__ int ring_front(Ring& r) {
+  const int st = r.g % STAGES; const uint32_t par = (uint32_t)(r.g / STAGES) & 1u;
+  mbar_wait(r.full(st), par);
+  return st;
+}
+__device__ __forceinline__ void ring_pop(Ring& r, int st, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(r.empty(st));
+  r.g++;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------------
 // out[n] (for the CTA's ROWS rows) = bias[n] + sum_k in[k] * Wt[k][n];   in: shared [K][ROWS]
-// Thread (kg, nq) = (tid >> 6, tid & 63) owns outputs 4nq..4nq+3 for the k with k % 4 == kg: one coalesced LDG.128 of
-// W^T and one broadcast LDS.128 of the activations feed 16 FMAs; the four k-groups are summed through shared memory.
+// Thread (kg, nq) = (tid >> 6, tid & 63) owns outputs 4nq..4nq+3 for the k with k % 4 == kg: one conflict-free LDS.128 of
+// the staged W^T chunk and one broadcast LDS.128 of the activations feed 16 FMAs; the four k-groups are summed through
+// shared memory.
 __device__ __forceinline__ float4 ldg128(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 __device__ __forceinline__ void fma16(float4 (&acc)[4], const float4 wv, const float4 xv) {
@@ -60,32 +138,35 @@ __device__ __forceinline__ void fma16(float4 (&acc)[4], const float4 wv, const f
 }
 
 template <bool RELU>
-__device__ __forceinline__ void dense(const float* __restrict__ wt, int NP, const float* __restrict__ bias, int N,
-                                      const float4* s_in, int K, float4* s_red /*[4][256]*/, float4* s_out,
-                                      float* g_out, int ld_out, int row0, int rows, int tid) {
-  const int kg = tid >> 6, nq = tid & 63;
+__device__ __forceinline__ void dense(Ring& ring, int NP, const float* __restrict__ bias, int N, const float4* s_in, int K,
+                                      float4* s_red /*[4][256]*/, float4* s_out, float* g_out, int ld_out, int row0,
+                                      int rows, int tid) {
+  const int kg = tid >> 6, nq = tid & 63, lane = tid & 31;
+  const int np4 = NP >> 2;
+  const bool active = nq < np4;
   float4 acc[4];
 #pragma unroll
   for (int j = 0; j < 4; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (4 * nq < NP) {
-    const float* w = wt + 4 * nq;
-    int k = kg;
-#pragma unroll 1
-    for (; k + 12 < K; k += 16) {
-      const float4 w0 = ldg128(w + (size_t)k * NP), w1 = ldg128(w + (size_t)(k + 4) * NP),
-                   w2 = ldg128(w + (size_t)(k + 8) * NP), w3 = ldg128(w + (size_t)(k + 12) * NP);
-      const float4 x0 = s_in[k], x1 = s_in[k + 4], x2 = s_in[k + 8], x3 = s_in[k + 12];
-      fma16(acc, w0, x0); fma16(acc, w1, x1); fma16(acc, w2, x2); fma16(acc, w3, x3);
+  for (int k0 = 0; k0 < K; k0 += KCH) {
+    const int st = ring_front(ring);
+    const uint32_t w = ring.stage(st) + 16u * (uint32_t)nq;
+    const int kr = min(KCH, K - k0);
+    if (active) {
+      if (kr == KCH) {
+#pragma unroll
+        for (int kk = 0; kk < KCH / 4; kk++) {
+          const int k = kg + 4 * kk;
+          fma16(acc, lds128(w + 16u * (uint32_t)(k * np4)), s_in[k0 + k]);
+        }
+      } else {
+        for (int k = kg; k < kr; k += 4) fma16(acc, lds128(w + 16u * (uint32_t)(k * np4)), s_in[k0 + k]);
+      }
     }
-    for (; k < K; k += 4) {
-      const float4 w0 = ldg128(w + (size_t)k * NP);
-      const float4 x0 = s_in[k];
-      fma16(acc, w0, x0);
-    }
+    ring_pop(ring, st, lane);
   }
 #pragma unroll
   for (int j = 0; j < 4; j++) s_red[kg * MW + 4 * nq + j] = acc[j];
-  __syncthreads();
+  consumer_sync();
   if (tid < N) {
     const float b = bias ? __ldg(bias + tid) : 0.f;
     const float4 p0 = s_red[tid], p1 = s_red[MW + tid], p2 = s_red[2 * MW + tid], p3 = s_red[3 * MW + tid];
@@ -100,23 +181,46 @@ __device__ __forceinline__ void dense(const float* __restrict__ wt, int NP, cons
       if (rows > 3) g_out[(size_t)(row0 + 3) * ld_out + tid] = a3;
     }
   }
-  __syncthreads();
+  consumer_sync();
 }
 
-__global__ void __launch_bounds__(256) mlp_fwd_kernel(MlpFwd a) {
-  __shared__ float4 s_x[2][INP_LD + MW];  // each buffer: [x_emb (63) | time feature (Tt)] at 0..in0-1, hidden at in0..in0+255
-  __shared__ float4 s_te[32];             // time embedding (Et <= 21)
-  __shared__ float4 s_th[MW];             // timenet hidden
-  __shared__ float4 s_red[4 * MW];        // partial sums of the four k-groups
+struct FwdSmem {
+  float4 x[2][INP_LD + MW];  // each buffer: [x_emb (63) | time feature (Tt)] at 0..in0-1, hidden at in0..in0+255
+  float4 te[32];             // time embedding (Et <= 21)
+  float4 th[MW];             // timenet hidden
+  float4 red[4 * MW];        // partial sums of the four k-groups
+  uint64_t bars[2 * STAGES];
+};
+constexpr size_t FWD_SMEM_BYTES = (size_t)STAGES * FWD_STAGE_BYTES + sizeof(FwdSmem);
+
+__global__ void __launch_bounds__(MLP_THREADS) mlp_fwd_kernel(MlpFwd a) {
+  extern __shared__ __align__(128) unsigned char mlp_smem[];
+  FwdSmem& S = *reinterpret_cast<FwdSmem*>(mlp_smem + (size_t)STAGES * FWD_STAGE_BYTES);
   const int tid = threadIdx.x;
   const int row0 = blockIdx.x * ROWS;
   const int rows = min(ROWS, a.rows - row0);
   const MlpLayers& L = a.layers;
   const int Et = a.Et, Tt = a.Tt;
   const int in0 = EX + Tt;
+  Ring ring;
+  ring_setup(ring, mlp_smem, FWD_STAGE_BYTES, S.bars, tid);
+
+  if (tid >= CONSUMERS) {   // producer warp: stream W^T of every layer, in layer order, KCH rows per chunk
+    if (tid == CONSUMERS) {
+      for (int li = 0; li < L.count; li++) {
+        const MlpLayer& ly = L.layer[li];
+        const float* src = L.wt + ly.wt_off;
+        for (int k0 = 0; k0 < ly.K; k0 += KCH)
+          ring_push(ring, src + (size_t)k0 * ly.NP, (uint32_t)(min(KCH, ly.K - k0) * ly.NP) * 4u);
+      }
+    }
+    return;
+  }
+  float4 (*s_x)[INP_LD + MW] = S.x;
+  float4* s_te = S.te; float4* s_th = S.th; float4* s_red = S.red;
 
   // positional embeddings: [v, sin(2^0 v), cos(2^0 v), ..., sin(2^(F-1) v), cos(2^(F-1) v)] per input dimension block
-  for (int e = tid; e < EX + Et; e += 256) {
+  for (int e = tid; e < EX + Et; e += CONSUMERS) {
     float v[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; r++) {
@@ -151,56 +255,33 @@ __global__ void __launch_bounds__(256) mlp_fwd_kernel(MlpFwd a) {
         }
     }
   }
-  __syncthreads();
+  consumer_sync();
   int li = 0;
   if (a.has_timenet) {
     const MlpLayer& t1 = L.layer[li++];
-    dense<true>(L.wt + t1.wt_off, t1.NP, t1.b, t1.N, s_te, t1.K, s_red, s_th, a.save_th, MW, row0, rows, tid);
+    dense<true>(ring, t1.NP, t1.b, t1.N, s_te, t1.K, s_red, s_th, a.save_th, MW, row0, rows, tid);
     const MlpLayer& t2 = L.layer[li++];
-    dense<false>(L.wt + t2.wt_off, t2.NP, t2.b, t2.N, s_th, t2.K, s_red, s_x[0] + EX, a.save_inp ? a.save_inp + EX : nullptr,
+    dense<false>(ring, t2.NP, t2.b, t2.N, s_th, t2.K, s_red, s_x[0] + EX, a.save_inp ? a.save_inp + EX : nullptr,
                  INP_LD, row0, rows, tid);
     if (tid < Tt) s_x[1][EX + tid] = s_x[0][EX + tid];
-    __syncthreads();
+    consumer_sync();
   }
   int cur = 0;   // layer l writes its hidden block into s_x[cur] + in0 and reads from s_x[cur ^ 1]
   for (int l = 0; l < MD; l++) {
     const MlpLayer& ly = L.layer[li++];
     float* save = a.save_h ? a.save_h + (size_t)l * a.rows * MW : nullptr;
     const float4* in = (l == 0 || l == SKIP + 1) ? s_x[cur ^ 1] : s_x[cur ^ 1] + in0;   // skip layer reads [x, t, h] contiguously
-    dense<true>(L.wt + ly.wt_off, ly.NP, ly.b, ly.N, in, ly.K, s_red, s_x[cur] + in0, save, MW, row0, rows, tid);
+    dense<true>(ring, ly.NP, ly.b, ly.N, in, ly.K, s_red, s_x[cur] + in0, save, MW, row0, rows, tid);
     cur ^= 1;
   }
   // heads: concatenated outputs [warp 3 | scaling 2 | rotation 4 | local 4 | opacity 1] -> (rows, NH)
   const MlpLayer& hd = L.layer[li];
-  dense<false>(L.wt + hd.wt_off, hd.NP, hd.b, hd.N, s_x[cur ^ 1] + in0, MW, s_red, nullptr, a.out, a.NH, row0, rows, tid);
+  dense<false>(ring, hd.NP, hd.b, hd.N, s_x[cur ^ 1] + in0, MW, s_red, nullptr, a.out, a.NH, row0, rows, tid);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// backward, activation gradients: thread k owns input feature k; g_in[k] = sum_n G[n] * W[n][k]
+// backward, activation gradients: g_in[k] = sum_n G[n] * W[n][k], W streamed in its native (N, K) layout, NCH rows a chunk
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 back_dense(const float* __restrict__ W, int K, int N, const float4* s_g, int k) {
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  const float* w = W + k;
-  int n = 0;
-#pragma unroll 1
-  for (; n + 8 <= N; n += 8) {
-    float wv[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) wv[u] = __ldg(w + (size_t)(n + u) * K);
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const float4 g = s_g[n + u];
-      a0 = fmaf(wv[u], g.x, a0); a1 = fmaf(wv[u], g.y, a1); a2 = fmaf(wv[u], g.z, a2); a3 = fmaf(wv[u], g.w, a3);
-    }
-  }
-  for (; n < N; n++) {
-    const float wv = __ldg(w + (size_t)n * K);
-    const float4 g = s_g[n];
-    a0 = fmaf(wv, g.x, a0); a1 = fmaf(wv, g.y, a1); a2 = fmaf(wv, g.z, a2); a3 = fmaf(wv, g.w, a3);
-  }
-  return make_float4(a0, a1, a2, a3);
-}
-
 __device__ __forceinline__ void store_rows(float* g, int ld, int row0, int rows, int col, float4 v) {
   if (rows > 0) g[(size_t)(row0 + 0) * ld + col] = v.x;
   if (rows > 1) g[(size_t)(row0 + 1) * ld + col] = v.y;
@@ -218,94 +299,152 @@ __device__ __forceinline__ float4 load_rows(const float* g, int ld, int row0, in
 __device__ __forceinline__ float4 relu_mask(float4 g, float4 h) {
   return make_float4(h.x > 0.f ? g.x : 0.f, h.y > 0.f ? g.y : 0.f, h.z > 0.f ? g.z : 0.f, h.w > 0.f ? g.w : 0.f);
 }
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void fma4(float4& acc, float w, const float4 g) {
+  acc.x = fmaf(w, g.x, acc.x); acc.y = fmaf(w, g.y, acc.y); acc.z = fmaf(w, g.z, acc.z); acc.w = fmaf(w, g.w, acc.w);
+}
 
-// K == 256 fast path: thread (ng, kq) = (tid >> 6, tid & 63) owns inputs 4kq..4kq+3 for the n with n % 4 == ng (one
-// LDG.128 of a W row + one broadcast LDS.128 of G feed 16 FMAs); the four n-groups are summed through shared memory and
+// K == 256: thread (ng, kq) = (tid >> 6, tid & 63) owns inputs 4kq..4kq+3 for the n with n % 4 == ng (one LDS.128 of the
+// staged W rows + one broadcast LDS.128 of G feed 16 FMAs); the four n-groups are summed through shared memory and
 // thread tid returns g_in[tid].
-__device__ __forceinline__ float4 back_dense_k256(const float* __restrict__ W, int N, const float4* s_g, float4* s_red, int tid) {
-  const int ng = tid >> 6, kq = tid & 63;
+__device__ __forceinline__ float4 back_dense_k256(Ring& ring, int N, const float4* s_g, float4* s_red, int tid) {
+  const int ng = tid >> 6, kq = tid & 63, lane = tid & 31;
   float4 acc[4];
 #pragma unroll
   for (int j = 0; j < 4; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float* w = W + 4 * kq;
-  int n = ng;
-#pragma unroll 1
-  for (; n + 12 < N; n += 16) {
-    const float4 w0 = ldg128(w + (size_t)n * MW), w1 = ldg128(w + (size_t)(n + 4) * MW), w2 = ldg128(w + (size_t)(n + 8) * MW),
-                 w3 = ldg128(w + (size_t)(n + 12) * MW);
-    const float4 g0 = s_g[n], g1 = s_g[n + 4], g2 = s_g[n + 8], g3 = s_g[n + 12];
-    fma16(acc, w0, g0); fma16(acc, w1, g1); fma16(acc, w2, g2); fma16(acc, w3, g3);
-  }
-  for (; n < N; n += 4) {
-    const float4 w0 = ldg128(w + (size_t)n * MW);
-    const float4 g0 = s_g[n];
-    fma16(acc, w0, g0);
+  for (int n0 = 0; n0 < N; n0 += NCH) {
+    const int st = ring_front(ring);
+    const uint32_t w = ring.stage(st) + 16u * (uint32_t)kq;
+    const int nr = min(NCH, N - n0);
+    if (nr == NCH) {
+#pragma unroll
+      for (int nn = 0; nn < NCH / 4; nn++) {
+        const int n = ng + 4 * nn;
+        fma16(acc, lds128(w + 16u * (uint32_t)(n * (MW / 4))), s_g[n0 + n]);
+      }
+    } else {
+      for (int n = ng; n < nr; n += 4) fma16(acc, lds128(w + 16u * (uint32_t)(n * (MW / 4))), s_g[n0 + n]);
+    }
+    ring_pop(ring, st, lane);
   }
 #pragma unroll
   for (int j = 0; j < 4; j++) s_red[ng * MW + 4 * kq + j] = acc[j];
-  __syncthreads();
+  consumer_sync();
   const float4 p0 = s_red[tid], p1 = s_red[MW + tid], p2 = s_red[2 * MW + tid], p3 = s_red[3 * MW + tid];
-  __syncthreads();
+  consumer_sync();
   return make_float4((p0.x + p1.x) + (p2.x + p3.x), (p0.y + p1.y) + (p2.y + p3.y), (p0.z + p1.z) + (p2.z + p3.z),
                      (p0.w + p1.w) + (p2.w + p3.w));
 }
+// general K (the skip layer, K = 93 + 256, and layer 0, K = 93; rows are not 16-B aligned): thread tid accumulates input
+// column `col_main + tid` (when col_main >= 0) and, for tid < Tt, the time-feature column EX + tid.
+__device__ __forceinline__ void back_dense_cols(Ring& ring, int K, int N, const float4* s_g, int col_main, int Tt, int tid,
+                                                float4& g_main, float4& g_time) {
+  const int lane = tid & 31;
+  g_main = make_float4(0.f, 0.f, 0.f, 0.f);
+  g_time = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool do_t = tid < Tt;
+  for (int n0 = 0; n0 < N; n0 += NCH) {
+    const int st = ring_front(ring);
+    const uint32_t base = ring.stage(st);
+    const int nr = min(NCH, N - n0);
+    if (col_main >= 0) {
+      const uint32_t w = base + 4u * (uint32_t)(col_main + tid);
+#pragma unroll 8
+      for (int n = 0; n < nr; n++) fma4(g_main, lds32(w + 4u * (uint32_t)(n * K)), s_g[n0 + n]);
+    }
+    if (do_t) {
+      const uint32_t w = base + 4u * (uint32_t)(EX + tid);
+#pragma unroll 8
+      for (int n = 0; n < nr; n++) fma4(g_time, lds32(w + 4u * (uint32_t)(n * K)), s_g[n0 + n]);
+    }
+    ring_pop(ring, st, lane);
+  }
+}
 
-__global__ void __launch_bounds__(256) mlp_bwd_act_kernel(MlpBwd a) {
-  __shared__ float4 s_g[2][MW];      // pre-activation gradient of the current layer (ping-pong)
-  __shared__ float4 s_gh[16];        // head gradients
-  __shared__ float4 s_gt[32];        // gradient of the time feature (Tt <= 30)
-  __shared__ float4 s_red[4 * MW];
+struct BwdSmem {
+  float4 g[2][MW];      // pre-activation gradient of the current layer (ping-pong)
+  float4 gh[16];        // head gradients
+  float4 gt[32];        // gradient of the time feature (Tt <= 30)
+  float4 red[4 * MW];
+  uint64_t bars[2 * STAGES];
+};
+constexpr size_t BWD_SMEM_BYTES_MLP = (size_t)STAGES * BWD_STAGE_BYTES + sizeof(BwdSmem);
+
+__global__ void __launch_bounds__(MLP_THREADS) mlp_bwd_act_kernel(MlpBwd a) {
+  extern __shared__ __align__(128) unsigned char mlp_smem[];
+  BwdSmem& S = *reinterpret_cast<BwdSmem*>(mlp_smem + (size_t)STAGES * BWD_STAGE_BYTES);
   const int tid = threadIdx.x;
   const int row0 = blockIdx.x * ROWS;
   const int rows = min(ROWS, a.rows - row0);
   const MlpLayers& L = a.layers;
   const int Tt = a.Tt, in0 = EX + Tt;
   const int first_trunk = a.has_timenet ? 2 : 0;
+  Ring ring;
+  ring_setup(ring, mlp_smem, BWD_STAGE_BYTES, S.bars, tid);
+
+  if (tid >= CONSUMERS) {   // producer warp: heads, linear.7 .. linear.0, timenet.2 — W rows in chunks of NCH
+    if (tid == CONSUMERS) {
+      for (int q = 0; q < MD + 1 + (a.has_timenet ? 1 : 0); q++) {
+        const int li = q == 0 ? first_trunk + MD : (q <= MD ? first_trunk + MD - q : 1);
+        const MlpLayer& ly = L.layer[li];
+        for (int n0 = 0; n0 < ly.N; n0 += NCH)
+          ring_push(ring, ly.W + (size_t)n0 * ly.K, (uint32_t)(min(NCH, ly.N - n0) * ly.K) * 4u);
+      }
+    }
+    return;
+  }
+  float4 (*s_g)[MW] = S.g;
+  float4* s_gh = S.gh; float4* s_gt = S.gt; float4* s_red = S.red;
   if (tid < 16) s_gh[tid] = tid < a.NH ? load_rows(a.g_out, a.NH, row0, rows, tid) : make_float4(0.f, 0.f, 0.f, 0.f);
   if (tid < 32) s_gt[tid] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncthreads();
+  consumer_sync();
   // heads -> h7
   const MlpLayer& hd = L.layer[first_trunk + MD];
   int cur = 0;
   {
-    float4 g = back_dense_k256(hd.W, hd.N, s_gh, s_red, tid);
+    float4 g = back_dense_k256(ring, hd.N, s_gh, s_red, tid);
     const float4 h = load_rows(a.save_h + (size_t)(MD - 1) * a.rows * MW, MW, row0, rows, tid);
     g = relu_mask(g, h);
     s_g[cur][tid] = g;
     store_rows(a.G + (size_t)(MD - 1) * a.rows * MW, MW, row0, rows, tid, g);
   }
-  __syncthreads();
+  consumer_sync();
   for (int l = MD - 1; l >= 1; l--) {
     const MlpLayer& ly = L.layer[first_trunk + l];     // input of layer l is h_{l-1} (plus [x,t] for l == SKIP+1)
-    const int K = ly.K;
     float4 g;
-    if (l == SKIP + 1) {                               // K = in0 + 256: rows are not 16-B aligned, scalar loads
-      g = back_dense(ly.W, K, MW, s_g[cur], in0 + tid);
-      if (tid < Tt) s_gt[tid] = back_dense(ly.W, K, MW, s_g[cur], EX + tid);   // time feature through the skip input
+    if (l == SKIP + 1) {                               // K = in0 + 256
+      float4 gt;
+      back_dense_cols(ring, ly.K, MW, s_g[cur], in0, Tt, tid, g, gt);
+      if (tid < Tt) s_gt[tid] = gt;                    // time feature through the skip input
     } else {
-      g = back_dense_k256(ly.W, MW, s_g[cur], s_red, tid);
+      g = back_dense_k256(ring, MW, s_g[cur], s_red, tid);
     }
     const float4 h = load_rows(a.save_h + (size_t)(l - 1) * a.rows * MW, MW, row0, rows, tid);
     g = relu_mask(g, h);
     s_g[cur ^ 1][tid] = g;
     store_rows(a.G + (size_t)(l - 1) * a.rows * MW, MW, row0, rows, tid, g);
-    __syncthreads();
+    consumer_sync();
     cur ^= 1;
   }
   // layer 0 input: only the time feature needs a gradient (node positions are detached)
   {
     const MlpLayer& l0 = L.layer[first_trunk];
+    float4 unused, gt;
+    back_dense_cols(ring, l0.K, MW, s_g[cur], -1, Tt, tid, unused, gt);
     if (tid < Tt) {
-      const float4 gt = back_dense(l0.W, l0.K, MW, s_g[cur], EX + tid);
       const float4 o = s_gt[tid];
       s_gt[tid] = make_float4(o.x + gt.x, o.y + gt.y, o.z + gt.z, o.w + gt.w);
     }
   }
-  __syncthreads();
+  consumer_sync();
   if (a.has_timenet) {
     if (tid < Tt) store_rows(a.g_tfeat, 32, row0, rows, tid, s_gt[tid]);
     const MlpLayer& t2 = L.layer[1];
-    float4 g = back_dense_k256(t2.W, t2.N, s_gt, s_red, tid);
+    float4 g = back_dense_k256(ring, t2.N, s_gt, s_red, tid);
     const float4 h = load_rows(a.save_th, MW, row0, rows, tid);
     g = relu_mask(g, h);
     store_rows(a.G_t1, MW, row0, rows, tid, g);
@@ -389,11 +528,15 @@ void mlp_launch_transpose(const MlpLayers& L, cudaStream_t s) {
 }
 void mlp_launch_forward(const MlpFwd& a, cudaStream_t s) {
   if (a.rows <= 0) return;
-  mlp_fwd_kernel<<<(a.rows + ROWS - 1) / ROWS, 256, 0, s>>>(a);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM_BYTES); attr = true; }
+  mlp_fwd_kernel<<<(a.rows + ROWS - 1) / ROWS, MLP_THREADS, FWD_SMEM_BYTES, s>>>(a);
 }
 void mlp_launch_backward(const MlpBwd& a, const MlpWJobs& J, cudaStream_t s) {
   if (a.rows <= 0) return;
-  mlp_bwd_act_kernel<<<(a.rows + ROWS - 1) / ROWS, 256, 0, s>>>(a);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(mlp_bwd_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES_MLP); attr = true; }
+  mlp_bwd_act_kernel<<<(a.rows + ROWS - 1) / ROWS, MLP_THREADS, BWD_SMEM_BYTES_MLP, s>>>(a);
   int tiles = 0;
   for (int j = 0; j < J.count; j++) tiles += J.job[j].tiles;
   mlp_bwd_w_kernel<<<tiles, 256, 0, s>>>(J, a.rows);
