@@ -398,14 +398,34 @@ __device__ __forceinline__ void store_sh_chunk(const BwdParams& p, float* dL_dsh
   }
 }
 
+constexpr int SH_WARP_FLOATS = 32 * 45 + 32 * 3;   // per-warp staging of the split SH layout: rest block + DC block
+
 __global__ void __launch_bounds__(256, 3) preprocess_bwd_kernel(
     BwdParams p, const SurfelRec* __restrict__ rec, const uint8_t* __restrict__ clamped,
     const int* __restrict__ radii, float* __restrict__ grad_rec, float* __restrict__ dL_dmeans2D,
     float* __restrict__ dL_dcolors, float* __restrict__ dL_dopacity, float* __restrict__ dL_dmeans3D,
     float* __restrict__ dL_dtransMat, float* __restrict__ dL_dsh, float* __restrict__ dL_dsh_rest,
-    float* __restrict__ dL_dscales, float* __restrict__ dL_drot, float* __restrict__ dL_dscales_raw) {
+    float* __restrict__ dL_dscales, float* __restrict__ dL_drot, float* __restrict__ dL_dscales_raw, const bool staged) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= p.P) return;
+  // Split SH layout (DC (P,1,3) + rest (P,15,3), the trainer's parameters): a warp's 32 surfels own one contiguous
+  // 5760-B block of `rest`, so the warp moves it with coalesced 16-B accesses through shared memory — each thread then
+  // reads / overwrites its own 45 floats there (stride 45 words: conflict-free) instead of issuing 48 scalar global
+  // loads and 48 scalar stores at a 180-B stride.
+  extern __shared__ float s_sh[];
+  const int lane = threadIdx.x & 31;
+  float* wrest = s_sh + (threadIdx.x >> 5) * SH_WARP_FLOATS;
+  float* wdc = wrest + 32 * 45;
+  const int wbase = idx - lane;                       // first surfel of this warp
+  const int nsurf = min(32, p.P - wbase);             // <= 0 for a warp past the end
+  if (staged && nsurf > 0) {
+    const int nrest = nsurf * 45, nvec = nrest >> 2;
+    const float4* src = reinterpret_cast<const float4*>(p.sh_rest + (size_t)wbase * 45);
+    for (int v = lane; v < nvec; v += 32) reinterpret_cast<float4*>(wrest)[v] = __ldg(src + v);
+    for (int f = 4 * nvec + lane; f < nrest; f += 32) wrest[f] = __ldg(p.sh_rest + (size_t)wbase * 45 + f);
+    for (int f = lane; f < nsurf * 3; f += 32) wdc[f] = __ldg(p.shs + (size_t)wbase * 3 + f);
+    __syncwarp();
+  }
+  if (idx < p.P) {
   const bool visible = radii[idx] > 0;
   Activated act;
   if (p.raw && visible) act = activate_surfel(idx, p.means3D, p.d_means3D, p.scales, p.d_scales, p.rotations, p.d_rotations, p.opacities);
@@ -519,7 +539,15 @@ __global__ void __launch_bounds__(256, 3) preprocess_bwd_kernel(
 #pragma unroll
       for (int c = 0; c < 4; c++) {
         float sv[12], go[12];
-        load_sh_chunk(p, idx, c, ncoef, sv);
+        if (staged) {
+#pragma unroll
+          for (int i = 0; i < 12; i++) {
+            const int f = 12 * c + i;
+            sv[i] = (f < 3) ? wdc[lane * 3 + f] : wrest[lane * 45 + (f - 3)];
+          }
+        } else {
+          load_sh_chunk(p, idx, c, ncoef, sv);
+        }
 #pragma unroll
         for (int t = 0; t < 4; t++) {
           const int k = 4 * c + t;
@@ -549,7 +577,15 @@ __global__ void __launch_bounds__(256, 3) preprocess_bwd_kernel(
             dL_ddir.x += bx * sg; dL_ddir.y += by * sg; dL_ddir.z += bz * sg;
           }
         }
-        store_sh_chunk(p, dL_dsh, dL_dsh_rest, idx, c, go);
+        if (staged) {
+#pragma unroll
+          for (int i = 0; i < 12; i++) {
+            const int f = 12 * c + i;
+            if (f < 3) wdc[lane * 3 + f] = go[i]; else wrest[lane * 45 + (f - 3)] = go[i];
+          }
+        } else {
+          store_sh_chunk(p, dL_dsh, dL_dsh_rest, idx, c, go);
+        }
       }
       // derivative of v/|v|
       const v3 v = dir_orig, dv = dL_ddir;
@@ -573,11 +609,27 @@ __global__ void __launch_bounds__(256, 3) preprocess_bwd_kernel(
   if (dL_dscales_raw) reinterpret_cast<float2*>(dL_dscales_raw)[idx] = dscale_raw;
   if (dL_drot) reinterpret_cast<float4*>(dL_drot)[idx] = drot;
   if (dL_dsh && p.M > 0 && !sh_written) {   // culled surfel: the gradient row is zero
-    float zero12[12];
+    if (staged) {
 #pragma unroll
-    for (int i = 0; i < 12; i++) zero12[i] = 0.f;
+      for (int f = 0; f < 3; f++) wdc[lane * 3 + f] = 0.f;
 #pragma unroll
-    for (int c = 0; c < 4; c++) store_sh_chunk(p, dL_dsh, dL_dsh_rest, idx, c, zero12);
+      for (int f = 0; f < 45; f++) wrest[lane * 45 + f] = 0.f;
+    } else {
+      float zero12[12];
+#pragma unroll
+      for (int i = 0; i < 12; i++) zero12[i] = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; c++) store_sh_chunk(p, dL_dsh, dL_dsh_rest, idx, c, zero12);
+    }
+  }
+  }   // idx < P
+  if (staged && nsurf > 0) {
+    __syncwarp();
+    const int nrest = nsurf * 45, nvec = nrest >> 2;
+    float4* dst = reinterpret_cast<float4*>(dL_dsh_rest + (size_t)wbase * 45);
+    for (int v = lane; v < nvec; v += 32) dst[v] = reinterpret_cast<const float4*>(wrest)[v];
+    for (int f = 4 * nvec + lane; f < nrest; f += 32) dL_dsh_rest[(size_t)wbase * 45 + f] = wrest[f];
+    for (int f = lane; f < nsurf * 3; f += 32) dL_dsh[(size_t)wbase * 3 + f] = wdc[f];
   }
 }
 
@@ -586,9 +638,12 @@ void launch_preprocess_bwd(const BwdParams& p, const SurfelRec* rec, const uint8
                            float* dL_dmeans3D, float* dL_dtransMat, float* dL_dsh, float* dL_dsh_rest,
                            float* dL_dscales, float* dL_drot, float* dL_dscales_raw, cudaStream_t s) {
   if (p.P == 0) return;
-  preprocess_bwd_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p, rec, clamped, radii, grad_rec, dL_dmeans2D, dL_dcolors,
-                                                         dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh, dL_dsh_rest,
-                                                         dL_dscales, dL_drot, dL_dscales_raw);
+  const auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool staged = p.shs && p.sh_rest && p.M == 16 && dL_dsh && dL_dsh_rest && al16(p.sh_rest) && al16(dL_dsh_rest);
+  const size_t smem = staged ? sizeof(float) * SH_WARP_FLOATS * 8 : 0;
+  preprocess_bwd_kernel<<<(p.P + 255) / 256, 256, smem, s>>>(p, rec, clamped, radii, grad_rec, dL_dmeans2D, dL_dcolors,
+                                                            dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh, dL_dsh_rest,
+                                                            dL_dscales, dL_drot, dL_dscales_raw, staged);
 }
 
 }  // namespace d2gs
