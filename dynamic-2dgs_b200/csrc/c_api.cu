@@ -406,10 +406,53 @@ int d2gs_deform_forward(const D2gsDeformFwdArgs* a, void* stream) {
   h.trans = a->node_trans; h.rot = a->node_rot; h.scale = a->node_scale; h.local_rot = a->node_local_rot;
   h.mask = a->motion_mask; h.nn_idx = a->nn_idx; h.nn_dist = a->nn_dist; h.nn_weight = a->nn_weight;
   h.d_xyz = a->d_xyz; h.d_rot = a->d_rotation; h.d_scale = a->d_scaling;
-  h.attr_stride = a->node_attr_stride;
+  h.attr_stride = a->node_attr_stride; h.order = a->order;
   const char* err = nullptr;
   { StageTimer t(ST_DEF_F, (cudaStream_t)stream);
     if (deform_forward_launch(h, (cudaStream_t)stream, &err) != 0) return fail(D2GS_ERR_INVALID_ARG, err); }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(D2GS_ERR_CUDA, cudaGetErrorString(e));
+  return D2GS_OK;
+}
+
+namespace {
+struct OrderLayout { size_t bbox, keys, keys_out, vals, temp, temp_bytes, total; };
+OrderLayout order_layout(int P) {
+  OrderLayout L{};
+  const size_t n = (size_t)(P > 0 ? P : 1);
+  size_t o = 0;
+  L.bbox = o; o = align_up(o + 6 * sizeof(unsigned int));
+  L.keys = o; o = align_up(o + 4 * n);
+  L.keys_out = o; o = align_up(o + 4 * n);
+  L.vals = o; o = align_up(o + 4 * n);
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, (unsigned int*)nullptr, (unsigned int*)nullptr, (int*)nullptr, (int*)nullptr, (int)n, 0, 30);
+  L.temp = o; L.temp_bytes = tmp; o = align_up(o + tmp);
+  L.total = o + 256;
+  return L;
+}
+}  // namespace
+
+int d2gs_deform_order_workspace(int P, size_t* bytes) {
+  if (!bytes || P < 0) return fail(D2GS_ERR_INVALID_ARG, "bad arguments");
+  *bytes = order_layout(P).total;
+  return D2GS_OK;
+}
+
+int d2gs_deform_order(int P, const float* xyz, int32_t* order, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (P < 0) return fail(D2GS_ERR_INVALID_ARG, "bad sizes");
+  if (P == 0) return D2GS_OK;
+  if (!xyz || !order || !workspace) return fail(D2GS_ERR_INVALID_ARG, "missing buffers");
+  const OrderLayout L = order_layout(P);
+  if (workspace_bytes < L.total) return fail(D2GS_ERR_WORKSPACE, "order workspace too small");
+  char* ws = aligned_base(workspace);
+  unsigned int* keys = (unsigned int*)(ws + L.keys);
+  unsigned int* keys_out = (unsigned int*)(ws + L.keys_out);
+  int* vals = (int*)(ws + L.vals);
+  deform_order_keys_launch(P, xyz, (unsigned int*)(ws + L.bbox), keys, vals, stream);
+  size_t tmp = L.temp_bytes;
+  D2GS_CUDA_OK(cub::DeviceRadixSort::SortPairs(ws + L.temp, tmp, keys, keys_out, vals, (int*)order, P, 0, 30, stream));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(D2GS_ERR_CUDA, cudaGetErrorString(e));
   return D2GS_OK;
@@ -432,7 +475,7 @@ int d2gs_deform_backward(const D2gsDeformBwdArgs* a, void* stream) {
   h.d_trans = a->dL_dnode_trans; h.d_rot = a->dL_dnode_rot; h.d_scale = a->dL_dnode_scale;
   h.d_local_rot = a->dL_dnode_local_rot; h.d_nodes = a->dL_dnodes; h.d_radius_log = a->dL_dnode_radius_log;
   h.d_weight_logit = a->dL_dnode_weight_logit; h.d_feature = a->dL_dfeature; h.d_mask = a->dL_dmotion_mask;
-  h.attr_stride = a->node_attr_stride;
+  h.attr_stride = a->node_attr_stride; h.order = a->order;
   const char* err = nullptr;
   { StageTimer t(ST_DEF_B, (cudaStream_t)stream);
     if (deform_backward_launch(h, (cudaStream_t)stream, &err) != 0) return fail(D2GS_ERR_INVALID_ARG, err); }

@@ -10,6 +10,7 @@
 namespace d2gs {
 
 extern int g_deform_bwd_smem;
+constexpr unsigned FULL = 0xffffffffu;
 constexpr int MAX_K = 8;
 constexpr int MAX_D = 3 + 16;   // 3 spatial + up to 16 hyper coordinates
 
@@ -52,6 +53,7 @@ struct DeformFwdP {
   int64_t* nn_idx; float* nn_dist; float* nn_weight;
   float* d_xyz; float* d_rot; float* d_scale;
   int st_t, st_r, st_s, st_l;   // row strides of the node attribute tables (3,4,2,4 or the packed MLP output width)
+  const int* order;             // optional: thread t handles surfel order[t] (spatially coherent warps)
 };
 
 // K nearest control nodes by an unordered "replace the current worst" set: every step is a predicated select, so a
@@ -77,8 +79,11 @@ __global__ void __launch_bounds__(256) deform_fwd_kernel(DeformFwdP a) {
     s_nodes[t] = v;
   }
   __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.P) return;
+  const int t_lin = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t_lin >= a.P) return;
+  // With a Morton processing order the 32 surfels of a warp are neighbours in space and see (almost) the same nodes
+  // enter their K-sets: the divergent `offer` body runs for ~30 of the 512 nodes instead of ~240 (random order).
+  const int i = a.order ? __ldg(a.order + t_lin) : t_lin;
 
   float2 q2[DP];   // query coordinate d duplicated in both packed lanes
 #pragma unroll
@@ -204,6 +209,7 @@ struct DeformBwdP {
   float* d_feature; float* d_mask;
   int use_smem;   // 1: per-CTA shared accumulators for the node gradients
   int st_t, st_r, st_s, st_l;
+  const int* order;
 };
 
 // per-node gradient row inside the accumulator: [0..2] trans [3..6] rot [7..8] scale [9..12] local_rot
@@ -230,7 +236,8 @@ __global__ void __launch_bounds__(256) deform_bwd_kernel(DeformBwdP a) {
   };
 
   const int K = a.K;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.P; i += gridDim.x * blockDim.x) {
+  for (int t_lin = blockIdx.x * blockDim.x + threadIdx.x; t_lin < a.P; t_lin += gridDim.x * blockDim.x) {
+    const int i = a.order ? __ldg(a.order + t_lin) : t_lin;
     const float mk = a.mask ? a.mask[i] : 1.0f;
     const float x0 = a.xyz[3 * (size_t)i], x1 = a.xyz[3 * (size_t)i + 1], x2 = a.xyz[3 * (size_t)i + 2];
     const float gx0 = a.g_xyz[3 * (size_t)i], gx1 = a.g_xyz[3 * (size_t)i + 1], gx2 = a.g_xyz[3 * (size_t)i + 2];
@@ -353,6 +360,241 @@ __global__ void __launch_bounds__(256) deform_bwd_kernel(DeformBwdP a) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward for spatially coherent warps (a processing order is given)
+// ---------------------------------------------------------------------------------------------------------------
+// Sum 32 per-lane values across the warp with 31 shuffles: afterwards lane L holds the warp total of g[L] in g[0].
+__device__ __forceinline__ void warp_transpose_reduce32(float (&g)[32], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const float send = b4 ? g[i] : g[i + 16];
+    const float keep = b4 ? g[i + 16] : g[i];
+    g[i] = keep + __shfl_xor_sync(FULL, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const float send = b3 ? g[i] : g[i + 8];
+    const float keep = b3 ? g[i + 8] : g[i];
+    g[i] = keep + __shfl_xor_sync(FULL, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float send = b2 ? g[i] : g[i + 4];
+    const float keep = b2 ? g[i + 4] : g[i];
+    g[i] = keep + __shfl_xor_sync(FULL, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const float send = b1 ? g[i] : g[i + 2];
+    const float keep = b1 ? g[i + 2] : g[i];
+    g[i] = keep + __shfl_xor_sync(FULL, send, 2);
+  }
+  {
+    const float send = b0 ? g[0] : g[1];
+    const float keep = b0 ? g[1] : g[0];
+    g[0] = keep + __shfl_xor_sync(FULL, send, 1);
+  }
+}
+
+// Neighbouring surfels share their control nodes, so the warp walks over the DISTINCT nodes its 32 x K pairs refer to
+// (about 9 with a Morton order): every lane contributes the gradient row of its pair with that node (or zeros), one
+// 32-value transposed butterfly sums the rows, and lanes 0..NG-1 issue ONE global reduction each.  92 shared-memory CAS
+// loops per surfel become ~9 x NG fire-and-forget REDs per warp, and the node attributes are warp-uniform loads.
+// A warp whose surfels are not coherent (more than MAX_DISTINCT different nearest nodes) falls back to per-lane REDs.
+template <int K>
+__global__ void __launch_bounds__(256) deform_bwd_coherent_kernel(DeformBwdP a) {
+  constexpr int HMAX = MAX_D - 3;
+  constexpr int MAX_DISTINCT = 12;
+  const int NG = NG_FIXED + a.hyper;
+  const int nstride = 3 + a.hyper;
+  const int lane = threadIdx.x & 31;
+  auto dst_of = [&](int m, int c) -> float* {
+    if (c < 3) return a.d_trans + a.st_t * m + c;
+    if (c < 7) return a.d_rot + a.st_r * m + (c - 3);
+    if (c < 9) return a.d_scale + a.st_s * m + (c - 7);
+    if (c < 13) return a.d_local_rot ? a.d_local_rot + a.st_l * m + (c - 9) : nullptr;
+    if (c == 13) return a.d_radius_log + m;
+    if (c == 14) return a.d_weight_logit ? a.d_weight_logit + m : nullptr;
+    return a.d_nodes + (size_t)m * nstride + 3 + (c - NG_FIXED);
+  };
+  const int t_lin = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = t_lin < a.P;
+  const int i = live ? (a.order ? __ldg(a.order + t_lin) : t_lin) : 0;
+
+  float x[3] = {0.f, 0.f, 0.f}, Gx[3] = {0.f, 0.f, 0.f}, Gr[4] = {0.f, 0.f, 0.f, 0.f}, Gs[2] = {0.f, 0.f};
+  float fh[HMAX];
+#pragma unroll
+  for (int d = 0; d < HMAX; d++) fh[d] = 0.f;
+  int idx[K];
+  float wk[K], du[K], dist[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) { idx[k] = -1; wk[k] = 0.f; du[k] = 0.f; dist[k] = 0.f; }
+
+  if (live) {
+    const float mk = a.mask ? a.mask[i] : 1.0f;
+    float g_x[3], g_r[4], g_s[2];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { x[c] = a.xyz[3 * (size_t)i + c]; g_x[c] = a.g_xyz[3 * (size_t)i + c]; Gx[c] = g_x[c] * mk; }
+#pragma unroll
+    for (int c = 0; c < 4; c++) { g_r[c] = a.g_rot[4 * (size_t)i + c]; Gr[c] = g_r[c] * mk; }
+#pragma unroll
+    for (int c = 0; c < 2; c++) { g_s[c] = a.g_scale[2 * (size_t)i + c]; Gs[c] = g_s[c] * mk; }
+    const bool hyp = a.hyper > 0 && a.feature;
+    if (hyp) {
+#pragma unroll
+      for (int d = 0; d < HMAX; d++)
+        if (d < a.hyper) fh[d] = a.feature[(size_t)i * a.fstride + d];
+    }
+    // pass 1: blended outputs per neighbour -> dL/dw_k, the mask gradient
+    float dw[K];
+    float sum_w_dw = 0.f;
+    float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const int m = (int)a.nn_idx[(size_t)i * K + k];
+      const float w = a.nn_weight[(size_t)i * K + k];
+      idx[k] = m; wk[k] = w; dist[k] = a.nn_dist[(size_t)i * K + k];
+      const float tr0 = __ldg(a.trans + a.st_t * m), tr1 = __ldg(a.trans + a.st_t * m + 1), tr2 = __ldg(a.trans + a.st_t * m + 2);
+      float A0 = tr0, A1 = tr1, A2 = tr2;
+      if (a.local_rot) {
+        float lq[4] = {__ldg(a.local_rot + a.st_l * m) + 1.0f, __ldg(a.local_rot + a.st_l * m + 1), __ldg(a.local_rot + a.st_l * m + 2),
+                       __ldg(a.local_rot + a.st_l * m + 3)};
+        float R[9];
+        quat_to_matrix_raw(lq, R);
+        const float n0 = __ldg(a.nodes + (size_t)m * nstride), n1 = __ldg(a.nodes + (size_t)m * nstride + 1),
+                    n2 = __ldg(a.nodes + (size_t)m * nstride + 2);
+        const float e0 = x[0] - n0, e1 = x[1] - n1, e2 = x[2] - n2;
+        A0 = (R[0] * e0 + R[1] * e1 + R[2] * e2) + n0 + tr0;
+        A1 = (R[3] * e0 + R[4] * e1 + R[5] * e2) + n1 + tr1;
+        A2 = (R[6] * e0 + R[7] * e1 + R[8] * e2) + n2 + tr2;
+      }
+      const float rr0 = __ldg(a.rot + a.st_r * m), rr1 = __ldg(a.rot + a.st_r * m + 1), rr2 = __ldg(a.rot + a.st_r * m + 2),
+                  rr3 = __ldg(a.rot + a.st_r * m + 3);
+      const float ss0 = __ldg(a.scale + a.st_s * m), ss1 = __ldg(a.scale + a.st_s * m + 1);
+      const float d = Gx[0] * A0 + Gx[1] * A1 + Gx[2] * A2 + Gr[0] * rr0 + Gr[1] * rr1 + Gr[2] * rr2 + Gr[3] * rr3 + Gs[0] * ss0 + Gs[1] * ss1;
+      dw[k] = d;
+      sum_w_dw += w * d;
+      acc[0] += w * A0; acc[1] += w * A1; acc[2] += w * A2;
+      acc[3] += w * rr0; acc[4] += w * rr1; acc[5] += w * rr2; acc[6] += w * rr3;
+      acc[7] += w * ss0; acc[8] += w * ss1;
+    }
+    if (a.d_mask) {
+      if (a.local_rot) { acc[0] -= x[0]; acc[1] -= x[1]; acc[2] -= x[2]; }
+      a.d_mask[i] = g_x[0] * acc[0] + g_x[1] * acc[1] + g_x[2] * acc[2] + g_r[0] * acc[3] + g_r[1] * acc[4] + g_r[2] * acc[5] +
+                    g_r[3] * acc[6] + g_s[0] * acc[7] + g_s[1] * acc[8];
+    }
+    // un-normalised weights: u_k = e_k*sigma_k + 1e-7, w_k = u_k / S.  S is recovered from the nearest (w,u) pair.
+    float S;
+    {
+      const int m = idx[0];
+      const float r = expf(__ldg(a.radius_log + m));
+      const float e = expf(-dist[0] / (2 * (r * r)));
+      const float sg = a.weight_logit ? 1.0f / (1.0f + expf(-__ldg(a.weight_logit + m))) : 1.0f;
+      S = (e * sg + 1e-7f) / wk[0];
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) du[k] = (dw[k] - sum_w_dw) / S;
+    // gradient of the hyper coordinates of the QUERY (per surfel, no reduction)
+    if (a.d_feature) {
+      float dq_h[HMAX];
+#pragma unroll
+      for (int d = 0; d < HMAX; d++) dq_h[d] = 0.f;
+      if (hyp) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          const int m = idx[k];
+          const float r = expf(__ldg(a.radius_log + m));
+          const float inv2r2 = 1.0f / (2 * (r * r));
+          const float e = expf(-dist[k] * inv2r2);
+          const float sg = a.weight_logit ? 1.0f / (1.0f + expf(-__ldg(a.weight_logit + m))) : 1.0f;
+          const float dd = -(du[k] * sg) * e * inv2r2;
+#pragma unroll
+          for (int d = 0; d < HMAX; d++)
+            if (d < a.hyper) dq_h[d] += dd * 2.0f * (fh[d] - __ldg(a.nodes + (size_t)m * nstride + 3 + d));
+        }
+      }
+      for (int d = 0; d < a.fstride; d++) a.d_feature[(size_t)i * a.fstride + d] = (d < a.hyper) ? dq_h[d < HMAX ? d : 0] : 0.f;
+    }
+  }
+
+  // gradient row of the pair (this lane, node mm) with pair scalars (w, du, dist); all-zero scalars give an all-zero row
+  auto pair_row = [&](int mm, float w, float duk, float dk, float (&g)[32]) {
+#pragma unroll
+    for (int c = 0; c < 32; c++) g[c] = 0.f;
+    g[0] = w * Gx[0]; g[1] = w * Gx[1]; g[2] = w * Gx[2];
+    g[3] = w * Gr[0]; g[4] = w * Gr[1]; g[5] = w * Gr[2]; g[6] = w * Gr[3];
+    g[7] = w * Gs[0]; g[8] = w * Gs[1];
+    if (a.local_rot) {
+      float lq[4] = {__ldg(a.local_rot + a.st_l * mm) + 1.0f, __ldg(a.local_rot + a.st_l * mm + 1), __ldg(a.local_rot + a.st_l * mm + 2),
+                     __ldg(a.local_rot + a.st_l * mm + 3)};
+      const float e0 = x[0] - __ldg(a.nodes + (size_t)mm * nstride), e1 = x[1] - __ldg(a.nodes + (size_t)mm * nstride + 1),
+                  e2 = x[2] - __ldg(a.nodes + (size_t)mm * nstride + 2);
+      const float wg0 = g[0], wg1 = g[1], wg2 = g[2];
+      const float dR[9] = {wg0 * e0, wg0 * e1, wg0 * e2, wg1 * e0, wg1 * e1, wg1 * e2, wg2 * e0, wg2 * e1, wg2 * e2};
+      float dq[4];
+      quat_to_matrix_raw_vjp(lq, dR, dq);
+      g[9] = dq[0]; g[10] = dq[1]; g[11] = dq[2]; g[12] = dq[3];
+    }
+    const float r = expf(__ldg(a.radius_log + mm));
+    const float inv2r2 = 1.0f / (2 * (r * r));
+    const float e = expf(-dk * inv2r2);
+    const float sg = a.weight_logit ? 1.0f / (1.0f + expf(-__ldg(a.weight_logit + mm))) : 1.0f;
+    const float de = duk * sg;
+    g[13] = de * e * dk * 2.0f * inv2r2;
+    g[14] = a.weight_logit ? duk * e * sg * (1.0f - sg) : 0.f;
+    if (a.hyper > 0 && a.feature) {
+      const float dd = -de * e * inv2r2;
+#pragma unroll
+      for (int d = 0; d < HMAX; d++)
+        if (d < a.hyper) g[NG_FIXED + d] = -(dd * 2.0f * (fh[d] - __ldg(a.nodes + (size_t)mm * nstride + 3 + d)));
+    }
+  };
+
+  // coherent?  count the distinct nearest nodes of the warp
+  const uint32_t same = __match_any_sync(FULL, idx[0]);
+  const int distinct = __popc(__ballot_sync(FULL, (__ffs(same) - 1) == lane));
+  if (distinct > MAX_DISTINCT) {
+    if (live) {
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        float g[32];
+        pair_row(idx[k], wk[k], du[k], dist[k], g);
+#pragma unroll
+        for (int c = 0; c < 32; c++) {
+          if (c < NG && g[c] != 0.f) { float* q = dst_of(idx[k], c); if (q) atomicAdd(q, g[c]); }
+        }
+      }
+    }
+    return;
+  }
+  uint32_t todo = live ? ((1u << K) - 1u) : 0u;
+  while (true) {
+    const uint32_t have = __ballot_sync(FULL, todo != 0u);
+    if (have == 0u) break;
+    const int leader = __ffs(have) - 1;
+    int first_m = -1;
+#pragma unroll
+    for (int k = K - 1; k >= 0; k--)
+      if ((todo >> k) & 1u) first_m = idx[k];
+    const int mm = __shfl_sync(FULL, first_m, leader);
+    float w = 0.f, duk = 0.f, dk = 0.f;
+    uint32_t bit = 0u;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const bool hit = ((todo >> k) & 1u) && idx[k] == mm;
+      w = hit ? wk[k] : w; duk = hit ? du[k] : duk; dk = hit ? dist[k] : dk;
+      bit = hit ? (1u << k) : bit;
+    }
+    todo &= ~bit;
+    float g[32];
+    pair_row(mm, w, duk, dk, g);
+    warp_transpose_reduce32(g, lane);
+    if (lane < NG && g[0] != 0.f) { float* q = dst_of(mm, lane); if (q) atomicAdd(q, g[0]); }
+  }
+}
+
 int deform_forward_launch(const DeformFwdHost& h, cudaStream_t s, const char** err) {
   if (h.K < 1 || h.K > MAX_K || h.K > h.M) { *err = "K must be in [1, min(8, M)]"; return -1; }
   if (h.hyper < 0 || h.hyper > MAX_D - 3) { *err = "hyper_dim must be <= 16"; return -1; }
@@ -368,6 +610,7 @@ int deform_forward_launch(const DeformFwdHost& h, cudaStream_t s, const char** e
   a.d_xyz = h.d_xyz; a.d_rot = h.d_rot; a.d_scale = h.d_scale;
   a.st_t = h.attr_stride > 0 ? h.attr_stride : 3; a.st_r = h.attr_stride > 0 ? h.attr_stride : 4;
   a.st_s = h.attr_stride > 0 ? h.attr_stride : 2; a.st_l = h.attr_stride > 0 ? h.attr_stride : 4;
+  a.order = h.order;
   const int nq = (a.D + 3) / 4;
   const size_t smem = sizeof(float) * (size_t)((a.M + 1) & ~1) * 4 * nq;
   if (smem > 200 * 1024) { *err = "node table exceeds shared memory (M*(3+hyper) floats > 200 KB)"; return -1; }
@@ -416,6 +659,21 @@ int deform_backward_launch(const DeformBwdHost& h, cudaStream_t s, const char** 
   if (h.K < 1 || h.K > MAX_K) { *err = "K must be in [1, 8]"; return -1; }
   if (h.hyper < 0 || h.hyper > MAX_D - 3) { *err = "hyper_dim must be <= 16"; return -1; }
   if (h.P == 0) return 0;
+  a.order = h.order;
+  if (h.order && NG_FIXED + h.hyper <= 32) {
+    const int grid = (h.P + 255) / 256;
+    switch (h.K) {
+      case 1: deform_bwd_coherent_kernel<1><<<grid, 256, 0, s>>>(a); break;
+      case 2: deform_bwd_coherent_kernel<2><<<grid, 256, 0, s>>>(a); break;
+      case 3: deform_bwd_coherent_kernel<3><<<grid, 256, 0, s>>>(a); break;
+      case 4: deform_bwd_coherent_kernel<4><<<grid, 256, 0, s>>>(a); break;
+      case 5: deform_bwd_coherent_kernel<5><<<grid, 256, 0, s>>>(a); break;
+      case 6: deform_bwd_coherent_kernel<6><<<grid, 256, 0, s>>>(a); break;
+      case 7: deform_bwd_coherent_kernel<7><<<grid, 256, 0, s>>>(a); break;
+      default: deform_bwd_coherent_kernel<8><<<grid, 256, 0, s>>>(a); break;
+    }
+    return 0;
+  }
   const size_t smem = sizeof(float) * (size_t)h.M * (NG_FIXED + h.hyper);
   a.use_smem = g_deform_bwd_smem && smem <= 200 * 1024;
   int dev = 0, sms = 148;
@@ -429,6 +687,71 @@ int deform_backward_launch(const DeformBwdHost& h, cudaStream_t s, const char** 
   }
   deform_bwd_kernel<<<blocks, 256, a.use_smem ? smem : 0, s>>>(a);
   return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// processing order: 30-bit Morton keys of the surfel centres inside their bounding box (sorted by the caller with CUB)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int float_to_ordered(float f) {
+  const unsigned int b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(unsigned int u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__global__ void __launch_bounds__(256) order_bbox_kernel(int P, const float* __restrict__ xyz, unsigned int* __restrict__ bbox) {
+  unsigned int lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const float v = xyz[3 * (size_t)i + c];
+      if (v == v && fabsf(v) <= 3.0e38f) {   // NaN / inf centres do not stretch the box
+        const unsigned int u = float_to_ordered(v);
+        lo[c] = min(lo[c], u); hi[c] = max(hi[c], u);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    lo[c] = __reduce_min_sync(FULL, lo[c]);
+    hi[c] = __reduce_max_sync(FULL, hi[c]);
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) { atomicMin(bbox + c, lo[c]); atomicMax(bbox + 3 + c, hi[c]); }
+  }
+}
+__device__ __forceinline__ unsigned int spread10(unsigned int v) {
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+__global__ void __launch_bounds__(256) order_keys_kernel(int P, const float* __restrict__ xyz, const unsigned int* __restrict__ bbox,
+                                                         unsigned int* __restrict__ keys, int* __restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  unsigned int q[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const float lo = ordered_to_float(bbox[c]), hi = ordered_to_float(bbox[3 + c]);
+    const float v = xyz[3 * (size_t)i + c];
+    const float ext = hi - lo;
+    float u = (ext > 0.f && v == v) ? (v - lo) / ext : 0.f;
+    u = fminf(fmaxf(u, 0.f), 1.f);
+    q[c] = min(1023u, (unsigned int)(u * 1024.f));
+  }
+  keys[i] = spread10(q[0]) | (spread10(q[1]) << 1) | (spread10(q[2]) << 2);
+  vals[i] = i;
+}
+void deform_order_keys_launch(int P, const float* xyz, unsigned int* bbox, unsigned int* keys, int* vals, cudaStream_t s) {
+  if (P <= 0) return;
+  cudaMemsetAsync(bbox, 0xff, 3 * sizeof(unsigned int), s);       // running minima (ordered-uint encoding)
+  cudaMemsetAsync(bbox + 3, 0x00, 3 * sizeof(unsigned int), s);   // running maxima
+  order_bbox_kernel<<<min((P + 255) / 256, 592), 256, 0, s>>>(P, xyz, bbox);
+  order_keys_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, xyz, bbox, keys, vals);
 }
 
 }  // namespace d2gs

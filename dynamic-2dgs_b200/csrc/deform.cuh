@@ -13,6 +13,7 @@ struct DeformFwdHost {
   int64_t* nn_idx; float* nn_dist; float* nn_weight;
   float* d_xyz; float* d_rot; float* d_scale;
   int attr_stride;      // > 0: trans/rot/scale/local_rot are columns of one (M, attr_stride) matrix
+  const int* order;     // optional processing order (a permutation of 0..P-1): thread t handles surfel order[t]
 };
 
 struct DeformBwdHost {
@@ -25,9 +26,13 @@ struct DeformBwdHost {
   float* d_trans; float* d_rot; float* d_scale; float* d_local_rot; float* d_nodes; float* d_radius_log;
   float* d_weight_logit; float* d_feature; float* d_mask;
   int attr_stride;
+  const int* order;
 };
 
 int deform_forward_launch(const DeformFwdHost& h, cudaStream_t s, const char** err);
 int deform_backward_launch(const DeformBwdHost& h, cudaStream_t s, const char** err);
+
+// Morton order of the surfel centres (see d2gs_deform_order)
+void deform_order_keys_launch(int P, const float* xyz, unsigned int* bbox, unsigned int* keys, int* vals, cudaStream_t s);
 
 }  // namespace d2gs

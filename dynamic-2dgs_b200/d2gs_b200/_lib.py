@@ -67,7 +67,8 @@ class DeformFwdArgs(C.Structure):
                 ("node_trans", C.c_void_p), ("node_rot", C.c_void_p), ("node_scale", C.c_void_p),
                 ("node_local_rot", C.c_void_p), ("motion_mask", C.c_void_p),
                 ("nn_idx", C.c_void_p), ("nn_dist", C.c_void_p), ("nn_weight", C.c_void_p),
-                ("d_xyz", C.c_void_p), ("d_rotation", C.c_void_p), ("d_scaling", C.c_void_p), ("node_attr_stride", C.c_int)]
+                ("d_xyz", C.c_void_p), ("d_rotation", C.c_void_p), ("d_scaling", C.c_void_p), ("node_attr_stride", C.c_int),
+                ("order", C.c_void_p)]
 
 
 class DeformBwdArgs(C.Structure):
@@ -81,7 +82,7 @@ class DeformBwdArgs(C.Structure):
                 ("dL_dnode_trans", C.c_void_p), ("dL_dnode_rot", C.c_void_p), ("dL_dnode_scale", C.c_void_p),
                 ("dL_dnode_local_rot", C.c_void_p), ("dL_dnodes", C.c_void_p), ("dL_dnode_radius_log", C.c_void_p),
                 ("dL_dnode_weight_logit", C.c_void_p), ("dL_dfeature", C.c_void_p), ("dL_dmotion_mask", C.c_void_p),
-                ("node_attr_stride", C.c_int)]
+                ("node_attr_stride", C.c_int), ("order", C.c_void_p)]
 
 
 class EpilogueArgs(C.Structure):
@@ -109,6 +110,7 @@ EXPORTED_SYMBOLS = (
     "d2gs_raster_backward", "d2gs_mark_visible", "d2gs_raster_export_state", "d2gs_deform_forward",
     "d2gs_deform_backward", "d2gs_epilogue_forward", "d2gs_epilogue_backward",
     "d2gs_mlp_workspace", "d2gs_mlp_forward", "d2gs_mlp_backward", "d2gs_mlp_hidden",
+    "d2gs_deform_order_workspace", "d2gs_deform_order",
 )
 
 D2GS_OK = 0
@@ -151,6 +153,8 @@ def lib():
     L.d2gs_mlp_backward.argtypes = [C.POINTER(MlpArgs), C.c_void_p]
     L.d2gs_mlp_hidden.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.d2gs_mlp_hidden.restype = C.c_void_p
+    L.d2gs_deform_order_workspace.argtypes = [C.c_int, C.POINTER(C.c_size_t)]
+    L.d2gs_deform_order.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.d2gs_set_option.argtypes = [C.c_char_p, C.c_int]
     L.d2gs_profile_enable.argtypes = [C.c_int]
     L.d2gs_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]

@@ -41,7 +41,25 @@ def _f32(t):
     return None if t is None else t.detach().float().contiguous()
 
 
-def _blend_forward(ctx, xyz, feature, nodes, node_radius_log, node_weight_logit, attr_ptrs, attr_stride, motion_mask, K, hyper_dim):
+def processing_order(xyz: torch.Tensor) -> torch.Tensor:
+    """int32 permutation that sorts the surfel centres along a Morton curve (libd2gs.so: d2gs_deform_order).  Passed to
+    the blend kernels it makes the 32 surfels of a warp spatial neighbours; results do not depend on it."""
+    L = _lib.lib()
+    x = _f32(xyz)
+    P = int(x.shape[0])
+    order = torch.empty((P,), dtype=torch.int32, device=x.device)
+    if P:
+        nbytes = C.c_size_t()
+        _lib.check(L.d2gs_deform_order_workspace(P, C.byref(nbytes)), "d2gs_deform_order_workspace")
+        ws = torch.empty((nbytes.value,), dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(L.d2gs_deform_order(P, x.data_ptr(), order.data_ptr(), ws.data_ptr(), nbytes.value, _stream(x.device)),
+                       "d2gs_deform_order")
+    return order
+
+
+def _blend_forward(ctx, xyz, feature, nodes, node_radius_log, node_weight_logit, attr_ptrs, attr_stride, motion_mask, K, hyper_dim,
+                   order=None):
     """Shared forward of the two autograd Functions below.  attr_ptrs = device pointers of (trans, rot, scale, local_rot)."""
     L = _lib.lib()
     dev = xyz.device
@@ -65,6 +83,11 @@ def _blend_forward(ctx, xyz, feature, nodes, node_radius_log, node_weight_logit,
     a.node_trans, a.node_rot, a.node_scale, a.node_local_rot = attr_ptrs
     a.node_attr_stride = attr_stride
     a.motion_mask = _p(mask_)
+    if order is not None:
+        if order.dtype != torch.int32 or order.numel() != P or not order.is_contiguous() or order.device != dev:
+            raise ValueError("order must be a contiguous int32 permutation of 0..P-1 on the same device")
+        a.order = order.data_ptr()
+    ctx.order = order
     nn_idx = torch.empty((P, K), dtype=torch.int64, device=dev)
     nn_dist = torch.empty((P, K), dtype=torch.float32, device=dev)
     nn_weight = torch.empty((P, K), dtype=torch.float32, device=dev)
@@ -118,6 +141,8 @@ def _blend_backward(ctx, common, attr_ptrs, d_attr_ptrs, attr_stride, g_xyz, g_r
     a.node_trans, a.node_rot, a.node_scale, a.node_local_rot = attr_ptrs
     a.node_attr_stride = attr_stride
     a.motion_mask = _p(mask_)
+    if ctx.order is not None:
+        a.order = ctx.order.data_ptr()
     a.nn_idx, a.nn_dist, a.nn_weight = _p(nn_idx), _p(nn_dist), _p(nn_weight)
     a.dL_d_xyz, a.dL_d_rotation, a.dL_d_scaling = _p(g_xyz), _p(g_rot), _p(g_scale)
     a.dL_dnode_trans, a.dL_dnode_rot, a.dL_dnode_scale, a.dL_dnode_local_rot = d_attr_ptrs
@@ -135,10 +160,10 @@ class _NodeBlend(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xyz, feature, nodes, node_radius_log, node_weight_logit, node_trans, node_rot, node_scale,
-                node_local_rot, motion_mask, K, hyper_dim):
+                node_local_rot, motion_mask, K, hyper_dim, order=None):
         tr_, rt_, sc_, lr_ = _f32(node_trans), _f32(node_rot), _f32(node_scale), _f32(node_local_rot)
         common, outs = _blend_forward(ctx, xyz, feature, nodes, node_radius_log, node_weight_logit,
-                                      (_p(tr_), _p(rt_), _p(sc_), _p(lr_)), 0, motion_mask, K, hyper_dim)
+                                      (_p(tr_), _p(rt_), _p(sc_), _p(lr_)), 0, motion_mask, K, hyper_dim, order)
         ctx.has = [t is not None for t in common]
         ctx.save_for_backward(tr_, rt_, sc_, lr_, *[t for t in common if t is not None])
         return outs
@@ -158,7 +183,7 @@ class _NodeBlend(torch.autograd.Function):
             ctx, common, (_p(tr_), _p(rt_), _p(sc_), _p(lr_)), (_p(d_trans), _p(d_rot), _p(d_scale), _p(d_lr)), 0,
             g_xyz, g_rot, g_scale)
         # xyz is detached by the reference (time_utils.py:1136), node xyz columns too (:947,1151)
-        return (None, d_feat, d_nodes, d_rad, d_wl, d_trans, d_rot, d_scale, d_lr, d_mask, None, None)
+        return (None, d_feat, d_nodes, d_rad, d_wl, d_trans, d_rot, d_scale, d_lr, d_mask, None, None, None)
 
 
 class _NodeBlendPacked(torch.autograd.Function):
@@ -166,12 +191,13 @@ class _NodeBlendPacked(torch.autograd.Function):
     each attribute: no slicing copies forward, one (M, S) gradient matrix backward.  cols = (trans, rot, scale, local_rot | -1)."""
 
     @staticmethod
-    def forward(ctx, xyz, feature, nodes, node_radius_log, node_weight_logit, attrs, motion_mask, K, hyper_dim, cols):
+    def forward(ctx, xyz, feature, nodes, node_radius_log, node_weight_logit, attrs, motion_mask, K, hyper_dim, cols, order=None):
         at_ = _f32(attrs)
         S = int(at_.shape[1])
         base = at_.data_ptr()
         ptrs = tuple((base + 4 * c) if c >= 0 else None for c in cols)
-        common, outs = _blend_forward(ctx, xyz, feature, nodes, node_radius_log, node_weight_logit, ptrs, S, motion_mask, K, hyper_dim)
+        common, outs = _blend_forward(ctx, xyz, feature, nodes, node_radius_log, node_weight_logit, ptrs, S, motion_mask, K, hyper_dim,
+                                      order)
         ctx.cols = tuple(cols)
         ctx.has = [t is not None for t in common]
         ctx.save_for_backward(at_, *[t for t in common if t is not None])
@@ -187,20 +213,21 @@ class _NodeBlendPacked(torch.autograd.Function):
         ptrs = tuple((at_.data_ptr() + 4 * c) if c >= 0 else None for c in ctx.cols)
         d_ptrs = tuple((d_attrs.data_ptr() + 4 * c) if c >= 0 else None for c in ctx.cols)
         d_feat, d_nodes, d_rad, d_wl, d_mask = _blend_backward(ctx, common, ptrs, d_ptrs, S, g_xyz, g_rot, g_scale)
-        return (None, d_feat, d_nodes, d_rad, d_wl, d_attrs, d_mask, None, None, None)
+        return (None, d_feat, d_nodes, d_rad, d_wl, d_attrs, d_mask, None, None, None, None)
 
 
-def node_blend_packed(xyz, feature, nodes, node_radius_log, node_weight_logit, attrs, cols, motion_mask, K: int, hyper_dim: int):
+def node_blend_packed(xyz, feature, nodes, node_radius_log, node_weight_logit, attrs, cols, motion_mask, K: int, hyper_dim: int,
+                      order=None):
     d_xyz, d_rot, d_scale, w, d, i = _NodeBlendPacked.apply(xyz, feature, nodes, node_radius_log, node_weight_logit, attrs,
-                                                            motion_mask, K, hyper_dim, tuple(cols))
+                                                            motion_mask, K, hyper_dim, tuple(cols), order)
     return {"d_xyz": d_xyz, "d_rotation": d_rot, "d_scaling": d_scale, "nn_weight": w, "nn_dist": d, "nn_index": i, "nn_idx": i}
 
 
 def node_blend(xyz, feature, nodes, node_radius_log, node_weight_logit, node_trans, node_rot, node_scale,
-               node_local_rot, motion_mask, K: int, hyper_dim: int):
-    """Returns dict(d_xyz, d_rotation, d_scaling, nn_weight, nn_dist, nn_idx)."""
+               node_local_rot, motion_mask, K: int, hyper_dim: int, order=None):
+    """Returns dict(d_xyz, d_rotation, d_scaling, nn_weight, nn_dist, nn_idx).  ``order``: see processing_order()."""
     d_xyz, d_rot, d_scale, w, d, i = _NodeBlend.apply(xyz, feature, nodes, node_radius_log, node_weight_logit, node_trans,
-                                                      node_rot, node_scale, node_local_rot, motion_mask, K, hyper_dim)
+                                                      node_rot, node_scale, node_local_rot, motion_mask, K, hyper_dim, order)
     return {"d_xyz": d_xyz, "d_rotation": d_rot, "d_scaling": d_scale, "nn_weight": w, "nn_dist": d, "nn_idx": i}
 
 
@@ -580,6 +607,22 @@ class ControlNodeWarp(nn.Module):
         values = self.query_network(x=nodes, t=t, **kwargs)
         return {k: (v.view(*tshape[:-1], v.shape[-1]) if v is not None else None) for k, v in values.items()}
 
+    ORDER_REFRESH = 64   # forward calls between two rebuilds of the Morton processing order
+
+    def _processing_order(self, x):
+        """Cached spatial processing order of the surfels (speed only: a stale order is still a valid permutation, the
+        centres move by a learning-rate step per iteration).  Rebuilt when the surfel count or device changes
+        (densification / pruning) and every ORDER_REFRESH calls."""
+        if not x.is_cuda:
+            return None
+        c = getattr(self, "_order_cache", None)
+        P = int(x.shape[0])
+        if c is None or c[0] != P or c[1] != x.device or c[3] >= self.ORDER_REFRESH:
+            c = [P, x.device, processing_order(x), 0]
+            object.__setattr__(self, "_order_cache", c)
+        c[3] += 1
+        return c[2]
+
     def cal_nn_weight(self, x, K=None, feature=None, nodes=None, gs_kernel=True, temperature=1.):
         """Reference: utils/time_utils.py:934-967.  Returns (nn_weight (P,K), nn_dist (P,K), nn_idx (P,K) int64)."""
         if not gs_kernel or nodes is not None:
@@ -605,13 +648,16 @@ class ControlNodeWarp(nn.Module):
         packed = getattr(net, '_packed', None)
         wl = self._node_weight.reshape(-1) if self.with_node_weight else None
         mm = motion_mask if torch.is_tensor(motion_mask) else None
+        order = self._processing_order(x)
         if packed is not None and t.dim() == 2 and packed[0].shape[0] == self.nodes.shape[0]:
             net._packed = None
-            out = node_blend_packed(x, feature, self.nodes, self._node_radius, wl, packed[0], packed[1], mm, self.K, self.hyper_dim)
+            out = node_blend_packed(x, feature, self.nodes, self._node_radius, wl, packed[0], packed[1], mm, self.K, self.hyper_dim,
+                                    order=order)
         else:
             out = node_blend(x, feature, self.nodes, self._node_radius, wl,
                              node_attrs['d_xyz'], node_attrs['d_rotation'], node_attrs['d_scaling'],
-                             node_attrs.get('local_rotation') if self.local_frame else None, mm, self.K, self.hyper_dim)
+                             node_attrs.get('local_rotation') if self.local_frame else None, mm, self.K, self.hyper_dim,
+                             order=order)
         ret = {'d_xyz': out['d_xyz'], 'd_rotation': out['d_rotation'], 'd_scaling': out['d_scaling'],
                'd_opacity': None, 'd_color': None}
         if self.pred_opacity:

@@ -1,4 +1,2 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -q -m gpu --tb=short -x 2>&1 | grep -vE "^E\s+\[|^E\s+[0-9\.\-e, ]+\]|^E\s+\+|array\(" | tail -8 | cut -c1-600
-timeout 600 python bench.py --steps 60 --warmup 8 > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; tail -3 gpurun_out/bench_ours.err; cat gpurun_out/bench_ours.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['e2e']); print(d['roofline']['stages_ms'])"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"preprocess_bwd|deform_fwd|deform_bwd|mlp_fwd|mlp_bwd_act|mlp_bwd_w|epilogue_bwd|preprocess_fwd" -s 24 -c 8 -f -o gpurun_out/prof_misc_r1f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_misc.log 2>&1; tail -2 gpurun_out/ncu_misc.log | cut -c1-300; ls -la gpurun_out/*.ncu-rep
+timeout 1200 python -m pytest tests -q -m gpu --tb=short 2>&1 | grep -vE "^E\s+\[|^E\s+[0-9\.\-e, ]+\]|^E\s+\+|array\(" | tail -12 | cut -c1-600

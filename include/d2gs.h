@@ -285,6 +285,7 @@ typedef struct D2gsDeformFwdArgs {
   float* d_scaling;              /* (P,2) */
   int node_attr_stride;          /* 0: node_trans/rot/scale/local_rot are separate packed tables; > 0: they are columns
                                     of ONE (M,node_attr_stride) row-major matrix (the MLP head output), no slicing copies */
+  const int32_t* order;          /* optional (P): processing order from d2gs_deform_order; results do not depend on it */
 } D2gsDeformFwdArgs;
 
 D2GS_API int d2gs_deform_forward(const D2gsDeformFwdArgs* args, void* stream);
@@ -319,9 +320,18 @@ typedef struct D2gsDeformBwdArgs {
   float* dL_dfeature;            /* (P,feature_stride) or NULL */
   float* dL_dmotion_mask;        /* (P) or NULL */
   int node_attr_stride;          /* as in D2gsDeformFwdArgs; applies to node_* and dL_dnode_{trans,rot,scale,local_rot} */
+  const int32_t* order;          /* optional (P): with an order the node gradients are reduced per warp over the distinct
+                                    nodes of 32 neighbouring surfels instead of one atomic per (surfel, node, component) */
 } D2gsDeformBwdArgs;
 
 D2GS_API int d2gs_deform_backward(const D2gsDeformBwdArgs* args, void* stream);
+
+/* Spatial processing order for the two calls above: a permutation of 0..P-1 that sorts the surfel centres along a
+ * 30-bit Morton curve of their bounding box, so that the 32 surfels of a warp are neighbours and share their control
+ * nodes (the reference has no counterpart: pytorch3d.ops.knn_points, utils/time_utils.py:950, is order-agnostic).
+ * The order only affects speed; it may be reused for many frames while the centres move slowly. */
+D2GS_API int d2gs_deform_order_workspace(int P, size_t* bytes);
+D2GS_API int d2gs_deform_order(int P, const float* xyz, int32_t* order, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -80,6 +80,64 @@ def test_node_blend_matches_oracle(P, M, K, hyper, local_frame, with_mask, cuda_
         assert not m["nodes"].grad[:, :3].any()      # node positions are detached in the reference
 
 
+def test_processing_order_is_a_morton_permutation(cuda_device):
+    from d2gs_b200 import deform as dfm
+    g = torch.Generator().manual_seed(3)
+    for P in (1, 33, 10007):
+        x = torch.randn(P, 3, generator=g) * torch.tensor([1.0, 3.0, 0.2])
+        order = dfm.processing_order(x.to(cuda_device)).cpu().numpy()
+        assert order.dtype == np.int32 and sorted(order.tolist()) == list(range(P))
+        xs = x.numpy()
+        lo, hi = xs.min(0), xs.max(0)
+        ext = np.where(hi > lo, hi - lo, 1.0).astype(np.float32)
+        q = np.minimum(1023, ((xs - lo) / ext * np.float32(1024.0)).astype(np.int64)).astype(np.uint64)
+
+        def spread(v):
+            v = (v | (v << 16)) & 0x030000FF; v = (v | (v << 8)) & 0x0300F00F
+            v = (v | (v << 4)) & 0x030C30C3; v = (v | (v << 2)) & 0x09249249
+            return v
+        key = (spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)).astype(np.int64)[order]
+        # the device quantises with fp32 division too; a centre sitting on a cell boundary may land one cell off
+        assert P == 1 or (np.diff(key) < 0).mean() < 1e-3
+
+
+@pytest.mark.parametrize("P,M,K,hyper,local_frame,coherent", [(5000, 128, 4, 8, True, True), (5000, 128, 4, 8, True, False),
+                                                             (3001, 512, 3, 0, False, True), (2000, 40, 8, 16, True, True)])
+def test_node_blend_is_invariant_to_the_processing_order(P, M, K, hyper, local_frame, coherent, cuda_device):
+    """A processing order only regroups the surfels into warps: forward results bit-identical, gradients equal up to the
+    summation order of the node reductions.  `coherent=False` passes a random permutation (exercises the per-lane
+    fallback of the warp-aggregated backward)."""
+    from d2gs_b200 import deform as dfm
+    dev = cuda_device
+    x, feat, nodes, rad, wl, attrs = _case(P, M, K, hyper, seed=5 * P + M, local_frame=local_frame, with_mask=True)
+    gx, gr, gs = (torch.randn(P, c).to(dev) for c in (3, 4, 2))
+    order = dfm.processing_order(x.to(dev)) if coherent else torch.randperm(P, generator=torch.Generator().manual_seed(1)).to(torch.int32).to(dev)
+
+    def run(order):
+        mk = lambda t: t.clone().to(dev).requires_grad_(True)
+        m = dict(feat=mk(feat), nodes=mk(nodes), rad=mk(rad), wl=mk(wl), **{k: mk(v) for k, v in attrs.items()})
+        mask = torch.sigmoid(m["feat"][:, -1:])
+        out = dfm.node_blend(x.to(dev), m["feat"] if hyper else None, m["nodes"], m["rad"], m["wl"].reshape(-1), m["d_xyz"], m["d_rotation"],
+                             m["d_scaling"], m.get("local_rotation"), mask, K, hyper, order=order)
+        ((out["d_xyz"] * gx).sum() + (out["d_rotation"] * gr).sum() + (out["d_scaling"] * gs).sum()).backward()
+        torch.cuda.synchronize()
+        return out, {k: (v.grad.clone() if v.grad is not None else None) for k, v in m.items()}
+
+    o0, g0 = run(None)
+    o1, g1 = run(order)
+    for k in ("d_xyz", "d_rotation", "d_scaling", "nn_weight", "nn_dist", "nn_idx"):
+        assert torch.equal(o0[k], o1[k]), k
+    for k in g0:
+        if g0[k] is None:
+            assert g1[k] is None or not g1[k].any(), k
+            continue
+        a, b = g1[k].cpu().numpy(), g0[k].cpu().numpy()
+        if np.abs(b).max() < 1e-6:
+            assert np.abs(a).max() < 1e-5, k
+        else:
+            assert util.rel_err(a, b) < 2e-5, (k, util.rel_err(a, b))
+
+
 @pytest.mark.parametrize("rows,is_blender,local_frame,pred_opacity", [(512, True, True, False), (37, True, False, False),
                                                                        (300, False, True, True), (1, True, True, False)])
 def test_fused_mlp_matches_eager_layers(rows, is_blender, local_frame, pred_opacity, cuda_device):
