@@ -184,7 +184,7 @@ def build_deform_reference(wl: Workload):
     wl.deform_parameters = lambda: list(wl.net.values()) + [wl.nodes, wl.node_radius, wl.node_weight]
 
 
-def step_ours(wl: Workload, cam, gt):
+def step_ours(wl: Workload, cam, gt, gt_ready=None):
     from gaussian_renderer import render
     pc = wl.pc
     if wl.use_deform:
@@ -194,12 +194,14 @@ def step_ours(wl: Workload, cam, gt):
     else:
         d_xyz, d_rot, d_scale = 0.0, 0.0, 0.0
     out = render(cam, pc, wl.pipe, wl.bg, d_xyz, d_rot, d_scale)
+    if gt_ready is not None:
+        torch.cuda.current_stream().wait_event(gt_ready)     # the target image arrives on the copy stream
     loss = synthetic_loss(out, wl.wts, gt)
     loss.backward()
     return loss
 
 
-def step_reference(wl: Workload, cam, gt):
+def step_reference(wl: Workload, cam, gt, gt_ready=None):
     from oracle import reference_pipeline as rp
     pc = wl.pc
     if wl.use_deform:
@@ -209,6 +211,8 @@ def step_reference(wl: Workload, cam, gt):
     else:
         d_xyz, d_rot, d_scale = 0.0, 0.0, 0.0
     out = rp.render_reference(wl.ref_mod, cam, pc, wl.bg, d_xyz, d_rot, d_scale)
+    if gt_ready is not None:
+        torch.cuda.current_stream().wait_event(gt_ready)
     loss = synthetic_loss(out, wl.wts, gt)
     loss.backward()
     return loss
@@ -355,7 +359,10 @@ def main():
     params = list(wl.pc.raster_parameters()) + list(wl.deform_parameters())
     # flat gradient bucket: our backward kernels write parameter gradients straight into it (dist.claim), the reference arm's
     # autograd accumulates into pre-attached views; either way the all-reduce needs no pack step
-    bucket = ddist.FlatGradBucket(params, direct=(args.impl != "reference"))
+    # (surfel tables whose gradient is final after the rasterizer backward start their all-reduce early, overlapped with
+    # the deformation / MLP backward; `feature` also feeds the deformation blend, so it is not among them)
+    early = [p for p in wl.pc.raster_parameters() if p is not getattr(wl.pc, "feature", None)]
+    bucket = ddist.FlatGradBucket(params, direct=(args.impl != "reference"), early=early)
 
     def view_of(step):
         return wl.cams[ddist.view_for(step, rank, world, N_VIEWS)]
@@ -374,11 +381,15 @@ def main():
             cam.camera_center.copy_(hc[2], non_blocking=True)
             cam.fid.copy_(hc[3], non_blocking=True)
             cam.FoVx, cam.FoVy = c.FoVx, c.FoVy
+            # the 7.7 MB target image is only needed by the loss: it travels on a copy stream, overlapped with the
+            # deformation and the forward render (the previous step ended with a host read, so the buffer is free)
             gt = e2e_gt
-            gt.copy_(wl.gt_host, non_blocking=True)
+            with torch.cuda.stream(copy_stream):
+                gt.copy_(wl.gt_host, non_blocking=True)
+                gt_ready.record(copy_stream)
+            loss = step_fn(wl, cam, gt, gt_ready)
         else:
-            gt = wl.gt_dev
-        loss = step_fn(wl, cam, gt)
+            loss = step_fn(wl, cam, wl.gt_dev)
         bucket.all_reduce()      # finalize + (N > 1) ONE NCCL all-reduce over the flat buffer
         if e2e:
             return float(loss.item())   # device -> host read of the step's result
@@ -388,6 +399,8 @@ def main():
                   torch.as_tensor(c.camera_center).pin_memory(), torch.tensor([c.fid]).pin_memory()] for c in wl.cams_np]
     e2e_cam = mdl.ViewCamera(wl.cams_np[0], device)
     e2e_gt = torch.empty_like(wl.gt_dev)
+    copy_stream = torch.cuda.Stream(device)
+    gt_ready = torch.cuda.Event()
 
     def barrier():
         if dist is not None:

@@ -122,12 +122,28 @@ __global__ void __launch_bounds__(256) epilogue_bwd_kernel(int W, int H, const f
                                                            const float* __restrict__ g_dist, const float* __restrict__ g_depth,
                                                            const float* __restrict__ g_sn, const float* __restrict__ g_sp,
                                                            float* __restrict__ dA) {
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (x >= W || y >= H) return;
+  // The VJP of the normal at a pixel feeds its four neighbours: each CTA evaluates it ONCE per pixel of its 32x8 tile
+  // plus a one-pixel halo (340 evaluations for 256 threads) into shared memory, instead of four times per thread.
+  __shared__ float s_gdx[3][10][34], s_gdy[3][10][34];
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x = x0 + tx, y = y0 + ty;
   const Cam c = make_cam(view, fx, fy, W, H);
-  const size_t HW = (size_t)H * W, pix = (size_t)y * W + x;
+  const size_t HW = (size_t)H * W;
   const float* dplane = allmap + 5 * HW;
   const float* aplane = allmap + 1 * HW;
+  if (g_sn) {
+    for (int e = threadIdx.x; e < 340; e += 256) {
+      const int hy = e / 34, hx = e - hy * 34;
+      v3 a, b;
+      normal_vjp(c, dplane, aplane, g_sn, HW, W, H, x0 + hx - 1, y0 + hy - 1, a, b);   // zero outside the interior
+      s_gdx[0][hy][hx] = a.x; s_gdx[1][hy][hx] = a.y; s_gdx[2][hy][hx] = a.z;
+      s_gdy[0][hy][hx] = b.x; s_gdy[1][hy][hx] = b.y; s_gdy[2][hy][hx] = b.z;
+    }
+    __syncthreads();
+  }
+  if (x >= W || y >= H) return;
+  const size_t pix = (size_t)y * W + x;
   dA[0 * HW + pix] = 0.f;
   dA[1 * HW + pix] = g_alpha ? g_alpha[pix] : 0.f;
   float r0 = 0.f, r1 = 0.f, r2 = 0.f;
@@ -139,11 +155,13 @@ __global__ void __launch_bounds__(256) epilogue_bwd_kernel(int W, int H, const f
   v3 gP = {0.f, 0.f, 0.f};
   if (g_sp) gP = {g_sp[pix], g_sp[HW + pix], g_sp[2 * HW + pix]};
   if (g_sn) {
-    v3 a, b;
-    if (y >= 1) { normal_vjp(c, dplane, aplane, g_sn, HW, W, H, x, y - 1, a, b); gP = gP + a; }      // P(y,x) is the "+" end of dx at (y-1)
-    if (y <= H - 2) { normal_vjp(c, dplane, aplane, g_sn, HW, W, H, x, y + 1, a, b); gP = gP - a; }  // and the "-" end at (y+1)
-    if (x >= 1) { normal_vjp(c, dplane, aplane, g_sn, HW, W, H, x - 1, y, a, b); gP = gP + b; }
-    if (x <= W - 2) { normal_vjp(c, dplane, aplane, g_sn, HW, W, H, x + 1, y, a, b); gP = gP - b; }
+    // P(y,x) is the "+" end of dx at (y-1) and its "-" end at (y+1); likewise for dy along x.  Same order of additions
+    // as the per-thread version: +a(y-1), -a(y+1), +b(x-1), -b(x+1).
+    const int hx = tx + 1, hy = ty + 1;
+    gP.x = gP.x + s_gdx[0][hy - 1][hx]; gP.y = gP.y + s_gdx[1][hy - 1][hx]; gP.z = gP.z + s_gdx[2][hy - 1][hx];
+    gP.x = gP.x - s_gdx[0][hy + 1][hx]; gP.y = gP.y - s_gdx[1][hy + 1][hx]; gP.z = gP.z - s_gdx[2][hy + 1][hx];
+    gP.x = gP.x + s_gdy[0][hy][hx - 1]; gP.y = gP.y + s_gdy[1][hy][hx - 1]; gP.z = gP.z + s_gdy[2][hy][hx - 1];
+    gP.x = gP.x - s_gdy[0][hy][hx + 1]; gP.y = gP.y - s_gdy[1][hy][hx + 1]; gP.z = gP.z - s_gdy[2][hy][hx + 1];
   }
   const float draw = dplane[pix];
   float gd = g_depth ? g_depth[pix] : 0.f;

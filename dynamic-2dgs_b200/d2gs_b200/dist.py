@@ -52,34 +52,70 @@ def claim(t: Optional[torch.Tensor], zeroed: bool) -> Optional[torch.Tensor]:
     return s.view.view(t.shape)
 
 
+_ACTIVE = []  # weak references to the direct-mode buckets, for grads_ready()
+
+
+def grads_ready(stage: str) -> None:
+    """Called by the backward wrappers when a stage of the backward pass has written all its parameter gradients
+    ("raster": the per-surfel tables).  Buckets that declared those parameters `early` start their all-reduce now, on
+    the collective's own stream, overlapped with the rest of the backward (deformation blend, MLP)."""
+    for ref in list(_ACTIVE):
+        b = ref()
+        if b is None:
+            _ACTIVE.remove(ref)
+        else:
+            b._on_stage(stage)
+
+
 class FlatGradBucket:
-    """All parameter gradients as slices of one contiguous fp32 buffer, reduced with ONE collective.
+    """All parameter gradients as slices of one contiguous fp32 buffer, reduced with ONE collective (two when part of
+    it can start early).
 
     ``direct=True`` (default): ``.grad`` starts every step as None and the backward kernels write into the bucket
     through ``claim()``; autograd adopts those views, so a step costs no AccumulateGrad kernels and no pack.
     Small slots (< ``large_numel`` elements) sit first and are cleared by one fill per step; large slots (the per-surfel
     tables) are fully overwritten by the rasterizer backward and only cleared when a step does not claim them.
+    ``early``: parameters whose gradient is final as soon as the rasterizer backward has run (the surfel tables; NOT
+    parameters that also feed the deformation).  They are laid out last and contiguously, and their all-reduce is
+    issued from ``grads_ready("raster")`` while the deformation / MLP backward still runs.
     ``direct=False``: ``.grad`` is pre-set to the views and autograd accumulates in place."""
 
     ALIGN = 64   # floats
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], direct: bool = True, large_numel: int = 1 << 20):
+    def __init__(self, params: Iterable[torch.nn.Parameter], direct: bool = True, large_numel: int = 1 << 20,
+                 early: Optional[Iterable[torch.nn.Parameter]] = None):
         ps = [p for p in params if p.requires_grad]
         assert ps, "no trainable parameters"
-        self.params = [p for p in ps if p.numel() < large_numel] + [p for p in ps if p.numel() >= large_numel]
+        early_ids = {id(p) for p in (early or [])} if direct else set()
+        is_early = lambda p: id(p) in early_ids
+        is_large = lambda p: p.numel() >= large_numel or is_early(p)
+        self.params = [p for p in ps if not is_large(p)] + [p for p in ps if is_large(p) and not is_early(p)] + \
+                      [p for p in ps if is_early(p)]
         dev = self.params[0].device
         # every slot starts on a 256-byte boundary, like a tensor from the CUDA caching allocator: the backward kernels
         # store gradients with 16-byte vector instructions
         pad = lambda n: (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.numel = sum(pad(p.numel()) for p in self.params)
-        self.n_small = sum(pad(p.numel()) for p in self.params if p.numel() < large_numel)
+        self.n_small = sum(pad(p.numel()) for p in self.params if not is_large(p))
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
         self.direct = direct
         self.slots: List[_Slot] = []
+        self.early_slots: List[_Slot] = []
         off = 0
+        self.early_begin = None
         for p in self.params:
-            self.slots.append(_Slot(self.flat[off: off + p.numel()].view_as(p), p.numel() >= large_numel))
+            sl = _Slot(self.flat[off: off + p.numel()].view_as(p), is_large(p))
+            self.slots.append(sl)
+            if is_early(p):
+                if self.early_begin is None:
+                    self.early_begin = off
+                self.early_slots.append(sl)
             off += pad(p.numel())
+        self._early_work = None
+        self._group = None
+        if direct:
+            import weakref
+            _ACTIVE.append(weakref.ref(self))
         self.attach()
 
     def attach(self) -> None:
@@ -93,12 +129,16 @@ class FlatGradBucket:
     def detach(self) -> None:
         for p in self.params:
             _SLOTS.pop(p.data_ptr(), None)
+        _ACTIVE[:] = [r for r in _ACTIVE if r() is not None and r() is not self]
 
     def zero(self) -> None:
         """Start of a step."""
         if not self.direct:
             self.flat.zero_()
             return
+        if self._early_work is not None:       # a step that never reached all_reduce()
+            self._early_work.wait()
+            self._early_work = None
         if self.n_small:
             self.flat[: self.n_small].zero_()
         for p, s in zip(self.params, self.slots):
@@ -109,21 +149,36 @@ class FlatGradBucket:
 
     begin_step = zero
 
+    def set_group(self, group) -> None:
+        """Process group used by the early all-reduce (default group when never called)."""
+        self._group = group
+
+    def _on_stage(self, stage: str) -> None:
+        if stage != "raster" or not self.early_slots or self._early_work is not None:
+            return
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(self._group) > 1):
+            return
+        if not all(s.claimed for s in self.early_slots):
+            return            # some table was not written by the kernels this step: everything goes at the end
+        self._early_work = dist.all_reduce(self.flat[self.early_begin:], op=dist.ReduceOp.SUM, group=self._group, async_op=True)
+
     def finalize(self) -> None:
         """After backward: every ``.grad`` is its bucket slice and the slice holds this step's gradient."""
         if not self.direct:
             return
+        early = set(map(id, self.early_slots)) if self._early_work is not None else ()
         for p, s in zip(self.params, self.slots):
             g = p.grad
             if g is None:
-                if s.dirty and not s.claimed:
-                    s.view.zero_()
-                    s.dirty = False
-                elif s.claimed:            # handed out but never returned to autograd: not a gradient
+                if id(s) in early:
+                    raise RuntimeError("a parameter declared `early` was claimed but received no gradient")
+                if s.dirty:                # stale data of an earlier step, or handed out but never returned to autograd
                     s.view.zero_()
                     s.dirty = False
                 p.grad = s.view
             elif g.data_ptr() != s.view.data_ptr():
+                if id(s) in early:
+                    raise RuntimeError("a parameter declared `early` received a second gradient after the rasterizer backward")
                 s.view.copy_(g)
                 s.dirty = True
                 p.grad = s.view
@@ -131,7 +186,12 @@ class FlatGradBucket:
     def all_reduce(self, group=None, average: bool = False) -> None:
         self.finalize()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            if self._early_work is not None:
+                dist.all_reduce(self.flat[: self.early_begin], op=dist.ReduceOp.SUM, group=group)
+                self._early_work.wait()
+                self._early_work = None
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
             if average:
                 self.flat.div_(dist.get_world_size(group))
 

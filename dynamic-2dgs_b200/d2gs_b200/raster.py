@@ -334,6 +334,8 @@ class _RasterizeSurfelsRaw(torch.autograd.Function):
                             grad_out_color.float().contiguous(), grad_depth.float().contiguous(), sh_, shr_, rs.sh_degree,
                             campos, rctx, rs.debug, want=want, raw_params=True, opacities=op_, d_means3D=dx_, d_scales=ds_,
                             d_rotations=dr_, out=out)
+        from .dist import grads_ready
+        grads_ready("raster")      # the surfel-table gradients are final: buckets may start reducing them now
         hd = ctx.has_delta
         alias = lambda t: t.view_as(t)   # a second tensor object on the same memory, so autograd can adopt the first as .grad
         return (g["dL_dmeans3D"], alias(g["dL_dmeans3D"]) if hd[0] else None, g["dL_dscales_raw"], g["dL_dscales"] if hd[1] else None,

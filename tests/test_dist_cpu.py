@@ -141,3 +141,48 @@ def test_direct_bucket_adopts_kernel_written_gradients():
             assert float(b.flat.sum()) == pytest.approx(float(small.grad.sum() + big.grad.sum()), rel=1e-5, abs=1e-5)
     finally:
         b.detach()
+
+
+def _early_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    table = torch.nn.Parameter(torch.randn(50, 3))       # "surfel table": final after the first backward stage
+    late = torch.nn.Parameter(torch.randn(7))            # gets its gradient later in the same backward
+    b = ddist.FlatGradBucket([late, table], large_numel=1 << 20, early=[table])
+    assert b.params[-1] is table and b.early_begin == b.numel - 192      # early slots are laid out last (50*3 -> 3 x 64 floats)
+
+    class Notify(torch.autograd.Function):            # stands for the end of the rasterizer backward
+        @staticmethod
+        def forward(ctx, x):
+            return x.clone()
+
+        @staticmethod
+        def backward(ctx, g):
+            ddist.grads_ready("raster")
+            return g
+
+    launched = []
+    for step in range(3):
+        b.zero()
+        scale = float(rank + 1 + step)
+        y = _ClaimingSquare.apply(table)                  # scalar sum(table^2); its backward claims the table's slot
+        z = Notify.apply(late * 1.0)
+        (scale * y).backward()                            # stage 1: the table gradient is written into its slot
+        (scale * (z * z).sum()).backward()                # stage 2: Notify.backward -> early all-reduce, then late's gradient
+        launched.append(b._early_work is not None)
+        b.all_reduce()
+        exp_table = sum(2.0 * (r + 1 + step) for r in range(world)) * table.data
+        exp_late = sum(2.0 * (r + 1 + step) for r in range(world)) * late.data
+        assert torch.allclose(table.grad, exp_table, rtol=1e-5), step
+        assert torch.allclose(late.grad, exp_late, rtol=1e-5), step
+    if rank == 0:
+        torch.save({"launched": launched}, out["path"])
+    dist.destroy_process_group()
+
+
+def test_early_allreduce_of_declared_tables(tmp_path):
+    world = 2
+    path = str(tmp_path / "early.pt")
+    mp.spawn(_early_worker, args=(world, _free_port(), {"path": path}), nprocs=world, join=True)
+    assert torch.load(path)["launched"] == [True, True, True]      # the early collective really ran ahead of the final one
