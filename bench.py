@@ -39,6 +39,7 @@ from d2gs_b200 import synthetic as syn
 METRIC = "fwd+bwd frames/sec @300k surfels 800x800"
 UNIT = "frames/s"
 N_VIEWS = 100
+TRAIN_LAMBDAS = (0.2, 0.02, 1000.0)   # lambda_dssim (arguments/__init__.py), lambda_normal / lambda_dist after iteration 8000 (train_gui.py:292-293)
 HEAD_SCALE = 1e3      # default head init is ~1e-5, scaled so the deformation is non-trivial
 
 
@@ -155,6 +156,7 @@ class Workload:
         self.gt_host = torch.rand((3, self.H, self.W), generator=torch.Generator().manual_seed(5)).pin_memory()
         self.gt_dev = self.gt_host.to(device)
         self.use_deform = cfg["n_nodes"] > 0
+        self.loss_kind = "synthetic"
         self.deform_parameters = lambda: []
 
 
@@ -196,7 +198,12 @@ def step_ours(wl: Workload, cam, gt, gt_ready=None):
     out = render(cam, pc, wl.pipe, wl.bg, d_xyz, d_rot, d_scale)
     if gt_ready is not None:
         torch.cuda.current_stream().wait_event(gt_ready)     # the target image arrives on the copy stream
-    loss = synthetic_loss(out, wl.wts, gt)
+    if wl.loss_kind == "train":
+        # the training loss of train_gui.py:292-313 (L1 + D-SSIM + normal consistency + distortion), fused
+        from d2gs_b200 import loss as fl
+        loss = fl.surfel_loss(out["render"], gt, out["rend_normal"], out["surf_normal"], out["rend_dist"], *TRAIN_LAMBDAS)
+    else:
+        loss = synthetic_loss(out, wl.wts, gt)
     loss.backward()
     return loss
 
@@ -213,7 +220,11 @@ def step_reference(wl: Workload, cam, gt, gt_ready=None):
     out = rp.render_reference(wl.ref_mod, cam, pc, wl.bg, d_xyz, d_rot, d_scale)
     if gt_ready is not None:
         torch.cuda.current_stream().wait_event(gt_ready)
-    loss = synthetic_loss(out, wl.wts, gt)
+    if wl.loss_kind == "train":
+        from oracle import loss_oracle as lo      # eager restatement of utils/loss_utils.py + train_gui.py:292-313
+        loss = lo.surfel_loss(out["render"], gt, out["rend_normal"], out["surf_normal"], out["rend_dist"], *TRAIN_LAMBDAS)[0]
+    else:
+        loss = synthetic_loss(out, wl.wts, gt)
     loss.backward()
     return loss
 
@@ -296,6 +307,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C3")
+    ap.add_argument("--loss", choices=["synthetic", "train"], default="synthetic",
+                    help="synthetic: seeded random-weighted sum + L1 (SURVEY 8(d), the headline); train: the reference's training loss "
+                         "(L1 + D-SSIM + normal + distortion), fused kernel in our arm, eager torch in the reference arm")
+    ap.add_argument("--early-allreduce", type=int, default=0, help="1: start the all-reduce of the surfel-table gradients right after the rasterizer backward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="diagnosis only: do not sample clocks during the timed region")
     args = ap.parse_args()
@@ -329,6 +344,7 @@ def main():
 
     from d2gs_b200 import model as mdl
     wl = Workload(args.config, device, args.impl)
+    wl.loss_kind = args.loss
     cfg = wl.cfg
 
     impl_note = None
@@ -362,7 +378,7 @@ def main():
     # (surfel tables whose gradient is final after the rasterizer backward start their all-reduce early, overlapped with
     # the deformation / MLP backward; `feature` also feeds the deformation blend, so it is not among them)
     early = [p for p in wl.pc.raster_parameters() if p is not getattr(wl.pc, "feature", None)]
-    bucket = ddist.FlatGradBucket(params, direct=(args.impl != "reference"), early=early)
+    bucket = ddist.FlatGradBucket(params, direct=(args.impl != "reference"), early=early if args.early_allreduce else None)
 
     def view_of(step):
         return wl.cams[ddist.view_for(step, rank, world, N_VIEWS)]
@@ -466,6 +482,8 @@ def main():
            "data": "synthetic (seeded D-NeRF-shaped scene, random-init deform MLP)",
            "config": {"workload": f"{args.config}: {P} surfels + {cfg['n_nodes']} control nodes (K={cfg['K']}, hyper_dim 8, local_frame), "
                                   f"SH3, {cfg['W']}x{cfg['H']}, {N_VIEWS} views, 1 view/GPU/step, deform+render+loss+backward",
+                      "loss": "seeded random-weighted sum over the render outputs + L1 (SURVEY 8(d))" if args.loss == "synthetic" else
+                              "training loss of train_gui.py:292-313: L1 + D-SSIM(0.2) + normal(0.02) + distortion(1000)",
                       "parallelism": f"view-sharded x{world}" + (" + NCCL all-reduce of the flat gradient bucket" if world > 1 else ""),
                       "l2_policy": "no explicit flush: per-step working set (params+grads+workspaces ~0.3 GB) exceeds the 126 MB L2 and the view changes every step"},
            "clocks": clocks,

@@ -10,6 +10,7 @@
 #include "raster_common.cuh"
 #include "deform.cuh"
 #include "epilogue.cuh"
+#include "loss.cuh"
 #include "mlp.cuh"
 
 namespace d2gs {
@@ -38,7 +39,7 @@ static int fail(int code, const std::string& msg) {
   } while (0)
 
 // ---- optional per-stage timing (CUDA events on the launch stream) ------------------------------------------
-enum Stage { ST_PRE = 0, ST_SCAN, ST_DUP, ST_SORT, ST_RANGES, ST_BLEND_F, ST_BLEND_B, ST_PRE_B, ST_DEF_F, ST_DEF_B, ST_EPI_F, ST_EPI_B, ST_MLP_F, ST_MLP_B };
+enum Stage { ST_PRE = 0, ST_SCAN, ST_DUP, ST_SORT, ST_RANGES, ST_BLEND_F, ST_BLEND_B, ST_PRE_B, ST_DEF_F, ST_DEF_B, ST_EPI_F, ST_EPI_B, ST_MLP_F, ST_MLP_B, ST_LOSS_F, ST_LOSS_B };
 struct StageRec { int stage; cudaEvent_t a, b; };
 static bool g_profile = false;
 int g_deform_bwd_smem = 1;  // node-gradient accumulation of deform_bwd: 1 = per-CTA shared accumulators, 0 = global reductions
@@ -509,6 +510,68 @@ int d2gs_epilogue_backward(const D2gsEpilogueArgs* a, void* stream_) {
   return D2GS_OK;
 }
 
+}  // extern "C"
+
+namespace {
+struct LossLayout { size_t sums, maps, total; };
+LossLayout loss_layout(int W, int H) {
+  LossLayout L{};
+  size_t o = 0;
+  L.sums = o; o = align_up(o + 4 * sizeof(float));
+  L.maps = o; o = align_up(o + 9 * sizeof(float) * (size_t)W * H);
+  L.total = o + 256;
+  return L;
+}
+bool loss_args(const D2gsLossArgs* a, d2gs::LossArgs& k, bool backward) {
+  const LossLayout L = loss_layout(a->width, a->height);
+  if (!a->workspace || a->workspace_bytes < L.total) return false;
+  char* ws = aligned_base(a->workspace);
+  const size_t HW3 = 3 * (size_t)a->width * a->height;
+  k.W = a->width; k.H = a->height;
+  k.image = a->image; k.gt = a->gt; k.rend_normal = a->rend_normal; k.surf_normal = a->surf_normal; k.rend_dist = a->rend_dist;
+  k.l_dssim = a->lambda_dssim; k.l_normal = a->lambda_normal; k.l_dist = a->lambda_dist;
+  k.sums = (float*)(ws + L.sums); k.out = a->out;
+  float* maps = (float*)(ws + L.maps);
+  const bool keep = backward || a->save_for_backward;
+  k.d_mu1 = keep ? maps : nullptr; k.d_e11 = keep ? maps + HW3 : nullptr; k.d_e12 = keep ? maps + 2 * HW3 : nullptr;
+  k.upstream = a->upstream;
+  k.g_image = a->g_image; k.g_rend_normal = a->g_rend_normal; k.g_surf_normal = a->g_surf_normal; k.g_rend_dist = a->g_rend_dist;
+  return true;
+}
+}  // namespace
+
+extern "C" {
+int d2gs_loss_workspace(int width, int height, size_t* bytes) {
+  if (!bytes || width <= 0 || height <= 0) return fail(D2GS_ERR_INVALID_ARG, "bad arguments");
+  *bytes = loss_layout(width, height).total;
+  return D2GS_OK;
+}
+int d2gs_loss_forward(const D2gsLossArgs* a, void* stream_) {
+  if (!a) return fail(D2GS_ERR_INVALID_ARG, "null args");
+  if (a->width <= 0 || a->height <= 0) return fail(D2GS_ERR_INVALID_ARG, "bad sizes");
+  if (!a->image || !a->gt || !a->out) return fail(D2GS_ERR_INVALID_ARG, "missing buffers");
+  d2gs::LossArgs k{};
+  if (!loss_args(a, k, false)) return fail(D2GS_ERR_WORKSPACE, "loss workspace missing or too small");
+  { StageTimer t(ST_LOSS_F, (cudaStream_t)stream_);
+    d2gs::launch_loss_forward(k, (cudaStream_t)stream_); }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(D2GS_ERR_CUDA, cudaGetErrorString(e));
+  return D2GS_OK;
+}
+int d2gs_loss_backward(const D2gsLossArgs* a, void* stream_) {
+  if (!a) return fail(D2GS_ERR_INVALID_ARG, "null args");
+  if (a->width <= 0 || a->height <= 0) return fail(D2GS_ERR_INVALID_ARG, "bad sizes");
+  if (!a->image || !a->gt || !a->g_image) return fail(D2GS_ERR_INVALID_ARG, "missing buffers");
+  if ((a->g_rend_normal && !a->surf_normal) || (a->g_surf_normal && !a->rend_normal))
+    return fail(D2GS_ERR_INVALID_ARG, "normal gradients need both normal maps");
+  d2gs::LossArgs k{};
+  if (!loss_args(a, k, true)) return fail(D2GS_ERR_WORKSPACE, "loss workspace missing or too small");
+  { StageTimer t(ST_LOSS_B, (cudaStream_t)stream_);
+    d2gs::launch_loss_backward(k, (cudaStream_t)stream_); }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(D2GS_ERR_CUDA, cudaGetErrorString(e));
+  return D2GS_OK;
+}
 }  // extern "C"
 
 namespace d2gs {

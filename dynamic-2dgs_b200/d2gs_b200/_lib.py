@@ -94,6 +94,15 @@ class EpilogueArgs(C.Structure):
                 ("g_surf_normal", C.c_void_p), ("g_surf_point", C.c_void_p), ("dL_dallmap", C.c_void_p)]
 
 
+class LossArgs(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("image", C.c_void_p), ("gt", C.c_void_p),
+                ("rend_normal", C.c_void_p), ("surf_normal", C.c_void_p), ("rend_dist", C.c_void_p),
+                ("lambda_dssim", C.c_float), ("lambda_normal", C.c_float), ("lambda_dist", C.c_float),
+                ("out", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("save_for_backward", C.c_int),
+                ("upstream", C.c_void_p), ("g_image", C.c_void_p), ("g_rend_normal", C.c_void_p), ("g_surf_normal", C.c_void_p),
+                ("g_rend_dist", C.c_void_p)]
+
+
 class MlpArgs(C.Structure):
     _fields_ = [("rows", C.c_int), ("is_blender", C.c_int), ("num_out", C.c_int), ("x", C.c_void_p), ("t", C.c_void_p),
                 ("t_stride", C.c_int),
@@ -111,6 +120,7 @@ EXPORTED_SYMBOLS = (
     "d2gs_deform_backward", "d2gs_epilogue_forward", "d2gs_epilogue_backward",
     "d2gs_mlp_workspace", "d2gs_mlp_forward", "d2gs_mlp_backward", "d2gs_mlp_hidden",
     "d2gs_deform_order_workspace", "d2gs_deform_order",
+    "d2gs_loss_workspace", "d2gs_loss_forward", "d2gs_loss_backward",
 )
 
 D2GS_OK = 0
@@ -155,6 +165,9 @@ def lib():
     L.d2gs_mlp_hidden.restype = C.c_void_p
     L.d2gs_deform_order_workspace.argtypes = [C.c_int, C.POINTER(C.c_size_t)]
     L.d2gs_deform_order.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.d2gs_loss_workspace.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+    L.d2gs_loss_forward.argtypes = [C.POINTER(LossArgs), C.c_void_p]
+    L.d2gs_loss_backward.argtypes = [C.POINTER(LossArgs), C.c_void_p]
     L.d2gs_set_option.argtypes = [C.c_char_p, C.c_int]
     L.d2gs_profile_enable.argtypes = [C.c_int]
     L.d2gs_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
@@ -182,7 +195,7 @@ def workspace_sizes(P: int, W: int, H: int, R: int = 0):
 
 
 STAGE_NAMES = ("preprocess_fwd", "scan", "duplicate", "sort", "ranges", "blend_fwd", "blend_bwd", "preprocess_bwd",
-               "deform_fwd", "deform_bwd", "epilogue_fwd", "epilogue_bwd", "mlp_fwd", "mlp_bwd")
+               "deform_fwd", "deform_bwd", "epilogue_fwd", "epilogue_bwd", "mlp_fwd", "mlp_bwd", "loss_fwd", "loss_bwd")
 
 
 def profile_enable(on: bool) -> None:

@@ -51,9 +51,9 @@ typedef struct D2gsConfig {
 
 /* Per-stage device timing with CUDA events recorded on the launch stream (for bench.py's roofline line).
  * Stages: 0 preprocess_fwd, 1 scan, 2 duplicate, 3 sort, 4 ranges, 5 blend_fwd, 6 blend_bwd, 7 preprocess_bwd,
- *         8 deform_fwd, 9 deform_bwd, 10 epilogue_fwd, 11 epilogue_bwd, 12 mlp_fwd, 13 mlp_bwd.  d2gs_profile_collect synchronises the device, adds the elapsed times of all
+ *         8 deform_fwd, 9 deform_bwd, 10 epilogue_fwd, 11 epilogue_bwd, 12 mlp_fwd, 13 mlp_bwd, 14 loss_fwd, 15 loss_bwd.  d2gs_profile_collect synchronises the device, adds the elapsed times of all
  * recorded launches to total_ms[stage] / launches[stage] (arrays of D2GS_NUM_STAGES) and clears the record. */
-#define D2GS_NUM_STAGES 14
+#define D2GS_NUM_STAGES 16
 /* Runtime switches.  "cull" (default 1): warp-level cull boxes in the blend kernels; results are identical either way. */
 D2GS_API int d2gs_set_option(const char* name, int value);
 D2GS_API int d2gs_profile_enable(int on);
@@ -221,6 +221,37 @@ typedef struct D2gsEpilogueArgs {
 
 D2GS_API int d2gs_epilogue_forward(const D2gsEpilogueArgs* args, void* stream);
 D2GS_API int d2gs_epilogue_backward(const D2gsEpilogueArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Photometric loss of the training step, fused.  Replaces l1_loss / ssim
+ * (utils/loss_utils.py:18-19,33-76: 11x11 Gaussian window, sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2, mean over
+ * all elements) and the normal-consistency / distortion terms and their composition (train_gui.py:292-313):
+ *   loss = (1 - lambda_dssim) * L1 + lambda_dssim * (1 - SSIM) + lambda_normal * mean(1 - <rend_normal, surf_normal>)
+ *        + lambda_dist * mean(rend_dist)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct D2gsLossArgs {
+  int width, height;
+  const float* image;          /* (3,H,W) rendered */
+  const float* gt;             /* (3,H,W) target */
+  const float* rend_normal;    /* (3,H,W) or NULL: the normal term is dropped */
+  const float* surf_normal;    /* (3,H,W) or NULL */
+  const float* rend_dist;      /* (1,H,W) or NULL: the distortion term is dropped */
+  float lambda_dssim, lambda_normal, lambda_dist;
+  float* out;                  /* device (5): loss, L1, SSIM, weighted normal term, weighted distortion term */
+  void* workspace;             /* d2gs_loss_workspace bytes: reduction scratch + the three SSIM partial-derivative maps */
+  size_t workspace_bytes;
+  int save_for_backward;       /* 0: forward only (the maps are not written) */
+  /* backward (reads the workspace written by the forward call with the same inputs) */
+  const float* upstream;       /* device scalar dL/dloss, or NULL (= 1) */
+  float* g_image;              /* (3,H,W) fully written */
+  float* g_rend_normal;        /* (3,H,W) or NULL */
+  float* g_surf_normal;        /* (3,H,W) or NULL */
+  float* g_rend_dist;          /* (1,H,W) or NULL */
+} D2gsLossArgs;
+
+D2GS_API int d2gs_loss_workspace(int width, int height, size_t* bytes);
+D2GS_API int d2gs_loss_forward(const D2gsLossArgs* args, void* stream);
+D2GS_API int d2gs_loss_backward(const D2gsLossArgs* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Deformation MLP, fused.  Replaces DeformNetwork.forward (utils/time_utils.py:410-453: embedders :208-256,
