@@ -310,7 +310,7 @@ def main():
     ap.add_argument("--loss", choices=["synthetic", "train"], default="synthetic",
                     help="synthetic: seeded random-weighted sum + L1 (SURVEY 8(d), the headline); train: the reference's training loss "
                          "(L1 + D-SSIM + normal + distortion), fused kernel in our arm, eager torch in the reference arm")
-    ap.add_argument("--early-allreduce", type=int, default=0, help="1: start the all-reduce of the surfel-table gradients right after the rasterizer backward")
+    ap.add_argument("--early-allreduce", type=int, default=1, help="1 (default): start the all-reduce of the surfel-table gradients right after the rasterizer backward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="diagnosis only: do not sample clocks during the timed region")
     args = ap.parse_args()

@@ -120,12 +120,25 @@ __global__ void __launch_bounds__(256) deform_fwd_kernel(DeformFwdP a) {
     }
   };
   const int npairs = MP >> 1;
+  constexpr int HEAD = DP / 2 < 2 ? DP / 2 : 2;   // float4 chunks of the first (up to) four coordinates: x, y, z, h0
   for (int pr = 0; pr < npairs; pr++) {
     const float4* n4 = s_nodes4 + pr * (DP / 2);
     float2 dist = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int c = 0; c < DP / 2; c++) {
+    for (int c = 0; c < HEAD; c++) {
       const float4 v = n4[c];   // (dim 2c: node A, node B), (dim 2c+1: node A, node B)
+      float2 df = __fadd2_rn(q2[2 * c], make_float2(-v.x, -v.y));
+      dist = __ffma2_rn(df, df, dist);
+      df = __fadd2_rn(q2[2 * c + 1], make_float2(-v.z, -v.w));
+      dist = __ffma2_rn(df, df, dist);
+    }
+    // The running sums only grow (squares are added in the same order as the full loop), so a pair whose spatial prefix
+    // already reaches the current worst cannot enter the set: skip its remaining coordinates.  With coherent warps this
+    // is a whole-warp skip for most of the node table.
+    if (!(dist.x < wd || dist.y < wd)) continue;
+#pragma unroll
+    for (int c = HEAD; c < DP / 2; c++) {
+      const float4 v = n4[c];
       float2 df = __fadd2_rn(q2[2 * c], make_float2(-v.x, -v.y));
       dist = __ffma2_rn(df, df, dist);
       df = __fadd2_rn(q2[2 * c + 1], make_float2(-v.z, -v.w));
