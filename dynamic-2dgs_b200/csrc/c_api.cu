@@ -11,6 +11,7 @@
 #include "deform.cuh"
 #include "epilogue.cuh"
 #include "loss.cuh"
+#include "optim.cuh"
 #include "mlp.cuh"
 
 namespace d2gs {
@@ -510,6 +511,44 @@ int d2gs_epilogue_backward(const D2gsEpilogueArgs* a, void* stream_) {
   return D2GS_OK;
 }
 
+}  // extern "C"
+
+extern "C" {
+int d2gs_adam_step(const D2gsAdamTensor* tensors, int count, void* stream_) {
+  if (count < 0 || (count > 0 && !tensors)) return fail(D2GS_ERR_INVALID_ARG, "bad arguments");
+  d2gs::AdamBatch B{};
+  int acc = 0;
+  auto flush = [&]() { if (B.count) d2gs::launch_adam(B, (cudaStream_t)stream_); B.count = 0; acc = 0; };
+  for (int i = 0; i < count; i++) {
+    const D2gsAdamTensor& t = tensors[i];
+    if (t.numel == 0) continue;
+    if (t.numel < 0 || !t.param || !t.grad || !t.exp_avg || !t.exp_avg_sq) return fail(D2GS_ERR_INVALID_ARG, "bad tensor descriptor");
+    if (!(t.bias_correction2_sqrt > 0.f)) return fail(D2GS_ERR_INVALID_ARG, "bias_correction2_sqrt must be positive (step >= 1)");
+    d2gs::AdamTensor& k = B.t[B.count];
+    k.param = t.param; k.grad = t.grad; k.exp_avg = t.exp_avg; k.exp_avg_sq = t.exp_avg_sq; k.numel = t.numel;
+    k.w1 = (float)(1.0 - t.beta1); k.beta2 = (float)t.beta2; k.w2 = (float)(1.0 - t.beta2); k.eps = t.eps;
+    k.neg_step_size = -t.step_size;
+    k.inv_bc2_sqrt = 1.0f / t.bias_correction2_sqrt;
+    k.vec4 = ((((uintptr_t)t.param | (uintptr_t)t.grad | (uintptr_t)t.exp_avg | (uintptr_t)t.exp_avg_sq) & 15) == 0) ? 1 : 0;
+    acc += d2gs::adam_chunks(t.numel);
+    B.chunk_end[B.count] = acc;
+    if (++B.count == d2gs::ADAM_MAX_TENSORS) flush();
+  }
+  flush();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(D2GS_ERR_CUDA, cudaGetErrorString(e));
+  return D2GS_OK;
+}
+int d2gs_densification_stats(int P, const float* viewspace_grad, int grad_stride, const uint8_t* update_filter,
+                             float* xyz_gradient_accum, float* denom, void* stream_) {
+  if (P < 0 || grad_stride < 2) return fail(D2GS_ERR_INVALID_ARG, "bad sizes");
+  if (P == 0) return D2GS_OK;
+  if (!viewspace_grad || !update_filter || !xyz_gradient_accum || !denom) return fail(D2GS_ERR_INVALID_ARG, "missing buffers");
+  d2gs::launch_densify_stats(P, viewspace_grad, grad_stride, update_filter, xyz_gradient_accum, denom, (cudaStream_t)stream_);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(D2GS_ERR_CUDA, cudaGetErrorString(e));
+  return D2GS_OK;
+}
 }  // extern "C"
 
 namespace {

@@ -103,6 +103,12 @@ class LossArgs(C.Structure):
                 ("g_rend_dist", C.c_void_p)]
 
 
+class AdamTensor(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", C.c_int64), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_float),
+                ("step_size", C.c_float), ("bias_correction2_sqrt", C.c_float)]
+
+
 class MlpArgs(C.Structure):
     _fields_ = [("rows", C.c_int), ("is_blender", C.c_int), ("num_out", C.c_int), ("x", C.c_void_p), ("t", C.c_void_p),
                 ("t_stride", C.c_int),
@@ -121,6 +127,7 @@ EXPORTED_SYMBOLS = (
     "d2gs_mlp_workspace", "d2gs_mlp_forward", "d2gs_mlp_backward", "d2gs_mlp_hidden",
     "d2gs_deform_order_workspace", "d2gs_deform_order",
     "d2gs_loss_workspace", "d2gs_loss_forward", "d2gs_loss_backward",
+    "d2gs_adam_step", "d2gs_densification_stats",
 )
 
 D2GS_OK = 0
@@ -168,6 +175,8 @@ def lib():
     L.d2gs_loss_workspace.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_size_t)]
     L.d2gs_loss_forward.argtypes = [C.POINTER(LossArgs), C.c_void_p]
     L.d2gs_loss_backward.argtypes = [C.POINTER(LossArgs), C.c_void_p]
+    L.d2gs_adam_step.argtypes = [C.POINTER(AdamTensor), C.c_int, C.c_void_p]
+    L.d2gs_densification_stats.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.d2gs_set_option.argtypes = [C.c_char_p, C.c_int]
     L.d2gs_profile_enable.argtypes = [C.c_int]
     L.d2gs_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]

@@ -1,4 +1,1 @@
-mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -q -m gpu --tb=short 2>&1 | grep -vE "^E\s+\[|^E\s+[0-9\.\-e, ]+\]|^E\s+\+|array\(" | tail -5 | cut -c1-600
-timeout 600 python bench.py --steps 60 --warmup 8 --no-cpu-baseline > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; tail -3 gpurun_out/bench_ours.err; cat gpurun_out/bench_ours.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['e2e']); print(d['roofline']['stages_ms'])"
-timeout 600 python bench.py --config C5 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err; tail -3 gpurun_out/bench_c5.err; cat gpurun_out/bench_c5.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('C5', d['ms_per_step'], d['value'], d['num_rendered']); print(d['roofline']['stages_ms'])"
+timeout 1200 python -m pytest tests/test_optim_gpu.py -q -m gpu --tb=short -s 2>&1 | grep -vE "^E\s+\[|^E\s+[0-9\.\-e, ]+\]|^E\s+\+|array\(" | tail -8 | cut -c1-600

@@ -254,6 +254,33 @@ D2GS_API int d2gs_loss_forward(const D2gsLossArgs* args, void* stream);
 D2GS_API int d2gs_loss_backward(const D2gsLossArgs* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Optimiser step, fused.  Replaces the per-step work of the two torch.optim.Adam instances
+ * the reference builds (scene/gaussian_model.py:181-203: seven surfel groups, lr=0.0, eps=1e-15; the deformation
+ * optimiser; stepped in train_gui.py:426-432) with ONE launch per optimiser: the arithmetic of torch's
+ * _single_tensor_adam (no weight decay, no amsgrad, maximize off).  The bias corrections are computed by the caller
+ * from its step count, in double like torch:  step_size = lr / (1 - beta1^t),  bias_correction2_sqrt = sqrt(1 - beta2^t).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct D2gsAdamTensor {
+  float* param;            /* updated in place */
+  const float* grad;
+  float* exp_avg;          /* first moment, updated in place */
+  float* exp_avg_sq;       /* second moment, updated in place */
+  int64_t numel;
+  double beta1, beta2;          /* double: torch forms 1 - beta in double before rounding to the tensor's float */
+  float eps;
+  float step_size;              /* lr / bias_correction1 */
+  float bias_correction2_sqrt;  /* sqrt(1 - beta2^t) */
+} D2gsAdamTensor;
+
+/* `tensors` is a HOST array; any count (split into launches of 48 descriptors). */
+D2GS_API int d2gs_adam_step(const D2gsAdamTensor* tensors, int count, void* stream);
+
+/* add_densification_stats (scene/gaussian_model.py:484-486): accum[i] += |viewspace_grad[i,:2]|, denom[i] += 1 where
+ * update_filter[i] (bool, 1 byte) — one kernel, no boolean-mask indexing (which forces a device synchronisation). */
+D2GS_API int d2gs_densification_stats(int P, const float* viewspace_grad, int grad_stride, const uint8_t* update_filter,
+                                      float* xyz_gradient_accum, float* denom, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Deformation MLP, fused.  Replaces DeformNetwork.forward (utils/time_utils.py:410-453: embedders :208-256,
  * timenet :344-346, 8x256 trunk with the skip concat :348-352,416-420, heads :363-371,422-452) and its autograd
  * backward.  Fixed architecture of the reference: D=8, W=256, multires=10, skip after layer 4; is_blender selects the
