@@ -517,7 +517,8 @@ def main():
         out["num_rendered"] = R
         # hand-written kernels launched per stage call (CUB scan/sort launches are library code and not counted)
         mine_kernels = {"preprocess_fwd": 1, "duplicate": 1, "ranges": 1, "blend_fwd": 1, "blend_bwd": 1, "preprocess_bwd": 1,
-                        "deform_fwd": 1, "deform_bwd": 1, "epilogue_fwd": 1, "epilogue_bwd": 1, "mlp_fwd": 2, "mlp_bwd": 2}
+                        "deform_fwd": 1, "deform_bwd": 1, "epilogue_fwd": 1, "epilogue_bwd": 1, "mlp_fwd": 2, "mlp_bwd": 2,
+                        "loss_fwd": 2, "loss_bwd": 1}
         out["gpu_launches"] = int(sum(stage[k][1] * n for k, n in mine_kernels.items() if k in stage))
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -13,8 +13,11 @@
 
 namespace d2gs {
 
-constexpr int BWD_BATCH = 80;   // instances staged per round
-constexpr int NWARP = TILE_PIX / 32;
+constexpr int BWD_BATCH = 64;   // instances staged per round
+// Each 16x16 tile is worked on by TWO CTAs of 4 warps (rows 0-7 / 8-15, blockIdx.z): barriers then wait for the
+// slowest of 4 patches instead of 8, and six small CTAs per SM interleave where three large ones stalled together.
+constexpr int BWD_THREADS = TILE_PIX / 2;
+constexpr int NWARP = BWD_THREADS / 32;
 constexpr int ACC_STRIDE = 19;   // 18 components, odd stride keeps the flush free of bank conflicts
 constexpr unsigned FULL = 0xffffffffu;
 // dynamic shared memory of blend_bwd_kernel
@@ -60,7 +63,7 @@ __device__ __forceinline__ void warp_transpose_reduce16(float (&g)[16], int lane
   g[0] += __shfl_xor_sync(FULL, g[0], 1);
 }
 
-__global__ void __launch_bounds__(TILE_PIX, 3) blend_bwd_kernel(
+__global__ void __launch_bounds__(BWD_THREADS, 6) blend_bwd_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
     const float* __restrict__ bg, const SurfelRec* __restrict__ rec, const float* __restrict__ final_Ts,
     const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
@@ -71,16 +74,17 @@ __global__ void __launch_bounds__(TILE_PIX, 3) blend_bwd_kernel(
   uint32_t* s_max = s_id + 2 * BWD_BATCH;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gwarp = warp + NWARP * (int)blockIdx.z;      // patch index inside the tile (0..7)
   int lx, ly;
-  pixel_of_thread_b(tid, lx, ly);
+  pixel_of_thread_b(tid + BWD_THREADS * (int)blockIdx.z, lx, ly);
   const uint32_t pix_x = blockIdx.x * TILE_X + lx, pix_y = blockIdx.y * TILE_Y + ly;
   const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
   const uint32_t pix_id = W * pix_y + pix_x;
   const size_t HW = (size_t)H * W;
   const float2 pixf = {(float)pix_x + 0.5f, (float)pix_y + 0.5f};
   const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
-  const float pcx0 = (float)(blockIdx.x * TILE_X + ((warp & 1) << 3)) + 0.5f, pcx1 = pcx0 + 7.0f;
-  const float pcy0 = (float)(blockIdx.y * TILE_Y + ((warp >> 1) << 2)) + 0.5f, pcy1 = pcy0 + 3.0f;
+  const float pcx0 = (float)(blockIdx.x * TILE_X + ((gwarp & 1) << 3)) + 0.5f, pcx1 = pcx0 + 7.0f;
+  const float pcy0 = (float)(blockIdx.y * TILE_Y + ((gwarp >> 1) << 2)) + 0.5f, pcy1 = pcy0 + 3.0f;
   const uint32_t sq_base = smem_addr(bwd_smem);
   constexpr uint32_t QS = 16u * BWD_BATCH;   // bytes per staged quad plane
   float* my_acc = s_acc + (size_t)warp * BWD_BATCH * ACC_STRIDE;
@@ -95,11 +99,11 @@ __global__ void __launch_bounds__(TILE_PIX, 3) blend_bwd_kernel(
     const uint32_t m = __reduce_max_sync(FULL, last_contributor);
     if (lane == 0) s_max[warp] = m;
   }
-  for (int i = tid; i < NWARP * BWD_BATCH * ACC_STRIDE; i += TILE_PIX) s_acc[i] = 0.f;
+  for (int i = tid; i < NWARP * BWD_BATCH * ACC_STRIDE; i += BWD_THREADS) s_acc[i] = 0.f;
   __syncthreads();
   uint32_t len = 0;
 #pragma unroll
-  for (int i = 0; i < TILE_PIX / 32; i++) len = max(len, s_max[i]);
+  for (int i = 0; i < NWARP; i++) len = max(len, s_max[i]);
   len = min(len, range.y - range.x);
   if (len == 0) return;
 
@@ -314,8 +318,8 @@ __global__ void __launch_bounds__(TILE_PIX, 3) blend_bwd_kernel(
     // fold the 8 warp-private accumulators and issue one global reduction per (tile, instance, component);
     // two threads per instance, nine components each
     {
-      const int slot = tid >> 1, half = tid & 1;
-      if (slot < n) {
+      const int half = tid & 1;
+      for (int slot = tid >> 1; slot < n; slot += BWD_THREADS / 2) {
         float* dst = grad_rec + (size_t)cur_id[slot] * GRAD_REC_FLOATS;
 #pragma unroll
         for (int q = 0; q < 9; q++) {
@@ -338,13 +342,13 @@ __global__ void __launch_bounds__(TILE_PIX, 3) blend_bwd_kernel(
 void launch_blend_bwd(const BwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
                       const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, const float* dL_dothers,
                       float* grad_rec, int cull, cudaStream_t s) {
-  dim3 grid(p.gx, p.gy, 1);
+  dim3 grid(p.gx, p.gy, 2);
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES);
     configured = true;
   }
-  blend_bwd_kernel<<<grid, TILE_PIX, BWD_SMEM_BYTES, s>>>(ranges, point_list, p.W, p.H, p.bg, rec, final_T, n_contrib, dL_dpix,
+  blend_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM_BYTES, s>>>(ranges, point_list, p.W, p.H, p.bg, rec, final_T, n_contrib, dL_dpix,
                                             dL_dothers, grad_rec, cull);
 }
 

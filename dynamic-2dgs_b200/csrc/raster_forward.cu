@@ -227,6 +227,9 @@ void launch_ranges(int64_t R, const uint64_t* keys_sorted, uint2* ranges, cudaSt
 // (broadcast LDS.128 in the inner loop).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int BLEND_BATCH = 128;   // instances per staged batch (double buffered)
+// Two CTAs of 4 warps per 16x16 tile (rows 0-7 / 8-15, blockIdx.z): barriers wait for 4 patches instead of 8, a half
+// tile whose pixels are all saturated stops on its own, and eight small CTAs per SM interleave.
+constexpr int FWD_THREADS = TILE_PIX / 2;
 
 __device__ __forceinline__ void pixel_of_thread(int tid, int& lx, int& ly) {
   const int w = tid >> 5, l = tid & 31;
@@ -237,7 +240,7 @@ __device__ __forceinline__ void pixel_of_thread(int tid, int& lx, int& ly) {
 // One CTA per 16x16 tile, one thread per pixel, each warp a compact 8x4 patch.  Per staged instance a warp first tests
 // the instance's cull box against its patch (uniform branch, one broadcast LDS.128), then each lane runs the exact
 // prefilter (q0..q2) and only survivors pay for the divisions / exp / accumulation.
-__global__ void __launch_bounds__(TILE_PIX) blend_fwd_kernel(
+__global__ void __launch_bounds__(FWD_THREADS, 8) blend_fwd_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
     const SurfelRec* __restrict__ rec, const float* __restrict__ bg, float* __restrict__ final_T,
     uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, float* __restrict__ out_others, int cull) {
@@ -245,14 +248,14 @@ __global__ void __launch_bounds__(TILE_PIX) blend_fwd_kernel(
 
   const int tid = threadIdx.x;
   int lx, ly;
-  pixel_of_thread(tid, lx, ly);
+  pixel_of_thread(tid + FWD_THREADS * (int)blockIdx.z, lx, ly);
   const uint32_t pix_x = blockIdx.x * TILE_X + lx, pix_y = blockIdx.y * TILE_Y + ly;
   const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
   const uint32_t pix_id = W * pix_y + pix_x;
   const float2 pixf = {(float)pix_x + 0.5f, (float)pix_y + 0.5f};
   bool done = !inside;
   // pixel-centre bounds of this warp's patch
-  const int wq = tid >> 5;
+  const int wq = (tid >> 5) + (FWD_THREADS / 32) * (int)blockIdx.z;
   const float pcx0 = (float)(blockIdx.x * TILE_X + ((wq & 1) << 3)) + 0.5f, pcx1 = pcx0 + 7.0f;
   const float pcy0 = (float)(blockIdx.y * TILE_Y + ((wq >> 1) << 2)) + 0.5f, pcy1 = pcy0 + 3.0f;
 
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(TILE_PIX) blend_fwd_kernel(
   uint32_t pre_id = slot_id(1);
   for (int i = 0; i < rounds; i++, toDo -= BLEND_BATCH) {
     // every warp has left batch i-1 (so its buffer may be refilled) — and if all pixels are finished the tile is done
-    if (__syncthreads_count(done) == TILE_PIX) break;
+    if (__syncthreads_count(done) == FWD_THREADS) break;
     const int buf = i & 1;
     if (i + 1 < rounds) {
       stage(buf ^ 1, pre_id);
@@ -398,8 +401,8 @@ __global__ void __launch_bounds__(TILE_PIX) blend_fwd_kernel(
 
 void launch_blend_fwd(const FwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
                       float* final_T, uint32_t* n_contrib, float* out_color, float* out_others, int cull, cudaStream_t s) {
-  dim3 grid(p.gx, p.gy, 1);
-  blend_fwd_kernel<<<grid, TILE_PIX, 0, s>>>(ranges, point_list, p.W, p.H, rec, p.bg, final_T, n_contrib, out_color,
+  dim3 grid(p.gx, p.gy, 2);
+  blend_fwd_kernel<<<grid, FWD_THREADS, 0, s>>>(ranges, point_list, p.W, p.H, rec, p.bg, final_T, n_contrib, out_color,
                                             out_others, cull);
 }
 
