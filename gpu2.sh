@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_raster_gpu.py tests/test_render_gpu.py -q -m gpu --tb=short 2>&1 | tail -3 | cut -c1-300
-timeout 600 python bench.py --steps 60 --warmup 8 --no-cpu-baseline > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; tail -3 gpurun_out/bench_ours.err; cat gpurun_out/bench_ours.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['e2e']); print(d['roofline']['stages_ms'])"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:blend_ -s 2 -c 2 -f -o gpurun_out/prof_blend_r1g python tests/gpu_one_frame.py C3 2 > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log | cut -c1-200
