@@ -417,7 +417,7 @@ __device__ __forceinline__ void warp_transpose_reduce32(float (&g)[32], int lane
 // loops per surfel become ~9 x NG fire-and-forget REDs per warp, and the node attributes are warp-uniform loads.
 // A warp whose surfels are not coherent (more than MAX_DISTINCT different nearest nodes) falls back to per-lane REDs.
 template <int K>
-__global__ void __launch_bounds__(256) deform_bwd_coherent_kernel(DeformBwdP a) {
+__global__ void __launch_bounds__(256, 3) deform_bwd_coherent_kernel(DeformBwdP a) {
   constexpr int HMAX = MAX_D - 3;
   constexpr int MAX_DISTINCT = 12;
   const int NG = NG_FIXED + a.hyper;

@@ -479,17 +479,22 @@ __global__ void __launch_bounds__(256) mlp_bwd_w_kernel(MlpWJobs J, int rows) {
   const float* gcol = jb.G + n;
   const float* acol = (k < jb.Ka) ? jb.A + k : jb.B + (k - jb.Ka);
   const int lda = (k < jb.Ka) ? jb.ldA : jb.ldB;
-  for (int r0 = 0; r0 < rows; r0 += WROWS) {
-    float gv[WROWS / 4], av[WROWS / 4];
+  // software pipeline: the global loads of chunk c+1 are in flight while chunk c is multiplied out of shared memory
+  float gv[WROWS / 4], av[WROWS / 4];
+  auto fetch = [&](int r0) {
 #pragma unroll
     for (int u = 0; u < WROWS / 4; u++) {
       const int rr = r0 + rq + 4 * u;
       gv[u] = (n_ok && rr < rows) ? __ldg(gcol + (size_t)rr * jb.ldG) : 0.f;
       av[u] = (k_ok && rr < rows) ? __ldg(acol + (size_t)rr * lda) : 0.f;
     }
+  };
+  fetch(0);
+  for (int r0 = 0; r0 < rows; r0 += WROWS) {
 #pragma unroll
     for (int u = 0; u < WROWS / 4; u++) { sG[rq + 4 * u][c] = gv[u]; sA[rq + 4 * u][c] = av[u]; }
     __syncthreads();
+    if (r0 + WROWS < rows) fetch(r0 + WROWS);
 #pragma unroll 8
     for (int r = 0; r < WROWS; r++) {
       const float4 g4 = *reinterpret_cast<const float4*>(&sG[r][tn * 4]);
