@@ -312,6 +312,12 @@ def main():
                          "(L1 + D-SSIM + normal + distortion), fused kernel in our arm, eager torch in the reference arm")
     ap.add_argument("--early-allreduce", type=int, default=1, help="1 (default): start the all-reduce of the surfel-table gradients right after the rasterizer backward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sync-count", action="store_true",
+                    help="read num_rendered back every forward like the reference (one stream synchronisation per frame) instead of "
+                         "the deferred-count binning mode")
+    ap.add_argument("--graph", choices=["auto", "on", "off"], default="auto",
+                    help="replay the step (deform + render + loss + backward + all-reduce) as ONE CUDA graph captured through the public API; "
+                         "auto = fall back to eager launches if capture fails.  The reference arm is always eager (it synchronises inside).")
     ap.add_argument("--no-clocks", action="store_true", help="diagnosis only: do not sample clocks during the timed region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -351,6 +357,7 @@ def main():
     if args.impl == "ours":
         from d2gs_b200 import _lib, raster
         _lib.lib()   # fail loudly if the CUDA extension is missing
+        raster.set_deferred_count(not args.sync_count)
         if wl.use_deform:
             build_deform_ours(wl)
         step_fn = step_ours
@@ -380,43 +387,73 @@ def main():
     early = [p for p in wl.pc.raster_parameters() if p is not getattr(wl.pc, "feature", None)]
     bucket = ddist.FlatGradBucket(params, direct=(args.impl != "reference"), early=early if args.early_allreduce else None)
 
-    def view_of(step):
-        return wl.cams[ddist.view_for(step, rank, world, N_VIEWS)]
+    def view_index(step):
+        return ddist.view_for(step, rank, world, N_VIEWS)
 
-    def run_step(step, e2e=False):
-        bucket.zero()
-        cam = view_of(step)
-        if e2e:
-            # per-step inputs come from pinned host memory: camera matrices, time, target image
-            vi = ddist.view_for(step, rank, world, N_VIEWS)
-            c = wl.cams_np[vi]
-            hc = host_cams[vi]
-            cam = e2e_cam
-            cam.world_view_transform.copy_(hc[0], non_blocking=True)
-            cam.full_proj_transform.copy_(hc[1], non_blocking=True)
-            cam.camera_center.copy_(hc[2], non_blocking=True)
-            cam.fid.copy_(hc[3], non_blocking=True)
-            cam.FoVx, cam.FoVy = c.FoVx, c.FoVy
-            # the 7.7 MB target image is only needed by the loss: it travels on a copy stream, overlapped with the
-            # deformation and the forward render (the previous step ended with a host read, so the buffer is free)
-            gt = e2e_gt
-            with torch.cuda.stream(copy_stream):
-                gt.copy_(wl.gt_host, non_blocking=True)
-                gt_ready.record(copy_stream)
-            loss = step_fn(wl, cam, gt, gt_ready)
-        else:
-            loss = step_fn(wl, cam, wl.gt_dev)
-        bucket.all_reduce()      # finalize + (N > 1) ONE NCCL all-reduce over the flat buffer
-        if e2e:
-            return float(loss.item())   # device -> host read of the step's result
-        return loss
-
-    host_cams = [[torch.as_tensor(c.world_view_transform).pin_memory(), torch.as_tensor(c.full_proj_transform).pin_memory(),
-                  torch.as_tensor(c.camera_center).pin_memory(), torch.tensor([c.fid]).pin_memory()] for c in wl.cams_np]
-    e2e_cam = mdl.ViewCamera(wl.cams_np[0], device)
+    # One device camera whose tensors are views of a single 36-float block (view 16 | proj 16 | centre 3 | time 1): a step
+    # selects its view with ONE small copy into it — from the device-resident table (`value`) or from pinned host memory (`e2e`).
+    def cam_block(c):
+        return torch.cat([torch.as_tensor(c.world_view_transform, dtype=torch.float32).reshape(-1),
+                          torch.as_tensor(c.full_proj_transform, dtype=torch.float32).reshape(-1),
+                          torch.as_tensor(c.camera_center, dtype=torch.float32).reshape(-1), torch.tensor([c.fid], dtype=torch.float32)])
+    host_blocks = [cam_block(c).pin_memory() for c in wl.cams_np]
+    dev_blocks = torch.stack(host_blocks).to(device)
+    step_block = torch.empty(36, dtype=torch.float32, device=device)
+    step_cam = mdl.ViewCamera(wl.cams_np[0], device)
+    step_cam.world_view_transform = step_block[0:16].view(4, 4)
+    step_cam.full_proj_transform = step_block[16:32].view(4, 4)
+    step_cam.camera_center = step_block[32:35]
+    step_cam.fid = step_block[35:36]
+    stage_block = torch.empty(36, dtype=torch.float32).pin_memory()     # e2e: the host writes the step's camera here
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()        # e2e: the step's result lands here
     e2e_gt = torch.empty_like(wl.gt_dev)
     copy_stream = torch.cuda.Stream(device)
     gt_ready = torch.cuda.Event()
+
+    def step_body(e2e):
+        """Device work of one step, issued on the current stream (eagerly, or once under CUDA-graph capture)."""
+        bucket.zero()
+        if e2e:
+            # per-step inputs come from pinned host memory: camera block and the 7.7 MB target image; the image is only
+            # needed by the loss, so it travels on a copy stream overlapped with the deformation and the forward render
+            copy_stream.wait_stream(torch.cuda.current_stream())
+            step_block.copy_(stage_block, non_blocking=True)
+            with torch.cuda.stream(copy_stream):
+                e2e_gt.copy_(wl.gt_host, non_blocking=True)
+                gt_ready.record(copy_stream)
+            loss = step_fn(wl, step_cam, e2e_gt, gt_ready)
+        else:
+            loss = step_fn(wl, step_cam, wl.gt_dev)
+        bucket.all_reduce()      # finalize + (N > 1) ONE NCCL all-reduce over the flat buffer
+        if e2e:
+            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        return loss
+
+    graphs = {}
+
+    def run_step(step, e2e=False):
+        vi = view_index(step)
+        g = graphs.get(e2e)
+        if e2e:
+            stage_block.copy_(host_blocks[vi])           # host -> pinned staging (the previous step ended with a host read)
+        else:
+            step_block.copy_(dev_blocks[vi], non_blocking=True)
+        if g is not None:
+            g.replay()
+        else:
+            step_body(e2e)
+        if e2e:
+            torch.cuda.current_stream().synchronize()    # device -> host read of the step's result
+            return float(loss_host[0])
+        return None
+
+    def capture(e2e):
+        """The step as ONE CUDA graph, recorded through the same public calls (DeformModel.step, render, loss, backward)."""
+        torch.cuda.synchronize(device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            step_body(e2e)
+        graphs[e2e] = g
 
     def barrier():
         if dist is not None:
@@ -444,25 +481,69 @@ def main():
 
     for s in range(args.warmup):
         run_step(s)
-    if args.impl == "ours":
-        from d2gs_b200 import _lib, raster
+    use_graph = args.impl == "ours" and args.graph != "off"
+    graph_note = None
+    if use_graph:
+        try:
+            capture(False)
+            for s in range(3):
+                run_step(s)
+            torch.cuda.synchronize(device)
+        except Exception as ex:      # noqa: BLE001 — capture problems must not hide the eager number
+            if args.graph == "on":
+                raise
+            graphs.pop(False, None)
+            graph_note = f"CUDA-graph capture failed, eager launches timed instead: {type(ex).__name__}: {str(ex)[:200]}"
+            log(graph_note)
+            torch.cuda.synchronize(device)
+    graphed = graphs.get(False) is not None
+    if args.impl == "ours" and not graphed:      # eager timed region: the stage timers run inside it
+        from d2gs_b200 import _lib
         _lib.profile_collect()
         _lib.profile_enable(True)
-        launches_before = raster.launch_counts()
     ms, clocks = timed(args.steps, False, args.warmup)
-    stage = None
-    if args.impl == "ours":
-        stage = _lib.profile_collect()
+    stage, ms_eager = None, None
+    if args.impl == "ours" and not graphed:
+        stage, ms_eager = _lib.profile_collect(), ms
         _lib.profile_enable(False)
-        R = raster._R_HINT.get((device.index, cfg["P"], cfg["W"], cfg["H"]), 0)
-    else:
-        R = None
     value = args.steps * world / (ms / 1e3)
+
+    # end to end: per-step inputs from pinned host memory, result read back by the host, every step
     for s in range(3):
         run_step(s, e2e=True)
+    if use_graph and graphed:
+        try:
+            capture(True)
+            for s in range(3):
+                run_step(s, e2e=True)
+        except Exception as ex:      # noqa: BLE001
+            graphs.pop(True, None)
+            graph_note = f"CUDA-graph capture of the e2e step failed, eager launches timed instead: {type(ex).__name__}: {str(ex)[:200]}"
+            log(graph_note)
+            torch.cuda.synchronize(device)
     ms_e2e, _ = timed(args.steps, True, args.warmup)
     e2e_value = args.steps * world / (ms_e2e / 1e3)
-    h2d = 64 + 64 + 12 + 4 + 3 * wl.H * wl.W * 4
+    e2e_graphed = graphs.get(True) is not None
+
+    # per-stage CUDA-event timers (roofline) and launch counts: K eager steps of the same workload, stage events around
+    # every launch.  (When the timed region replays a CUDA graph it contains the same launches, but events inside a graph
+    # cannot be read per launch, so the stage timers run right after it.)
+    if args.impl == "ours":
+        from d2gs_b200 import _lib, raster
+        if graphed:
+            graphs.clear()
+            for s in range(3):
+                run_step(s)
+            _lib.profile_collect()
+            _lib.profile_enable(True)
+            ms_eager, _ = timed(args.steps, False, args.warmup)
+            stage = _lib.profile_collect()
+            _lib.profile_enable(False)
+        raster.check_deferred_counts(device)     # a frame that overflowed its binning capacity would have rendered NaN
+        R = raster.last_num_rendered(device, cfg["P"], cfg["W"], cfg["H"])
+    else:
+        R = None
+    h2d = 36 * 4 + 3 * wl.H * wl.W * 4
 
     if rank != 0:
         if dist is not None:
@@ -485,6 +566,9 @@ def main():
                       "loss": "seeded random-weighted sum over the render outputs + L1 (SURVEY 8(d))" if args.loss == "synthetic" else
                               "training loss of train_gui.py:292-313: L1 + D-SSIM(0.2) + normal(0.02) + distortion(1000)",
                       "parallelism": f"view-sharded x{world}" + (" + NCCL all-reduce of the flat gradient bucket" if world > 1 else ""),
+                      "binning": "synchronous count readback" if args.sync_count else "deferred count (no host synchronisation in the step)",
+                      "launch": ("one CUDA graph per step (captured through the public API)" if graphed else "eager launches") +
+                                (" | e2e: graph incl. H2D/D2H copies" if e2e_graphed else " | e2e: eager"),
                       "l2_policy": "no explicit flush: per-step working set (params+grads+workspaces ~0.3 GB) exceeds the 126 MB L2 and the view changes every step"},
            "clocks": clocks,
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps}}
@@ -515,6 +599,12 @@ def main():
                                      "frac": frame_bytes(P, R, HW, wl.use_deform) / (ms / args.steps * 1e-3) / 1e9 / hbm_peak},
                            "stages_ms": {k: (v[0] / v[1] if v[1] else None) for k, v in stage.items()}}
         out["num_rendered"] = R
+        out["eager_ms_per_step"] = ms_eager / args.steps
+        if graph_note:
+            out["graph_note"] = graph_note
+        out["roofline"]["timing"] = ("CUDA events around every launch of the stage, averaged over %d eager steps run right after the "
+                                     "timed region (which replays the same launches as a CUDA graph)" % args.steps) if graphed else \
+                                    "CUDA events around every launch of the stage inside the timed region"
         # hand-written kernels launched per stage call (CUB scan/sort launches are library code and not counted)
         mine_kernels = {"preprocess_fwd": 1, "duplicate": 1, "ranges": 1, "blend_fwd": 1, "blend_bwd": 1, "preprocess_bwd": 1,
                         "deform_fwd": 1, "deform_bwd": 1, "epilogue_fwd": 1, "epilogue_bwd": 1, "mlp_fwd": 2, "mlp_bwd": 2,

@@ -71,6 +71,7 @@ GeomLayout geom_layout(int P) {
   cub::DeviceScan::InclusiveSum(nullptr, tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, P > 0 ? P : 1);
   L.scan_temp_bytes = tmp;
   L.scan_temp = o; o = align_up(o + tmp);
+  L.status = o; o = align_up(o + 2 * sizeof(uint32_t));   // deferred-count mode: {R, overflow flag}
   L.total = o + 256;
   return L;
 }
@@ -235,14 +236,28 @@ int d2gs_raster_forward(const D2gsRasterFwdArgs* a, void* stream_) {
       D2GS_CUDA_OK(cub::DeviceScan::InclusiveSum(gb + GL.scan_temp, tmp, tiles_touched, point_offsets, P, stream)); }
     D2GS_STAGE("scan", a->debug, stream);
   }
-  uint32_t R32 = 0;
-  D2GS_CUDA_OK(cudaMemcpyAsync(&R32, point_offsets + P - 1, 4, cudaMemcpyDeviceToHost, stream));
-  D2GS_CUDA_OK(cudaStreamSynchronize(stream));
-  const int64_t R = R32;
-  *a->num_rendered = R;
+  uint32_t* status = (uint32_t*)(gb + GL.status);
+  const bool deferred = a->binning_capacity > 0;
+  int64_t R = 0;       // instance slots the binning stage works on: the exact count, or the caller's capacity
+  if (deferred) {
+    // Deferred-count mode: nothing is read back, so the host never waits for the device.  The binning stage runs on
+    // exactly `binning_capacity` slots; slots past the real count carry all-ones keys and sort to the end.
+    if (a->binning_capacity > 0xffffffffll) return fail(D2GS_ERR_INVALID_ARG, "binning_capacity exceeds 2^32-1 instances");
+    R = a->binning_capacity;
+    *a->num_rendered = R;
+  } else {
+    uint32_t R32 = 0;
+    D2GS_CUDA_OK(cudaMemcpyAsync(&R32, point_offsets + P - 1, 4, cudaMemcpyDeviceToHost, stream));
+    D2GS_CUDA_OK(cudaStreamSynchronize(stream));
+    R = R32;
+    *a->num_rendered = R;
+  }
   const BinLayout BL = bin_layout(R);
   if (a->binning_required) *a->binning_required = BL.total;
-  if (a->binning_bytes < BL.total || !a->binning_buffer) return D2GS_NEED_BINNING;
+  if (a->binning_bytes < BL.total || !a->binning_buffer) {
+    if (deferred) return fail(D2GS_ERR_WORKSPACE, "binning workspace smaller than binning_capacity instances need");
+    return D2GS_NEED_BINNING;
+  }
 
   char* bb = aligned_base(a->binning_buffer);
   uint64_t* keys_unsorted = (uint64_t*)(bb + BL.keys_unsorted);
@@ -250,8 +265,12 @@ int d2gs_raster_forward(const D2gsRasterFwdArgs* a, void* stream_) {
   uint32_t* vals_unsorted = (uint32_t*)(bb + BL.vals_unsorted);
   uint32_t* point_list = (uint32_t*)(bb + BL.point_list);
 
-  { StageTimer t(ST_DUP, stream); launch_duplicate(P, rec, a->radii, point_offsets, keys_unsorted, vals_unsorted, p.gx, p.gy, stream); }
+  { StageTimer t(ST_DUP, stream);
+    launch_duplicate(P, rec, a->radii, point_offsets, keys_unsorted, vals_unsorted, p.gx, p.gy, (uint32_t)R, stream);
+    if (deferred) launch_pad_keys((uint32_t)R, point_offsets + P - 1, keys_unsorted, status, stream); }
   D2GS_STAGE("duplicate", a->debug, stream);
+  if (deferred && a->num_rendered_async)
+    D2GS_CUDA_OK(cudaMemcpyAsync(a->num_rendered_async, status, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
   if (R > 0) {
     const int bit = (int)higher_msb(p.gx * p.gy);
     size_t tmp = BL.sort_temp_bytes;
@@ -262,10 +281,12 @@ int d2gs_raster_forward(const D2gsRasterFwdArgs* a, void* stream_) {
   }
   { StageTimer t(ST_RANGES, stream);
     D2GS_CUDA_OK(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)p.gx * p.gy, stream));
-    launch_ranges(R, keys_sorted, ranges, stream); }
+    if (deferred) launch_ranges_deferred((uint32_t)R, status, keys_sorted, ranges, stream);
+    else launch_ranges(R, keys_sorted, ranges, stream); }
   D2GS_STAGE("ranges", a->debug, stream);
   { StageTimer t(ST_BLEND_F, stream);
-    launch_blend_fwd(p, ranges, point_list, rec, final_T, n_contrib, a->out_color, a->out_others, g_cull, stream); }
+    launch_blend_fwd(p, ranges, point_list, rec, final_T, n_contrib, a->out_color, a->out_others, g_cull,
+                     deferred ? status : nullptr, stream); }
   D2GS_STAGE("blend", a->debug, stream);
   return D2GS_OK;
 }

@@ -299,11 +299,6 @@ __device__ __forceinline__ float4 load_rows(const float* g, int ld, int row0, in
 __device__ __forceinline__ float4 relu_mask(float4 g, float4 h) {
   return make_float4(h.x > 0.f ? g.x : 0.f, h.y > 0.f ? g.y : 0.f, h.z > 0.f ? g.z : 0.f, h.w > 0.f ? g.w : 0.f);
 }
-__device__ __forceinline__ float lds32(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-  return v;
-}
 __device__ __forceinline__ void fma4(float4& acc, float w, const float4 g) {
   acc.x = fmaf(w, g.x, acc.x); acc.y = fmaf(w, g.y, acc.y); acc.z = fmaf(w, g.z, acc.z); acc.w = fmaf(w, g.w, acc.w);
 }

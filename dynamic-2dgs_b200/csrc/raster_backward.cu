@@ -1,10 +1,12 @@
 // Backward kernels of the surfel rasterizer for sm_100a.
 // Behavioural contract: DSR/cuda_rasterizer/backward.cu:143-449 (blend), :599-649 (AABB), :451-597 (per surfel),
 // :20-139 (SH).  Design differences (results agree to fp32 re-association):
-//   * the reference issues up to 16 global float atomics per contributing (pixel, surfel) pair; here each warp
-//     first reduces its 32 pixels with a transposed butterfly (16 shuffles for 16 values), adds the warp totals
-//     into a per-instance shared-memory accumulator, and the CTA issues one global reduction per
-//     (tile, instance, component) — R*18 instead of pairs*16;
+//   * the reference issues up to 16 global float atomics per contributing (pixel, surfel) pair; here the contributing
+//     lanes of a warp (8.7 of 32 on average) write their 18 gradient components as compacted rows of a small
+//     per-warp shared-memory scratch, 18 lanes sum one column each, the warp totals go into a per-instance
+//     shared-memory accumulator, and the CTA issues one global reduction per (tile, instance, component) —
+//     R*18 instead of pairs*16.  (The cost scales with the contributing lanes: ~35 instructions per surviving
+//     (patch, instance) pair, where a 32-lane shuffle butterfly over 16+2 values cost ~110.);
 //   * traversal starts at the deepest instance any pixel of the tile actually consumed (block max of n_contrib)
 //     instead of the end of the tile list;
 //   * AABB backward, the transMat/normal/SH backward and the clearing of the gradient scratch are one
@@ -20,12 +22,18 @@ constexpr int BWD_THREADS = TILE_PIX / 2;
 constexpr int NWARP = BWD_THREADS / 32;
 constexpr int ACC_STRIDE = 19;   // 18 components, odd stride keeps the flush free of bank conflicts
 constexpr unsigned FULL = 0xffffffffu;
+// per-warp reduction scratch: RED_ROWS rows of RED_STRIDE floats.  A row holds one contributing lane's 18 components in
+// accumulator-slot order; 80-byte rows put the 16-byte stores of 8 consecutive rows on 8 distinct bank groups.
+constexpr int RED_ROWS = 16;
+constexpr int RED_STRIDE = 20;
+constexpr int RED_COMPS = 18;
 // dynamic shared memory of blend_bwd_kernel
 constexpr int BWD_WORDS = (BWD_BATCH + 31) / 32;
 constexpr size_t BWD_SMEM_Q1 = sizeof(float4) * REC_QUADS * BWD_BATCH;                 // one staging buffer
 constexpr size_t BWD_SMEM_Q = 2 * BWD_SMEM_Q1;                                         // double buffered (cp.async)
 constexpr size_t BWD_SMEM_ACC = sizeof(float) * NWARP * BWD_BATCH * ACC_STRIDE;        // per-warp private accumulators
-constexpr size_t BWD_SMEM_BYTES = BWD_SMEM_Q + BWD_SMEM_ACC + sizeof(uint32_t) * (2 * BWD_BATCH + NWARP);
+constexpr size_t BWD_SMEM_RED = sizeof(float) * NWARP * RED_ROWS * RED_STRIDE;         // per-warp reduction scratch
+constexpr size_t BWD_SMEM_BYTES = BWD_SMEM_Q + BWD_SMEM_ACC + BWD_SMEM_RED + sizeof(uint32_t) * (2 * BWD_BATCH + NWARP);
 
 __device__ __forceinline__ void pixel_of_thread_b(int tid, int& lx, int& ly) {
   const int w = tid >> 5, l = tid & 31;
@@ -33,44 +41,18 @@ __device__ __forceinline__ void pixel_of_thread_b(int tid, int& lx, int& ly) {
   ly = ((w >> 1) << 2) | (l >> 3);
 }
 
-// Sum 16 per-lane values across the warp with 16 shuffles: after the call lanes with an even index hold the
-// warp total of component ((lane>>4)&1)*8 + ((lane>>3)&1)*4 + ((lane>>2)&1)*2 + ((lane>>1)&1) in g[0].
-__device__ __forceinline__ void warp_transpose_reduce16(float (&g)[16], int lane) {
-  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const float send = b4 ? g[i] : g[i + 8];
-    const float keep = b4 ? g[i + 8] : g[i];
-    g[i] = keep + __shfl_xor_sync(FULL, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const float send = b3 ? g[i] : g[i + 4];
-    const float keep = b3 ? g[i + 4] : g[i];
-    g[i] = keep + __shfl_xor_sync(FULL, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; i++) {
-    const float send = b2 ? g[i] : g[i + 2];
-    const float keep = b2 ? g[i + 2] : g[i];
-    g[i] = keep + __shfl_xor_sync(FULL, send, 4);
-  }
-  {
-    const float send = b1 ? g[0] : g[1];
-    const float keep = b1 ? g[1] : g[0];
-    g[0] = keep + __shfl_xor_sync(FULL, send, 2);
-  }
-  g[0] += __shfl_xor_sync(FULL, g[0], 1);
-}
-
-__global__ void __launch_bounds__(BWD_THREADS, 6) blend_bwd_kernel(
+#ifndef D2GS_BWD_MINBLOCKS
+#define D2GS_BWD_MINBLOCKS 5   // 93 registers: at 6 CTAs per SM (80) the compiler re-derives pixel coordinates and shared addresses inside the loop
+#endif
+__global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_MINBLOCKS) blend_bwd_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
     const float* __restrict__ bg, const SurfelRec* __restrict__ rec, const float* __restrict__ final_Ts,
     const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
     const float* __restrict__ dL_dothers, float* __restrict__ grad_rec, int cull) {
   extern __shared__ __align__(16) unsigned char bwd_smem[];
   float* s_acc = reinterpret_cast<float*>(bwd_smem + BWD_SMEM_Q);        // [warp][slot][ACC_STRIDE]
-  uint32_t* s_id = reinterpret_cast<uint32_t*>(bwd_smem + BWD_SMEM_Q + BWD_SMEM_ACC);   // [2][BWD_BATCH]
+  float* s_red = reinterpret_cast<float*>(bwd_smem + BWD_SMEM_Q + BWD_SMEM_ACC);        // [warp][RED_ROWS][RED_STRIDE]
+  uint32_t* s_id = reinterpret_cast<uint32_t*>(bwd_smem + BWD_SMEM_Q + BWD_SMEM_ACC + BWD_SMEM_RED);   // [2][BWD_BATCH]
   uint32_t* s_max = s_id + 2 * BWD_BATCH;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -88,6 +70,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 6) blend_bwd_kernel(
   const uint32_t sq_base = smem_addr(bwd_smem);
   constexpr uint32_t QS = 16u * BWD_BATCH;   // bytes per staged quad plane
   float* my_acc = s_acc + (size_t)warp * BWD_BATCH * ACC_STRIDE;
+  const uint32_t lanes_below = (1u << lane) - 1u;
+  const uint32_t red_w = smem_addr(s_red + (size_t)warp * RED_ROWS * RED_STRIDE);   // this warp's reduction scratch
+  const uint32_t red_col = red_w + 4u * (uint32_t)lane;                               // column `lane` of its first row
+  const uint32_t acc_col = smem_addr(my_acc) + 4u * (uint32_t)lane;                   // component `lane` of accumulator slot 0
 
   const float T_final = inside ? final_Ts[pix_id] : 0;
   float T = T_final;
@@ -187,9 +173,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 6) blend_bwd_kernel(
       m &= m - 1u;
       const uint32_t contributor = len - 1 - (uint32_t)(i * BWD_BATCH + j);   // 0-based list position
       const uint32_t off = (uint32_t)j << 4;
-      float g[16];          // written only by contributing lanes; zero-filled lazily before a reduction
+      float g[16];          // written only by contributing lanes
       float gm0 = 0.f, gm1 = 0.f;
-      bool contrib = false, flat = false;
+      bool contrib = false;
       do {
         if (!inside || contributor >= last_contributor) break;
         const float4 a = lds128(sb0 + off), b = lds128(sb1 + off), c = lds128(sb2 + off);
@@ -283,33 +269,44 @@ __global__ void __launch_bounds__(BWD_THREADS, 6) blend_bwd_kernel(
 #pragma unroll
           for (int q = 0; q < 8; q++) g[q] = 0.f;
           g[8] = dL_dz;
-          flat = true;
         }
         g[12] = G * dL_dalpha;
         contrib = true;
       } while (0);
 
-      if (__any_sync(FULL, contrib)) {
-        if (!contrib) {
-#pragma unroll
-          for (int q = 0; q < 16; q++) g[q] = 0.f;
-        }
-        warp_transpose_reduce16(g, lane);
-        if ((lane & 1) == 0) {
-          const int v = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-          const int slot = v < 9 ? v : v + 2;   // 0..8 transMat | 11..13 normal | 14 opacity | 15..17 colour
-          my_acc[j * ACC_STRIDE + slot] += g[0];   // slot private to this warp: plain read-modify-write
-        }
-        if (__any_sync(FULL, flat)) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            gm0 += __shfl_xor_sync(FULL, gm0, o);
-            gm1 += __shfl_xor_sync(FULL, gm1, o);
+      // Warp reduction over the contributing lanes only: the lane holding the r-th set bit of the ballot writes row r of
+      // the scratch (accumulator-slot order: 0..8 transMat | 9,10 mean2D | 11..13 normal | 14 opacity | 15..17 colour),
+      // every lane then sums one column over the rows (columns >= 18 are never used) and lanes 0..17 add theirs to this
+      // warp's private accumulator of instance j.  Shared-memory addresses are precomputed 32-bit registers.
+      const uint32_t cmask = __ballot_sync(FULL, contrib);
+      if (cmask != 0u) {
+        const int nrow = __popc(cmask);
+        const int row = __popc(cmask & lanes_below);
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll 1
+        for (int base = 0; base < nrow; base += RED_ROWS) {      // one round unless more than 16 lanes contribute
+          if (contrib && (unsigned)(row - base) < (unsigned)RED_ROWS) {
+            const uint32_t dst = red_w + (uint32_t)(row - base) * (RED_STRIDE * 4);
+            sts128(dst, g[0], g[1], g[2], g[3]);
+            sts128(dst + 16, g[4], g[5], g[6], g[7]);
+            sts128(dst + 32, g[8], gm0, gm1, g[9]);
+            sts128(dst + 48, g[10], g[11], g[12], g[13]);
+            sts64(dst + 64, g[14], g[15]);
           }
-          if (lane == 0) {
-            my_acc[j * ACC_STRIDE + G_M2D] += gm0;
-            my_acc[j * ACC_STRIDE + G_M2D + 1] += gm1;
+          __syncwarp();
+          const int nr = min(RED_ROWS, nrow - base);
+          uint32_t ad = red_col;
+          int r = 0;
+          for (; r + 4 <= nr; r += 4, ad += 4 * RED_STRIDE * 4) {
+            t0 += lds32(ad); t1 += lds32(ad + RED_STRIDE * 4); t2 += lds32(ad + 2 * RED_STRIDE * 4); t3 += lds32(ad + 3 * RED_STRIDE * 4);
           }
+          if (r + 2 <= nr) { t0 += lds32(ad); t1 += lds32(ad + RED_STRIDE * 4); ad += 2 * RED_STRIDE * 4; r += 2; }
+          if (r < nr) t2 += lds32(ad);
+          __syncwarp();
+        }
+        if (lane < RED_COMPS) {
+          const uint32_t a = acc_col + (uint32_t)j * (ACC_STRIDE * 4);   // slot private to this warp: plain read-modify-write
+          sts32(a, lds32(a) + ((t0 + t1) + (t2 + t3)));
         }
       }
       }
@@ -346,6 +343,8 @@ void launch_blend_bwd(const BwdParams& p, const uint2* ranges, const uint32_t* p
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES);
+    // five CTAs of 37.4 KB (+1 KB each reserved by the system) need a large shared-memory carve-out
+    cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
   blend_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM_BYTES, s>>>(ranges, point_list, p.W, p.H, p.bg, rec, final_T, n_contrib, dL_dpix,

@@ -54,7 +54,7 @@ constexpr int G_T = 0, G_M2D = 9, G_NRM = 11, G_OPA = 14, G_COL = 15;
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 struct GeomLayout {
-  size_t rec, clamped, tiles_touched, point_offsets, scan_temp, total;
+  size_t rec, clamped, tiles_touched, point_offsets, scan_temp, status, total;
   size_t scan_temp_bytes;
 };
 struct ImgLayout {
@@ -133,6 +133,19 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
+}
+
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t addr, float x, float y) {
+  asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
 
 // Tile rectangle of a surfel (reference: auxiliary.h:64-74).  Float arithmetic and the float->int truncation
@@ -234,11 +247,21 @@ __device__ __forceinline__ Activated activate_surfel(int idx, const float* means
 
 void launch_preprocess_fwd(const FwdParams& p, SurfelRec* rec, uint8_t* clamped, int* radii, uint32_t* tiles_touched,
                            cudaStream_t s);
+// `capacity`: number of instance slots behind keys/vals; instances past it are dropped (deferred-count mode reports
+// that as an overflow; with the exact count of the synchronous mode nothing is ever dropped)
 void launch_duplicate(int P, const SurfelRec* rec, const int* radii, const uint32_t* offsets, uint64_t* keys,
-                      uint32_t* vals, uint32_t gx, uint32_t gy, cudaStream_t s);
+                      uint32_t* vals, uint32_t gx, uint32_t gy, uint32_t capacity, cudaStream_t s);
 void launch_ranges(int64_t R, const uint64_t* keys_sorted, uint2* ranges, cudaStream_t s);
+// Deferred-count mode (no host readback of the instance count R = offsets[P-1]):
+//   pad_keys : status = {R, R > capacity}; keys[R..capacity) = all ones, so a stable sort of all `capacity` slots leaves
+//              the R real instances first, in exactly the order a sort of R items produces
+//   ranges   : same as launch_ranges with L = min(status[0], capacity) read on the device
+void launch_pad_keys(uint32_t capacity, const uint32_t* total, uint64_t* keys, uint32_t* status, cudaStream_t s);
+void launch_ranges_deferred(uint32_t capacity, const uint32_t* status, const uint64_t* keys_sorted, uint2* ranges, cudaStream_t s);
+// `status` (may be NULL): when status[1] != 0 the binning overflowed and the colour planes are poisoned with NaN
 void launch_blend_fwd(const FwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
-                      float* final_T, uint32_t* n_contrib, float* out_color, float* out_others, int cull, cudaStream_t s);
+                      float* final_T, uint32_t* n_contrib, float* out_color, float* out_others, int cull,
+                      const uint32_t* status, cudaStream_t s);
 
 struct BwdParams {
   int P, D, M, W, H;

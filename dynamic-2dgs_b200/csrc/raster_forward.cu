@@ -174,12 +174,13 @@ __global__ void __launch_bounds__(256) duplicate_kernel(int P, const SurfelRec* 
                                                         const int* __restrict__ radii,
                                                         const uint32_t* __restrict__ offsets,
                                                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                                        uint32_t gx, uint32_t gy) {
+                                                        uint32_t gx, uint32_t gy, uint32_t capacity) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= P) return;
   const int rad = radii[idx];
   if (rad <= 0) return;
   uint32_t off = (idx == 0) ? 0 : offsets[idx - 1];
+  if (offsets[idx] > capacity) return;   // only possible in deferred-count mode; pad_keys flags the overflow
   const float4 q2 = __ldg(&rec[idx].q2);
   const float depth = __ldg(&rec[idx].q3.w);
   const RectU r = tile_rect(q2.y, q2.z, rad, gx, gy);
@@ -194,9 +195,23 @@ __global__ void __launch_bounds__(256) duplicate_kernel(int P, const SurfelRec* 
 }
 
 void launch_duplicate(int P, const SurfelRec* rec, const int* radii, const uint32_t* offsets, uint64_t* keys,
-                      uint32_t* vals, uint32_t gx, uint32_t gy, cudaStream_t s) {
+                      uint32_t* vals, uint32_t gx, uint32_t gy, uint32_t capacity, cudaStream_t s) {
   if (P == 0) return;
-  duplicate_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, rec, radii, offsets, keys, vals, gx, gy);
+  duplicate_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, rec, radii, offsets, keys, vals, gx, gy, capacity);
+}
+
+__global__ void __launch_bounds__(256) pad_keys_kernel(uint32_t capacity, const uint32_t* __restrict__ total,
+                                                       uint64_t* __restrict__ keys, uint32_t* __restrict__ status) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t R = *total;
+  if (idx == 0) { status[0] = R; status[1] = R > capacity ? 1u : 0u; }
+  // (on overflow the frame renders nothing and is poisoned — ranges_deferred_kernel / blend_fwd_kernel — so the
+  // stale keys the sort then sees are never used)
+  if (idx < capacity && idx >= R) keys[idx] = ~0ull;
+}
+
+void launch_pad_keys(uint32_t capacity, const uint32_t* total, uint64_t* keys, uint32_t* status, cudaStream_t s) {
+  pad_keys_kernel<<<(capacity + 255) / 256 + (capacity == 0), 256, 0, s>>>(capacity, total, keys, status);
 }
 
 __global__ void __launch_bounds__(256) ranges_kernel(int64_t L, const uint64_t* __restrict__ keys,
@@ -221,6 +236,29 @@ void launch_ranges(int64_t R, const uint64_t* keys_sorted, uint2* ranges, cudaSt
   ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(R, keys_sorted, ranges);
 }
 
+__global__ void __launch_bounds__(256) ranges_deferred_kernel(uint32_t capacity, const uint32_t* __restrict__ status,
+                                                              const uint64_t* __restrict__ keys, uint2* __restrict__ ranges) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t L = status[1] ? 0u : min(status[0], capacity);   // an overflowed frame renders nothing (and is poisoned)
+  if (idx >= L) return;
+  const uint32_t cur = (uint32_t)(keys[idx] >> 32);
+  if (idx == 0) {
+    ranges[cur].x = 0;
+  } else {
+    const uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
+    if (cur != prev) {
+      ranges[prev].y = idx;
+      ranges[cur].x = idx;
+    }
+  }
+  if (idx == L - 1) ranges[cur].y = L;
+}
+
+void launch_ranges_deferred(uint32_t capacity, const uint32_t* status, const uint64_t* keys_sorted, uint2* ranges, cudaStream_t s) {
+  if (capacity == 0) return;
+  ranges_deferred_kernel<<<(capacity + 255) / 256, 256, 0, s>>>(capacity, status, keys_sorted, ranges);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // per-tile front-to-back blend.  One CTA per 16x16 tile, one thread per pixel; each warp owns a compact
 // 8x4 pixel patch.  Instances are staged 256 at a time into shared memory as five float4 planes
@@ -243,7 +281,8 @@ __device__ __forceinline__ void pixel_of_thread(int tid, int& lx, int& ly) {
 __global__ void __launch_bounds__(FWD_THREADS, 8) blend_fwd_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
     const SurfelRec* __restrict__ rec, const float* __restrict__ bg, float* __restrict__ final_T,
-    uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, float* __restrict__ out_others, int cull) {
+    uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, float* __restrict__ out_others, int cull,
+    const uint32_t* __restrict__ status) {
   __shared__ float4 s_q[2][REC_QUADS][BLEND_BATCH];
 
   const int tid = threadIdx.x;
@@ -385,9 +424,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 8) blend_fwd_kernel(
     final_T[pix_id + 2 * HW] = dist2;
     n_contrib[pix_id] = last_contributor;
     n_contrib[pix_id + HW] = median_contributor;   // 0 when nothing contributed (the reference converts -1.0f: undefined)
-    out_color[0 * HW + pix_id] = C[0] + T * bg[0];
-    out_color[1 * HW + pix_id] = C[1] + T * bg[1];
-    out_color[2 * HW + pix_id] = C[2] + T * bg[2];
+    // deferred-count mode: a frame whose instance count exceeded the binning capacity is never silently wrong
+    const bool poisoned = status != nullptr && status[1] != 0u;
+    const float qnan = __int_as_float(0x7fc00000);
+    out_color[0 * HW + pix_id] = poisoned ? qnan : C[0] + T * bg[0];
+    out_color[1 * HW + pix_id] = poisoned ? qnan : C[1] + T * bg[1];
+    out_color[2 * HW + pix_id] = poisoned ? qnan : C[2] + T * bg[2];
     out_others[0 * HW + pix_id] = Dacc;
     out_others[1 * HW + pix_id] = 1 - T;
     out_others[2 * HW + pix_id] = N[0];
@@ -400,10 +442,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 8) blend_fwd_kernel(
 }
 
 void launch_blend_fwd(const FwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
-                      float* final_T, uint32_t* n_contrib, float* out_color, float* out_others, int cull, cudaStream_t s) {
+                      float* final_T, uint32_t* n_contrib, float* out_color, float* out_others, int cull,
+                      const uint32_t* status, cudaStream_t s) {
   dim3 grid(p.gx, p.gy, 2);
   blend_fwd_kernel<<<grid, FWD_THREADS, 0, s>>>(ranges, point_list, p.W, p.H, rec, p.bg, final_T, n_contrib, out_color,
-                                            out_others, cull);
+                                            out_others, cull, status);
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,

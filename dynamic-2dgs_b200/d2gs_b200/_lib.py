@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libd2gs.so")
+# D2GS_LIB: another build of the same C ABI (A/B timing of kernel variants); default = the in-tree library
+LIB_PATH = os.environ.get("D2GS_LIB") or os.path.join(_HERE, "libd2gs.so")
 
 c_float_p = C.c_void_p  # raw device addresses are passed as integers
 
@@ -33,7 +34,8 @@ class RasterFwdArgs(C.Structure):
                 ("binning_buffer", C.c_void_p), ("binning_bytes", C.c_size_t),
                 ("resume", C.c_int),
                 ("num_rendered", C.POINTER(C.c_int64)), ("binning_required", C.POINTER(C.c_size_t)),
-                ("raw_params", C.c_int), ("d_means3D", C.c_void_p), ("d_scales", C.c_void_p), ("d_rotations", C.c_void_p)]
+                ("raw_params", C.c_int), ("d_means3D", C.c_void_p), ("d_scales", C.c_void_p), ("d_rotations", C.c_void_p),
+                ("binning_capacity", C.c_int64), ("num_rendered_async", C.c_void_p)]
 
 
 class RasterBwdArgs(C.Structure):

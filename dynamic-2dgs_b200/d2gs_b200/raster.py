@@ -15,8 +15,14 @@ import torch
 
 from . import _lib
 
-# (device index, P, W, H) -> last num_rendered; sizes the binning workspace so forward is one C call
+# (device index, P, W, H) -> last known num_rendered; sizes the binning workspace so forward is one C call
 _R_HINT: dict = {}
+# Deferred-count mode (include/d2gs.h "binning_capacity"): after `warmup` synchronous frames of a (device, P, W, H)
+# combination the forward stops reading the instance count back and bins into max-seen-count * margin slots, so the host
+# runs ahead of the device.  Counts arrive through pinned memory and are folded in by later calls; a frame that would
+# overflow its slots renders NaN and the next rasterizer call raises (the following frames use the larger count).
+_DEFERRED = {"on": True, "warmup": 4, "margin": 1.5}
+_TRACK: dict = {}          # hint key -> _CountTrack
 # (device index, P) -> zeroed (P,20) fp32 scratch the blend backward accumulates into (left zero by the library)
 _GRAD_SCRATCH: dict = {}
 _LAUNCH_COUNT = {"forward": 0, "backward": 0}
@@ -62,9 +68,78 @@ def grad_scratch(device: torch.device, P: int) -> torch.Tensor:
     return t
 
 
+def set_deferred_count(on: bool = True, warmup: int = 4, margin: float = 1.5) -> None:
+    """Switch the host-synchronisation-free binning mode (default on).  ``on=False`` restores the reference's behaviour:
+    one stream synchronisation per forward to read num_rendered (rasterizer_impl.cu:281-282)."""
+    _DEFERRED.update(on=bool(on), warmup=int(warmup), margin=float(margin))
+
+
+class _CountTrack:
+    __slots__ = ("max_R", "frames", "pending", "overflow", "captured", "spare")
+
+    def __init__(self):
+        self.max_R, self.frames, self.pending, self.overflow = 0, 0, [], None
+        self.spare = []        # pinned count buffers set aside for captures (pinned allocation is illegal while capturing)
+        self.captured = []     # (pinned {R, overflow}, capacity) of frames recorded into CUDA graphs: rewritten by every replay
+
+    def observe(self, R: int) -> None:
+        # slow decay so the capacity follows a scene that shrinks; growth is immediate
+        self.max_R = max(int(R), int(self.max_R * 0.999))
+        self.frames += 1
+
+    def poll(self, key, block: bool = False) -> None:
+        """Fold in the counts of earlier deferred frames whose copy has landed (oldest first; they complete in order)."""
+        done = 0
+        for ev, host, cap in self.pending:
+            if block:
+                ev.synchronize()
+            elif not ev.query():
+                break
+            R, ovf = host.tolist()
+            R &= 0xffffffff
+            self.observe(R)
+            _R_HINT[key] = R
+            if ovf:
+                self.overflow = (R, cap)
+            done += 1
+        if done:
+            del self.pending[:done]
+        for host, cap in self.captured:      # values of the most recent completed replay (no event: a replay is not a call)
+            R, ovf = host.tolist()
+            R &= 0xffffffff
+            if R:
+                self.max_R = max(self.max_R, R)
+                _R_HINT[key] = R
+            if ovf:
+                self.overflow = (R, cap)
+
+    def raise_if_overflowed(self) -> None:
+        if self.overflow is not None:
+            R, cap = self.overflow
+            self.overflow = None
+            raise _lib.D2gsError(
+                f"an earlier frame produced {R} (surfel, tile) instances but was binned into {cap} slots (deferred-count "
+                "mode): its images were filled with NaN and its gradients are zero.  The capacity has been raised; repeat "
+                "the step, or call d2gs_b200.raster.set_deferred_count(False) for views that change this abruptly.")
+
+
 class RasterContext:
-    """Opaque forward state kept for backward (the reference's geomBuffer / binningBuffer / imgBuffer)."""
-    __slots__ = ("P", "D", "M", "W", "H", "num_rendered", "geom", "binning", "img")
+    """Opaque forward state kept for backward (the reference's geomBuffer / binningBuffer / imgBuffer).
+
+    ``layout_R`` is the number of instance slots the binning workspace was laid out for (what the C ABI calls
+    num_rendered in backward / export_state); ``num_rendered`` is the true instance count — in deferred-count mode
+    reading it waits for the asynchronous copy of the count."""
+    __slots__ = ("P", "D", "M", "W", "H", "layout_R", "_count", "_count_event", "_count_host", "geom", "binning", "img")
+
+    @property
+    def num_rendered(self) -> int:
+        if self._count is None:
+            if self._count_event is None:      # recorded into a CUDA graph: the last replay's count
+                torch.cuda.synchronize(self.geom.device)
+                return int(self._count_host[0]) & 0xffffffff
+            self._count_event.synchronize()
+            self._count = int(self._count_host[0]) & 0xffffffff
+        return self._count
 
 
 def raster_forward(bg, means3D, colors_precomp, opacities, scales, rotations, scale_modifier, transMat_precomp,
@@ -95,8 +170,31 @@ def raster_forward(bg, means3D, colors_precomp, opacities, scales, rotations, sc
     ctx.geom = torch.empty((gbytes,), dtype=torch.uint8, device=dev)
     ctx.img = torch.empty((ibytes,), dtype=torch.uint8, device=dev)
     hint_key = (dev.index, P, W, H)
-    r_hint = _R_HINT.get(hint_key, 4 * P + 1024)
-    _, _, bbytes = _lib.workspace_sizes(P, W, H, int(r_hint * 1.25) + 1024)
+    track = _TRACK.get(hint_key)
+    if track is None:
+        if len(_TRACK) > 64:
+            _TRACK.clear(); _R_HINT.clear()
+        track = _TRACK[hint_key] = _CountTrack()
+    # CUDA-graph capture: nothing may synchronise or query, so the frame is recorded in deferred-count mode with the
+    # capacity the eager frames before it established (the count still lands in pinned memory on every replay:
+    # check_deferred_counts()).
+    capturing = torch.cuda.is_current_stream_capturing()
+    if capturing:
+        if debug or P == 0 or track.max_R <= 0:
+            raise _lib.D2gsError("CUDA-graph capture of the rasterizer needs debug=False and at least one eager frame of this "
+                                 "(P, width, height) first: the binning capacity comes from observed instance counts")
+        deferred = True
+    else:
+        track.poll(hint_key)
+        track.raise_if_overflowed()
+        if not track.spare:
+            track.spare = [torch.zeros((2,), dtype=torch.int32).pin_memory() for _ in range(4)]
+        deferred = bool(_DEFERRED["on"]) and P > 0 and not debug and track.frames >= _DEFERRED["warmup"] and track.max_R > 0
+    if deferred:
+        capacity = int(track.max_R * _DEFERRED["margin"]) + 4096
+    else:
+        capacity = int(_R_HINT.get(hint_key, 4 * P + 1024) * 1.25) + 1024
+    _, _, bbytes = _lib.workspace_sizes(P, W, H, capacity)
     ctx.binning = torch.empty((bbytes,), dtype=torch.uint8, device=dev)
 
     num_rendered = C.c_int64(0)
@@ -119,6 +217,16 @@ def raster_forward(bg, means3D, colors_precomp, opacities, scales, rotations, sc
     a.d_means3D, a.d_scales, a.d_rotations = _ptr(d_means3D), _ptr(d_scales), _ptr(d_rotations)
     a.num_rendered = C.pointer(num_rendered)
     a.binning_required = C.pointer(required)
+    ctx._count, ctx._count_event, ctx._count_host = None, None, None
+    if deferred:
+        if capturing:
+            if not track.spare:
+                raise _lib.D2gsError("more than 4 rasterizer frames of one (P, width, height) captured without an eager frame in between")
+            host = track.spare.pop()
+        else:
+            host = torch.empty((2,), dtype=torch.int32, pin_memory=True)   # torch's pinned allocator recycles these
+        a.binning_capacity, a.num_rendered_async = capacity, host.data_ptr()
+        ctx._count_host = host
     stream = _stream_ptr(dev)
     with torch.cuda.device(dev):
         rc = L.d2gs_raster_forward(C.byref(a), stream)
@@ -127,13 +235,23 @@ def raster_forward(bg, means3D, colors_precomp, opacities, scales, rotations, sc
             ctx.binning = torch.empty((bbytes,), dtype=torch.uint8, device=dev)
             a.binning_buffer, a.binning_bytes, a.resume = ctx.binning.data_ptr(), bbytes, 1
             rc = L.d2gs_raster_forward(C.byref(a), stream)
+        if deferred and rc == _lib.D2GS_OK and not capturing:
+            ctx._count_event = torch.cuda.Event()
+            ctx._count_event.record(torch.cuda.current_stream(dev))
     _lib.check(rc, "d2gs_raster_forward")
     if rc != _lib.D2GS_OK:
         raise _lib.D2gsError(f"d2gs_raster_forward returned {rc}")
-    ctx.num_rendered = int(num_rendered.value)
-    _R_HINT[hint_key] = ctx.num_rendered
+    ctx.layout_R = int(num_rendered.value)
+    if capturing:
+        track.captured.append((host, capacity))
+    elif deferred:
+        track.pending.append((ctx._count_event, host, capacity))
+    else:
+        ctx._count = ctx.layout_R
+        track.observe(ctx._count)
+        _R_HINT[hint_key] = ctx._count
     _LAUNCH_COUNT["forward"] += 1
-    return ctx.num_rendered, color, others, radii, ctx
+    return ctx.layout_R, color, others, radii, ctx
 
 
 def raster_backward(bg, means3D, radii, colors_precomp, scales, rotations, scale_modifier, transMat_precomp, viewmatrix,
@@ -186,7 +304,7 @@ def raster_backward(bg, means3D, radii, colors_precomp, scales, rotations, scale
             if g[k] is not None: g[k].zero_()
     a = _lib.RasterBwdArgs()
     a.P, a.D, a.M, a.width, a.height = P, int(degree), M, ctx.W, ctx.H
-    a.num_rendered = ctx.num_rendered
+    a.num_rendered = ctx.layout_R
     a.background = _ptr(bg); a.means3D = _ptr(means3D); a.shs = _ptr(sh); a.sh_rest = _ptr(sh_rest)
     a.colors_precomp = _ptr(colors_precomp); a.scales = _ptr(scales); a.rotations = _ptr(rotations)
     a.transMat_precomp = _ptr(transMat_precomp); a.scale_modifier = float(scale_modifier)
@@ -241,7 +359,7 @@ class _RasterizeSurfels(torch.autograd.Function):
         else:
             num_rendered, color, others, radii, rctx = raster_forward(*args)
         ctx.raster_settings = rs
-        ctx.num_rendered = num_rendered
+        ctx.num_rendered = num_rendered   # slot count of the binning layout (== the instance count in synchronous mode)
         ctx.rctx = rctx
         ctx.prepped = (bg, view, proj, campos)
         ctx.save_for_backward(col_, m3, sc_, rot_, cov_, radii, sh_, shr_)
@@ -374,7 +492,7 @@ def export_state(rctx: RasterContext) -> dict:
     """Parity/debug: the intermediates the reference hides in its three byte buffers, as torch tensors."""
     L = _lib.lib()
     dev = rctx.geom.device
-    P, W, H, R = rctx.P, rctx.W, rctx.H, rctx.num_rendered
+    P, W, H, R = rctx.P, rctx.W, rctx.H, rctx.layout_R
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
     f32 = dict(dtype=torch.float32, device=dev)
     out = dict(means2D=torch.zeros((P, 2), **f32), depths=torch.zeros((P,), **f32), transMat=torch.zeros((P, 9), **f32),
@@ -395,7 +513,31 @@ def export_state(rctx: RasterContext) -> dict:
         _lib.check(L.d2gs_raster_export_state(P, W, H, R, rctx.geom.data_ptr(), rctx.binning.data_ptr(),
                                               rctx.img.data_ptr(), C.byref(st), _stream_ptr(dev)),
                    "d2gs_raster_export_state")
+    n = rctx.num_rendered        # deferred-count mode lays the workspace out for more slots than there are instances
+    if n < R:
+        for k in ("keys_unsorted", "values_unsorted", "keys_sorted", "point_list"):
+            out[k] = out[k][:n]
     return out
+
+
+def check_deferred_counts(device=None, wait: bool = True) -> None:
+    """Fold in every outstanding asynchronous instance count (eager deferred frames and CUDA-graph replays) and raise
+    if one of those frames overflowed its binning capacity.  For loops that only replay graphs — where no later
+    rasterizer call would report it — call this after synchronising; an overflowed frame is NaN either way."""
+    for key, track in list(_TRACK.items()):
+        if device is not None and key[0] != torch.device(device).index:
+            continue
+        track.poll(key, block=wait)
+        track.raise_if_overflowed()
+
+
+def last_num_rendered(device, P: int, W: int, H: int, wait: bool = True) -> int:
+    """Most recent instance count seen for this (device, P, W, H) — waits for pending asynchronous counts by default."""
+    key = (torch.device(device).index, P, W, H)
+    track = _TRACK.get(key)
+    if track is not None:
+        track.poll(key, block=wait)
+    return int(_R_HINT.get(key, 0))
 
 
 def launch_counts() -> dict:

@@ -113,11 +113,21 @@ typedef struct D2gsRasterFwdArgs {
   const float* d_means3D;         /* (P,3) or NULL */
   const float* d_scales;          /* (P,2) or NULL */
   const float* d_rotations;       /* (P,4) or NULL */
+  /* Deferred-count mode (binning_capacity > 0): the instance count R is NOT read back, so the call never synchronises.
+   * The binning stage works on exactly `binning_capacity` slots (binning_bytes must cover d2gs_raster_workspace(...,
+   * binning_capacity)); slots past R carry all-ones keys, and the stable sort leaves the R real instances first in the
+   * order a sort of R items produces, so every result is identical to the synchronous mode.  *num_rendered is set to
+   * binning_capacity: pass that value to d2gs_raster_backward / d2gs_raster_export_state (it fixes the workspace
+   * layout).  If R > binning_capacity the frame renders nothing and out_color is filled with NaN (never silently
+   * wrong).  num_rendered_async: optional PINNED HOST pair {R, overflow flag}, written by an asynchronous copy on
+   * `stream` — read it after an event recorded behind this call. */
+  int64_t binning_capacity;
+  uint32_t* num_rendered_async;
 } D2gsRasterFwdArgs;
 
-/* Forward.  Synchronises `stream` once (the reference's blocking readback of num_rendered,
- * rasterizer_impl.cu:281-282) to size the binning stage.  If binning_bytes is too small returns
- * D2GS_NEED_BINNING with *binning_required set. */
+/* Forward.  With binning_capacity == 0 it synchronises `stream` once (the reference's blocking readback of
+ * num_rendered, rasterizer_impl.cu:281-282) to size the binning stage; if binning_bytes is too small it returns
+ * D2GS_NEED_BINNING with *binning_required set.  With binning_capacity > 0 see "deferred-count mode" above. */
 D2GS_API int d2gs_raster_forward(const D2gsRasterFwdArgs* args, void* stream);
 
 typedef struct D2gsRasterBwdArgs {

@@ -19,3 +19,14 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+@pytest.fixture(autouse=True)
+def _fresh_binning_state():
+    """Every test starts with the rasterizer's instance-count history cleared (so its first frames run in the
+    synchronous mode and deferred-count capacities never leak between scenes of different tests)."""
+    from d2gs_b200 import raster
+    raster._TRACK.clear()
+    raster._R_HINT.clear()
+    raster.set_deferred_count(True)
+    yield

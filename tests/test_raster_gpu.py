@@ -293,3 +293,52 @@ def test_full_size_properties(cfg, cuda_device):
     assert util.rel_err(np_(o2["ins"]["shs"].grad), 2 * np_(s1)) < 1e-5
     for k in ("means3D", "shs", "scales", "rotations", "opacities"):
         assert torch.isfinite(o["ins"][k].grad).all(), k
+
+
+@pytest.mark.parametrize("cfg,cam_index", [("T0", 2), ("T1", 5), ("C2", 17)])
+def test_deferred_count_mode_is_identical(cfg, cam_index, cuda_device):
+    """Deferred-count mode (include/d2gs.h: binning_capacity) never reads the instance count back; the binning stage
+    sorts a fixed number of slots whose tail carries all-ones keys.  Everything the synchronous mode produces — images,
+    radii, sorted keys, instance list, tile ranges, n_contrib — must be bit-identical, gradients equal to re-association."""
+    from d2gs_b200 import raster
+    act, kw = util.raster_inputs(cfg, cam_index=cam_index, n_cams=100 if cfg == "C2" else 8)
+    gc, go = util.upstream_grads(kw["image_height"], kw["image_width"], seed=6)
+    raster.set_deferred_count(False)
+    a = run_ours(act, kw, cuda_device, gc, go)
+    sa = raster.export_state(a["ctx"])
+    assert a["ctx"].layout_R == a["ctx"].num_rendered
+    raster.set_deferred_count(True, warmup=1, margin=1.37)
+    b = run_ours(act, kw, cuda_device, gc, go)
+    sb = raster.export_state(b["ctx"])
+    R = a["ctx"].num_rendered
+    assert b["ctx"].layout_R == int(R * 1.37) + 4096 and b["ctx"].num_rendered == R > 0      # the mode was really on
+    assert torch.equal(a["color"], b["color"]) and torch.equal(a["allmap"], b["allmap"]) and torch.equal(a["radii"], b["radii"])
+    for k in ("keys_unsorted", "values_unsorted", "keys_sorted", "point_list", "ranges", "n_contrib", "final_T", "point_offsets"):
+        assert torch.equal(sa[k], sb[k]), k
+    for k in ("means3D", "shs", "scales", "rotations", "opacities"):
+        assert util.rel_err(np_(a["ins"][k].grad), np_(b["ins"][k].grad)) < 2e-5, k
+    assert raster.last_num_rendered(cuda_device, act["means3D"].shape[0], kw["image_width"], kw["image_height"]) == R
+
+
+def test_deferred_count_overflow_is_loud(cuda_device):
+    """A frame with more instances than slots must not look like a valid image: NaN colours, zero gradients, and the next
+    rasterizer call raises; after that the capacity has grown and the same frame renders normally."""
+    from d2gs_b200 import _lib, raster
+    small, kw = util.raster_inputs("T1", s_med=0.003)      # R = 34 653 (CPU oracle)
+    big, _ = util.raster_inputs("T1", s_med=0.03)          # R = 131 205
+    gc, go = util.upstream_grads(kw["image_height"], kw["image_width"], seed=6)
+    raster.set_deferred_count(False)
+    ref = run_ours(big, kw, cuda_device, gc, go)
+    raster._TRACK.clear()
+    raster.set_deferred_count(True, warmup=1, margin=1.0)
+    s = run_ours(small, kw, cuda_device)                       # synchronous warm-up frame: small instance count
+    assert ref["ctx"].num_rendered > 2 * s["ctx"].num_rendered + 4096
+    o = run_ours(big, kw, cuda_device, gc, go)                  # same P, W, H -> binned into the small capacity
+    assert o["ctx"].num_rendered == ref["ctx"].num_rendered > o["ctx"].layout_R
+    assert bool(torch.isnan(o["color"]).all())
+    assert float(o["ins"]["means3D"].grad.abs().sum()) == 0.0
+    with pytest.raises(_lib.D2gsError, match="deferred-count"):
+        run_ours(big, kw, cuda_device)
+    again = run_ours(big, kw, cuda_device, gc, go)
+    assert again["ctx"].layout_R >= ref["ctx"].num_rendered
+    assert torch.equal(again["color"], ref["color"]) and torch.equal(again["allmap"], ref["allmap"])

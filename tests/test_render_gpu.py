@@ -129,3 +129,63 @@ def test_fused_epilogue_equals_eager(cuda_device):
     o3 = epilogue.render_epilogue(A3, cam)
     (o3[1] * ups[1]).sum().backward()
     assert torch.isfinite(A3.grad).all() and not A3.grad[5].any()
+
+
+def test_step_replays_as_cuda_graph(cuda_device):
+    """DeformModel.step + render + fused loss + backward recorded ONCE as a CUDA graph through the public API (the
+    rasterizer switches to its deferred-count mode: nothing synchronises), then replayed for a DIFFERENT view and time
+    written into the static camera tensors: images and gradients must equal the eager result for that view."""
+    from d2gs_b200 import deform as dfm, model as mdl, raster, synthetic as syn
+    from d2gs_b200.loss import surfel_loss
+    from gaussian_renderer import render
+    dev = cuda_device
+    c = syn.CONFIGS["T1"]
+    sc = syn.make_scene(c["P"], c["seed"], c["s_med"], n_nodes=c["n_nodes"], hyper_dim=8)
+    cams = syn.fibonacci_cameras(8, c["W"], c["H"])
+    pc, pipe = mdl.SurfelModel(sc, dev), mdl.PipelineParams()
+    torch.manual_seed(0)
+    dm = dfm.DeformModel(deform_type="node", is_blender=True, K=c["K"], hyper_dim=8, node_num=c["n_nodes"], local_frame=True)
+    with torch.no_grad():
+        dm.deform.nodes.copy_(torch.as_tensor(sc.nodes, device=dev))
+        dm.deform._node_radius.copy_(torch.as_tensor(sc.node_radius, device=dev))
+        dm.deform.network.gaussian_warp.weight.mul_(1e3)
+    bg = torch.tensor([0.1, 0.2, 0.3], device=dev)
+    gt = torch.rand((3, c["H"], c["W"]), generator=torch.Generator().manual_seed(1)).to(dev)
+    params = [pc._xyz, pc._features_dc, pc._features_rest, pc._opacity, pc._scaling, pc._rotation, dm.deform.network.gaussian_warp.weight]
+    cam = mdl.ViewCamera(cams[1], dev)          # the static camera the graph reads
+
+    def set_view(i):
+        v = mdl.ViewCamera(cams[i], dev)
+        for n in ("world_view_transform", "full_proj_transform", "camera_center", "fid"):
+            getattr(cam, n).copy_(getattr(v, n))
+
+    def step():
+        for p in params:
+            p.grad = None
+        d = dm.step(pc.get_xyz.detach(), dm.deform.expand_time(cam.fid), feature=pc.feature, motion_mask=pc.motion_mask)
+        out = render(cam, pc, pipe, bg, d["d_xyz"], d["d_rotation"], d["d_scaling"])
+        loss = surfel_loss(out["render"], gt, out["rend_normal"], out["surf_normal"], out["rend_dist"], 0.2, 0.02, 100.0)
+        loss.backward()
+        return out["render"], loss, [p.grad for p in params]
+
+    for i in (1, 2, 3):       # eager frames: they establish the instance-count history the capture sizes its binning from
+        set_view(i)
+        step()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+        image, loss, grads = step()
+    set_view(6)
+    g.replay()
+    torch.cuda.synchronize()
+    got = [image.clone(), loss.clone()] + [x.clone() for x in grads]
+    raster.check_deferred_counts(dev)
+    del g
+    raster.set_deferred_count(False)
+    image_e, loss_e, grads_e = step()
+    torch.cuda.synchronize()
+    assert torch.equal(got[0], image_e)
+    assert abs(float(got[1]) - float(loss_e)) <= 1e-6 * abs(float(loss_e))
+    for a, b, p in zip(got[2:], grads_e, params):
+        assert util.rel_err(a.cpu().numpy(), b.cpu().numpy()) < 2e-5, tuple(p.shape)
+    assert float(got[0].std()) > 0.01
