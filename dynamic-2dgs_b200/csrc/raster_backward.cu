@@ -15,7 +15,10 @@
 
 namespace d2gs {
 
-constexpr int BWD_BATCH = 64;   // instances staged per round
+#ifndef D2GS_BWD_BATCH
+#define D2GS_BWD_BATCH 64
+#endif
+constexpr int BWD_BATCH = D2GS_BWD_BATCH;   // instances staged per round
 // Each 16x16 tile is worked on by TWO CTAs of 4 warps (rows 0-7 / 8-15, blockIdx.z): barriers then wait for the
 // slowest of 4 patches instead of 8, and six small CTAs per SM interleave where three large ones stalled together.
 constexpr int BWD_THREADS = TILE_PIX / 2;
@@ -42,7 +45,7 @@ __device__ __forceinline__ void pixel_of_thread_b(int tid, int& lx, int& ly) {
 }
 
 #ifndef D2GS_BWD_MINBLOCKS
-#define D2GS_BWD_MINBLOCKS 5   // 93 registers: at 6 CTAs per SM (80) the compiler re-derives pixel coordinates and shared addresses inside the loop
+#define D2GS_BWD_MINBLOCKS 6   // 79 registers, no spills
 #endif
 __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_MINBLOCKS) blend_bwd_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
@@ -111,10 +114,7 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_MINBLOCKS) blend_bwd_ker
   const float final_A = 1 - T_final;
   const float bg_dot_dpixel = bg[0] * dL_dpixel[0] + bg[1] * dL_dpixel[1] + bg[2] * dL_dpixel[2];
 
-  float accum_rec[3] = {0.f, 0.f, 0.f}, last_color[3] = {0.f, 0.f, 0.f};
-  float last_alpha = 0.f, last_depth = 0.f, last_normal[3] = {0.f, 0.f, 0.f};
-  float accum_depth_rec = 0.f, accum_alpha_rec = 0.f, accum_normal_rec[3] = {0.f, 0.f, 0.f};
-  float last_dL_dT = 0.f;
+  float Q = T_final * bg_dot_dpixel;   // see "ONE running scalar" below
 
   const int rounds = (len + BWD_BATCH - 1) / BWD_BATCH;
   // instance id of this thread's slot in batch bi (back to front: slot t holds list position len-1-(bi*B+t))
@@ -203,17 +203,25 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_MINBLOCKS) blend_bwd_ker
         const float normal[3] = {nrm.x, nrm.y, nrm.z};
         const float color[3] = {col.x, col.y, col.z};
 
+        // Back-to-front compositing gradient with ONE running scalar.  With T the transmittance in front of this splat,
+        // w = alpha*T its blend weight, E the sum over all output channels of (this splat's channel value) x (upstream
+        // gradient of that channel) plus the distortion weight term, and Q = T_final*(bg . dL_dpixel) + sum of w*E over
+        // the splats behind:   dL/dalpha = T*E - Q/(1-alpha).
+        // (The reference carries per-channel "colour seen behind" recurrences — accum_rec, last_color, last_alpha, ...
+        // for 3 colour + depth + alpha + 3 normal channels and last_dL_dT, backward.cu:292-372; dotted with the upstream
+        // gradients they all collapse into Q.  Same value up to fp32 re-association.)
         const float inv_1ma = __fdividef(1.0f, 1.f - alpha);   // gradients are compared to 1e-4: 2-ulp reciprocal
         T = T * inv_1ma;
         const float w = alpha * T;
-        float dL_dalpha = 0.0f;
+        float E = dL_daccum;
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
-          accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-          last_color[ch] = color[ch];
-          dL_dalpha += (color[ch] - accum_rec[ch]) * dL_dpixel[ch];
+          E = fmaf(color[ch], dL_dpixel[ch], E);
+          E = fmaf(normal[ch], dL_dnormal2D[ch], E);
           g[13 + ch] = w * dL_dpixel[ch];
+          g[9 + ch] = w * dL_dnormal2D[ch];
         }
+        E = fmaf(c_d, dL_ddepth, E);
         float dL_dz = 0.0f, dL_dweight = 0.f;
         // depth mapped to [0,1]; fp32 here (gradients are compared to 1e-4, not bit-wise)
         const float inv_d = __fdividef(1.0f, c_d);
@@ -224,26 +232,11 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_MINBLOCKS) blend_bwd_ker
           dL_dweight += dL_dmax_dweight;
         }
         dL_dweight += (final_D2 + m_d * m_d * final_A - 2 * m_d * final_D) * dL_dreg;
-        dL_dalpha += dL_dweight - last_dL_dT;
-        last_dL_dT = dL_dweight * alpha + (1 - alpha) * last_dL_dT;
-        const float dL_dmd = 2.0f * (T * alpha) * (m_d * final_A - final_D) * dL_dreg;
+        E += dL_dweight;
+        const float dL_dalpha = T * E - Q * inv_1ma;
+        Q = fmaf(w, E, Q);
+        const float dL_dmd = 2.0f * w * (m_d * final_A - final_D) * dL_dreg;
         dL_dz += dL_dmd * dmd_dd;
-
-        accum_depth_rec = last_alpha * last_depth + (1.f - last_alpha) * accum_depth_rec;
-        last_depth = c_d;
-        dL_dalpha += (c_d - accum_depth_rec) * dL_ddepth;
-        accum_alpha_rec = __fadd_rn(last_alpha, __fmul_rn(1.f - last_alpha, accum_alpha_rec));
-        dL_dalpha += (1 - accum_alpha_rec) * dL_daccum;
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-          accum_normal_rec[ch] = last_alpha * last_normal[ch] + (1.f - last_alpha) * accum_normal_rec[ch];
-          last_normal[ch] = normal[ch];
-          dL_dalpha += (normal[ch] - accum_normal_rec[ch]) * dL_dnormal2D[ch];
-          g[9 + ch] = w * dL_dnormal2D[ch];
-        }
-        dL_dalpha *= T;
-        last_alpha = alpha;
-        dL_dalpha += (-T_final * inv_1ma) * bg_dot_dpixel;
 
         const float dL_dG = opac * dL_dalpha;
         dL_dz += w * dL_ddepth;
