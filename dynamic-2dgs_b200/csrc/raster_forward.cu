@@ -264,7 +264,10 @@ void launch_ranges_deferred(uint32_t capacity, const uint32_t* status, const uin
 // 8x4 pixel patch.  Instances are staged 256 at a time into shared memory as five float4 planes
 // (broadcast LDS.128 in the inner loop).
 // ------------------------------------------------------------------------------------------------------------
-constexpr int BLEND_BATCH = 128;   // instances per staged batch (double buffered)
+#ifndef D2GS_FWD_BATCH
+#define D2GS_FWD_BATCH 128
+#endif
+constexpr int BLEND_BATCH = D2GS_FWD_BATCH;   // instances per staged batch (double buffered)
 // Two CTAs of 4 warps per 16x16 tile (rows 0-7 / 8-15, blockIdx.z): barriers wait for 4 patches instead of 8, a half
 // tile whose pixels are all saturated stops on its own, and eight small CTAs per SM interleave.
 constexpr int FWD_THREADS = TILE_PIX / 2;
@@ -278,7 +281,10 @@ __device__ __forceinline__ void pixel_of_thread(int tid, int& lx, int& ly) {
 // One CTA per 16x16 tile, one thread per pixel, each warp a compact 8x4 patch.  Per staged instance a warp first tests
 // the instance's cull box against its patch (uniform branch, one broadcast LDS.128), then each lane runs the exact
 // prefilter (q0..q2) and only survivors pay for the divisions / exp / accumulation.
-__global__ void __launch_bounds__(FWD_THREADS, 8) blend_fwd_kernel(
+#ifndef D2GS_FWD_MINBLOCKS
+#define D2GS_FWD_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
     const SurfelRec* __restrict__ rec, const float* __restrict__ bg, float* __restrict__ final_T,
     uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, float* __restrict__ out_others, int cull,
