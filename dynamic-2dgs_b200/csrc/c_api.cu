@@ -430,6 +430,11 @@ int d2gs_deform_forward(const D2gsDeformFwdArgs* a, void* stream) {
   h.mask = a->motion_mask; h.nn_idx = a->nn_idx; h.nn_dist = a->nn_dist; h.nn_weight = a->nn_weight;
   h.d_xyz = a->d_xyz; h.d_rot = a->d_rotation; h.d_scale = a->d_scaling;
   h.attr_stride = a->node_attr_stride; h.order = a->order;
+  h.node_workspace = nullptr;
+  if (a->node_workspace) {
+    if (a->node_workspace_bytes < deform_node_workspace_bytes(a->M)) return fail(D2GS_ERR_WORKSPACE, "node workspace too small");
+    h.node_workspace = aligned_base(a->node_workspace);
+  }
   const char* err = nullptr;
   { StageTimer t(ST_DEF_F, (cudaStream_t)stream);
     if (deform_forward_launch(h, (cudaStream_t)stream, &err) != 0) return fail(D2GS_ERR_INVALID_ARG, err); }
@@ -455,6 +460,12 @@ OrderLayout order_layout(int P) {
   return L;
 }
 }  // namespace
+
+int d2gs_deform_node_workspace(int M, size_t* bytes) {
+  if (!bytes || M <= 0) return fail(D2GS_ERR_INVALID_ARG, "bad arguments");
+  *bytes = deform_node_workspace_bytes(M);
+  return D2GS_OK;
+}
 
 int d2gs_deform_order_workspace(int P, size_t* bytes) {
   if (!bytes || P < 0) return fail(D2GS_ERR_INVALID_ARG, "bad arguments");

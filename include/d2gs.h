@@ -354,8 +354,14 @@ typedef struct D2gsDeformFwdArgs {
   int node_attr_stride;          /* 0: node_trans/rot/scale/local_rot are separate packed tables; > 0: they are columns
                                     of ONE (M,node_attr_stride) row-major matrix (the MLP head output), no slicing copies */
   const int32_t* order;          /* optional (P): processing order from d2gs_deform_order; results do not depend on it */
+  /* optional device scratch of d2gs_deform_node_workspace(M) bytes (speed only, M <= 2048): the call first sorts the nodes
+   * along a Morton curve and boxes every 16 of them, so that a warp of neighbouring surfels evaluates distances only for
+   * the node blocks whose box can still hold one of its K nearest; nn_idx / nn_dist / outputs are identical without it */
+  void* node_workspace;
+  size_t node_workspace_bytes;
 } D2gsDeformFwdArgs;
 
+D2GS_API int d2gs_deform_node_workspace(int M, size_t* bytes);
 D2GS_API int d2gs_deform_forward(const D2gsDeformFwdArgs* args, void* stream);
 
 typedef struct D2gsDeformBwdArgs {
