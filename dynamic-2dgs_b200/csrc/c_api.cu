@@ -44,6 +44,7 @@ enum Stage { ST_PRE = 0, ST_SCAN, ST_DUP, ST_SORT, ST_RANGES, ST_BLEND_F, ST_BLE
 struct StageRec { int stage; cudaEvent_t a, b; };
 static bool g_profile = false;
 int g_deform_bwd_smem = 1;  // node-gradient accumulation of deform_bwd: 1 = per-CTA shared accumulators, 0 = global reductions
+int g_knn_filter = 1;       // warp-level candidate filter of the K-nearest-node search (0: every node is visited; same results)
 static int g_cull = 1;   // warp-level cull boxes in the blend kernels (tests switch it off to prove it changes nothing)
 static std::vector<StageRec> g_recs;
 static std::vector<cudaEvent_t> g_free_events;
@@ -134,6 +135,7 @@ int d2gs_set_option(const char* name, int value) {
   if (!name) return fail(D2GS_ERR_INVALID_ARG, "null option name");
   if (std::strcmp(name, "cull") == 0) { g_cull = value != 0; return D2GS_OK; }
   if (std::strcmp(name, "deform_bwd_smem") == 0) { g_deform_bwd_smem = value != 0; return D2GS_OK; }
+  if (std::strcmp(name, "knn_filter") == 0) { g_knn_filter = value != 0; return D2GS_OK; }
   return fail(D2GS_ERR_INVALID_ARG, std::string("unknown option ") + name);
 }
 
@@ -430,11 +432,6 @@ int d2gs_deform_forward(const D2gsDeformFwdArgs* a, void* stream) {
   h.mask = a->motion_mask; h.nn_idx = a->nn_idx; h.nn_dist = a->nn_dist; h.nn_weight = a->nn_weight;
   h.d_xyz = a->d_xyz; h.d_rot = a->d_rotation; h.d_scale = a->d_scaling;
   h.attr_stride = a->node_attr_stride; h.order = a->order;
-  h.node_workspace = nullptr;
-  if (a->node_workspace) {
-    if (a->node_workspace_bytes < deform_node_workspace_bytes(a->M)) return fail(D2GS_ERR_WORKSPACE, "node workspace too small");
-    h.node_workspace = aligned_base(a->node_workspace);
-  }
   const char* err = nullptr;
   { StageTimer t(ST_DEF_F, (cudaStream_t)stream);
     if (deform_forward_launch(h, (cudaStream_t)stream, &err) != 0) return fail(D2GS_ERR_INVALID_ARG, err); }
@@ -460,12 +457,6 @@ OrderLayout order_layout(int P) {
   return L;
 }
 }  // namespace
-
-int d2gs_deform_node_workspace(int M, size_t* bytes) {
-  if (!bytes || M <= 0) return fail(D2GS_ERR_INVALID_ARG, "bad arguments");
-  *bytes = deform_node_workspace_bytes(M);
-  return D2GS_OK;
-}
 
 int d2gs_deform_order_workspace(int P, size_t* bytes) {
   if (!bytes || P < 0) return fail(D2GS_ERR_INVALID_ARG, "bad arguments");

@@ -10,6 +10,7 @@
 namespace d2gs {
 
 extern int g_deform_bwd_smem;
+extern int g_knn_filter;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int MAX_K = 8;
 constexpr int MAX_D = 3 + 16;   // 3 spatial + up to 16 hyper coordinates
@@ -62,241 +63,229 @@ struct DeformFwdP {
   float* d_xyz; float* d_rot; float* d_scale;
   int st_t, st_r, st_s, st_l;   // row strides of the node attribute tables (3,4,2,4 or the packed MLP output width)
   const int* order;             // optional: thread t handles surfel order[t] (spatially coherent warps)
-  // optional node blocks (node_blocks_kernel): the nodes along a Morton curve + the bounding box of every 16 of them
-  const int* node_perm;         // [MB*16] storage position -> node index, -1 = padding
-  const float* node_bbox;       // [MB][8]: lo.xyz, pad, hi.xyz, pad
-  int MB;                       // number of 16-node blocks (0: no blocks, every node is visited)
+  int filter;                   // 1: warp-level candidate filter (below); 0: every node is visited (same results)
 };
 
-// K nearest control nodes by an unordered "replace the current worst" set: every step is a predicated select, so a
-// warp whose lanes insert at different nodes does not serialise a sorted-insertion ladder (measured 3.5x faster than the
-// insertion sort it replaces at M=512).  Ties: a candidate must be strictly closer than the current worst to enter, and
-// the worst among equal distances is the one with the larger index, so lower node indices win like a stable sort.
-// Distances are evaluated for TWO nodes per instruction with the packed fp32 pipe of sm_100 (FADD2 / FFMA2): node pairs
-// are interleaved in shared memory as [pair][dim][2]; each packed lane still accumulates its node's squared distance
-// sequentially over the coordinates, so the value is bit-identical to the scalar loop.
+// K nearest control nodes of every surfel + the radial-basis blend of the node outputs, one thread per surfel.
+//
+// The K-set is an unordered "replace the current worst" set keyed by (distance, node index): a candidate enters iff it
+// is lexicographically smaller than the current worst, so the result does not depend on the order — or on the subset —
+// in which nodes are offered, as long as every node that belongs to the final set is offered once.  Every step is a
+// predicated select: lanes that insert at different nodes do not serialise a sorted-insertion ladder.  Ties resolve to
+// the lower node index like a stable sort (pytorch3d's knn_points).
+//
+// Warp-level candidate filter.  With the Morton processing order the 32 surfels of a warp sit in a small box B.  A node
+// whose spatial distance to B exceeds the largest "current worst" of the 32 lanes (wmax) cannot enter any lane's set
+// (the hyper coordinates only add to the distance), so the warp
+//   1. gives every lane the node nearest to B among "its" nodes (slots lane, lane+32, ...) and visits those 32 nodes:
+//      every lane now holds K real candidates and wmax is finite;
+//   2. walks the node table in chunks of 32: lane l bounds the distance of node 32c+l to B (one LDS.128 + 12 ALU),
+//      a ballot collects the nodes with bound <= wmax, the warp visits exactly those, wmax is refreshed per chunk.
+// At C3 (512 uniform nodes, K=4) a warp evaluates distances for ~70 nodes instead of 512.  The bound is shrunk by 1e-5
+// relative — far above the fp32 error of either side — so a rejected node is strictly farther than every lane's worst;
+// nn_idx / nn_dist are bit-identical to the exhaustive search (filter = 0; test_knn_candidate_filter_changes_nothing).
+// Distances accumulate coordinate by coordinate with fused multiply-adds in storage order, in both modes.
+//
+// Persistent warps: the node table (slot = node index, [M][4*NQ] floats) is staged once per CTA; warp w of the grid
+// handles surfels 32*w.., stepping by the number of warps, with no barrier after the staging.
 template <int K, int NQ>   // NQ = round_up(D, 4) / 4 coordinate quads
 __global__ void __launch_bounds__(256) deform_fwd_kernel(DeformFwdP a) {
-  extern __shared__ float4 s_nodes4[];   // [ceil(M/2)][4*NQ dims][2 nodes] floats: one LDS.128 = 2 dims x 2 nodes
-  float* s_nodes = reinterpret_cast<float*>(s_nodes4);
+  extern __shared__ float4 s_node4[];   // [MP][NQ]
   constexpr int DP = 4 * NQ;
   const int D = a.D;
   const int nstride = 3 + a.hyper;
-  const bool blocks = a.MB > 0;
-  // storage slots: with node blocks the table is staged in Morton order (slot p holds node node_perm[p]), padded to 16
-  const int MP = blocks ? a.MB * 16 : ((a.M + 1) & ~1);
-  int* s_perm = reinterpret_cast<int*>(s_nodes + (size_t)MP * DP);          // [MP] slot -> node index (blocks only)
-  float4* s_bbox = reinterpret_cast<float4*>(s_perm + MP);                   // [MB][2] (blocks only; MP % 4 == 0)
-  for (int t = threadIdx.x; t < MP * DP; t += blockDim.x) {
-    const int pr = t / (2 * DP), r = t - pr * 2 * DP, d = r >> 1, which = r & 1;
-    const int slot = 2 * pr + which;
-    const int m = blocks ? __ldg(a.node_perm + slot) : (slot < a.M ? slot : -1);
-    float v = 0.f;
-    if (d < D) v = (m >= 0) ? a.nodes[(size_t)m * nstride + d] : 1e30f;   // padding node: infinitely far
-    s_nodes[t] = v;
-  }
-  if (blocks) {
-    for (int t = threadIdx.x; t < MP; t += blockDim.x) s_perm[t] = __ldg(a.node_perm + t);
-    for (int t = threadIdx.x; t < 2 * a.MB; t += blockDim.x) s_bbox[t] = __ldg(reinterpret_cast<const float4*>(a.node_bbox) + t);
+  const int MP = (a.M + 31) & ~31;       // whole chunks of 32 slots; padding slots are infinitely far
+  {
+    float* s_node = reinterpret_cast<float*>(s_node4);
+    for (int t = threadIdx.x; t < MP * DP; t += blockDim.x) {
+      const int m = t / DP, d = t - m * DP;
+      float v = 0.f;
+      if (d < D) v = (m < a.M) ? a.nodes[(size_t)m * nstride + d] : 1e30f;
+      s_node[t] = v;
+    }
   }
   __syncthreads();
-  const int t_raw = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t_raw - (int)(threadIdx.x & 31) >= a.P) return;          // the whole warp is past the end
-  const bool live = t_raw < a.P;
-  const int t_lin = live ? t_raw : a.P - 1;                      // idle lanes of the last warp shadow the last surfel
-  // With a Morton processing order the 32 surfels of a warp are neighbours in space and see (almost) the same nodes
-  // enter their K-sets: the divergent `offer` body runs for ~30 of the 512 nodes instead of ~240 (random order).
-  const int i = a.order ? __ldg(a.order + t_lin) : t_lin;
+  const int lane = threadIdx.x & 31;
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const int nch = MP >> 5;
+  for (int base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; base < a.P; base += nwarps * 32) {
+    const int t_raw = base + lane;
+    const bool live = t_raw < a.P;
+    const int t_lin = live ? t_raw : a.P - 1;                      // idle lanes of the last warp shadow the last surfel
+    const int i = a.order ? __ldg(a.order + t_lin) : t_lin;
 
-  float2 q2[DP];   // query coordinate d duplicated in both packed lanes
+    float q[DP];
 #pragma unroll
-  for (int d = 0; d < DP; d++) {
-    float v = 0.f;
-    if (d < 3) v = a.xyz[3 * (size_t)i + d];
-    else if (d < D) v = a.feature[(size_t)i * a.fstride + (d - 3)];
-    q2[d] = make_float2(v, v);
-  }
+    for (int d = 0; d < DP; d++) {
+      float v = 0.f;
+      if (d < 3) v = a.xyz[3 * (size_t)i + d];
+      else if (d < D) v = a.feature[(size_t)i * a.fstride + (d - 3)];
+      q[d] = v;
+    }
 
-  // K nearest by (distance, node index), kept as an unordered set with a tracked worst element.  A candidate enters if it
-  // is lexicographically smaller than the worst, so the result does not depend on the order the nodes are visited in.
-  float bd[K];
-  int bi[K];
+    float bd[K];
+    int bi[K];
 #pragma unroll
-  for (int k = 0; k < K; k++) { bd[k] = INFINITY; bi[k] = 0x7ffffff0 - k; }
-  float wd = INFINITY;   // current worst (largest (dist, idx)) of the set, its index and its slot
-  int wi = 0x7ffffff0, ws = 0;
-  auto offer = [&](float dist, int m) {
-    if (dist < wd || (dist == wd && m < wi)) {
+    for (int k = 0; k < K; k++) { bd[k] = INFINITY; bi[k] = 0x7ffffff0 - k; }
+    float wd = INFINITY;   // current worst (largest (dist, idx)) of the set, its index and its slot
+    int wi = 0x7ffffff0, ws = 0;
+    auto offer = [&](float dist, int m) {
+      if (dist < wd || (dist == wd && m < wi)) {
 #pragma unroll
-      for (int k = 0; k < K; k++) {
-        const bool sel = (k == ws);
-        bd[k] = sel ? dist : bd[k];
-        bi[k] = sel ? m : bi[k];
+        for (int k = 0; k < K; k++) {
+          const bool sel = (k == ws);
+          bd[k] = sel ? dist : bd[k];
+          bi[k] = sel ? m : bi[k];
+        }
+        wd = bd[0]; ws = 0; wi = bi[0];
+#pragma unroll
+        for (int k = 1; k < K; k++) {
+          const bool worse = (bd[k] > wd) || (bd[k] == wd && bi[k] > wi);
+          wd = worse ? bd[k] : wd;
+          wi = worse ? bi[k] : wi;
+          ws = worse ? k : ws;
+        }
       }
-      wd = bd[0]; ws = 0; wi = bi[0];
-#pragma unroll
-      for (int k = 1; k < K; k++) {
-        const bool worse = (bd[k] > wd) || (bd[k] == wd && bi[k] > wi);
-        wd = worse ? bd[k] : wd;
-        wi = worse ? bi[k] : wi;
-        ws = worse ? k : ws;
-      }
-    }
-  };
-  constexpr int HEAD = DP / 2 < 2 ? DP / 2 : 2;   // float4 chunks of the first (up to) four coordinates: x, y, z, h0
-  // distance of the query to the two nodes of storage pair `pr`, offered to the set
-  auto visit_pair = [&](int pr) {
-    const float4* n4 = s_nodes4 + pr * (DP / 2);
-    float2 dist = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int c = 0; c < HEAD; c++) {
-      const float4 v = n4[c];   // (dim 2c: node A, node B), (dim 2c+1: node A, node B)
-      float2 df = __fadd2_rn(q2[2 * c], make_float2(-v.x, -v.y));
-      dist = __ffma2_rn(df, df, dist);
-      df = __fadd2_rn(q2[2 * c + 1], make_float2(-v.z, -v.w));
-      dist = __ffma2_rn(df, df, dist);
-    }
-    // The running sums only grow (squares are added in the same order as the full loop), so a pair whose spatial prefix
-    // already exceeds the current worst cannot enter the set: skip its remaining coordinates.  With coherent warps this
-    // is a whole-warp skip for most of the node table.
-    if (!(dist.x <= wd || dist.y <= wd)) return;
-#pragma unroll
-    for (int c = HEAD; c < DP / 2; c++) {
-      const float4 v = n4[c];
-      float2 df = __fadd2_rn(q2[2 * c], make_float2(-v.x, -v.y));
-      dist = __ffma2_rn(df, df, dist);
-      df = __fadd2_rn(q2[2 * c + 1], make_float2(-v.z, -v.w));
-      dist = __ffma2_rn(df, df, dist);
-    }
-    if (blocks) {
-      const int2 mm = *reinterpret_cast<const int2*>(s_perm + 2 * pr);
-      offer(dist.x, mm.x >= 0 ? mm.x : 0x7fffffff);
-      offer(dist.y, mm.y >= 0 ? mm.y : 0x7fffffff);
-    } else {
-      offer(dist.x, 2 * pr);
-      offer(dist.y, 2 * pr + 1);
-    }
-  };
-  if (!blocks) {
-    const int npairs = MP >> 1;
-    for (int pr = 0; pr < npairs; pr++) visit_pair(pr);
-  } else {
-    // Node blocks: every lane bounds the squared distance between the warp's query box and the box of one block (spatial
-    // coordinates only — the hyper coordinates can only add).  The nearest block is visited first, then every block whose
-    // bound (shrunk by 1e-5 relative, far above the fp32 error of either side) does not exceed the largest current worst
-    // of the warp.  A skipped block holds only nodes that are farther than every lane's worst: the K-set is unchanged.
-    float qlo[3], qhi[3];
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      const unsigned int u = float_to_ordered(q2[c].x);
-      qlo[c] = ordered_to_float(__reduce_min_sync(FULL, u));
-      qhi[c] = ordered_to_float(__reduce_max_sync(FULL, u));
-    }
-    const int lane = threadIdx.x & 31;
-    constexpr int MAXCH = 4;               // up to 128 blocks = 2048 nodes
-    float lb[MAXCH];
-    unsigned int best = 0xffffffffu;
-#pragma unroll
-    for (int ch = 0; ch < MAXCH; ch++) {
-      const int b = ch * 32 + lane;
-      float v = INFINITY;
-      if (b < a.MB) {
-        const float4 lo = s_bbox[2 * b], hi = s_bbox[2 * b + 1];
-        const float dx = fmaxf(fmaxf(lo.x - qhi[0], qlo[0] - hi.x), 0.f);
-        const float dy = fmaxf(fmaxf(lo.y - qhi[1], qlo[1] - hi.y), 0.f);
-        const float dz = fmaxf(fmaxf(lo.z - qhi[2], qlo[2] - hi.z), 0.f);
-        v = (dx * dx + dy * dy + dz * dz) * 0.99999f;
-        if (!(v == v)) v = 0.f;            // a NaN box is never skipped
-        best = min(best, (__float_as_uint(v) & 0xffffff80u) | (unsigned int)b);
-      }
-      lb[ch] = v;
-    }
-    best = __reduce_min_sync(FULL, best);
-    const int b0 = (int)(best & 0x7fu);
-    auto visit_block = [&](int b) {
-#pragma unroll 2
-      for (int pr = 8 * b; pr < 8 * b + 8; pr++) visit_pair(pr);
     };
-    if (best != 0xffffffffu) visit_block(b0);
-    float wmax = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(wd)));   // wd >= 0 (or +inf): bit order = value order
+    // squared distance of the lane's query to the node in slot `s` (warp-uniform: broadcast LDS.128), offered to the set
+    auto visit = [&](int s) {
+      const float4* n4 = s_node4 + (size_t)s * NQ;
+      float dist = 0.f;
+      {
+        const float4 v = n4[0];
+        float df = __fsub_rn(q[0], v.x); dist = __fmaf_rn(df, df, dist);
+        df = __fsub_rn(q[1], v.y); dist = __fmaf_rn(df, df, dist);
+        df = __fsub_rn(q[2], v.z); dist = __fmaf_rn(df, df, dist);
+        df = __fsub_rn(q[3], v.w); dist = __fmaf_rn(df, df, dist);
+      }
+      if (NQ > 1) {
+        // the running sum only grows: a node whose prefix (x, y, z, h0) already exceeds the lane's worst cannot enter
+        if (!(dist <= wd)) return;
 #pragma unroll
-    for (int ch = 0; ch < MAXCH; ch++) {
-      if (ch * 32 >= a.MB) break;
-      uint32_t cand = __ballot_sync(FULL, lb[ch] <= wmax);
-      while (cand) {
-        const int l = __ffs(cand) - 1;
-        cand &= cand - 1;
-        const int b = ch * 32 + l;
-        if (b == b0) continue;
-        if (__shfl_sync(FULL, lb[ch], l) > wmax) continue;       // the bound tightened since the ballot
-        visit_block(b);
+        for (int c = 1; c < NQ; c++) {
+          const float4 v = n4[c];
+          float df = __fsub_rn(q[4 * c], v.x); dist = __fmaf_rn(df, df, dist);
+          df = __fsub_rn(q[4 * c + 1], v.y); dist = __fmaf_rn(df, df, dist);
+          df = __fsub_rn(q[4 * c + 2], v.z); dist = __fmaf_rn(df, df, dist);
+          df = __fsub_rn(q[4 * c + 3], v.w); dist = __fmaf_rn(df, df, dist);
+        }
+      }
+      offer(dist, s < a.M ? s : 0x7fffffff);
+    };
+
+    if (!a.filter) {
+      for (int s = 0; s < MP; s++) visit(s);
+    } else {
+      // the warp's query box (ordered-integer min/max: one REDUX each)
+      float qlo[3], qhi[3];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const unsigned int u = float_to_ordered(q[c]);
+        qlo[c] = ordered_to_float(__reduce_min_sync(FULL, u));
+        qhi[c] = ordered_to_float(__reduce_max_sync(FULL, u));
+      }
+      // lower bound of the squared distance between any query of the warp and the node in slot s
+      auto bound = [&](int s) {
+        const float4 v = s_node4[(size_t)s * NQ];
+        const float dx = fmaxf(fmaxf(qlo[0] - v.x, v.x - qhi[0]), 0.f);
+        const float dy = fmaxf(fmaxf(qlo[1] - v.y, v.y - qhi[1]), 0.f);
+        const float dz = fmaxf(fmaxf(qlo[2] - v.z, v.z - qhi[2]), 0.f);
+        float b = (dx * dx + dy * dy + dz * dz) * 0.99999f;
+        return (b == b) ? b : 0.f;          // NaN (a NaN node or query): never rejected
+      };
+      // 1. every lane nominates the nearest of its own nodes
+      float nb = INFINITY;
+      int nch_sel = 0;
+      for (int c = 0; c < nch; c++) {
+        const float b = bound(32 * c + lane);
+        if (b < nb) { nb = b; nch_sel = c; }
+      }
+      const int nominated = 32 * nch_sel + lane;
+#pragma unroll 1
+      for (int l = 0; l < 32; l++) visit(__shfl_sync(FULL, nominated, l));
+      float wmax = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(wd)));   // wd >= 0 or +inf: bit order = value order
+      // 2. chunks of 32 nodes: visit those that can still matter
+#pragma unroll 1
+      for (int c = 0; c < nch; c++) {
+        const float b = bound(32 * c + lane);
+        uint32_t cand = __ballot_sync(FULL, b <= wmax && c != nch_sel);       // the nominated node was visited above
+        if (!cand) continue;
+        while (cand) {
+          const int l = __ffs(cand) - 1;
+          cand &= cand - 1;
+          visit(32 * c + l);
+        }
         wmax = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(wd)));
       }
     }
-  }
-  // order the K survivors by (distance, index): tiny odd-even transposition network
+    // order the K survivors by (distance, index): tiny odd-even transposition network
 #pragma unroll
-  for (int pass = 0; pass < K; pass++) {
+    for (int pass = 0; pass < K; pass++) {
 #pragma unroll
-    for (int k = (pass & 1); k + 1 < K; k += 2) {
-      const bool sw = (bd[k + 1] < bd[k]) || (bd[k + 1] == bd[k] && bi[k + 1] < bi[k]);
-      const float td = bd[k]; const int ti = bi[k];
-      bd[k] = sw ? bd[k + 1] : bd[k]; bi[k] = sw ? bi[k + 1] : bi[k];
-      bd[k + 1] = sw ? td : bd[k + 1]; bi[k + 1] = sw ? ti : bi[k + 1];
+      for (int k = (pass & 1); k + 1 < K; k += 2) {
+        const bool sw = (bd[k + 1] < bd[k]) || (bd[k + 1] == bd[k] && bi[k + 1] < bi[k]);
+        const float td = bd[k]; const int ti = bi[k];
+        bd[k] = sw ? bd[k + 1] : bd[k]; bi[k] = sw ? bi[k + 1] : bi[k];
+        bd[k + 1] = sw ? td : bd[k + 1]; bi[k + 1] = sw ? ti : bi[k + 1];
+      }
     }
-  }
+    // a query with NaN/Inf coordinates accepts no node: its set keeps the initial sentinels; point them at node k
+#pragma unroll
+    for (int k = 0; k < K; k++) bi[k] = ((unsigned int)bi[k] < (unsigned int)a.M) ? bi[k] : k;
 
-  // radial-basis weights
-  float w[K];
-  float wsum = 0.f;
+    // radial-basis weights
+    float w[K];
+    float wsum = 0.f;
 #pragma unroll
-  for (int k = 0; k < K; k++) {
-    const int m = bi[k];
-    const float r = expf(__ldg(a.radius_log + m));
-    float wk = expf(-bd[k] / (2 * (r * r)));
-    if (a.weight_logit) wk = wk * (1.0f / (1.0f + expf(-__ldg(a.weight_logit + m))));
-    wk = wk + 1e-7f;
-    w[k] = wk;
-    wsum += wk;
-  }
-  const float x0 = q2[0].x, x1 = q2[1].x, x2 = q2[2].x;
-  float t0 = 0.f, t1 = 0.f, t2 = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, s0 = 0.f, s1 = 0.f;
-#pragma unroll
-  for (int k = 0; k < K; k++) {
-    const int m = bi[k];
-    const float wk = w[k] / wsum;
-    const float tr0 = __ldg(a.trans + a.st_t * m), tr1 = __ldg(a.trans + a.st_t * m + 1), tr2 = __ldg(a.trans + a.st_t * m + 2);
-    if (a.local_rot) {
-      float lq[4] = {__ldg(a.local_rot + a.st_l * m) + 1.0f, __ldg(a.local_rot + a.st_l * m + 1), __ldg(a.local_rot + a.st_l * m + 2),
-                     __ldg(a.local_rot + a.st_l * m + 3)};
-      float R[9];
-      quat_to_matrix_raw(lq, R);
-      const float n0 = __ldg(a.nodes + (size_t)m * nstride), n1 = __ldg(a.nodes + (size_t)m * nstride + 1),
-                  n2 = __ldg(a.nodes + (size_t)m * nstride + 2);
-      const float e0 = x0 - n0, e1 = x1 - n1, e2 = x2 - n2;
-      const float A0 = (R[0] * e0 + R[1] * e1 + R[2] * e2) + n0 + tr0;
-      const float A1 = (R[3] * e0 + R[4] * e1 + R[5] * e2) + n1 + tr1;
-      const float A2 = (R[6] * e0 + R[7] * e1 + R[8] * e2) + n2 + tr2;
-      t0 += A0 * wk; t1 += A1 * wk; t2 += A2 * wk;
-    } else {
-      t0 += tr0 * wk; t1 += tr1 * wk; t2 += tr2 * wk;
+    for (int k = 0; k < K; k++) {
+      const int m = bi[k];
+      const float r = expf(__ldg(a.radius_log + m));
+      float wk = expf(-bd[k] / (2 * (r * r)));
+      if (a.weight_logit) wk = wk * (1.0f / (1.0f + expf(-__ldg(a.weight_logit + m))));
+      wk = wk + 1e-7f;
+      w[k] = wk;
+      wsum += wk;
     }
-    r0 += __ldg(a.rot + a.st_r * m) * wk; r1 += __ldg(a.rot + a.st_r * m + 1) * wk;
-    r2 += __ldg(a.rot + a.st_r * m + 2) * wk; r3 += __ldg(a.rot + a.st_r * m + 3) * wk;
-    s0 += __ldg(a.scale + a.st_s * m) * wk; s1 += __ldg(a.scale + a.st_s * m + 1) * wk;
+    const float x0 = q[0], x1 = q[1], x2 = q[2];
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const int m = bi[k];
+      const float wk = w[k] / wsum;
+      const float tr0 = __ldg(a.trans + a.st_t * m), tr1 = __ldg(a.trans + a.st_t * m + 1), tr2 = __ldg(a.trans + a.st_t * m + 2);
+      if (a.local_rot) {
+        float lq[4] = {__ldg(a.local_rot + a.st_l * m) + 1.0f, __ldg(a.local_rot + a.st_l * m + 1), __ldg(a.local_rot + a.st_l * m + 2),
+                       __ldg(a.local_rot + a.st_l * m + 3)};
+        float R[9];
+        quat_to_matrix_raw(lq, R);
+        const float4 nv = s_node4[(size_t)m * NQ];
+        const float n0 = nv.x, n1 = nv.y, n2 = nv.z;
+        const float e0 = x0 - n0, e1 = x1 - n1, e2 = x2 - n2;
+        const float A0 = (R[0] * e0 + R[1] * e1 + R[2] * e2) + n0 + tr0;
+        const float A1 = (R[3] * e0 + R[4] * e1 + R[5] * e2) + n1 + tr1;
+        const float A2 = (R[6] * e0 + R[7] * e1 + R[8] * e2) + n2 + tr2;
+        t0 += A0 * wk; t1 += A1 * wk; t2 += A2 * wk;
+      } else {
+        t0 += tr0 * wk; t1 += tr1 * wk; t2 += tr2 * wk;
+      }
+      r0 += __ldg(a.rot + a.st_r * m) * wk; r1 += __ldg(a.rot + a.st_r * m + 1) * wk;
+      r2 += __ldg(a.rot + a.st_r * m + 2) * wk; r3 += __ldg(a.rot + a.st_r * m + 3) * wk;
+      s0 += __ldg(a.scale + a.st_s * m) * wk; s1 += __ldg(a.scale + a.st_s * m + 1) * wk;
+      if (live) {
+        if (a.nn_idx) a.nn_idx[(size_t)i * K + k] = m;
+        if (a.nn_dist) a.nn_dist[(size_t)i * K + k] = bd[k];
+        if (a.nn_weight) a.nn_weight[(size_t)i * K + k] = wk;
+      }
+    }
     if (live) {
-      if (a.nn_idx) a.nn_idx[(size_t)i * K + k] = m;
-      if (a.nn_dist) a.nn_dist[(size_t)i * K + k] = bd[k];
-      if (a.nn_weight) a.nn_weight[(size_t)i * K + k] = wk;
+      if (a.local_rot) { t0 -= x0; t1 -= x1; t2 -= x2; }
+      const float mk = a.mask ? a.mask[i] : 1.0f;
+      a.d_xyz[3 * (size_t)i] = t0 * mk; a.d_xyz[3 * (size_t)i + 1] = t1 * mk; a.d_xyz[3 * (size_t)i + 2] = t2 * mk;
+      a.d_rot[4 * (size_t)i] = r0 * mk; a.d_rot[4 * (size_t)i + 1] = r1 * mk; a.d_rot[4 * (size_t)i + 2] = r2 * mk;
+      a.d_rot[4 * (size_t)i + 3] = r3 * mk;
+      a.d_scale[2 * (size_t)i] = s0 * mk; a.d_scale[2 * (size_t)i + 1] = s1 * mk;
     }
   }
-  if (!live) return;
-  if (a.local_rot) { t0 -= x0; t1 -= x1; t2 -= x2; }
-  const float mk = a.mask ? a.mask[i] : 1.0f;
-  a.d_xyz[3 * (size_t)i] = t0 * mk; a.d_xyz[3 * (size_t)i + 1] = t1 * mk; a.d_xyz[3 * (size_t)i + 2] = t2 * mk;
-  a.d_rot[4 * (size_t)i] = r0 * mk; a.d_rot[4 * (size_t)i + 1] = r1 * mk; a.d_rot[4 * (size_t)i + 2] = r2 * mk;
-  a.d_rot[4 * (size_t)i + 3] = r3 * mk;
-  a.d_scale[2 * (size_t)i] = s0 * mk; a.d_scale[2 * (size_t)i + 1] = s1 * mk;
 }
 
 struct DeformBwdP {
@@ -698,96 +687,6 @@ __global__ void __launch_bounds__(256, 3) deform_bwd_coherent_kernel(DeformBwdP 
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// node blocks: the control nodes sorted along a 30-bit Morton curve of their bounding box, cut into blocks of 16, with
-// the spatial bounding box of every block.  One CTA (M <= 2048 nodes): bitonic sort of (morton << 32 | index) in shared
-// memory.  Speed only — deform_fwd_kernel gives the same K-sets with or without it.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int NODE_BLOCKS_MAX_M = 2048;
-__device__ __forceinline__ unsigned int spread10(unsigned int v);
-__global__ void __launch_bounds__(1024) node_blocks_kernel(int M, int nstride, const float* __restrict__ nodes,
-                                                           int* __restrict__ perm, float* __restrict__ bbox) {
-  __shared__ unsigned long long s_key[NODE_BLOCKS_MAX_M];
-  __shared__ unsigned int s_box[6];
-  const int tid = threadIdx.x;
-  if (tid < 3) s_box[tid] = 0xffffffffu;
-  else if (tid < 6) s_box[tid] = 0u;
-  __syncthreads();
-  unsigned int lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
-  for (int m = tid; m < M; m += 1024) {
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      const float v = nodes[(size_t)m * nstride + c];
-      if (v == v && fabsf(v) <= 3.0e38f) {
-        const unsigned int u = float_to_ordered(v);
-        lo[c] = min(lo[c], u); hi[c] = max(hi[c], u);
-      }
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < 3; c++) {
-    lo[c] = __reduce_min_sync(FULL, lo[c]);
-    hi[c] = __reduce_max_sync(FULL, hi[c]);
-    if ((tid & 31) == 0) { atomicMin(&s_box[c], lo[c]); atomicMax(&s_box[3 + c], hi[c]); }
-  }
-  __syncthreads();
-  int n2 = 32;
-  while (n2 < M) n2 <<= 1;                    // power of two >= M (<= 2048)
-  for (int m = tid; m < n2; m += 1024) {
-    unsigned long long key = ~0ull;           // padding sorts to the end
-    if (m < M) {
-      unsigned int q[3];
-#pragma unroll
-      for (int c = 0; c < 3; c++) {
-        const float l = ordered_to_float(s_box[c]), h = ordered_to_float(s_box[3 + c]);
-        const float v = nodes[(size_t)m * nstride + c];
-        const float ext = h - l;
-        float u = (ext > 0.f && v == v) ? (v - l) / ext : 0.f;
-        u = fminf(fmaxf(u, 0.f), 1.f);
-        q[c] = min(1023u, (unsigned int)(u * 1024.f));
-      }
-      const unsigned int mort = spread10(q[0]) | (spread10(q[1]) << 1) | (spread10(q[2]) << 2);
-      key = ((unsigned long long)mort << 32) | (unsigned int)m;
-    }
-    s_key[m] = key;
-  }
-  __syncthreads();
-  for (int k = 2; k <= n2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < n2; t += 1024) {
-        const int p = t ^ j;
-        if (p > t) {
-          const unsigned long long x = s_key[t], y = s_key[p];
-          const bool up = (t & k) == 0;
-          if ((x > y) == up) { s_key[t] = y; s_key[p] = x; }
-        }
-      }
-      __syncthreads();
-    }
-  }
-  const int MB = (M + 15) / 16;
-  for (int p = tid; p < MB * 16; p += 1024) perm[p] = (p < M) ? (int)(unsigned int)(s_key[p] & 0xffffffffull) : -1;
-  for (int b = tid; b < MB; b += 1024) {
-    float l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int p = 16 * b; p < min(16 * b + 16, M); p++) {
-      const int m = (int)(unsigned int)(s_key[p] & 0xffffffffull);
-#pragma unroll
-      for (int c = 0; c < 3; c++) {
-        const float v = nodes[(size_t)m * nstride + c];
-        l[c] = fminf(l[c], v); h[c] = fmaxf(h[c], v);
-        if (!(v == v)) { l[c] = -INFINITY; h[c] = INFINITY; }   // a NaN coordinate: the block is never skipped
-      }
-    }
-    float* o = bbox + 8 * (size_t)b;
-    o[0] = l[0]; o[1] = l[1]; o[2] = l[2]; o[3] = 0.f; o[4] = h[0]; o[5] = h[1]; o[6] = h[2]; o[7] = 0.f;
-  }
-}
-
-size_t deform_node_workspace_bytes(int M) {
-  const size_t MB = (size_t)(M + 15) / 16;
-  return MB * 16 * sizeof(int) + MB * 8 * sizeof(float) + 256;
-}
-
 int deform_forward_launch(const DeformFwdHost& h, cudaStream_t s, const char** err) {
   if (h.K < 1 || h.K > MAX_K || h.K > h.M) { *err = "K must be in [1, min(8, M)]"; return -1; }
   if (h.hyper < 0 || h.hyper > MAX_D - 3) { *err = "hyper_dim must be <= 16"; return -1; }
@@ -804,23 +703,21 @@ int deform_forward_launch(const DeformFwdHost& h, cudaStream_t s, const char** e
   a.st_t = h.attr_stride > 0 ? h.attr_stride : 3; a.st_r = h.attr_stride > 0 ? h.attr_stride : 4;
   a.st_s = h.attr_stride > 0 ? h.attr_stride : 2; a.st_l = h.attr_stride > 0 ? h.attr_stride : 4;
   a.order = h.order;
+  a.filter = g_knn_filter;
   const int nq = (a.D + 3) / 4;
-  // node blocks (optional workspace, M <= 2048): Morton-ordered node table + per-16-node boxes, built by one small kernel
-  a.MB = 0;
-  if (h.node_workspace && h.M <= NODE_BLOCKS_MAX_M && h.M >= 32) {
-    const int MB = (h.M + 15) / 16;
-    int* perm = reinterpret_cast<int*>(h.node_workspace);
-    float* bbox = reinterpret_cast<float*>(perm + (size_t)MB * 16);
-    node_blocks_kernel<<<1, 1024, 0, s>>>(h.M, 3 + h.hyper, h.nodes, perm, bbox);
-    a.node_perm = perm; a.node_bbox = bbox; a.MB = MB;
-  }
-  const size_t slots = a.MB ? (size_t)a.MB * 16 : (size_t)((a.M + 1) & ~1);
-  const size_t smem = sizeof(float) * slots * 4 * nq + (a.MB ? sizeof(int) * slots + 32 * (size_t)a.MB : 0);
+  const size_t smem = sizeof(float4) * (size_t)((a.M + 31) & ~31) * nq;
   if (smem > 200 * 1024) { *err = "node table exceeds shared memory (M*(3+hyper) floats > 200 KB)"; return -1; }
-  const int grid = (h.P + 255) / 256;
+  // persistent warps: as many CTAs as are resident at once (the node table is staged once per CTA), capped by the work
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int chunks = (h.P + 255) / 256;
 #define D2GS_KNN_LAUNCH(KK, QQ)                                                                                  \
   do {                                                                                                          \
     cudaFuncSetAttribute(deform_fwd_kernel<KK, QQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+    int per_sm = 1;                                                                                             \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, deform_fwd_kernel<KK, QQ>, 256, smem);               \
+    const int grid = min(chunks, sms * max(per_sm, 1));                                                         \
     deform_fwd_kernel<KK, QQ><<<grid, 256, smem, s>>>(a);                                                        \
   } while (0)
 #define D2GS_KNN_Q(KK)                                                                     \

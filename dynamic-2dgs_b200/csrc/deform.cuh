@@ -14,7 +14,6 @@ struct DeformFwdHost {
   float* d_xyz; float* d_rot; float* d_scale;
   int attr_stride;      // > 0: trans/rot/scale/local_rot are columns of one (M, attr_stride) matrix
   const int* order;     // optional processing order (a permutation of 0..P-1): thread t handles surfel order[t]
-  void* node_workspace; // optional scratch of deform_node_workspace_bytes(M) (256-B aligned): enables the node-block KNN
 };
 
 struct DeformBwdHost {
@@ -30,7 +29,6 @@ struct DeformBwdHost {
   const int* order;
 };
 
-size_t deform_node_workspace_bytes(int M);
 int deform_forward_launch(const DeformFwdHost& h, cudaStream_t s, const char** err);
 int deform_backward_launch(const DeformBwdHost& h, cudaStream_t s, const char** err);
 

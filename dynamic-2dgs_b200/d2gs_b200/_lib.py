@@ -70,7 +70,7 @@ class DeformFwdArgs(C.Structure):
                 ("node_local_rot", C.c_void_p), ("motion_mask", C.c_void_p),
                 ("nn_idx", C.c_void_p), ("nn_dist", C.c_void_p), ("nn_weight", C.c_void_p),
                 ("d_xyz", C.c_void_p), ("d_rotation", C.c_void_p), ("d_scaling", C.c_void_p), ("node_attr_stride", C.c_int),
-                ("order", C.c_void_p), ("node_workspace", C.c_void_p), ("node_workspace_bytes", C.c_size_t)]
+                ("order", C.c_void_p)]
 
 
 class DeformBwdArgs(C.Structure):
@@ -127,7 +127,7 @@ EXPORTED_SYMBOLS = (
     "d2gs_raster_backward", "d2gs_mark_visible", "d2gs_raster_export_state", "d2gs_deform_forward",
     "d2gs_deform_backward", "d2gs_epilogue_forward", "d2gs_epilogue_backward",
     "d2gs_mlp_workspace", "d2gs_mlp_forward", "d2gs_mlp_backward", "d2gs_mlp_hidden",
-    "d2gs_deform_order_workspace", "d2gs_deform_order", "d2gs_deform_node_workspace",
+    "d2gs_deform_order_workspace", "d2gs_deform_order",
     "d2gs_loss_workspace", "d2gs_loss_forward", "d2gs_loss_backward",
     "d2gs_adam_step", "d2gs_densification_stats",
 )
@@ -173,7 +173,6 @@ def lib():
     L.d2gs_mlp_hidden.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.d2gs_mlp_hidden.restype = C.c_void_p
     L.d2gs_deform_order_workspace.argtypes = [C.c_int, C.POINTER(C.c_size_t)]
-    L.d2gs_deform_node_workspace.argtypes = [C.c_int, C.POINTER(C.c_size_t)]
     L.d2gs_deform_order.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.d2gs_loss_workspace.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_size_t)]
     L.d2gs_loss_forward.argtypes = [C.POINTER(LossArgs), C.c_void_p]

@@ -58,19 +58,6 @@ def processing_order(xyz: torch.Tensor) -> torch.Tensor:
     return order
 
 
-NODE_BLOCKS = True     # False: the K-nearest search visits every node (same results; tests compare the two)
-_NODE_WS_BYTES: dict = {}
-
-
-def _node_workspace_bytes(M: int) -> int:
-    n = _NODE_WS_BYTES.get(M)
-    if n is None:
-        b = C.c_size_t(0)
-        _lib.check(_lib.lib().d2gs_deform_node_workspace(M, C.byref(b)), "d2gs_deform_node_workspace")
-        n = _NODE_WS_BYTES[M] = int(b.value)
-    return n
-
-
 def _blend_forward(ctx, xyz, feature, nodes, node_radius_log, node_weight_logit, attr_ptrs, attr_stride, motion_mask, K, hyper_dim,
                    order=None):
     """Shared forward of the two autograd Functions below.  attr_ptrs = device pointers of (trans, rot, scale, local_rot)."""
@@ -109,11 +96,6 @@ def _blend_forward(ctx, xyz, feature, nodes, node_radius_log, node_weight_logit,
     d_scale = torch.empty((P, 2), dtype=torch.float32, device=dev)
     a.nn_idx, a.nn_dist, a.nn_weight = _p(nn_idx), _p(nn_dist), _p(nn_weight)
     a.d_xyz, a.d_rotation, a.d_scaling = _p(d_xyz), _p(d_rot), _p(d_scale)
-    node_ws = None
-    if NODE_BLOCKS and 32 <= M <= 2048:
-        # scratch for the node-block KNN (Morton-ordered nodes + a box per 16 nodes, rebuilt by every call: the nodes train)
-        node_ws = torch.empty((_node_workspace_bytes(M),), dtype=torch.uint8, device=dev)
-        a.node_workspace, a.node_workspace_bytes = node_ws.data_ptr(), node_ws.numel()
     with torch.cuda.device(dev):
         _lib.check(L.d2gs_deform_forward(C.byref(a), _stream(dev)), "d2gs_deform_forward")
     ctx.K, ctx.use_hyper = int(K), use_hyper

@@ -54,7 +54,10 @@ typedef struct D2gsConfig {
  *         8 deform_fwd, 9 deform_bwd, 10 epilogue_fwd, 11 epilogue_bwd, 12 mlp_fwd, 13 mlp_bwd, 14 loss_fwd, 15 loss_bwd.  d2gs_profile_collect synchronises the device, adds the elapsed times of all
  * recorded launches to total_ms[stage] / launches[stage] (arrays of D2GS_NUM_STAGES) and clears the record. */
 #define D2GS_NUM_STAGES 16
-/* Runtime switches.  "cull" (default 1): warp-level cull boxes in the blend kernels; results are identical either way. */
+/* Runtime switches (speed only; results are identical either way, the tests flip them to prove it).
+ *   "cull"       (default 1): warp-level cull boxes in the blend kernels
+ *   "knn_filter" (default 1): warp-level candidate filter of the K-nearest-node search in d2gs_deform_forward
+ *   "deform_bwd_smem" (default 1): per-CTA shared accumulators in the incoherent d2gs_deform_backward path */
 D2GS_API int d2gs_set_option(const char* name, int value);
 D2GS_API int d2gs_profile_enable(int on);
 D2GS_API int d2gs_profile_collect(double* total_ms, int64_t* launches);
@@ -354,14 +357,8 @@ typedef struct D2gsDeformFwdArgs {
   int node_attr_stride;          /* 0: node_trans/rot/scale/local_rot are separate packed tables; > 0: they are columns
                                     of ONE (M,node_attr_stride) row-major matrix (the MLP head output), no slicing copies */
   const int32_t* order;          /* optional (P): processing order from d2gs_deform_order; results do not depend on it */
-  /* optional device scratch of d2gs_deform_node_workspace(M) bytes (speed only, M <= 2048): the call first sorts the nodes
-   * along a Morton curve and boxes every 16 of them, so that a warp of neighbouring surfels evaluates distances only for
-   * the node blocks whose box can still hold one of its K nearest; nn_idx / nn_dist / outputs are identical without it */
-  void* node_workspace;
-  size_t node_workspace_bytes;
 } D2gsDeformFwdArgs;
 
-D2GS_API int d2gs_deform_node_workspace(int M, size_t* bytes);
 D2GS_API int d2gs_deform_forward(const D2gsDeformFwdArgs* args, void* stream);
 
 typedef struct D2gsDeformBwdArgs {

@@ -140,44 +140,71 @@ def test_node_blend_is_invariant_to_the_processing_order(P, M, K, hyper, local_f
 
 @pytest.mark.parametrize("P,M,K,hyper,dup,coherent", [(20000, 512, 4, 8, False, True), (6000, 100, 3, 8, True, True),
                                                         (9000, 2048, 4, 8, False, True), (5000, 333, 8, 0, True, False),
-                                                        (4097, 512, 4, 8, True, True)])
-def test_node_block_knn_changes_nothing(P, M, K, hyper, dup, coherent, cuda_device):
-    """The node-block search (nodes along a Morton curve, one box per 16 nodes, blocks a warp cannot need are skipped)
-    must return exactly the K-sets of the exhaustive search: same nn_idx / nn_dist / outputs bit for bit — also with
-    DUPLICATED nodes (equal distances: the lower node index must win), ragged M, 2048 nodes (4 box chunks per lane) and
-    warps that are not spatially coherent (a random processing order)."""
-    from d2gs_b200 import deform as dfm
+                                                        (4097, 512, 4, 8, True, True), (3000, 9, 8, 8, True, True),
+                                                        (2500, 40, 1, 0, False, True)])
+def test_knn_candidate_filter_changes_nothing(P, M, K, hyper, dup, coherent, cuda_device):
+    """The warp-level candidate filter of the K-nearest-node search (a warp only evaluates the nodes whose distance to the
+    box of its 32 queries does not exceed the largest current worst) must return exactly the K-sets of the exhaustive
+    search: same nn_idx / nn_dist / outputs bit for bit — also with DUPLICATED nodes (equal distances: the lower node
+    index must win), ragged M (padding slots), fewer nodes than a chunk, 2048 nodes, and warps that are not spatially
+    coherent (a random processing order)."""
+    from d2gs_b200 import _lib, deform as dfm
     dev = cuda_device
     x, feat, nodes, rad, wl, attrs = _case(P, M, K, hyper, seed=3 * P + M, local_frame=True, with_mask=False)
     if dup:
         g = torch.Generator().manual_seed(4)
-        src = torch.randint(0, M, (M // 3,), generator=g)
-        dst = torch.randint(0, M, (M // 3,), generator=g)
+        src = torch.randint(0, M, (max(M // 3, 1),), generator=g)
+        dst = torch.randint(0, M, (max(M // 3, 1),), generator=g)
         nodes[dst] = nodes[src]                      # exact copies -> exact distance ties
     order = dfm.processing_order(x.to(dev)) if coherent else torch.randperm(P, generator=torch.Generator().manual_seed(2)).to(torch.int32).to(dev)
     res = {}
     try:
-        for blocks in (False, True):
-            dfm.NODE_BLOCKS = blocks
+        for filt in (0, 1):
+            _lib.set_option("knn_filter", filt)
             m = {k: v.clone().to(dev) for k, v in attrs.items()}
-            res[blocks] = dfm.node_blend(x.to(dev), feat.to(dev) if hyper else None, nodes.to(dev), rad.to(dev), wl.reshape(-1).to(dev),
-                                         m["d_xyz"], m["d_rotation"], m["d_scaling"], m.get("local_rotation"), None, K, hyper, order=order)
+            res[filt] = dfm.node_blend(x.to(dev), feat.to(dev) if hyper else None, nodes.to(dev), rad.to(dev), wl.reshape(-1).to(dev),
+                                       m["d_xyz"], m["d_rotation"], m["d_scaling"], m.get("local_rotation"), None, K, hyper, order=order)
             torch.cuda.synchronize()
     finally:
-        dfm.NODE_BLOCKS = True
+        _lib.set_option("knn_filter", 1)
     for k in ("nn_idx", "nn_dist", "nn_weight", "d_xyz", "d_rotation", "d_scaling"):
-        assert torch.equal(res[False][k], res[True][k]), k
+        assert torch.equal(res[0][k], res[1][k]), k
     # and the exhaustive search itself agrees with an explicit-distance top-k (ties -> lower index)
     q = torch.cat([x, feat[:, :hyper]], 1) if hyper else x
     d2 = ((q[:, None, :].double() - nodes[None, :, :q.shape[1]].double()) ** 2).sum(-1)
     ref_idx = torch.sort(d2, dim=1, stable=True).indices[:, :K]
-    got = res[True]["nn_idx"].cpu()
+    got = res[1]["nn_idx"].cpu()
+    assert int(got.min()) >= 0 and int(got.max()) < M
     assert (got == ref_idx).float().mean() > (0.97 if dup else 0.999)      # fp32 vs fp64 distances may order near-ties differently
+    assert bool((got.sort(dim=1).values[:, 1:] != got.sort(dim=1).values[:, :-1]).all())      # K distinct nodes per surfel
     if dup:
         # an exact duplicate pair can only appear as (lower index first)
-        dd = res[True]["nn_dist"].cpu()
+        dd = res[1]["nn_dist"].cpu()
         tie = dd[:, 1:] == dd[:, :-1]
         assert bool((got[:, 1:][tie] > got[:, :-1][tie]).all())
+
+
+def test_knn_with_non_finite_queries_stays_in_bounds(cuda_device):
+    """A surfel with NaN/Inf coordinates accepts no node; its neighbour indices must still be valid node indices (the
+    blend reads the node tables through them) and the other surfels of its warp are unaffected."""
+    from d2gs_b200 import deform as dfm
+    dev = cuda_device
+    P, M, K, hyper = 700, 64, 4, 8
+    x, feat, nodes, rad, wl, attrs = _case(P, M, K, hyper, seed=11, local_frame=True, with_mask=False)
+    bad = torch.tensor([3, 100, 101, 640])
+    xb = x.clone()
+    xb[bad[0], 0] = float("nan"); xb[bad[1], 1] = float("inf"); xb[bad[2]] = float("nan"); xb[bad[3], 2] = -float("inf")
+    out = {}
+    for name, xx in (("clean", x), ("bad", xb)):
+        m = {k: v.clone().to(dev) for k, v in attrs.items()}
+        out[name] = dfm.node_blend(xx.to(dev), feat.to(dev), nodes.to(dev), rad.to(dev), wl.reshape(-1).to(dev), m["d_xyz"],
+                                   m["d_rotation"], m["d_scaling"], m.get("local_rotation"), None, K, hyper)
+        torch.cuda.synchronize()
+    idx = out["bad"]["nn_idx"].cpu()
+    assert int(idx.min()) >= 0 and int(idx.max()) < M
+    good = torch.ones(P, dtype=torch.bool); good[bad] = False
+    for k in ("nn_idx", "nn_dist", "d_xyz", "d_rotation", "d_scaling"):
+        assert torch.equal(out["bad"][k].cpu()[good], out["clean"][k].cpu()[good]), k
 
 
 @pytest.mark.parametrize("rows,is_blender,local_frame,pred_opacity", [(512, True, True, False), (37, True, False, False),
