@@ -13,6 +13,7 @@
 #include "loss.cuh"
 #include "optim.cuh"
 #include "mlp.cuh"
+#include "knn.cuh"
 
 namespace d2gs {
 
@@ -478,6 +479,50 @@ int d2gs_deform_order(int P, const float* xyz, int32_t* order, void* workspace, 
   deform_order_keys_launch(P, xyz, (unsigned int*)(ws + L.bbox), keys, vals, stream);
   size_t tmp = L.temp_bytes;
   D2GS_CUDA_OK(cub::DeviceRadixSort::SortPairs(ws + L.temp, tmp, keys, keys_out, vals, (int*)order, P, 0, 30, stream));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(D2GS_ERR_CUDA, cudaGetErrorString(e));
+  return D2GS_OK;
+}
+
+namespace {
+struct KnnLayout { OrderLayout ord; size_t order, sp, leaf, group, total; };
+KnnLayout knn_layout(int P) {
+  KnnLayout L{};
+  L.ord = order_layout(P);
+  const size_t n = (size_t)(P > 0 ? P : 1);
+  const size_t nleaf = (n + 31) / 32, ngroup = (nleaf + 31) / 32;
+  size_t o = align_up(L.ord.total);
+  L.order = o; o = align_up(o + 4 * n);
+  L.sp = o; o = align_up(o + 16 * 32 * nleaf);
+  L.leaf = o; o = align_up(o + 32 * nleaf);
+  L.group = o; o = align_up(o + 32 * ngroup);
+  L.total = o + 256;
+  return L;
+}
+}  // namespace
+
+int d2gs_knn_mean_dist2_workspace(int P, size_t* bytes) {
+  if (!bytes || P < 0) return fail(D2GS_ERR_INVALID_ARG, "bad arguments");
+  *bytes = knn_layout(P).total;
+  return D2GS_OK;
+}
+
+int d2gs_knn_mean_dist2(int P, const float* points, float* mean_dist2, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (P < 0) return fail(D2GS_ERR_INVALID_ARG, "bad sizes");
+  if (P == 0) return D2GS_OK;
+  if (!points || !mean_dist2 || !workspace) return fail(D2GS_ERR_INVALID_ARG, "missing buffers");
+  const KnnLayout L = knn_layout(P);
+  if (workspace_bytes < L.total) return fail(D2GS_ERR_WORKSPACE, "knn workspace too small");
+  char* ws = aligned_base(workspace);
+  unsigned int* keys = (unsigned int*)(ws + L.ord.keys);
+  unsigned int* keys_out = (unsigned int*)(ws + L.ord.keys_out);
+  int* vals = (int*)(ws + L.ord.vals);
+  int* order = (int*)(ws + L.order);
+  deform_order_keys_launch(P, points, (unsigned int*)(ws + L.ord.bbox), keys, vals, stream);
+  size_t tmp = L.ord.temp_bytes;
+  D2GS_CUDA_OK(cub::DeviceRadixSort::SortPairs(ws + L.ord.temp, tmp, keys, keys_out, vals, order, P, 0, 30, stream));
+  knn_mean_dist2_launch(P, points, order, (float4*)(ws + L.sp), (float4*)(ws + L.leaf), (float4*)(ws + L.group), mean_dist2, stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(D2GS_ERR_CUDA, cudaGetErrorString(e));
   return D2GS_OK;

@@ -127,7 +127,7 @@ EXPORTED_SYMBOLS = (
     "d2gs_raster_backward", "d2gs_mark_visible", "d2gs_raster_export_state", "d2gs_deform_forward",
     "d2gs_deform_backward", "d2gs_epilogue_forward", "d2gs_epilogue_backward",
     "d2gs_mlp_workspace", "d2gs_mlp_forward", "d2gs_mlp_backward", "d2gs_mlp_hidden",
-    "d2gs_deform_order_workspace", "d2gs_deform_order",
+    "d2gs_deform_order_workspace", "d2gs_deform_order", "d2gs_knn_mean_dist2_workspace", "d2gs_knn_mean_dist2",
     "d2gs_loss_workspace", "d2gs_loss_forward", "d2gs_loss_backward",
     "d2gs_adam_step", "d2gs_densification_stats",
 )
@@ -174,6 +174,8 @@ def lib():
     L.d2gs_mlp_hidden.restype = C.c_void_p
     L.d2gs_deform_order_workspace.argtypes = [C.c_int, C.POINTER(C.c_size_t)]
     L.d2gs_deform_order.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.d2gs_knn_mean_dist2_workspace.argtypes = [C.c_int, C.POINTER(C.c_size_t)]
+    L.d2gs_knn_mean_dist2.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.d2gs_loss_workspace.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_size_t)]
     L.d2gs_loss_forward.argtypes = [C.POINTER(LossArgs), C.c_void_p]
     L.d2gs_loss_backward.argtypes = [C.POINTER(LossArgs), C.c_void_p]

@@ -404,6 +404,15 @@ D2GS_API int d2gs_deform_backward(const D2gsDeformBwdArgs* args, void* stream);
 D2GS_API int d2gs_deform_order_workspace(int P, size_t* bytes);
 D2GS_API int d2gs_deform_order(int P, const float* xyz, int32_t* order, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Mean squared distance of every point to its 3 nearest neighbours (the point itself excluded by index): replaces
+ * simple_knn._C.distCUDA2 (submodules/simple-knn/spatial.cu:15-26 -> SimpleKNN::knn, simple_knn.cu:185-220), which
+ * scene/gaussian_model.py:162 calls once to initialise the surfel scales.  points: (P,3) float32, mean_dist2: (P).
+ * Exact 3-NN (two-level boxes over a Morton order, one warp per 32 neighbouring queries); all work on `stream`, no
+ * allocation, no host synchronisation (the reference allocates with cudaMalloc/thrust and copies its bounding box to
+ * the host twice). */
+D2GS_API int d2gs_knn_mean_dist2_workspace(int P, size_t* bytes);
+D2GS_API int d2gs_knn_mean_dist2(int P, const float* points, float* mean_dist2, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
