@@ -14,6 +14,7 @@
 #include "optim.cuh"
 #include "mlp.cuh"
 #include "knn.cuh"
+#include "gs3d.cuh"
 
 namespace d2gs {
 
@@ -807,6 +808,202 @@ int d2gs_mlp_backward(const D2gsMlpArgs* a, void* stream_) {
     mlp_launch_backward(b, J, stream); }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(D2GS_ERR_CUDA, cudaGetErrorString(e));
+  return D2GS_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------
+// 3-D Gaussian rasterizer with depth and alpha outputs (gs3d.cu)
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+struct G3GeomLayout { size_t rec, cov3D, clamped, tiles_touched, point_offsets, scan_temp, scan_temp_bytes, total; };
+G3GeomLayout g3_geom_layout(int P) {
+  G3GeomLayout L{};
+  const size_t n = (size_t)(P > 0 ? P : 1);
+  size_t o = 0;
+  L.rec = o; o = align_up(o + sizeof(G3Rec) * n);
+  L.cov3D = o; o = align_up(o + 24 * n);
+  L.clamped = o; o = align_up(o + n);
+  L.tiles_touched = o; o = align_up(o + 4 * n);
+  L.point_offsets = o; o = align_up(o + 4 * n);
+  size_t tmp = 0;
+  cub::DeviceScan::InclusiveSum(nullptr, tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
+  L.scan_temp_bytes = tmp;
+  L.scan_temp = o; o = align_up(o + tmp);
+  L.total = o + 256;
+  return L;
+}
+struct G3ImgLayout { size_t ranges, n_contrib, total; };
+G3ImgLayout g3_img_layout(int W, int H) {
+  G3ImgLayout L{};
+  const size_t tiles = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
+  size_t o = 0;
+  L.ranges = o; o = align_up(o + 8 * tiles);
+  L.n_contrib = o; o = align_up(o + 4 * (size_t)W * H);
+  L.total = o + 256;
+  return L;
+}
+G3Params g3_params(int P, int D, int M, int W, int H, const float* bg, const float* means3D, const float* shs,
+                   const float* colors_precomp, const float* opacities, const float* scales, float scale_modifier,
+                   const float* rotations, const float* cov3D_precomp, const float* view, const float* proj,
+                   const float* campos, float tan_fovx, float tan_fovy, int prefiltered) {
+  G3Params p{};
+  p.P = P; p.D = D; p.M = M; p.W = W; p.H = H; p.bg = bg; p.means3D = means3D; p.shs = shs;
+  p.colors_precomp = colors_precomp; p.opacities = opacities; p.scales = scales; p.scale_modifier = scale_modifier;
+  p.rotations = rotations; p.cov3D_precomp = cov3D_precomp; p.view = view; p.proj = proj; p.campos = campos;
+  p.tan_fovx = tan_fovx; p.tan_fovy = tan_fovy;
+  p.focal_y = H / (2.0f * tan_fovy);
+  p.focal_x = W / (2.0f * tan_fovx);
+  p.prefiltered = prefiltered;
+  p.gx = (W + TILE_X - 1) / TILE_X; p.gy = (H + TILE_Y - 1) / TILE_Y;
+  return p;
+}
+}  // namespace
+
+extern "C" {
+
+int d2gs_gs3d_workspace(int P, int width, int height, int64_t num_rendered, size_t* geom_bytes, size_t* img_bytes,
+                        size_t* binning_bytes) {
+  if (P < 0 || width <= 0 || height <= 0 || num_rendered < 0) return fail(D2GS_ERR_INVALID_ARG, "bad sizes");
+  if (geom_bytes) *geom_bytes = g3_geom_layout(P).total;
+  if (img_bytes) *img_bytes = g3_img_layout(width, height).total;
+  if (binning_bytes) *binning_bytes = bin_layout(num_rendered).total;
+  return D2GS_OK;
+}
+
+int d2gs_gs3d_forward(const D2gsGs3dFwdArgs* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!a) return fail(D2GS_ERR_INVALID_ARG, "null args");
+  if (a->P < 0 || a->width <= 0 || a->height <= 0) return fail(D2GS_ERR_INVALID_ARG, "bad sizes");
+  if (!a->out_color || !a->out_depth || !a->out_alpha || !a->num_rendered) return fail(D2GS_ERR_INVALID_ARG, "missing outputs");
+  const int P = a->P, W = a->width, H = a->height;
+  const size_t HW = (size_t)W * H;
+  if (P == 0) {   // rasterize_points.cu:64-66,84: zero images for an empty scene
+    D2GS_CUDA_OK(cudaMemsetAsync(a->out_color, 0, 4 * 3 * HW, stream));
+    D2GS_CUDA_OK(cudaMemsetAsync(a->out_depth, 0, 4 * HW, stream));
+    D2GS_CUDA_OK(cudaMemsetAsync(a->out_alpha, 0, 4 * HW, stream));
+    *a->num_rendered = 0;
+    return D2GS_OK;
+  }
+  if (!a->means3D || !a->opacities || !a->viewmatrix || !a->projmatrix || !a->campos || !a->background || !a->radii)
+    return fail(D2GS_ERR_INVALID_ARG, "missing inputs");
+  if ((a->shs == nullptr) == (a->colors_precomp == nullptr))
+    return fail(D2GS_ERR_INVALID_ARG, "provide exactly one of SHs or precomputed colours");
+  if (((a->scales == nullptr) || (a->rotations == nullptr)) == (a->cov3D_precomp == nullptr))
+    return fail(D2GS_ERR_INVALID_ARG, "provide exactly one of scale/rotation pair or precomputed 3D covariance");
+  if (a->shs && (a->M < 1 || a->M > 16 || a->D < 0 || a->D > 3 || (a->D + 1) * (a->D + 1) > a->M))
+    return fail(D2GS_ERR_INVALID_ARG, "SH degree / coefficient count out of range (deg<=3, M<=16)");
+  if (a->rotations && ((uintptr_t)a->rotations & 15)) return fail(D2GS_ERR_INVALID_ARG, "rotations must be 16-byte aligned");
+
+  const G3GeomLayout GL = g3_geom_layout(P);
+  const G3ImgLayout IL = g3_img_layout(W, H);
+  if (a->geom_bytes < GL.total || !a->geom_buffer) return fail(D2GS_ERR_WORKSPACE, "geometry workspace too small");
+  if (a->img_bytes < IL.total || !a->img_buffer) return fail(D2GS_ERR_WORKSPACE, "image workspace too small");
+  char* gb = aligned_base(a->geom_buffer);
+  char* ib = aligned_base(a->img_buffer);
+  G3Rec* rec = (G3Rec*)(gb + GL.rec);
+  float* cov3D = (float*)(gb + GL.cov3D);
+  uint8_t* clamped = (uint8_t*)(gb + GL.clamped);
+  uint32_t* tiles_touched = (uint32_t*)(gb + GL.tiles_touched);
+  uint32_t* point_offsets = (uint32_t*)(gb + GL.point_offsets);
+  uint2* ranges = (uint2*)(ib + IL.ranges);
+  uint32_t* n_contrib = (uint32_t*)(ib + IL.n_contrib);
+  const G3Params p = g3_params(P, a->D, a->M, W, H, a->background, a->means3D, a->shs, a->colors_precomp, a->opacities, a->scales,
+                               a->scale_modifier, a->rotations, a->cov3D_precomp, a->viewmatrix, a->projmatrix, a->campos,
+                               a->tan_fovx, a->tan_fovy, a->prefiltered);
+  if (!a->resume) {
+    g3_launch_preprocess_fwd(p, rec, cov3D, clamped, a->radii, tiles_touched, stream);
+    D2GS_STAGE("gs3d preprocess", a->debug, stream);
+    size_t tmp = GL.scan_temp_bytes;
+    D2GS_CUDA_OK(cub::DeviceScan::InclusiveSum(gb + GL.scan_temp, tmp, tiles_touched, point_offsets, P, stream));
+    D2GS_STAGE("gs3d scan", a->debug, stream);
+  }
+  uint32_t R32 = 0;    // the reference's blocking readback (DGR/cuda_rasterizer/rasterizer_impl.cu:270-271)
+  D2GS_CUDA_OK(cudaMemcpyAsync(&R32, point_offsets + P - 1, 4, cudaMemcpyDeviceToHost, stream));
+  D2GS_CUDA_OK(cudaStreamSynchronize(stream));
+  const int64_t R = R32;
+  *a->num_rendered = R;
+  const BinLayout BL = bin_layout(R);
+  if (a->binning_required) *a->binning_required = BL.total;
+  if (a->binning_bytes < BL.total || !a->binning_buffer) return D2GS_NEED_BINNING;
+  char* bb = aligned_base(a->binning_buffer);
+  uint64_t* keys_unsorted = (uint64_t*)(bb + BL.keys_unsorted);
+  uint64_t* keys_sorted = (uint64_t*)(bb + BL.keys_sorted);
+  uint32_t* vals_unsorted = (uint32_t*)(bb + BL.vals_unsorted);
+  uint32_t* point_list = (uint32_t*)(bb + BL.point_list);
+  g3_launch_duplicate(P, rec, a->radii, point_offsets, keys_unsorted, vals_unsorted, p.gx, p.gy, stream);
+  D2GS_STAGE("gs3d duplicate", a->debug, stream);
+  if (R > 0) {
+    const int bit = (int)higher_msb(p.gx * p.gy);
+    size_t tmp = BL.sort_temp_bytes;
+    D2GS_CUDA_OK(cub::DeviceRadixSort::SortPairs(bb + BL.sort_temp, tmp, keys_unsorted, keys_sorted, vals_unsorted, point_list,
+                                                 (int)R, 0, 32 + bit, stream));
+    D2GS_STAGE("gs3d sort", a->debug, stream);
+  }
+  D2GS_CUDA_OK(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)p.gx * p.gy, stream));
+  launch_ranges(R, keys_sorted, ranges, stream);
+  D2GS_STAGE("gs3d ranges", a->debug, stream);
+  g3_launch_blend_fwd(p, ranges, point_list, rec, a->out_color, a->out_depth, a->out_alpha, n_contrib, stream);
+  D2GS_STAGE("gs3d blend", a->debug, stream);
+  return D2GS_OK;
+}
+
+int d2gs_gs3d_backward(const D2gsGs3dBwdArgs* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!a) return fail(D2GS_ERR_INVALID_ARG, "null args");
+  const int P = a->P, W = a->width, H = a->height;
+  if (P == 0) return D2GS_OK;
+  if (P < 0 || W <= 0 || H <= 0 || a->num_rendered < 0) return fail(D2GS_ERR_INVALID_ARG, "bad sizes");
+  if (!a->geom_buffer || !a->img_buffer || !a->binning_buffer || !a->grad_scratch || !a->radii || !a->out_alpha ||
+      !a->dL_dout_color || !a->dL_dout_depth || !a->dL_dout_alpha || !a->means3D || !a->viewmatrix || !a->projmatrix ||
+      !a->campos || !a->background)
+    return fail(D2GS_ERR_INVALID_ARG, "missing buffers");
+  const G3GeomLayout GL = g3_geom_layout(P);
+  const G3ImgLayout IL = g3_img_layout(W, H);
+  const BinLayout BL = bin_layout(a->num_rendered);
+  char* gb = aligned_base(a->geom_buffer);
+  char* ib = aligned_base(a->img_buffer);
+  char* bb = aligned_base(a->binning_buffer);
+  const G3Rec* rec = (const G3Rec*)(gb + GL.rec);
+  const G3Params p = g3_params(P, a->D, a->M, W, H, a->background, a->means3D, a->shs, a->colors_precomp, nullptr, a->scales,
+                               a->scale_modifier, a->rotations, a->cov3D_precomp, a->viewmatrix, a->projmatrix, a->campos,
+                               a->tan_fovx, a->tan_fovy, 0);
+  D2GS_CUDA_OK(cudaMemsetAsync(a->grad_scratch, 0, sizeof(float) * G3_GRAD_FLOATS * (size_t)P, stream));
+  g3_launch_blend_bwd(p, (const uint2*)(ib + IL.ranges), (const uint32_t*)(bb + BL.point_list), rec, a->out_alpha,
+                      (const uint32_t*)(ib + IL.n_contrib), a->dL_dout_color, a->dL_dout_depth, a->dL_dout_alpha, a->grad_scratch,
+                      stream);
+  D2GS_STAGE("gs3d blend backward", a->debug, stream);
+  g3_launch_preprocess_bwd(p, (const float*)(gb + GL.cov3D), (const uint8_t*)(gb + GL.clamped), a->radii, a->grad_scratch,
+                           a->dL_dmeans2D, a->dL_dcolors, a->dL_dopacity, a->dL_dmeans3D, a->dL_dcov3D, a->dL_dsh, a->dL_dscales,
+                           a->dL_drotations, stream);
+  D2GS_STAGE("gs3d preprocess backward", a->debug, stream);
+  return D2GS_OK;
+}
+
+/* intermediates for parity tests (what the reference keeps in its geometry / binning / image buffers) */
+int d2gs_gs3d_export_state(int P, int width, int height, int64_t num_rendered, const void* geom_buffer, const void* binning_buffer,
+                           const void* img_buffer, const D2gsGs3dState* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!out || !geom_buffer || !img_buffer) return fail(D2GS_ERR_INVALID_ARG, "missing buffers");
+  if (P <= 0) return D2GS_OK;
+  const G3GeomLayout GL = g3_geom_layout(P);
+  const G3ImgLayout IL = g3_img_layout(width, height);
+  char* gb = aligned_base(geom_buffer);
+  char* ib = aligned_base(img_buffer);
+  if (out->rec) D2GS_CUDA_OK(cudaMemcpyAsync(out->rec, gb + GL.rec, sizeof(G3Rec) * (size_t)P, cudaMemcpyDeviceToDevice, stream));
+  if (out->cov3D) D2GS_CUDA_OK(cudaMemcpyAsync(out->cov3D, gb + GL.cov3D, 24 * (size_t)P, cudaMemcpyDeviceToDevice, stream));
+  if (out->clamped) D2GS_CUDA_OK(cudaMemcpyAsync(out->clamped, gb + GL.clamped, (size_t)P, cudaMemcpyDeviceToDevice, stream));
+  if (out->tiles_touched) D2GS_CUDA_OK(cudaMemcpyAsync(out->tiles_touched, gb + GL.tiles_touched, 4 * (size_t)P, cudaMemcpyDeviceToDevice, stream));
+  if (out->n_contrib) D2GS_CUDA_OK(cudaMemcpyAsync(out->n_contrib, ib + IL.n_contrib, 4 * (size_t)width * height, cudaMemcpyDeviceToDevice, stream));
+  const size_t tiles = (size_t)((width + TILE_X - 1) / TILE_X) * ((height + TILE_Y - 1) / TILE_Y);
+  if (out->ranges) D2GS_CUDA_OK(cudaMemcpyAsync(out->ranges, ib + IL.ranges, 8 * tiles, cudaMemcpyDeviceToDevice, stream));
+  if (binning_buffer && num_rendered > 0) {
+    const BinLayout BL = bin_layout(num_rendered);
+    char* bb = aligned_base(binning_buffer);
+    if (out->keys_sorted) D2GS_CUDA_OK(cudaMemcpyAsync(out->keys_sorted, bb + BL.keys_sorted, 8 * (size_t)num_rendered, cudaMemcpyDeviceToDevice, stream));
+    if (out->point_list) D2GS_CUDA_OK(cudaMemcpyAsync(out->point_list, bb + BL.point_list, 4 * (size_t)num_rendered, cudaMemcpyDeviceToDevice, stream));
+  }
   return D2GS_OK;
 }
 

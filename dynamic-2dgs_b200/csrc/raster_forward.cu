@@ -4,6 +4,7 @@
 // rasterizer_impl.cu:70-111 (instance emission), :116-138 (ranges).  Tile/sort indices must be bit-exact, so the
 // float expressions that feed integer decisions are written in the same association order as the reference's.
 #include "raster_common.cuh"
+#include "sh_basis.cuh"
 
 namespace d2gs {
 
@@ -36,30 +37,6 @@ __device__ __forceinline__ void load_sh(const FwdParams& p, int idx, int ncoef, 
     for (int i = 3; i < 48; i++)
       if (i < ncoef * 3) sh[i] = __ldg(rest + i - 3);
   }
-}
-
-// SH basis evaluation, degree <= 3 (reference: forward.cu:20-71).  Returns the colour before "+0.5 / clamp".
-__device__ __forceinline__ v3 eval_sh(int deg, v3 dir, const float* sh) {
-  auto S = [&](int k) { return v3{sh[3 * k], sh[3 * k + 1], sh[3 * k + 2]}; };
-  v3 result = kSH_C0 * S(0);
-  if (deg > 0) {
-    float x = dir.x, y = dir.y, z = dir.z;
-    result = result - kSH_C1 * y * S(1) + kSH_C1 * z * S(2) - kSH_C1 * x * S(3);
-    if (deg > 1) {
-      float xx = x * x, yy = y * y, zz = z * z;
-      float xy = x * y, yz = y * z, xz = x * z;
-      result = result + kSH_C2[0] * xy * S(4) + kSH_C2[1] * yz * S(5) + kSH_C2[2] * (2.0f * zz - xx - yy) * S(6) +
-               kSH_C2[3] * xz * S(7) + kSH_C2[4] * (xx - yy) * S(8);
-      if (deg > 2) {
-        result = result + kSH_C3[0] * y * (3.0f * xx - yy) * S(9) + kSH_C3[1] * xy * z * S(10) +
-                 kSH_C3[2] * y * (4.0f * zz - xx - yy) * S(11) +
-                 kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * S(12) +
-                 kSH_C3[4] * x * (4.0f * zz - xx - yy) * S(13) + kSH_C3[5] * z * (xx - yy) * S(14) +
-                 kSH_C3[6] * x * (xx - 3.0f * yy) * S(15);
-      }
-    }
-  }
-  return result;
 }
 
 __global__ void __launch_bounds__(256) preprocess_fwd_kernel(FwdParams p, SurfelRec* __restrict__ rec,

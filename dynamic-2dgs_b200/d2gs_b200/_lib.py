@@ -38,6 +38,37 @@ class RasterFwdArgs(C.Structure):
                 ("binning_capacity", C.c_int64), ("num_rendered_async", C.c_void_p)]
 
 
+class Gs3dFwdArgs(C.Structure):
+    _fields_ = [("P", C.c_int), ("D", C.c_int), ("M", C.c_int), ("width", C.c_int), ("height", C.c_int),
+                ("background", C.c_void_p), ("means3D", C.c_void_p), ("shs", C.c_void_p), ("colors_precomp", C.c_void_p),
+                ("opacities", C.c_void_p), ("scales", C.c_void_p), ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p),
+                ("scale_modifier", C.c_float), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
+                ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("prefiltered", C.c_int), ("debug", C.c_int),
+                ("out_color", C.c_void_p), ("out_depth", C.c_void_p), ("out_alpha", C.c_void_p), ("radii", C.c_void_p),
+                ("geom_buffer", C.c_void_p), ("geom_bytes", C.c_size_t), ("img_buffer", C.c_void_p), ("img_bytes", C.c_size_t),
+                ("binning_buffer", C.c_void_p), ("binning_bytes", C.c_size_t), ("resume", C.c_int),
+                ("num_rendered", C.POINTER(C.c_int64)), ("binning_required", C.POINTER(C.c_size_t))]
+
+
+class Gs3dBwdArgs(C.Structure):
+    _fields_ = [("P", C.c_int), ("D", C.c_int), ("M", C.c_int), ("width", C.c_int), ("height", C.c_int),
+                ("num_rendered", C.c_int64),
+                ("background", C.c_void_p), ("means3D", C.c_void_p), ("shs", C.c_void_p), ("colors_precomp", C.c_void_p),
+                ("scales", C.c_void_p), ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p), ("scale_modifier", C.c_float),
+                ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
+                ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("radii", C.c_void_p), ("out_alpha", C.c_void_p),
+                ("geom_buffer", C.c_void_p), ("binning_buffer", C.c_void_p), ("img_buffer", C.c_void_p),
+                ("dL_dout_color", C.c_void_p), ("dL_dout_depth", C.c_void_p), ("dL_dout_alpha", C.c_void_p),
+                ("debug", C.c_int), ("grad_scratch", C.c_void_p),
+                ("dL_dmeans2D", C.c_void_p), ("dL_dcolors", C.c_void_p), ("dL_dopacity", C.c_void_p), ("dL_dmeans3D", C.c_void_p),
+                ("dL_dcov3D", C.c_void_p), ("dL_dsh", C.c_void_p), ("dL_dscales", C.c_void_p), ("dL_drotations", C.c_void_p)]
+
+
+class Gs3dState(C.Structure):
+    _fields_ = [("rec", C.c_void_p), ("cov3D", C.c_void_p), ("clamped", C.c_void_p), ("tiles_touched", C.c_void_p),
+                ("keys_sorted", C.c_void_p), ("point_list", C.c_void_p), ("ranges", C.c_void_p), ("n_contrib", C.c_void_p)]
+
+
 class RasterBwdArgs(C.Structure):
     _fields_ = [("P", C.c_int), ("D", C.c_int), ("M", C.c_int), ("width", C.c_int), ("height", C.c_int),
                 ("num_rendered", C.c_int64),
@@ -128,6 +159,7 @@ EXPORTED_SYMBOLS = (
     "d2gs_deform_backward", "d2gs_epilogue_forward", "d2gs_epilogue_backward",
     "d2gs_mlp_workspace", "d2gs_mlp_forward", "d2gs_mlp_backward", "d2gs_mlp_hidden",
     "d2gs_deform_order_workspace", "d2gs_deform_order", "d2gs_knn_mean_dist2_workspace", "d2gs_knn_mean_dist2",
+    "d2gs_gs3d_workspace", "d2gs_gs3d_forward", "d2gs_gs3d_backward", "d2gs_gs3d_export_state",
     "d2gs_loss_workspace", "d2gs_loss_forward", "d2gs_loss_backward",
     "d2gs_adam_step", "d2gs_densification_stats",
 )
@@ -174,6 +206,12 @@ def lib():
     L.d2gs_mlp_hidden.restype = C.c_void_p
     L.d2gs_deform_order_workspace.argtypes = [C.c_int, C.POINTER(C.c_size_t)]
     L.d2gs_deform_order.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.d2gs_gs3d_workspace.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                      C.POINTER(C.c_size_t)]
+    L.d2gs_gs3d_forward.argtypes = [C.POINTER(Gs3dFwdArgs), C.c_void_p]
+    L.d2gs_gs3d_backward.argtypes = [C.POINTER(Gs3dBwdArgs), C.c_void_p]
+    L.d2gs_gs3d_export_state.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.POINTER(Gs3dState), C.c_void_p]
     L.d2gs_knn_mean_dist2_workspace.argtypes = [C.c_int, C.POINTER(C.c_size_t)]
     L.d2gs_knn_mean_dist2.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.d2gs_loss_workspace.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_size_t)]

@@ -413,6 +413,103 @@ D2GS_API int d2gs_deform_order(int P, const float* xyz, int32_t* order, void* wo
 D2GS_API int d2gs_knn_mean_dist2_workspace(int P, size_t* bytes);
 D2GS_API int d2gs_knn_mean_dist2(int P, const float* points, float* mean_dist2, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * 3-D Gaussian rasterizer with colour, depth and alpha outputs.  Replaces
+ * CudaRasterizer::Rasterizer::{forward,backward} of the reference's second rasterizer
+ * (DGR = submodules/diff-gaussian-rasterization: DGR/cuda_rasterizer/rasterizer.h, rasterizer_impl.cu:196-446) and
+ * its torch wrappers RasterizeGaussiansCUDA / RasterizeGaussiansBackwardCUDA (DGR/rasterize_points.cu:35-217), which
+ * render_flow (gaussian_renderer/__init__.py:222-337) calls.  d2gs_mark_visible serves both rasterizers.
+ * Same protocol as d2gs_raster_forward: caller-owned workspaces, one stream synchronisation to read the instance
+ * count (DGR rasterizer_impl.cu:270-271), D2GS_NEED_BINNING + resume when the binning workspace is too small.
+ * Quaternions are used as given (the reference's variant does not normalise them, forward.cu:127).
+ * ---------------------------------------------------------------------------------------------- */
+D2GS_API int d2gs_gs3d_workspace(int P, int width, int height, int64_t num_rendered, size_t* geom_bytes, size_t* img_bytes,
+                                 size_t* binning_bytes);
+
+typedef struct D2gsGs3dFwdArgs {
+  int P, D, M, width, height;     /* Gaussians, active SH degree, SH coefficients per Gaussian (0 with colours) */
+  const float* background;        /* (3) */
+  const float* means3D;           /* (P,3) */
+  const float* shs;               /* (P,M,3) or NULL */
+  const float* colors_precomp;    /* (P,3) or NULL */
+  const float* opacities;         /* (P) */
+  const float* scales;            /* (P,3) or NULL */
+  const float* rotations;         /* (P,4) (r,x,y,z), 16-byte aligned, or NULL */
+  const float* cov3D_precomp;     /* (P,6) upper triangle or NULL */
+  float scale_modifier;
+  const float* viewmatrix;        /* (4,4) transposed world->view */
+  const float* projmatrix;        /* (4,4) transposed full projection */
+  const float* campos;            /* (3) */
+  float tan_fovx, tan_fovy;
+  int prefiltered;
+  int debug;
+  float* out_color;               /* (3,H,W) */
+  float* out_depth;               /* (1,H,W): sum_i w_i depth_i */
+  float* out_alpha;               /* (1,H,W): sum_i w_i; kept by the caller for the backward */
+  int* radii;                     /* (P) */
+  void* geom_buffer;   size_t geom_bytes;
+  void* img_buffer;    size_t img_bytes;
+  void* binning_buffer; size_t binning_bytes;
+  int resume;                     /* 1: per-Gaussian stage already done by a call that returned D2GS_NEED_BINNING */
+  int64_t* num_rendered;          /* host */
+  size_t* binning_required;       /* host */
+} D2gsGs3dFwdArgs;
+
+D2GS_API int d2gs_gs3d_forward(const D2gsGs3dFwdArgs* args, void* stream);
+
+typedef struct D2gsGs3dBwdArgs {
+  int P, D, M, width, height;
+  int64_t num_rendered;
+  const float* background;
+  const float* means3D;
+  const float* shs;
+  const float* colors_precomp;
+  const float* scales;
+  const float* rotations;
+  const float* cov3D_precomp;
+  float scale_modifier;
+  const float* viewmatrix;
+  const float* projmatrix;
+  const float* campos;
+  float tan_fovx, tan_fovy;
+  const int* radii;
+  const float* out_alpha;        /* (1,H,W) from the forward */
+  const void* geom_buffer;
+  const void* binning_buffer;
+  const void* img_buffer;
+  const float* dL_dout_color;    /* (3,H,W) */
+  const float* dL_dout_depth;    /* (1,H,W) */
+  const float* dL_dout_alpha;    /* (1,H,W) */
+  int debug;
+  float* grad_scratch;           /* (P,12) floats; cleared by the call */
+  /* outputs; every element is written, NULL = not wanted */
+  float* dL_dmeans2D;            /* (P,3): xy in NDC units (the densification statistic), z = 0 */
+  float* dL_dcolors;             /* (P,3) */
+  float* dL_dopacity;            /* (P,1) */
+  float* dL_dmeans3D;            /* (P,3) */
+  float* dL_dcov3D;              /* (P,6) */
+  float* dL_dsh;                 /* (P,M,3) */
+  float* dL_dscales;             /* (P,3) */
+  float* dL_drotations;          /* (P,4), 16-byte aligned */
+} D2gsGs3dBwdArgs;
+
+D2GS_API int d2gs_gs3d_backward(const D2gsGs3dBwdArgs* args, void* stream);
+
+/* Parity access to the intermediates (device arrays, NULL = skip).  rec: (P,12) floats = mean2D.xy, depth, prefilter
+ * threshold | conic.xyz, opacity | rgb, 0 */
+typedef struct D2gsGs3dState {
+  float* rec;
+  float* cov3D;              /* (P,6) */
+  uint8_t* clamped;          /* (P): bit c set = colour channel c clamped at 0 */
+  uint32_t* tiles_touched;   /* (P) */
+  uint64_t* keys_sorted;     /* (R) */
+  uint32_t* point_list;      /* (R) */
+  uint32_t* ranges;          /* (tiles,2) */
+  uint32_t* n_contrib;       /* (H,W) */
+} D2gsGs3dState;
+D2GS_API int d2gs_gs3d_export_state(int P, int width, int height, int64_t num_rendered, const void* geom_buffer,
+                                    const void* binning_buffer, const void* img_buffer, const D2gsGs3dState* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,160 @@
+"""GPU: the depth/alpha 3-D Gaussian rasterizer drop-in (``diff_gaussian_rasterization`` -> libd2gs.so: d2gs_gs3d_*) against
+the CPU oracle (oracle/gs3d_oracle.py), the golden outputs of the unmodified reference extension, and — when
+oracle/_ref/diff_gaussian_rasterization travelled to the box — the live reference extension."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from make_gs3d_golden import gs3d_cases, load_reference_dgr, run_module  # noqa: E402
+from oracle import gs3d_oracle as go  # noqa: E402
+import util  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+CASES = gs3d_cases()
+RTOL_MAPS = 1e-4        # north_star: RGB / depth maps within 1e-4 relative fp32
+RTOL_GRADS = 5e-4       # norm-wise; gradients sum 10^3-10^4 fp32 terms in nondeterministic order
+GRAD_KEYS = ("g_means2D", "g_means3D", "g_opacities", "g_shs", "g_colors_precomp", "g_scales", "g_rotations", "g_cov3D_precomp")
+
+
+def _golden(name):
+    p = os.path.join(HERE, "golden", f"gs3d_golden_{name}.npz")
+    return np.load(p) if os.path.exists(p) else None
+
+
+def _ours(name, device):
+    import diff_gaussian_rasterization as ours
+    from d2gs_b200 import gs3d
+    res = run_module(ours, CASES[name], device)
+    st = {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in gs3d.export_state().items()}
+    return res, st
+
+
+@pytest.mark.parametrize("name", list(CASES.keys()))
+def test_matches_oracle(name, cuda_device):
+    res, st = _ours(name, cuda_device)
+    c = CASES[name]
+    o32 = go.render(dtype=torch.float32, **c["inputs"])
+    o64, g64 = go.render_with_grads(c["inputs"], c["g_color"], c["g_depth"], c["g_alpha"], dtype=torch.float64)
+    # integer stages against the float32 oracle: a radius sits on a ceil() boundary for ~1 Gaussian in 10^4 (fma contraction)
+    rad_o = o32["radii"].numpy()
+    assert (res["radii"] == rad_o).mean() >= 0.998
+    same = res["radii"] == rad_o
+    assert np.array_equal(st["tiles_touched"][same], o32["tiles_touched"].numpy()[same])
+    assert abs(st["num_rendered"] - o32["num_rendered"]) <= 0.002 * o32["num_rendered"] + 8
+    for k in ("color", "depth", "alpha"):
+        assert util.rel_err(res[k], o64[k].numpy()) < RTOL_MAPS, (k, util.rel_err(res[k], o64[k].numpy()))
+    assert (st["n_contrib"] == o64["n_contrib"].numpy()).mean() > 0.999
+    names = dict(g_means2D="means2D", g_means3D="means3D", g_opacities="opacities", g_shs="shs", g_colors_precomp="colors_precomp",
+                 g_scales="scales", g_rotations="rotations", g_cov3D_precomp="cov3D_precomp")
+    errs = {k: util.rel_err(res[k], g64[names[k]].numpy().reshape(res[k].shape)) for k in GRAD_KEYS if k in res}
+    print(name, errs)
+    # G1 (camera inside the cloud, screen-filling Gaussians): fp32 gradients of BOTH implementations sit ~6e-4 from float64
+    tol = 2e-3 if name == "G1" else RTOL_GRADS
+    assert all(v < tol for v in errs.values()), errs
+
+
+@pytest.mark.parametrize("name", list(CASES.keys()))
+def test_matches_reference_golden(name, cuda_device):
+    g = _golden(name)
+    if g is None:
+        pytest.skip("golden not generated yet")
+    res, st = _ours(name, cuda_device)
+    vis = g["radii"] > 0
+    m = {}      # every metric is collected first (and written to gpurun_out/ for the parity table in DESIGN.md), then asserted
+    m["radii_equal"] = float((res["radii"] == g["radii"]).mean())
+    m["tiles_touched_equal"] = float((st["tiles_touched"].astype(np.uint32) == g["tiles_touched"]).mean())
+    m["num_rendered"] = [int(st["num_rendered"]), int(g["num_rendered"])]
+    same_R = st["num_rendered"] == int(g["num_rendered"])
+    m["point_list_equal"] = float((st["point_list"].astype(np.uint32) == g["point_list"]).mean()) if same_R else 0.0
+    m["keys_sorted_equal"] = float((st["keys_sorted"].astype(np.uint64) == g["keys_sorted"]).mean()) if same_R else 0.0
+    m["ranges_equal"] = float((st["ranges"].astype(np.uint32) == g["ranges"]).mean())
+    m["n_contrib_equal"] = float((st["n_contrib"].astype(np.uint32) == g["n_contrib"]).mean())
+    m["means2D_maxabs"] = float(np.abs(st["means2D"][vis] - g["means2D_pix"][vis]).max())
+    m["conic_rel"] = util.rel_err(st["conic_opacity"][vis], g["conic_opacity"][vis])
+    m["rgb_rel"] = util.rel_err(st["rgb"][vis], g["rgb"][vis])
+    for k in ("color", "depth", "alpha"):
+        m[k + "_rel"] = util.rel_err(res[k], g[k])
+    for k in GRAD_KEYS:
+        if k in res:
+            m[k + "_rel"] = util.rel_err(res[k], g[k])
+    os.makedirs(os.path.join(util.ROOT, "gpurun_out"), exist_ok=True)
+    import json
+    with open(os.path.join(util.ROOT, "gpurun_out", f"gs3d_parity_{name}.json"), "w") as f:
+        json.dump(m, f, indent=1)
+    print(name, json.dumps(m))
+    # tile lists: bit-exact (radii, tiles, depth-sorted instance list, ranges)
+    for k in ("radii_equal", "tiles_touched_equal", "point_list_equal", "keys_sorted_equal", "ranges_equal"):
+        assert m[k] == 1.0, (k, m)
+    assert m["num_rendered"][0] == m["num_rendered"][1], m
+    assert m["n_contrib_equal"] > 0.9995, m
+    assert m["means2D_maxabs"] < 1e-3 and m["conic_rel"] < 1e-5 and m["rgb_rel"] < 1e-6, m
+    for k in ("color", "depth", "alpha"):
+        assert m[k + "_rel"] < RTOL_MAPS, (k, m)
+    for k in GRAD_KEYS:
+        if k in res:
+            assert m[k + "_rel"] < RTOL_GRADS, (k, m)
+
+
+def test_matches_live_reference_at_scale(cuda_device):
+    """100 k Gaussians at 800x800 (the C2 size): ours against the unmodified reference extension on the same inputs, plus
+    size-independent properties — alpha = sum of weights <= 1, colour of an all-background pixel = background, radii == 0
+    exactly for the Gaussians behind the near plane."""
+    from d2gs_b200 import synthetic as syn
+    import diff_gaussian_rasterization as ours
+    rng = np.random.default_rng(77)
+    P, W, H = 100_000, 800, 800
+    d = rng.normal(size=(P, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    xyz = (d * rng.uniform(size=(P, 1)) ** (1 / 3)).astype(np.float32)
+    xyz[:50] += np.array([0, 0, 0], np.float32)
+    scales = np.exp(np.log(0.006) + 0.5 * rng.normal(size=(P, 3))).astype(np.float32)
+    q = rng.normal(size=(P, 4)); q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    cam = syn.fibonacci_cameras(100, W, H)[37]
+    case = dict(inputs=dict(means3D=xyz, opacities=rng.uniform(0.05, 0.95, size=(P, 1)).astype(np.float32),
+                            shs=np.concatenate([rng.normal(size=(P, 1, 3)), 0.1 * rng.normal(size=(P, 15, 3))], 1).astype(np.float32),
+                            sh_degree=3, scales=scales, rotations=q, scale_modifier=1.0, bg=np.array([0.3, 0.1, 0.7], np.float32),
+                            viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform, campos=cam.camera_center,
+                            tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, H=H, W=W),
+                g_color=rng.normal(size=(3, H, W)).astype(np.float32), g_depth=rng.normal(size=(1, H, W)).astype(np.float32),
+                g_alpha=rng.normal(size=(1, H, W)).astype(np.float32))
+    res = run_module(ours, case, cuda_device)
+    assert res["alpha"].max() <= 1.0 + 1e-5 and res["alpha"].min() >= 0.0
+    empty = res["alpha"][0] == 0
+    assert empty.any()
+    for ch in range(3):
+        assert np.all(res["color"][ch][empty] == case["inputs"]["bg"][ch])
+    ref = load_reference_dgr()
+    if ref is None:
+        pytest.skip("oracle/_ref/diff_gaussian_rasterization not present")
+    want = run_module(ref, case, cuda_device)
+    assert np.array_equal(res["radii"], want["radii"])
+    for k in ("color", "depth", "alpha"):
+        assert util.rel_err(res[k], want[k]) < RTOL_MAPS, (k, util.rel_err(res[k], want[k]))
+    for k in GRAD_KEYS:
+        if k in res:
+            assert util.rel_err(res[k], want[k]) < RTOL_GRADS, (k, util.rel_err(res[k], want[k]))
+
+
+def test_api_errors_and_empty_scene(cuda_device):
+    import diff_gaussian_rasterization as ours
+    dev = cuda_device
+    c = CASES["G2"]["inputs"]
+    t = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32, device=dev)
+    rs = ours.GaussianRasterizationSettings(48, 64, float(c["tanfovx"]), float(c["tanfovy"]), t(c["bg"]), 1.0, t(c["viewmatrix"]),
+                                            t(c["projmatrix"]), 1, t(c["campos"]), False, False)
+    r = ours.GaussianRasterizer(rs)
+    x, o = t(c["means3D"]), t(c["opacities"])
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(means3D=x, means2D=torch.zeros_like(x), opacities=o, scales=t(c["scales"]), rotations=t(c["rotations"]))
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(means3D=x, means2D=torch.zeros_like(x), opacities=o, shs=t(c["shs"]))
+    e = torch.zeros((0, 3), device=dev)
+    color, radii, depth, alpha = r(means3D=e, means2D=e, opacities=torch.zeros((0, 1), device=dev), shs=torch.zeros((0, 16, 3), device=dev),
+                                   scales=e, rotations=torch.zeros((0, 4), device=dev))
+    assert color.shape == (3, 48, 64) and float(color.abs().max()) == 0 and radii.numel() == 0 and float(alpha.abs().max()) == 0
+    vis = r.markVisible(x)
+    assert vis.dtype == torch.bool and vis.shape == (x.shape[0],)
