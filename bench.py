@@ -318,6 +318,8 @@ def main():
     ap.add_argument("--graph", choices=["auto", "on", "off"], default="auto",
                     help="replay the step (deform + render + loss + backward + all-reduce) as ONE CUDA graph captured through the public API; "
                          "auto = fall back to eager launches if capture fails.  The reference arm is always eager (it synchronises inside).")
+    ap.add_argument("--tile-sort", type=int, default=None, choices=[0, 1],
+                    help="binning: 1 = per-tile buckets + segmented sort, 0 = global radix sort (same lists); default: the library's")
     ap.add_argument("--no-clocks", action="store_true", help="diagnosis only: do not sample clocks during the timed region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -358,6 +360,8 @@ def main():
         from d2gs_b200 import _lib, raster
         _lib.lib()   # fail loudly if the CUDA extension is missing
         raster.set_deferred_count(not args.sync_count)
+        if args.tile_sort is not None:
+            _lib.set_option("tile_sort", args.tile_sort)
         if wl.use_deform:
             build_deform_ours(wl)
         step_fn = step_ours

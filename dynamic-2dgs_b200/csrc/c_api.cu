@@ -47,6 +47,7 @@ struct StageRec { int stage; cudaEvent_t a, b; };
 static bool g_profile = false;
 int g_deform_bwd_smem = 1;  // node-gradient accumulation of deform_bwd: 1 = per-CTA shared accumulators, 0 = global reductions
 int g_knn_filter = 1;       // warp-level candidate filter of the K-nearest-node search (0: every node is visited; same results)
+static int g_tile_sort = 1;   // binning: 0 = global radix sort of (tile | depth) keys, 1 = per-tile buckets + segmented sort (same lists)
 static int g_cull = 1;   // warp-level cull boxes in the blend kernels (tests switch it off to prove it changes nothing)
 static std::vector<StageRec> g_recs;
 static std::vector<cudaEvent_t> g_free_events;
@@ -74,7 +75,7 @@ GeomLayout geom_layout(int P) {
   cub::DeviceScan::InclusiveSum(nullptr, tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, P > 0 ? P : 1);
   L.scan_temp_bytes = tmp;
   L.scan_temp = o; o = align_up(o + tmp);
-  L.status = o; o = align_up(o + 2 * sizeof(uint32_t));   // deferred-count mode: {R, overflow flag}
+  L.status = o; o = align_up(o + 4 * sizeof(uint32_t));   // {R, overflow flag, number of long tiles (per-tile binning)}
   L.total = o + 256;
   return L;
 }
@@ -87,6 +88,9 @@ ImgLayout img_layout(int W, int H) {
   L.ranges = o; o = align_up(o + 8 * tiles);
   L.final_T = o; o = align_up(o + 4 * 3 * HW);
   L.n_contrib = o; o = align_up(o + 4 * 2 * HW);
+  L.tile_count = o; o = align_up(o + 4 * tiles);
+  L.seg_begin = o; o = align_up(o + 4 * tiles);
+  L.seg_end = o; o = align_up(o + 4 * tiles);
   L.total = o + 256;
   return L;
 }
@@ -138,6 +142,7 @@ int d2gs_set_option(const char* name, int value) {
   if (std::strcmp(name, "cull") == 0) { g_cull = value != 0; return D2GS_OK; }
   if (std::strcmp(name, "deform_bwd_smem") == 0) { g_deform_bwd_smem = value != 0; return D2GS_OK; }
   if (std::strcmp(name, "knn_filter") == 0) { g_knn_filter = value != 0; return D2GS_OK; }
+  if (std::strcmp(name, "tile_sort") == 0) { g_tile_sort = value != 0; return D2GS_OK; }
   return fail(D2GS_ERR_INVALID_ARG, std::string("unknown option ") + name);
 }
 
@@ -232,26 +237,38 @@ int d2gs_raster_forward(const D2gsRasterFwdArgs* a, void* stream_) {
   if (p.raw && (a->transMat_precomp || !a->scales || !a->rotations))
     return fail(D2GS_ERR_INVALID_ARG, "raw-parameter mode needs scales and rotations (no transMat_precomp)");
 
+  uint32_t* status = (uint32_t*)(gb + GL.status);
+  const bool deferred = a->binning_capacity > 0;
+  const uint32_t tiles = p.gx * p.gy;
+  const bool tile_sort = g_tile_sort && tiles <= (uint32_t)TILE_SORT_MAX_TILES;
+  uint32_t* tile_count = (uint32_t*)(ib + IL.tile_count);
+  uint32_t* seg_begin = (uint32_t*)(ib + IL.seg_begin);
+  uint32_t* big_list = (uint32_t*)(ib + IL.seg_end);
+  if (deferred && a->binning_capacity > 0xffffffffll) return fail(D2GS_ERR_INVALID_ARG, "binning_capacity exceeds 2^32-1 instances");
   if (!a->resume) {
     { StageTimer t(ST_PRE, stream); launch_preprocess_fwd(p, rec, clamped, a->radii, tiles_touched, stream); }
     D2GS_STAGE("preprocess", a->debug, stream);
-    size_t tmp = GL.scan_temp_bytes;
-    { StageTimer t(ST_SCAN, stream);
-      D2GS_CUDA_OK(cub::DeviceScan::InclusiveSum(gb + GL.scan_temp, tmp, tiles_touched, point_offsets, P, stream)); }
+    if (tile_sort) {
+      // per-tile counters -> ranges, instance total and overflow flag (no per-surfel scan)
+      StageTimer t(ST_SCAN, stream);
+      launch_tile_count(P, rec, a->radii, p.gx, p.gy, tile_count, stream);
+      launch_tile_scan(tiles, deferred ? (uint32_t)a->binning_capacity : 0xffffffffu, tile_count, seg_begin, ranges, big_list, status, stream);
+    } else {
+      size_t tmp = GL.scan_temp_bytes;
+      StageTimer t(ST_SCAN, stream);
+      D2GS_CUDA_OK(cub::DeviceScan::InclusiveSum(gb + GL.scan_temp, tmp, tiles_touched, point_offsets, P, stream));
+    }
     D2GS_STAGE("scan", a->debug, stream);
   }
-  uint32_t* status = (uint32_t*)(gb + GL.status);
-  const bool deferred = a->binning_capacity > 0;
   int64_t R = 0;       // instance slots the binning stage works on: the exact count, or the caller's capacity
   if (deferred) {
     // Deferred-count mode: nothing is read back, so the host never waits for the device.  The binning stage runs on
     // exactly `binning_capacity` slots; slots past the real count carry all-ones keys and sort to the end.
-    if (a->binning_capacity > 0xffffffffll) return fail(D2GS_ERR_INVALID_ARG, "binning_capacity exceeds 2^32-1 instances");
     R = a->binning_capacity;
     *a->num_rendered = R;
   } else {
     uint32_t R32 = 0;
-    D2GS_CUDA_OK(cudaMemcpyAsync(&R32, point_offsets + P - 1, 4, cudaMemcpyDeviceToHost, stream));
+    D2GS_CUDA_OK(cudaMemcpyAsync(&R32, tile_sort ? status : point_offsets + P - 1, 4, cudaMemcpyDeviceToHost, stream));
     D2GS_CUDA_OK(cudaStreamSynchronize(stream));
     R = R32;
     *a->num_rendered = R;
@@ -269,6 +286,18 @@ int d2gs_raster_forward(const D2gsRasterFwdArgs* a, void* stream_) {
   uint32_t* vals_unsorted = (uint32_t*)(bb + BL.vals_unsorted);
   uint32_t* point_list = (uint32_t*)(bb + BL.point_list);
 
+  if (tile_sort) {
+    { StageTimer t(ST_DUP, stream);
+      launch_tile_scatter(P, rec, a->radii, p.gx, p.gy, seg_begin, tile_count, status, keys_unsorted, stream); }
+    D2GS_STAGE("scatter", a->debug, stream);
+    if (deferred && a->num_rendered_async)
+      D2GS_CUDA_OK(cudaMemcpyAsync(a->num_rendered_async, status, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    if (R > 0) {
+      StageTimer t(ST_SORT, stream);
+      launch_tile_sort(tiles, ranges, big_list, status, keys_unsorted, keys_sorted, point_list, stream);
+      D2GS_STAGE("tile sort", a->debug, stream);
+    }
+  } else {
   { StageTimer t(ST_DUP, stream);
     launch_duplicate(P, rec, a->radii, point_offsets, keys_unsorted, vals_unsorted, p.gx, p.gy, (uint32_t)R, stream);
     if (deferred) launch_pad_keys((uint32_t)R, point_offsets + P - 1, keys_unsorted, status, stream); }
@@ -288,6 +317,7 @@ int d2gs_raster_forward(const D2gsRasterFwdArgs* a, void* stream_) {
     if (deferred) launch_ranges_deferred((uint32_t)R, status, keys_sorted, ranges, stream);
     else launch_ranges(R, keys_sorted, ranges, stream); }
   D2GS_STAGE("ranges", a->debug, stream);
+  }
   { StageTimer t(ST_BLEND_F, stream);
     launch_blend_fwd(p, ranges, point_list, rec, final_T, n_contrib, a->out_color, a->out_others, g_cull,
                      deferred ? status : nullptr, stream); }
@@ -393,16 +423,31 @@ int d2gs_raster_export_state(int P, int width, int height, int64_t R, const void
   const BinLayout BL = bin_layout(R);
   const size_t HW = (size_t)width * height;
   const size_t tiles = (size_t)((width + TILE_X - 1) / TILE_X) * ((height + TILE_Y - 1) / TILE_Y);
+  const bool tile_sort = g_tile_sort && tiles <= (size_t)TILE_SORT_MAX_TILES;
   if (geom_buffer) {
     char* gb = aligned_base(geom_buffer);
     export_geom_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, (const SurfelRec*)(gb + GL.rec),
                                                            (const uint8_t*)(gb + GL.clamped), *out);
     if (out->tiles_touched)
       D2GS_CUDA_OK(cudaMemcpyAsync(out->tiles_touched, gb + GL.tiles_touched, 4 * (size_t)P, cudaMemcpyDeviceToDevice, stream));
-    if (out->point_offsets)
-      D2GS_CUDA_OK(cudaMemcpyAsync(out->point_offsets, gb + GL.point_offsets, 4 * (size_t)P, cudaMemcpyDeviceToDevice, stream));
+    if (out->point_offsets) {
+      if (tile_sort) {   // the per-tile path never needs the per-surfel scan: produce it for the caller
+        size_t tmp = GL.scan_temp_bytes;
+        D2GS_CUDA_OK(cub::DeviceScan::InclusiveSum(gb + GL.scan_temp, tmp, (const uint32_t*)(gb + GL.tiles_touched), out->point_offsets, P, stream));
+      } else {
+        D2GS_CUDA_OK(cudaMemcpyAsync(out->point_offsets, gb + GL.point_offsets, 4 * (size_t)P, cudaMemcpyDeviceToDevice, stream));
+      }
+    }
   }
-  if (binning_buffer && R > 0) {
+  if (binning_buffer && R > 0 && tile_sort && img_buffer) {
+    // per-tile keys are (depth << 32 | id): hand out the reference's format (tile << 32 | depth) for the parity tests
+    char* bb = aligned_base(binning_buffer);
+    const uint2* rg = (const uint2*)(aligned_base(img_buffer) + IL.ranges);
+    if (out->keys_unsorted || out->values_unsorted)
+      launch_tile_export_keys((uint32_t)tiles, rg, (const uint64_t*)(bb + BL.keys_unsorted), out->keys_unsorted, out->values_unsorted, stream);
+    if (out->keys_sorted) launch_tile_export_keys((uint32_t)tiles, rg, (const uint64_t*)(bb + BL.keys_sorted), out->keys_sorted, nullptr, stream);
+    if (out->point_list) D2GS_CUDA_OK(cudaMemcpyAsync(out->point_list, bb + BL.point_list, 4 * (size_t)R, cudaMemcpyDeviceToDevice, stream));
+  } else if (binning_buffer && R > 0) {
     char* bb = aligned_base(binning_buffer);
     if (out->keys_unsorted) D2GS_CUDA_OK(cudaMemcpyAsync(out->keys_unsorted, bb + BL.keys_unsorted, 8 * (size_t)R, cudaMemcpyDeviceToDevice, stream));
     if (out->keys_sorted) D2GS_CUDA_OK(cudaMemcpyAsync(out->keys_sorted, bb + BL.keys_sorted, 8 * (size_t)R, cudaMemcpyDeviceToDevice, stream));

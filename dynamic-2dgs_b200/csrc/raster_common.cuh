@@ -58,12 +58,13 @@ struct GeomLayout {
   size_t scan_temp_bytes;
 };
 struct ImgLayout {
-  size_t ranges, final_T, n_contrib, total;
+  size_t ranges, final_T, n_contrib, tile_count, seg_begin, seg_end, total;
 };
 struct BinLayout {
   size_t keys_unsorted, keys_sorted, vals_unsorted, point_list, sort_temp, total;
   size_t sort_temp_bytes;
 };
+constexpr int TILE_SORT_MAX_TILES = 24576;   // per-tile binning keeps two counters per tile in shared memory (192 KB at the limit)
 
 GeomLayout geom_layout(int P);
 ImgLayout img_layout(int W, int H);
@@ -252,6 +253,17 @@ void launch_preprocess_fwd(const FwdParams& p, SurfelRec* rec, uint8_t* clamped,
 void launch_duplicate(int P, const SurfelRec* rec, const int* radii, const uint32_t* offsets, uint64_t* keys,
                       uint32_t* vals, uint32_t gx, uint32_t gy, uint32_t capacity, cudaStream_t s);
 void launch_ranges(int64_t R, const uint64_t* keys_sorted, uint2* ranges, cudaStream_t s);
+// Tile-bucketed binning (tile_binning.cu): count -> scan (ranges, R and overflow flag in status, list of long tiles) ->
+// scatter -> per-tile sort.  status: {R, overflow, number of long tiles}
+void launch_tile_count(int P, const SurfelRec* rec, const int* radii, uint32_t gx, uint32_t gy, uint32_t* tile_count, cudaStream_t s);
+void launch_tile_scan(uint32_t tiles, uint32_t capacity, uint32_t* tile_count, uint32_t* seg_begin, uint2* ranges, uint32_t* big_list,
+                      uint32_t* status, cudaStream_t s);
+void launch_tile_scatter(int P, const SurfelRec* rec, const int* radii, uint32_t gx, uint32_t gy, const uint32_t* seg_begin,
+                         uint32_t* cursor, const uint32_t* status, uint64_t* keys, cudaStream_t s);
+void launch_tile_sort(uint32_t tiles, const uint2* ranges, const uint32_t* big_list, const uint32_t* status, uint64_t* keys_in,
+                      uint64_t* keys_out, uint32_t* point_list, cudaStream_t s);
+void launch_tile_export_keys(uint32_t tiles, const uint2* ranges, const uint64_t* keys, uint64_t* out_keys, uint32_t* out_vals,
+                             cudaStream_t s);
 // Deferred-count mode (no host readback of the instance count R = offsets[P-1]):
 //   pad_keys : status = {R, R > capacity}; keys[R..capacity) = all ones, so a stable sort of all `capacity` slots leaves
 //              the R real instances first, in exactly the order a sort of R items produces

@@ -225,6 +225,10 @@ def lib():
     for name in EXPORTED_SYMBOLS:
         getattr(L, name)
     _lib = L
+    # D2GS_OPTIONS="tile_sort=1,cull=0": runtime switches for scripts that have no flag of their own (profiling targets)
+    for item in filter(None, os.environ.get("D2GS_OPTIONS", "").split(",")):
+        k, _, v = item.partition("=")
+        check(L.d2gs_set_option(k.strip().encode(), int(v or 1)), "d2gs_set_option")
     return L
 
 

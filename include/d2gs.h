@@ -57,6 +57,9 @@ typedef struct D2gsConfig {
 /* Runtime switches (speed only; results are identical either way, the tests flip them to prove it).
  *   "cull"       (default 1): warp-level cull boxes in the blend kernels
  *   "knn_filter" (default 1): warp-level candidate filter of the K-nearest-node search in d2gs_deform_forward
+ *   "tile_sort"  (default 1): binning of d2gs_raster_forward by per-tile buckets (count, scan, atomic scatter, one sort per
+ *                tile on depth bits | surfel id) instead of one global radix sort on tile | depth bits (0); the per-tile
+ *                lists, ranges and everything downstream are bit-identical
  *   "deform_bwd_smem" (default 1): per-CTA shared accumulators in the incoherent d2gs_deform_backward path */
 D2GS_API int d2gs_set_option(const char* name, int value);
 D2GS_API int d2gs_profile_enable(int on);

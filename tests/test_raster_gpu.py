@@ -313,8 +313,11 @@ def test_deferred_count_mode_is_identical(cfg, cam_index, cuda_device):
     R = a["ctx"].num_rendered
     assert b["ctx"].layout_R == int(R * 1.37) + 4096 and b["ctx"].num_rendered == R > 0      # the mode was really on
     assert torch.equal(a["color"], b["color"]) and torch.equal(a["allmap"], b["allmap"]) and torch.equal(a["radii"], b["radii"])
-    for k in ("keys_unsorted", "values_unsorted", "keys_sorted", "point_list", "ranges", "n_contrib", "final_T", "point_offsets"):
-        assert torch.equal(sa[k], sb[k]), k
+    for k in ("keys_sorted", "point_list", "ranges", "n_contrib", "final_T", "point_offsets"):
+        assert torch.equal(sa[k][:R] if k in ("keys_sorted", "point_list") else sa[k], sb[k][:R] if k in ("keys_sorted", "point_list") else sb[k]), k
+    # the unsorted instances: same multiset (the per-tile binning hands out bucket slots with atomics, in any order)
+    for k in ("keys_unsorted", "values_unsorted"):
+        assert torch.equal(torch.sort(sa[k][:R]).values, torch.sort(sb[k][:R]).values), k
     for k in ("means3D", "shs", "scales", "rotations", "opacities"):
         assert util.rel_err(np_(a["ins"][k].grad), np_(b["ins"][k].grad)) < 2e-5, k
     assert raster.last_num_rendered(cuda_device, act["means3D"].shape[0], kw["image_width"], kw["image_height"]) == R
@@ -342,3 +345,75 @@ def test_deferred_count_overflow_is_loud(cuda_device):
     again = run_ours(big, kw, cuda_device, gc, go)
     assert again["ctx"].layout_R >= ref["ctx"].num_rendered
     assert torch.equal(again["color"], ref["color"]) and torch.equal(again["allmap"], ref["allmap"])
+
+
+@pytest.mark.parametrize("cfg,cam_index,deferred,s_med", [("T0", 2, False, None), ("T1", 5, True, None), ("C2", 17, True, None),
+                                                           ("C2", 60, False, None), ("T1", 5, False, 0.06), ("T1", 3, True, 0.3)])
+def test_tile_bucket_binning_is_identical(cfg, cam_index, deferred, s_med, cuda_device):
+    """Tile-bucketed binning (d2gs_set_option("tile_sort", 1): per-tile counters -> scan -> atomic scatter -> per-tile sort on
+    (depth bits, surfel id)) must hand the blend kernels exactly the lists of the global stable radix sort on (tile, depth
+    bits): sorted keys, instance list, tile ranges, n_contrib and every image bit-identical — with the instance count read
+    back (synchronous) and in deferred-count mode, where it also stops sorting the padding slots.  The two T1 cases with
+    large splats have tile lists of 3 k and 18 k instances: the long-tile kernel (shared memory) and its in-place global path."""
+    from d2gs_b200 import _lib, raster
+    act, kw = util.raster_inputs(cfg, cam_index=cam_index, n_cams=100 if cfg == "C2" else 8, s_med=s_med)
+    gc, go = util.upstream_grads(kw["image_height"], kw["image_width"], seed=8)
+    res, st = {}, {}
+    try:
+        for mode in (0, 1):
+            _lib.set_option("tile_sort", mode)
+            raster._TRACK.clear(); raster._R_HINT.clear()
+            if deferred:
+                raster.set_deferred_count(True, warmup=1, margin=1.3)
+                run_ours(act, kw, cuda_device)                    # synchronous warm-up frame establishes the capacity
+            else:
+                raster.set_deferred_count(False)
+            res[mode] = run_ours(act, kw, cuda_device, gc, go)
+            st[mode] = raster.export_state(res[mode]["ctx"])
+            assert (res[mode]["ctx"].layout_R > res[mode]["ctx"].num_rendered) == deferred
+    finally:
+        _lib.set_option("tile_sort", 1)
+        raster.set_deferred_count(True)
+    a, b = res[0], res[1]
+    R = a["ctx"].num_rendered
+    assert b["ctx"].num_rendered == R > 0
+    longest = int((st[0]["ranges"][:, 1].long() - st[0]["ranges"][:, 0].long()).max())
+    if s_med == 0.06:
+        assert longest > 2304
+    if s_med == 0.3:
+        assert longest > 16384
+    assert torch.equal(a["color"], b["color"]) and torch.equal(a["allmap"], b["allmap"]) and torch.equal(a["radii"], b["radii"])
+    for k in ("ranges", "n_contrib", "final_T", "point_offsets"):
+        assert torch.equal(st[0][k], st[1][k]), k
+    for k in ("keys_sorted", "point_list"):
+        assert torch.equal(st[0][k][:R], st[1][k][:R]), k
+    # the unsorted buckets hold the same multiset of (tile | depth) keys
+    assert torch.equal(torch.sort(st[0]["keys_unsorted"][:R]).values, torch.sort(st[1]["keys_unsorted"][:R]).values)
+    for k in ("means3D", "shs", "scales", "rotations", "opacities"):
+        assert util.rel_err(np_(a["ins"][k].grad), np_(b["ins"][k].grad)) < 2e-5, k
+
+
+def test_tile_bucket_binning_overflow_is_loud(cuda_device):
+    """Same contract as test_deferred_count_overflow_is_loud with the per-tile binning path."""
+    from d2gs_b200 import _lib, raster
+    small, kw = util.raster_inputs("T1", s_med=0.003)
+    big, _ = util.raster_inputs("T1", s_med=0.03)
+    gc, go = util.upstream_grads(kw["image_height"], kw["image_width"], seed=6)
+    try:
+        _lib.set_option("tile_sort", 1)
+        raster.set_deferred_count(False)
+        ref = run_ours(big, kw, cuda_device, gc, go)
+        raster._TRACK.clear()
+        raster.set_deferred_count(True, warmup=1, margin=1.0)
+        run_ours(small, kw, cuda_device)
+        o = run_ours(big, kw, cuda_device, gc, go)
+        assert o["ctx"].num_rendered == ref["ctx"].num_rendered > o["ctx"].layout_R
+        assert bool(torch.isnan(o["color"]).all())
+        assert float(o["ins"]["means3D"].grad.abs().sum()) == 0.0
+        with pytest.raises(_lib.D2gsError, match="deferred-count"):
+            run_ours(big, kw, cuda_device)
+        again = run_ours(big, kw, cuda_device, gc, go)
+        assert torch.equal(again["color"], ref["color"]) and torch.equal(again["allmap"], ref["allmap"])
+    finally:
+        _lib.set_option("tile_sort", 1)
+        raster.set_deferred_count(True)
