@@ -76,6 +76,7 @@ GeomLayout geom_layout(int P) {
   L.scan_temp_bytes = tmp;
   L.scan_temp = o; o = align_up(o + tmp);
   L.status = o; o = align_up(o + 4 * sizeof(uint32_t));   // {R, overflow flag, number of long tiles (per-tile binning)}
+  L.tile_box = o; o = align_up(o + 16 * (size_t)P);       // packed tile rectangle + depth bits per surfel (per-tile binning)
   L.total = o + 256;
   return L;
 }
@@ -245,13 +246,15 @@ int d2gs_raster_forward(const D2gsRasterFwdArgs* a, void* stream_) {
   uint32_t* seg_begin = (uint32_t*)(ib + IL.seg_begin);
   uint32_t* big_list = (uint32_t*)(ib + IL.seg_end);
   if (deferred && a->binning_capacity > 0xffffffffll) return fail(D2GS_ERR_INVALID_ARG, "binning_capacity exceeds 2^32-1 instances");
+  uint4* tile_box = (uint4*)(gb + GL.tile_box);
+  p.tile_box = tile_sort ? tile_box : nullptr;
   if (!a->resume) {
     { StageTimer t(ST_PRE, stream); launch_preprocess_fwd(p, rec, clamped, a->radii, tiles_touched, stream); }
     D2GS_STAGE("preprocess", a->debug, stream);
     if (tile_sort) {
       // per-tile counters -> ranges, instance total and overflow flag (no per-surfel scan)
       StageTimer t(ST_SCAN, stream);
-      launch_tile_count(P, rec, a->radii, p.gx, p.gy, tile_count, stream);
+      launch_tile_count(P, tile_box, p.gx, p.gy, tile_count, stream);
       launch_tile_scan(tiles, deferred ? (uint32_t)a->binning_capacity : 0xffffffffu, tile_count, seg_begin, ranges, big_list, status, stream);
     } else {
       size_t tmp = GL.scan_temp_bytes;
@@ -288,7 +291,7 @@ int d2gs_raster_forward(const D2gsRasterFwdArgs* a, void* stream_) {
 
   if (tile_sort) {
     { StageTimer t(ST_DUP, stream);
-      launch_tile_scatter(P, rec, a->radii, p.gx, p.gy, seg_begin, tile_count, status, keys_unsorted, stream); }
+      launch_tile_scatter(P, tile_box, p.gx, p.gy, seg_begin, tile_count, status, keys_unsorted, stream); }
     D2GS_STAGE("scatter", a->debug, stream);
     if (deferred && a->num_rendered_async)
       D2GS_CUDA_OK(cudaMemcpyAsync(a->num_rendered_async, status, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));

@@ -54,7 +54,7 @@ constexpr int G_T = 0, G_M2D = 9, G_NRM = 11, G_OPA = 14, G_COL = 15;
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 struct GeomLayout {
-  size_t rec, clamped, tiles_touched, point_offsets, scan_temp, status, total;
+  size_t rec, clamped, tiles_touched, point_offsets, scan_temp, status, tile_box, total;
   size_t scan_temp_bytes;
 };
 struct ImgLayout {
@@ -220,6 +220,7 @@ struct FwdParams {
   const float* d_means3D;
   const float* d_scales;
   const float* d_rotations;
+  uint4* tile_box;         // optional (P): {x0 | x1 << 16, y0 | y1 << 16, depth bits, 0} of the tile rectangle, all zero when culled
 };
 
 // Activated surfel parameters from the raw ones, op for op what the eager glue computes
@@ -255,10 +256,10 @@ void launch_duplicate(int P, const SurfelRec* rec, const int* radii, const uint3
 void launch_ranges(int64_t R, const uint64_t* keys_sorted, uint2* ranges, cudaStream_t s);
 // Tile-bucketed binning (tile_binning.cu): count -> scan (ranges, R and overflow flag in status, list of long tiles) ->
 // scatter -> per-tile sort.  status: {R, overflow, number of long tiles}
-void launch_tile_count(int P, const SurfelRec* rec, const int* radii, uint32_t gx, uint32_t gy, uint32_t* tile_count, cudaStream_t s);
+void launch_tile_count(int P, const uint4* tile_box, uint32_t gx, uint32_t gy, uint32_t* tile_count, cudaStream_t s);
 void launch_tile_scan(uint32_t tiles, uint32_t capacity, uint32_t* tile_count, uint32_t* seg_begin, uint2* ranges, uint32_t* big_list,
                       uint32_t* status, cudaStream_t s);
-void launch_tile_scatter(int P, const SurfelRec* rec, const int* radii, uint32_t gx, uint32_t gy, const uint32_t* seg_begin,
+void launch_tile_scatter(int P, const uint4* tile_box, uint32_t gx, uint32_t gy, const uint32_t* seg_begin,
                          uint32_t* cursor, const uint32_t* status, uint64_t* keys, cudaStream_t s);
 void launch_tile_sort(uint32_t tiles, const uint2* ranges, const uint32_t* big_list, const uint32_t* status, uint64_t* keys_in,
                       uint64_t* keys_out, uint32_t* point_list, cudaStream_t s);

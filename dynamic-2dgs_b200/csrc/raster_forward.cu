@@ -39,13 +39,14 @@ __device__ __forceinline__ void load_sh(const FwdParams& p, int idx, int ncoef, 
   }
 }
 
-__global__ void __launch_bounds__(256) preprocess_fwd_kernel(FwdParams p, SurfelRec* __restrict__ rec,
+__global__ void __launch_bounds__(256, 3) preprocess_fwd_kernel(FwdParams p, SurfelRec* __restrict__ rec,
                                                              uint8_t* __restrict__ clamped, int* __restrict__ radii,
                                                              uint32_t* __restrict__ tiles_touched) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= p.P) return;
   radii[idx] = 0;
   tiles_touched[idx] = 0;
+  if (p.tile_box) p.tile_box[idx] = make_uint4(0u, 0u, 0u, 0u);
 
   const float* m = p.view;
   Activated act;
@@ -127,6 +128,8 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(FwdParams p, Surfel
 
   radii[idx] = (int)radius;
   tiles_touched[idx] = (r.y1 - r.y0) * (r.x1 - r.x0);
+  // packed tile rectangle + depth bits: all the per-tile binning needs of this surfel (16 B instead of two quads of the record)
+  if (p.tile_box) p.tile_box[idx] = make_uint4(r.x0 | (r.x1 << 16), r.y0 | (r.y1 << 16), __float_as_uint(depth), 0u);
   SurfelRec o;
   o.q0 = make_float4(T[0], T[1], T[2], T[3]);
   o.q1 = make_float4(T[4], T[5], T[6], T[7]);

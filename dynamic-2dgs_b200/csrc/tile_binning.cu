@@ -1,6 +1,7 @@
 // Tile-bucketed binning: an alternative to "emit (tile | depth) keys, radix-sort all of them, find the tile boundaries"
 // (rasterizer_impl.cu:70-138 of the reference; duplicate_kernel + CUB DeviceRadixSort + ranges_kernel here).
 //
+//   (preprocess_fwd writes a packed 16-byte {tile rectangle, depth bits} per surfel: all that the two passes below read)
 //   count    persistent CTAs histogram the tiles of their surfels' rectangles in shared memory and flush the non-empty
 //            bins with one global atomic each (R increments -> ~R/3 global atomics, ~3x less same-address contention)
 //   scan     one CTA scans the tile counters: ranges[t] = [start, start + count) — what the reference derives from the
@@ -28,19 +29,17 @@ namespace {
 constexpr int SMALL_TILE = 2304;     // 256 threads x 9 keys sorted in 18 KB of static shared memory by the per-tile kernel
 constexpr int BIG_TILE = 16384;      // keys sorted in 128 KB of dynamic shared memory by the long-tile kernel
 
-__global__ void __launch_bounds__(256) tile_count_kernel(int P, const SurfelRec* __restrict__ rec, const int* __restrict__ radii,
-                                                         uint32_t gx, uint32_t gy, uint32_t* __restrict__ tile_count) {
+__global__ void __launch_bounds__(256) tile_count_kernel(int P, const uint4* __restrict__ tile_box, uint32_t gx, uint32_t gy,
+                                                         uint32_t* __restrict__ tile_count) {
   extern __shared__ uint32_t s_hist[];
   const uint32_t tiles = gx * gy;
   for (uint32_t t = threadIdx.x; t < tiles; t += blockDim.x) s_hist[t] = 0u;
   __syncthreads();
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < P; idx += gridDim.x * blockDim.x) {
-    const int rad = radii[idx];
-    if (rad <= 0) continue;
-    const float4 q2 = __ldg(&rec[idx].q2);
-    const RectU r = tile_rect(q2.y, q2.z, rad, gx, gy);
-    for (uint32_t y = r.y0; y < r.y1; y++)
-      for (uint32_t x = r.x0; x < r.x1; x++) atomicAdd(s_hist + y * gx + x, 1u);
+    const uint4 b = __ldg(tile_box + idx);
+    const uint32_t x0 = b.x & 0xffffu, x1 = b.x >> 16, y0 = b.y & 0xffffu, y1 = b.y >> 16;
+    for (uint32_t y = y0; y < y1; y++)
+      for (uint32_t x = x0; x < x1; x++) atomicAdd(s_hist + y * gx + x, 1u);
   }
   __syncthreads();
   for (uint32_t t = threadIdx.x; t < tiles; t += blockDim.x) {
@@ -109,10 +108,9 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t tiles, uint32_
   if (threadIdx.x == 0) status[2] = s_nbig;
 }
 
-__global__ void __launch_bounds__(256) tile_scatter_kernel(int P, const SurfelRec* __restrict__ rec, const int* __restrict__ radii,
-                                                           uint32_t gx, uint32_t gy, const uint32_t* __restrict__ seg_begin,
-                                                           uint32_t* __restrict__ cursor, const uint32_t* __restrict__ status,
-                                                           uint64_t* __restrict__ keys) {
+__global__ void __launch_bounds__(256) tile_scatter_kernel(int P, const uint4* __restrict__ tile_box, uint32_t gx, uint32_t gy,
+                                                           const uint32_t* __restrict__ seg_begin, uint32_t* __restrict__ cursor,
+                                                           const uint32_t* __restrict__ status, uint64_t* __restrict__ keys) {
   extern __shared__ uint32_t s_mem[];
   if (status[1] != 0u) return;                          // overflow: nothing is binned
   const uint32_t tiles = gx * gy;
@@ -121,12 +119,10 @@ __global__ void __launch_bounds__(256) tile_scatter_kernel(int P, const SurfelRe
   for (uint32_t t = threadIdx.x; t < tiles; t += blockDim.x) s_hist[t] = 0u;
   __syncthreads();
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < P; idx += gridDim.x * blockDim.x) {
-    const int rad = radii[idx];
-    if (rad <= 0) continue;
-    const float4 q2 = __ldg(&rec[idx].q2);
-    const RectU r = tile_rect(q2.y, q2.z, rad, gx, gy);
-    for (uint32_t y = r.y0; y < r.y1; y++)
-      for (uint32_t x = r.x0; x < r.x1; x++) atomicAdd(s_hist + y * gx + x, 1u);
+    const uint4 b = __ldg(tile_box + idx);
+    const uint32_t x0 = b.x & 0xffffu, x1 = b.x >> 16, y0 = b.y & 0xffffu, y1 = b.y >> 16;
+    for (uint32_t y = y0; y < y1; y++)
+      for (uint32_t x = x0; x < x1; x++) atomicAdd(s_hist + y * gx + x, 1u);
   }
   __syncthreads();
   for (uint32_t t = threadIdx.x; t < tiles; t += blockDim.x) {
@@ -136,14 +132,11 @@ __global__ void __launch_bounds__(256) tile_scatter_kernel(int P, const SurfelRe
   }
   __syncthreads();
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < P; idx += gridDim.x * blockDim.x) {
-    const int rad = radii[idx];
-    if (rad <= 0) continue;
-    const float4 q2 = __ldg(&rec[idx].q2);
-    const float depth = __ldg(&rec[idx].q3.w);
-    const RectU r = tile_rect(q2.y, q2.z, rad, gx, gy);
-    const uint64_t key = ((uint64_t)__float_as_uint(depth) << 32) | (uint32_t)idx;
-    for (uint32_t y = r.y0; y < r.y1; y++)
-      for (uint32_t x = r.x0; x < r.x1; x++) {
+    const uint4 b = __ldg(tile_box + idx);
+    const uint32_t x0 = b.x & 0xffffu, x1 = b.x >> 16, y0 = b.y & 0xffffu, y1 = b.y >> 16;
+    const uint64_t key = ((uint64_t)b.z << 32) | (uint32_t)idx;
+    for (uint32_t y = y0; y < y1; y++)
+      for (uint32_t x = x0; x < x1; x++) {
         const uint32_t t = y * gx + x;
         keys[s_base[t] + atomicAdd(s_hist + t, 1u)] = key;
       }
@@ -268,23 +261,23 @@ int persistent_grid(int P) {
 }
 }  // namespace
 
-void launch_tile_count(int P, const SurfelRec* rec, const int* radii, uint32_t gx, uint32_t gy, uint32_t* tile_count, cudaStream_t s) {
+void launch_tile_count(int P, const uint4* tile_box, uint32_t gx, uint32_t gy, uint32_t* tile_count, cudaStream_t s) {
   const size_t smem = sizeof(uint32_t) * (size_t)gx * gy;
   cudaMemsetAsync(tile_count, 0, smem, s);
   if (P <= 0) return;
   cudaFuncSetAttribute(tile_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  tile_count_kernel<<<persistent_grid(P), 256, smem, s>>>(P, rec, radii, gx, gy, tile_count);
+  tile_count_kernel<<<persistent_grid(P), 256, smem, s>>>(P, tile_box, gx, gy, tile_count);
 }
 void launch_tile_scan(uint32_t tiles, uint32_t capacity, uint32_t* tile_count, uint32_t* seg_begin, uint2* ranges, uint32_t* big_list,
                       uint32_t* status, cudaStream_t s) {
   tile_scan_kernel<<<1, 1024, 0, s>>>(tiles, capacity, tile_count, seg_begin, ranges, big_list, status);
 }
-void launch_tile_scatter(int P, const SurfelRec* rec, const int* radii, uint32_t gx, uint32_t gy, const uint32_t* seg_begin,
-                         uint32_t* cursor, const uint32_t* status, uint64_t* keys, cudaStream_t s) {
+void launch_tile_scatter(int P, const uint4* tile_box, uint32_t gx, uint32_t gy, const uint32_t* seg_begin, uint32_t* cursor,
+                         const uint32_t* status, uint64_t* keys, cudaStream_t s) {
   if (P <= 0) return;
   const size_t smem = 2 * sizeof(uint32_t) * (size_t)gx * gy;
   cudaFuncSetAttribute(tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  tile_scatter_kernel<<<persistent_grid(P), 256, smem, s>>>(P, rec, radii, gx, gy, seg_begin, cursor, status, keys);
+  tile_scatter_kernel<<<persistent_grid(P), 256, smem, s>>>(P, tile_box, gx, gy, seg_begin, cursor, status, keys);
 }
 void launch_tile_sort(uint32_t tiles, const uint2* ranges, const uint32_t* big_list, const uint32_t* status, uint64_t* keys_in,
                       uint64_t* keys_out, uint32_t* point_list, cudaStream_t s) {
