@@ -570,7 +570,8 @@ def main():
                       "loss": "seeded random-weighted sum over the render outputs + L1 (SURVEY 8(d))" if args.loss == "synthetic" else
                               "training loss of train_gui.py:292-313: L1 + D-SSIM(0.2) + normal(0.02) + distortion(1000)",
                       "parallelism": f"view-sharded x{world}" + (" + NCCL all-reduce of the flat gradient bucket" if world > 1 else ""),
-                      "binning": "synchronous count readback" if args.sync_count else "deferred count (no host synchronisation in the step)",
+                      "binning": ("global radix sort" if args.tile_sort == 0 else "per-tile buckets + per-tile sort") + ", " +
+                                 ("synchronous count readback" if args.sync_count else "deferred count (no host synchronisation in the step)"),
                       "launch": ("one CUDA graph per step (captured through the public API)" if graphed else "eager launches") +
                                 (" | e2e: graph incl. H2D/D2H copies" if e2e_graphed else " | e2e: eager"),
                       "l2_policy": "no explicit flush: per-step working set (params+grads+workspaces ~0.3 GB) exceeds the 126 MB L2 and the view changes every step"},
@@ -613,6 +614,8 @@ def main():
         mine_kernels = {"preprocess_fwd": 1, "duplicate": 1, "ranges": 1, "blend_fwd": 1, "blend_bwd": 1, "preprocess_bwd": 1,
                         "deform_fwd": 1, "deform_bwd": 1, "epilogue_fwd": 1, "epilogue_bwd": 1, "mlp_fwd": 2, "mlp_bwd": 2,
                         "loss_fwd": 2, "loss_bwd": 1}
+        if args.tile_sort != 0:   # tile-bucketed binning (library default): count + scan | scatter | per-tile sort (2 kernels), no CUB
+            mine_kernels.update({"scan": 2, "duplicate": 1, "sort": 2})
         out["gpu_launches"] = int(sum(stage[k][1] * n for k, n in mine_kernels.items() if k in stage))
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -15,6 +15,12 @@ and is not installed here.  Its published semantics are restated: squared L2 dis
 ascending order, int64 indices, differentiable w.r.t. both point sets.  Ties: lower node index first.
 Everything else in this file is plain torch arithmetic and differentiable through torch autograd, which is how the
 gradients of the CUDA path are checked.
+
+PIN for everything but the K-NN: tests/golden/deform_golden.npz holds outputs and gradients of the reference's OWN
+``ControlNodeWarp`` class, imported from /root/reference/utils/time_utils.py and run on CPU by
+tests/golden/make_deform_golden.py (pytorch3d stubbed as above, ``Module.cuda`` a no-op); ``init_network_params`` loads into
+the reference's DeformNetwork with ``strict=True``, i.e. names and shapes are the reference's.  tests/test_deform_cpu.py
+checks this restatement against it (outputs 2e-6, gradients 1e-5), tests/test_deform_gpu.py the CUDA path.
 """
 from __future__ import annotations
 

@@ -87,3 +87,33 @@ def test_host_side_interface_mirror():
     assert set(dfm.model_dict) == {"mlp", "node", "static"}
     idx = dfm.farthest_point_sample(torch.randn(1, 200, 3), 10)
     assert idx.shape == (1, 10) and len(set(idx[0].tolist())) == 10
+
+
+@pytest.mark.parametrize("name", ["local", "plain"])
+def test_oracle_matches_the_references_own_control_node_warp(name):
+    """tests/golden/deform_golden.npz was produced by the reference's own ControlNodeWarp class (utils/time_utils.py, run on
+    CPU by tests/golden/make_deform_golden.py with pytorch3d.ops.knn_points replaced by its published semantics): outputs and
+    every gradient of the oracle's restatement must agree with it."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(util.ROOT, "tests", "golden"))
+    from make_deform_golden import deform_case
+    g = np.load(os.path.join(util.ROOT, "tests", "golden", "deform_golden.npz"))
+    c = deform_case(name)
+    net = {k: v.clone().requires_grad_(True) for k, v in c["net"].items()}
+    nodes, rad, wl = (c[k].clone().requires_grad_(True) for k in ("nodes", "node_radius", "node_weight"))
+    feature = c["feature"].clone().requires_grad_(True)
+    t = torch.full((c["M"], 1), c["fid"])
+    out = do.control_node_warp_forward(net, nodes, rad, wl, c["xyz"], t, feature, torch.ones(c["P"], 1), c["K"], c["hyper"],
+                                       local_frame=c["local_frame"])
+    for k in ("d_xyz", "d_rotation", "d_scaling"):
+        assert util.rel_err(out[k].detach().numpy(), g[f"{name}_{k}"]) < 2e-6, k
+    ((out["d_xyz"] * c["g_xyz"]).sum() + (out["d_rotation"] * c["g_rot"]).sum() + (out["d_scaling"] * c["g_scale"]).sum()).backward()
+    for k, v in (("g_feature", feature), ("g_nodes", nodes), ("g_node_radius", rad), ("g_node_weight", wl)):
+        assert util.rel_err(v.grad.numpy(), g[f"{name}_{k}"]) < 1e-5, k
+    for k, p in net.items():
+        gn = float(p.grad.double().norm()) if p.grad is not None else 0.0
+        want = float(g[f"{name}_gnorm_net_{k}"])
+        assert abs(gn - want) <= 1e-5 * max(want, 1e-12), k
+        if f"{name}_g_net_{k}" in g.files:
+            assert util.rel_err(p.grad.numpy(), g[f"{name}_g_net_{k}"]) < 1e-5, k

@@ -184,6 +184,34 @@ def test_knn_candidate_filter_changes_nothing(P, M, K, hyper, dup, coherent, cud
         assert bool((got[:, 1:][tie] > got[:, :-1][tie]).all())
 
 
+@pytest.mark.parametrize("P,M", [(300_000, 512), (1_000_000, 2048)])
+def test_knn_candidate_filter_at_benchmark_sizes(P, M, cuda_device):
+    """C3 / C5 sizes (no oracle at this scale): the filtered search equals the exhaustive one bit for bit on every surfel, and
+    2000 sampled rows equal an explicit float64 top-k."""
+    from d2gs_b200 import _lib, deform as dfm
+    dev = cuda_device
+    K, hyper = 4, 8
+    x, feat, nodes, rad, wl, attrs = _case(P, M, K, hyper, seed=P + M, local_frame=True, with_mask=False)
+    order = dfm.processing_order(x.to(dev))
+    res = {}
+    try:
+        for filt in (0, 1):
+            _lib.set_option("knn_filter", filt)
+            m = {k: v.clone().to(dev) for k, v in attrs.items()}
+            res[filt] = dfm.node_blend(x.to(dev), feat.to(dev), nodes.to(dev), rad.to(dev), wl.reshape(-1).to(dev), m["d_xyz"],
+                                       m["d_rotation"], m["d_scaling"], m.get("local_rotation"), None, K, hyper, order=order)
+            torch.cuda.synchronize()
+    finally:
+        _lib.set_option("knn_filter", 1)
+    for k in ("nn_idx", "nn_dist", "nn_weight", "d_xyz", "d_rotation", "d_scaling"):
+        assert torch.equal(res[0][k], res[1][k]), k
+    rows = torch.randperm(P, generator=torch.Generator().manual_seed(0))[:2000]
+    q = torch.cat([x, feat[:, :hyper]], 1)[rows]
+    d2 = ((q[:, None, :].double() - nodes[None, :, :q.shape[1]].double()) ** 2).sum(-1)
+    ref_idx = torch.sort(d2, dim=1, stable=True).indices[:, :K]
+    assert (res[1]["nn_idx"].cpu()[rows] == ref_idx).float().mean() > 0.999
+
+
 def test_knn_with_non_finite_queries_stays_in_bounds(cuda_device):
     """A surfel with NaN/Inf coordinates accepts no node; its neighbour indices must still be valid node indices (the
     blend reads the node tables through them) and the other surfels of its warp are unaffected."""
@@ -280,6 +308,43 @@ def test_control_node_warp_forward_and_cal_nn_weight(cuda_device):
     (out["d_xyz"].sum() + out["d_rotation"].sum()).backward()
     assert cn.network.linear[0].weight.grad is not None and feat.grad is not None and cn._node_radius.grad is not None
     assert cn.reg_loss == 0.
+
+
+@pytest.mark.parametrize("name", ["local", "plain"])
+def test_control_node_warp_matches_the_references_own_class(name, cuda_device):
+    """tests/golden/deform_golden.npz: outputs and gradients of the reference's own ControlNodeWarp (utils/time_utils.py run on
+    CPU, pytorch3d.ops.knn_points replaced by its published semantics).  Our drop-in class with the same state dict must agree:
+    outputs 1e-4 relative (north_star), gradients norm-wise 5e-4."""
+    import os
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(util.ROOT, "tests", "golden"))
+    from make_deform_golden import deform_case
+    from d2gs_b200 import deform as dfm
+    dev = cuda_device
+    g = np.load(os.path.join(util.ROOT, "tests", "golden", "deform_golden.npz"))
+    c = deform_case(name)
+    cn = dfm.ControlNodeWarp(is_blender=True, node_num=c["M"], K=c["K"], hyper_dim=c["hyper"], local_frame=c["local_frame"]).to(dev)
+    cn.network.load_state_dict(c["net"], strict=True)
+    with torch.no_grad():
+        cn.nodes.copy_(c["nodes"]); cn._node_radius.copy_(c["node_radius"]); cn._node_weight.copy_(c["node_weight"])
+    feature = c["feature"].to(dev).requires_grad_(True)
+    t = torch.full((c["M"], 1), c["fid"], device=dev)
+    out = cn(c["xyz"].to(dev), t, feature, torch.ones(c["P"], 1, device=dev))
+    for k in ("d_xyz", "d_rotation", "d_scaling"):
+        assert util.rel_err(out[k].detach().cpu().numpy(), g[f"{name}_{k}"]) < 1e-4, (k, util.rel_err(out[k].detach().cpu().numpy(), g[f"{name}_{k}"]))
+    ((out["d_xyz"] * c["g_xyz"].to(dev)).sum() + (out["d_rotation"] * c["g_rot"].to(dev)).sum() +
+     (out["d_scaling"] * c["g_scale"].to(dev)).sum()).backward()
+    pairs = dict(g_feature=feature.grad, g_nodes=cn.nodes.grad, g_node_radius=cn._node_radius.grad, g_node_weight=cn._node_weight.grad)
+    for k, v in pairs.items():
+        e = util.rel_err(v.cpu().numpy().reshape(g[f"{name}_{k}"].shape), g[f"{name}_{k}"])
+        assert e < 5e-4, (k, e)
+    for k, p in cn.network.named_parameters():
+        gn = float(p.grad.double().norm()) if p.grad is not None else 0.0
+        want = float(g[f"{name}_gnorm_net_{k}"])
+        assert abs(gn - want) <= 5e-4 * max(want, 1e-12), (k, gn, want)
+        if f"{name}_g_net_{k}" in g.files:
+            assert util.rel_err(p.grad.cpu().numpy(), g[f"{name}_g_net_{k}"]) < 5e-4, k
 
 
 def test_render_dropin_matches_reference_pipeline(cuda_device):
