@@ -146,3 +146,16 @@ def test_oracle_binning_invariants():
         assert (tiles[a:b] == t).all() and (a == 0 or tiles[a - 1] != t) and (b == R or tiles[b] != t)
     assert (st.n_contrib[0] <= (st.ranges[:, 1] - st.ranges[:, 0]).max()).all()
     assert so.mark_visible(act["means3D"], kw["viewmatrix"]).sum() >= (st.radii > 0).sum()
+
+
+def test_synthetic_cameras_follow_the_reference_conventions():
+    """tests/golden/camera_golden.npz: matrices built by the reference's getWorld2View2 / getProjectionMatrix and the Camera
+    constructor's products (scene/cameras.py:55-59) for the extrinsics of three synthetic cameras."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(util.ROOT, "tests", "golden"))
+    from make_camera_golden import camera_cases
+    g = np.load(os.path.join(util.ROOT, "tests", "golden", "camera_golden.npz"))
+    for name, cam in camera_cases().items():
+        for k in ("world_view_transform", "projection_matrix", "full_proj_transform", "camera_center"):
+            np.testing.assert_allclose(getattr(cam, k), g[f"{name}_{k}"], rtol=2e-6, atol=2e-6, err_msg=f"{name} {k}")
