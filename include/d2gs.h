@@ -121,8 +121,10 @@ typedef struct D2gsRasterFwdArgs {
   const float* d_rotations;       /* (P,4) or NULL */
   /* Deferred-count mode (binning_capacity > 0): the instance count R is NOT read back, so the call never synchronises.
    * The binning stage works on exactly `binning_capacity` slots (binning_bytes must cover d2gs_raster_workspace(...,
-   * binning_capacity)); slots past R carry all-ones keys, and the stable sort leaves the R real instances first in the
-   * order a sort of R items produces, so every result is identical to the synchronous mode.  *num_rendered is set to
+   * binning_capacity)).  With the per-tile binning (option "tile_sort", default) the slots are only capacity: R, the
+   * overflow flag and the tile ranges come from a device-side scan of per-tile counters.  With the global sort
+   * ("tile_sort" = 0) slots past R carry all-ones keys, and the stable sort leaves the R real instances first in the
+   * order a sort of R items produces.  Either way every result is identical to the synchronous mode.  *num_rendered is set to
    * binning_capacity: pass that value to d2gs_raster_backward / d2gs_raster_export_state (it fixes the workspace
    * layout).  If R > binning_capacity the frame renders nothing and out_color is filled with NaN (never silently
    * wrong).  num_rendered_async: optional PINNED HOST pair {R, overflow flag}, written by an asynchronous copy on
@@ -200,7 +202,7 @@ typedef struct D2gsRasterState {
   uint8_t* clamped;       /* (P,3) */
   uint32_t* tiles_touched;   /* (P) */
   uint32_t* point_offsets;   /* (P) */
-  uint64_t* keys_unsorted;   /* (R) */
+  uint64_t* keys_unsorted;   /* (R) reference format tile << 32 | depth bits; with per-tile binning: in bucket order */
   uint32_t* values_unsorted; /* (R) */
   uint64_t* keys_sorted;     /* (R) */
   uint32_t* point_list;      /* (R) */
