@@ -196,6 +196,7 @@ def step_ours(wl: Workload, cam, gt, gt_ready=None):
     else:
         d_xyz, d_rot, d_scale = 0.0, 0.0, 0.0
     out = render(cam, pc, wl.pipe, wl.bg, d_xyz, d_rot, d_scale)
+    wl.last_out = out
     if gt_ready is not None:
         torch.cuda.current_stream().wait_event(gt_ready)     # the target image arrives on the copy stream
     if wl.loss_kind == "train":
@@ -208,25 +209,148 @@ def step_ours(wl: Workload, cam, gt, gt_ready=None):
     return loss
 
 
+class RefStageTimer:
+    """CUDA-event stage timers of the REFERENCE arm: events around the eager deformation, around
+    the two native calls of the reference extension (`_C.rasterize_gaussians{,_backward}`, patched on its module object)
+    and around the whole step; "epilogue+loss fwd" and "autograd bwd outside the rasterizer" are the remainders."""
+
+    def __init__(self, ref_mod):
+        self.mod, self.on, self.ev, self.orig = ref_mod, False, [], {}
+
+    def _wrap(self, name, stage):
+        fn = getattr(self.mod._C, name)
+        self.orig[name] = fn
+
+        def timed(*a, **k):
+            if not self.on:
+                return fn(*a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            self.ev.append((stage, e0, e1))
+            return r
+        setattr(self.mod._C, name, timed)
+
+    def install(self):
+        self._wrap("rasterize_gaussians", "raster_fwd")
+        self._wrap("rasterize_gaussians_backward", "raster_bwd")
+
+    def mark(self, stage):
+        """Context manager: events around a python-level section."""
+        timer = self
+
+        class _M:
+            def __enter__(self_):
+                if timer.on:
+                    self_.e0 = torch.cuda.Event(enable_timing=True); self_.e0.record()
+
+            def __exit__(self_, *exc):
+                if timer.on:
+                    e1 = torch.cuda.Event(enable_timing=True); e1.record()
+                    timer.ev.append((stage, self_.e0, e1))
+        return _M()
+
+    def collect(self, steps):
+        torch.cuda.synchronize()
+        acc = {}
+        for stage, e0, e1 in self.ev:
+            acc[stage] = acc.get(stage, 0.0) + e0.elapsed_time(e1)
+        self.ev = []
+        out = {k: v / steps for k, v in acc.items()}
+        if "step" in out:
+            fwd_rest = out.get("forward", 0.0) - out.get("deform_fwd", 0.0) - out.get("raster_fwd", 0.0)
+            out["epilogue_loss_fwd"] = fwd_rest
+            out["autograd_bwd_outside_rasterizer"] = out.get("backward", 0.0) - out.get("raster_bwd", 0.0)
+        return out
+
+
+class _Null:
+    def __enter__(self): return self
+    def __exit__(self, *a): return False
+
+
 def step_reference(wl: Workload, cam, gt, gt_ready=None):
     from oracle import reference_pipeline as rp
     pc = wl.pc
-    if wl.use_deform:
-        d = rp.deform_reference(wl.net, wl.nodes, wl.node_radius, wl.node_weight, pc.get_xyz.detach(), cam.fid, pc.feature,
-                                pc.motion_mask, wl.K, 8, local_frame=True)
-        d_xyz, d_rot, d_scale = d["d_xyz"], d["d_rotation"], d["d_scaling"]
-    else:
-        d_xyz, d_rot, d_scale = 0.0, 0.0, 0.0
-    out = rp.render_reference(wl.ref_mod, cam, pc, wl.bg, d_xyz, d_rot, d_scale)
-    if gt_ready is not None:
-        torch.cuda.current_stream().wait_event(gt_ready)
-    if wl.loss_kind == "train":
-        from oracle import loss_oracle as lo      # eager restatement of utils/loss_utils.py + train_gui.py:292-313
-        loss = lo.surfel_loss(out["render"], gt, out["rend_normal"], out["surf_normal"], out["rend_dist"], *TRAIN_LAMBDAS)[0]
-    else:
-        loss = synthetic_loss(out, wl.wts, gt)
-    loss.backward()
+    tm = getattr(wl, "ref_timer", None)
+    mark = tm.mark if tm is not None else (lambda s_: _Null())
+    with mark("forward"):
+        with mark("deform_fwd"):
+            if wl.use_deform:
+                d = rp.deform_reference(wl.net, wl.nodes, wl.node_radius, wl.node_weight, pc.get_xyz.detach(), cam.fid, pc.feature,
+                                        pc.motion_mask, wl.K, 8, local_frame=True)
+                d_xyz, d_rot, d_scale = d["d_xyz"], d["d_rotation"], d["d_scaling"]
+            else:
+                d_xyz, d_rot, d_scale = 0.0, 0.0, 0.0
+        out = rp.render_reference(wl.ref_mod, cam, pc, wl.bg, d_xyz, d_rot, d_scale)
+        wl.last_out = out
+        if gt_ready is not None:
+            torch.cuda.current_stream().wait_event(gt_ready)
+        if wl.loss_kind == "train":
+            from oracle import loss_oracle as lo      # eager restatement of utils/loss_utils.py + train_gui.py:292-313
+            loss = lo.surfel_loss(out["render"], gt, out["rend_normal"], out["surf_normal"], out["rend_dist"], *TRAIN_LAMBDAS)[0]
+        else:
+            loss = synthetic_loss(out, wl.wts, gt)
+    with mark("backward"):
+        loss.backward()
     return loss
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# rasterizer-only comparison (north_star: ">= 3x the reference diff-surfel-rasterization fwd+bwd at 300 k / 800x800")
+# ----------------------------------------------------------------------------------------------------------------
+def raster_only(cfg_name: str, device, impl: str, ref_mod=None, n_views: int = 10, reps: int = 3) -> dict:
+    """fwd+bwd of the rasterizer OP ALONE through the reference's own module interface
+    (`GaussianRasterizer(settings)(means3D, means2D, shs, opacities, scales, rotations)` -> colour + 8 planes, loss = seeded
+    random-weighted sum over all 11 planes, `.backward()`): the scene of `cfg_name` with the deformation off (activated
+    parameters as render() would pass them), `n_views` of the bench's cameras, `reps` passes, eager launches with the
+    op's default settings in both arms (ours: per-tile binning, synchronous instance count — exactly what a trainer that
+    only swaps the package gets).  CUDA events over the whole loop, one synchronisation at the end."""
+    if impl == "ours":
+        import diff_surfel_rasterization as mod
+    else:
+        mod = ref_mod
+    cfg = syn.CONFIGS[cfg_name]
+    sc = syn.make_scene(cfg["P"], cfg["seed"], cfg["s_med"])
+    act = syn.activated(sc)
+    T = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32, device=device)
+    ins = {k: T(v).requires_grad_(True) for k, v in act.items()}
+    cams = syn.fibonacci_cameras(N_VIEWS, cfg["W"], cfg["H"])
+    views = [(i * 7 + 3) % N_VIEWS for i in range(n_views)]
+    g = torch.Generator().manual_seed(17)
+    gc = (torch.randn((3, cfg["H"], cfg["W"]), generator=g) / (cfg["H"] * cfg["W"])).to(device)
+    go = (torch.randn((8, cfg["H"], cfg["W"]), generator=g) / (cfg["H"] * cfg["W"])).to(device)
+    bg = torch.zeros(3, device=device)
+    settings = []
+    for v in views:
+        c = cams[v]
+        settings.append(mod.GaussianRasterizationSettings(
+            image_height=c.image_height, image_width=c.image_width, tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=bg, scale_modifier=1.0,
+            viewmatrix=T(c.world_view_transform), projmatrix=T(c.full_proj_transform), sh_degree=3, campos=T(c.camera_center),
+            prefiltered=False, debug=False))
+
+    def one(rs):
+        for t in ins.values():
+            t.grad = None
+        m2d = torch.zeros_like(ins["means3D"], requires_grad=True)
+        color, radii, allmap = mod.GaussianRasterizer(rs)(means3D=ins["means3D"], means2D=m2d, shs=ins["shs"], opacities=ins["opacities"],
+                                                          scales=ins["scales"], rotations=ins["rotations"])
+        ((color * gc).sum() + (allmap * go).sum()).backward()
+
+    for rs in settings[:3]:
+        one(rs)
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        for rs in settings:
+            one(rs)
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / (reps * len(settings))
+    return {"ms": ms, "frames_per_s": 1e3 / ms, "workload": f"{cfg_name} scene, deformation off: {cfg['P']} surfels, SH3, {cfg['W']}x{cfg['H']}, "
+            f"{len(settings)} views x {reps}, rasterizer op fwd+bwd through GaussianRasterizer (eager, default settings)"}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -310,6 +434,11 @@ def main():
     ap.add_argument("--loss", choices=["synthetic", "train"], default="synthetic",
                     help="synthetic: seeded random-weighted sum + L1 (SURVEY 8(d), the headline); train: the reference's training loss "
                          "(L1 + D-SSIM + normal + distortion), fused kernel in our arm, eager torch in the reference arm")
+    ap.add_argument("--train", action="store_true",
+                    help="C4-style training step (train_gui.py:292-432): --loss train + densification statistics (all-reduced across "
+                         "ranks) + max-radii bookkeeping + the optimiser steps of both parameter sets, all inside the timed step; "
+                         "ours: FusedAdam (1 launch per optimiser), reference arm: torch.optim.Adam as the reference runs it")
+    ap.add_argument("--no-raster-only", action="store_true", help="skip the rasterizer-only comparison block")
     ap.add_argument("--early-allreduce", type=int, default=1, help="1 (default): start the all-reduce of the surfel-table gradients right after the rasterizer backward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sync-count", action="store_true",
@@ -323,6 +452,8 @@ def main():
     ap.add_argument("--no-clocks", action="store_true", help="diagnosis only: do not sample clocks during the timed region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.train:
+        args.loss = "train"
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -380,6 +511,8 @@ def main():
         if wl.use_deform:
             build_deform_reference(wl)
         step_fn = step_reference
+        wl.ref_timer = RefStageTimer(wl.ref_mod)
+        wl.ref_timer.install()
         impl_note = "unmodified reference CUDA rasterizer (oracle/_ref) inside the reference's eager-torch pipeline (oracle/reference_pipeline.py)"
 
     from d2gs_b200 import dist as ddist
@@ -393,6 +526,50 @@ def main():
 
     def view_index(step):
         return ddist.view_for(step, rank, world, N_VIEWS)
+
+    # ---- training tail (--train): what train_gui.py does between loss.backward() and the next iteration (:388-432)
+    train_tail = None
+    if args.train:
+        pc = wl.pc
+        P_ = pc._xyz.shape[0]
+        # learning rates of arguments/__init__.py scaled by 1e-3: the optimiser does the same work per step, but 100+ steps
+        # against a random target image must not dissolve the synthetic scene the metric is quoted on
+        LR = 1e-3
+        groups = [{"params": [pc._xyz], "lr": 1.6e-4 * 5 * LR, "name": "xyz"}, {"params": [pc._features_dc], "lr": 2.5e-3 * LR, "name": "f_dc"},
+                  {"params": [pc._features_rest], "lr": 2.5e-3 / 20 * LR, "name": "f_rest"}, {"params": [pc._opacity], "lr": 0.05 * LR, "name": "opacity"},
+                  {"params": [pc._scaling], "lr": 5e-3 * LR, "name": "scaling"}, {"params": [pc._rotation], "lr": 1e-3 * LR, "name": "rotation"},
+                  {"params": [pc.feature], "lr": 1e-2 * LR, "name": "feature"}]
+        dgroups = [{"params": list(wl.deform_parameters()), "lr": 1.6e-4 * 5 * LR, "name": "deform"}] if wl.use_deform else []
+        if args.impl == "ours":
+            from d2gs_b200.optim import FusedAdam, add_densification_stats
+            opt_s = FusedAdam(groups, lr=0.0, eps=1e-15)
+            opt_d = FusedAdam(dgroups, lr=0.0, eps=1e-15) if dgroups else None
+        else:
+            opt_s = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+            opt_d = torch.optim.Adam(dgroups, lr=0.0, eps=1e-15) if dgroups else None
+        accum = torch.zeros((P_, 1), device=device)
+        denom = torch.zeros((P_, 1), device=device)
+        pc.max_radii2D = torch.zeros((P_,), dtype=torch.int32, device=device)
+
+        def train_tail():
+            out = wl.last_out
+            vs, vis, radii = out["viewspace_points"], out["visibility_filter"], out["radii"]
+            if world > 1:
+                # replicas must take identical densification decisions: SUM of the per-view statistics, MAX of the radii
+                gn = torch.linalg.vector_norm(vs.grad[:, :2], dim=-1)
+                a_, c_, r_ = ddist.reduce_densification_stats(gn, vis, radii)
+                accum.add_(a_.view(-1, 1)); denom.add_(c_.view(-1, 1))
+                torch.maximum(pc.max_radii2D, r_.to(pc.max_radii2D.dtype), out=pc.max_radii2D)
+            elif args.impl == "ours":
+                add_densification_stats(accum, denom, vs, vis)
+                torch.maximum(pc.max_radii2D, radii * vis, out=pc.max_radii2D)
+            else:
+                accum[vis] += torch.norm(vs.grad[vis, :2], dim=-1, keepdim=True)       # scene/gaussian_model.py:484-486
+                denom[vis] += 1
+                pc.max_radii2D[vis] = torch.max(pc.max_radii2D[vis], radii[vis])     # train_gui.py:389-391
+            opt_s.step()
+            if opt_d is not None:
+                opt_d.step()
 
     # One device camera whose tensors are views of a single 36-float block (view 16 | proj 16 | centre 3 | time 1): a step
     # selects its view with ONE small copy into it — from the device-resident table (`value`) or from pinned host memory (`e2e`).
@@ -446,6 +623,8 @@ def main():
             g.replay()
         else:
             step_body(e2e)
+        if train_tail is not None:
+            train_tail()      # eager: the Adam step sizes are host-computed per step (bias correction), 2 launches
         if e2e:
             torch.cuda.current_stream().synchronize()    # device -> host read of the step's result
             return float(loss_host[0])
@@ -532,12 +711,13 @@ def main():
     # per-stage CUDA-event timers (roofline) and launch counts: K eager steps of the same workload, stage events around
     # every launch.  (When the timed region replays a CUDA graph it contains the same launches, but events inside a graph
     # cannot be read per launch, so the stage timers run right after it.)
+    ref_stages = None
     if args.impl == "ours":
         from d2gs_b200 import _lib, raster
         if graphed:
             graphs.clear()
-            for s in range(3):
-                run_step(s)
+            for s_ in range(3):
+                run_step(s_)
             _lib.profile_collect()
             _lib.profile_enable(True)
             ms_eager, _ = timed(args.steps, False, args.warmup)
@@ -547,6 +727,40 @@ def main():
         R = raster.last_num_rendered(device, cfg["P"], cfg["W"], cfg["H"])
     else:
         R = None
+        # stage breakdown of the reference arm: the same K steps once more with CUDA events around the eager deformation,
+        # the reference extension's two native calls and the step (not part of the timed region above)
+        wl.ref_timer.on = True
+        n_st = min(args.steps, 20)
+        for s_ in range(n_st):
+            with wl.ref_timer.mark("step"):
+                run_step(args.warmup + s_)
+        ref_stages = wl.ref_timer.collect(n_st)
+        wl.ref_timer.on = False
+
+    # rasterizer-only fwd+bwd on the same scene with the deformation off (the comparison north_star's ">= 3x" names)
+    ronly = None
+    if rank == 0 and not args.no_raster_only:
+        try:
+            torch.cuda.empty_cache()
+            if args.impl == "ours":
+                from d2gs_b200 import raster as _r
+                _r.set_deferred_count(False)          # the op's default: what a trainer that only swaps the package gets
+                mine = raster_only(args.config, device, "ours")
+                ronly = {"ours_ms": mine["ms"], "ref_ms": None, "ratio": None, "workload": mine["workload"]}
+                # baseline leg (like cpu_baseline): the unmodified reference extension, when it travelled to this box
+                sys.path.insert(0, os.path.join(ROOT, "tests"))
+                import util as tutil
+                ref_mod = tutil.load_reference_ext()
+                if ref_mod is not None:
+                    theirs = raster_only(args.config, device, "reference", ref_mod=ref_mod)
+                    ronly.update(ref_ms=theirs["ms"], ratio=theirs["ms"] / mine["ms"])
+                else:
+                    ronly["note"] = "oracle/_ref not loadable on this box: reference side not timed"
+            else:
+                theirs = raster_only(args.config, device, "reference", ref_mod=wl.ref_mod)
+                ronly = {"ref_ms": theirs["ms"], "workload": theirs["workload"]}
+        except Exception as ex:      # noqa: BLE001 — must not hide the headline number
+            ronly = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
     h2d = 36 * 4 + 3 * wl.H * wl.W * 4
 
     if rank != 0:
@@ -565,22 +779,28 @@ def main():
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic (seeded D-NeRF-shaped scene, random-init deform MLP)",
+           # `config` is the WORKLOAD and is identical in both arms; how each arm executes it is in `execution`
            "config": {"workload": f"{args.config}: {P} surfels + {cfg['n_nodes']} control nodes (K={cfg['K']}, hyper_dim 8, local_frame), "
-                                  f"SH3, {cfg['W']}x{cfg['H']}, {N_VIEWS} views, 1 view/GPU/step, deform+render+loss+backward",
+                                  f"SH3, {cfg['W']}x{cfg['H']}, {N_VIEWS} views, 1 view/GPU/step, deform+render+loss+backward"
+                                  + (" + densification stats + Adam step of all parameters" if args.train else ""),
                       "loss": "seeded random-weighted sum over the render outputs + L1 (SURVEY 8(d))" if args.loss == "synthetic" else
                               "training loss of train_gui.py:292-313: L1 + D-SSIM(0.2) + normal(0.02) + distortion(1000)",
-                      "parallelism": f"view-sharded x{world}" + (" + NCCL all-reduce of the flat gradient bucket" if world > 1 else ""),
-                      "binning": ("global radix sort" if args.tile_sort == 0 else "per-tile buckets + per-tile sort") + ", " +
-                                 ("synchronous count readback" if args.sync_count else "deferred count (no host synchronisation in the step)"),
-                      "launch": ("one CUDA graph per step (captured through the public API)" if graphed else "eager launches") +
-                                (" | e2e: graph incl. H2D/D2H copies" if e2e_graphed else " | e2e: eager"),
+                      "parallelism": f"view-sharded x{world}",
                       "l2_policy": "no explicit flush: per-step working set (params+grads+workspaces ~0.3 GB) exceeds the 126 MB L2 and the view changes every step"},
+           "execution": {"binning": ("reference extension: global radix sort, synchronous count readback" if args.impl == "reference" else
+                                     ("global radix sort" if args.tile_sort == 0 else "per-tile buckets + per-tile sort") + ", " +
+                                     ("synchronous count readback" if args.sync_count else "deferred count (no host synchronisation in the step)")),
+                         "launch": ("one CUDA graph per step (captured through the public API)" if graphed else "eager launches") +
+                                   (" | e2e: graph incl. H2D/D2H copies" if e2e_graphed else " | e2e: eager"),
+                         "collective": ("NCCL all-reduce of the flat gradient bucket" + (", surfel tables early" if args.early_allreduce else "")) if world > 1 and args.impl == "ours"
+                                       else ("rank 0 only (the reference is single-GPU)" if world > 1 else "none")},
            "clocks": clocks,
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps}}
     if args.impl == "reference":
         out["impl"] = "reference"
         out["note"] = impl_note
         out["gpu_launches"] = 0
+        out["stages_ms"] = ref_stages
         out["cpu_baseline"] = {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
                                "sample": "the reference has no CPU rasterizer (rasterize_points.cu:27-28 asserts CUDA); this arm runs the unmodified reference CUDA extension on the same B200"}
     else:
@@ -617,11 +837,15 @@ def main():
         if args.tile_sort != 0:   # tile-bucketed binning (library default): count + scan | scatter | per-tile sort (2 kernels), no CUB
             mine_kernels.update({"scan": 2, "duplicate": 1, "sort": 2})
         out["gpu_launches"] = int(sum(stage[k][1] * n for k, n in mine_kernels.items() if k in stage))
+        if args.train:      # + FusedAdam (one launch per optimiser) and the densification-statistics kernel (single GPU)
+            out["gpu_launches"] += args.steps * ((2 if wl.use_deform else 1) + (1 if world == 1 else 0))
         if world == 1 and not args.no_cpu_baseline:
             try:
                 out["cpu_baseline"] = cpu_baseline(args.config)
             except Exception as ex:   # the oracle is a checker; its absence must not hide the GPU number
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+    if ronly is not None:
+        out["raster_only"] = ronly
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

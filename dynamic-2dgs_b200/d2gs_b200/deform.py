@@ -7,10 +7,13 @@ Mirrors the reference interface (paths relative to /root/reference):
                            ``cal_nn_weight``, ``node_deform``, ``query_network``, ``expand_time``, state-dict keys
                            (``nodes``, ``_node_radius``, ``_node_weight``, ``network.*``, buffer ``inited``)
   * ``DeformModel``        scene/deform_model.py:13-72   ``step(xyz, time_emb, iteration=0, **kwargs)``
-``install_into_reference()`` registers the classes in ``scene.deform_model.model_dict`` so train_gui.py runs unchanged.
-
-Out of scope here: ARAP regularisers, node densification/pruning, the interactive
-editing branches (node_trans_bias / animation_d_values), hash-grid and skinning variants — they raise.
+Two ways to use it:
+  * stand-alone (no reference tree): the classes above, with plain-torch versions of the regularisers
+    (``arap_loss`` / ``elastic_loss`` / ``acc_loss``) and of ``cal_nn_weight`` for the calls outside the fused kernel;
+  * ``install_into_reference()`` (reference tree importable): SUBCLASSES of the reference's own ``ControlNodeWarp`` /
+    ``DeformNetwork`` that override only ``forward`` / ``cal_nn_weight`` for the configurations the CUDA kernels cover and
+    inherit everything else (``as_gaussians``, ``densify``, ``arap_loss``, editing branches, ``gs_*`` state) — registered
+    in ``scene.deform_model.model_dict`` so train_gui.py runs unchanged.
 """
 from __future__ import annotations
 
@@ -335,19 +338,74 @@ def get_embedder(multires, i=1):
     return e, e.out_dim
 
 
-class DeformNetwork(nn.Module):
-    """Reference: utils/time_utils.py:310-458.  The dense layers are plain GEMMs on M (<= a few thousand) rows."""
+class _FusedNetworkMixin:
+    """Fast path of ``DeformNetwork.forward`` (the fused CUDA MLP); everything it does not cover goes to the next class
+    in the MRO — the eager layers below, or the reference's own class (``bind_reference``)."""
+
+    use_fused = True   # set False to force the eager torch layers (tests compare the two)
+
+    def _fusable(self, x, t) -> bool:
+        if not (self.use_fused and torch.is_tensor(x) and x.is_cuda and x.dim() == 2 and x.shape[1] == 3):
+            return False
+        if getattr(self, "pred_color", False) or getattr(self, "progressive_brand_time", False):
+            return False
+        xyz_ch = 63                                              # multires 10 on 3 coordinates, input included
+        in0 = xyz_ch + (30 if self.is_blender else 21)           # timenet output | PE(t; 10 frequencies)
+        lin = self.linear
+        return (self.D == 8 and self.W == 256 and list(self.skips) == [4] and len(lin) == 8 and lin[0].in_features == in0
+                and lin[5].in_features == 256 + in0 and t.shape[-1] == 1 and (t.numel() == x.shape[0] or t.numel() == 1))
+
+    def _forward_fused(self, x, t):
+        self._packed = None
+        heads = [self.gaussian_warp, self.gaussian_scaling, self.gaussian_rotation]
+        if self.local_frame:
+            heads.append(self.local_rotation)
+        if self.pred_opacity:
+            heads.append(self.gaussian_opacity)
+        hw = torch.cat([h.weight for h in heads], 0)
+        hb = torch.cat([h.bias for h in heads], 0)
+        ws = []
+        if self.is_blender:
+            ws += [self.timenet[0].weight, self.timenet[0].bias, self.timenet[2].weight, self.timenet[2].bias]
+        for l in self.linear:
+            ws += [l.weight, l.bias]
+        out, hidden = _FusedMLP.apply(x, t, self.is_blender, int(hw.shape[0]), *ws, hw, hb)
+        scaling = out[:, 3:5]
+        if self.max_d_scale > 0:
+            scaling = torch.tanh(scaling) * math.log(self.max_d_scale)
+        ret = {'d_xyz': out[:, 0:3], 'd_rotation': out[:, 5:9], 'd_scaling': scaling, 'hidden': hidden, 'd_opacity': None, 'd_color': None}
+        c = 9
+        if self.local_frame:
+            ret['local_rotation'] = out[:, c:c + 4]; c += 4
+        if self.max_d_scale <= 0:
+            # the un-sliced head matrix + column map, so ControlNodeWarp can blend without slicing copies
+            self._packed = (out, (0, 5, 3, 9 if self.local_frame else -1))
+        if self.pred_opacity:
+            ret['d_opacity'] = out[:, c:c + 1]
+        return ret
+
+    def forward(self, x, t, **kwargs):
+        if self._fusable(x, t):
+            return self._forward_fused(x, t)
+        return super().forward(x, t, **kwargs)
+
+
+class _EagerDeformNetwork(nn.Module):
+    """Reference: utils/time_utils.py:310-458 — constructor (parameter names / shapes / initialisers are the state-dict
+    contract) and the eager layer sequence."""
 
     def __init__(self, D=8, W=256, input_ch=3, output_ch=59, t_multires=6, multires=10, is_blender=False,
                  local_frame=False, pred_opacity=False, pred_color=False, resnet_color=True, hash_color=False,
                  color_wrt_dir=False, progressive_brand_time=False, max_d_scale=-1, **kwargs):
         super().__init__()
         if pred_color or hash_color or progressive_brand_time:
-            raise NotImplementedError("pred_color / hash_color / progressive_brand_time are outside the hot path")
+            raise NotImplementedError("pred_color / hash_color / progressive_brand_time are outside the hot path (use the "
+                                      "reference classes through d2gs_b200.install_into_reference())")
         self.name = 'mlp'
         self.D, self.W = D, W
         self.t_multires = 6 if is_blender else 10
         self.skips = [D // 2]
+        self.progressive_brand_time = False
         self.embed_time_fn, time_input_ch = get_embedder(self.t_multires, 1)
         self.embed_fn, xyz_input_ch = get_embedder(multires, 3)
         self.input_ch = xyz_input_ch + time_input_ch
@@ -388,45 +446,7 @@ class DeformNetwork(nn.Module):
     def trainable_parameters(self):
         return [{'params': list(self.parameters()), 'name': 'mlp'}]
 
-    use_fused = True   # set False to force the eager torch layers (tests compare the two)
-
-    def _fusable(self, x, t) -> bool:
-        return (self.use_fused and x.is_cuda and self.D == 8 and self.W == 256 and self.skips == [4] and x.dim() == 2 and x.shape[1] == 3
-                and isinstance(self.embed_fn, Embedder) and self.embed_fn.multires == 10 and t.shape[-1] == 1
-                and (t.numel() == x.shape[0] or t.numel() == 1))
-
-    def _forward_fused(self, x, t):
-        self._packed = None
-        heads = [self.gaussian_warp, self.gaussian_scaling, self.gaussian_rotation]
-        if self.local_frame:
-            heads.append(self.local_rotation)
-        if self.pred_opacity:
-            heads.append(self.gaussian_opacity)
-        hw = torch.cat([h.weight for h in heads], 0)
-        hb = torch.cat([h.bias for h in heads], 0)
-        ws = []
-        if self.is_blender:
-            ws += [self.timenet[0].weight, self.timenet[0].bias, self.timenet[2].weight, self.timenet[2].bias]
-        for l in self.linear:
-            ws += [l.weight, l.bias]
-        out, hidden = _FusedMLP.apply(x, t, self.is_blender, int(hw.shape[0]), *ws, hw, hb)
-        scaling = out[:, 3:5]
-        if self.max_d_scale > 0:
-            scaling = torch.tanh(scaling) * math.log(self.max_d_scale)
-        ret = {'d_xyz': out[:, 0:3], 'd_rotation': out[:, 5:9], 'd_scaling': scaling, 'hidden': hidden, 'd_opacity': None, 'd_color': None}
-        c = 9
-        if self.local_frame:
-            ret['local_rotation'] = out[:, c:c + 4]; c += 4
-        if self.max_d_scale <= 0:
-            # the un-sliced head matrix + column map, so ControlNodeWarp can blend without slicing copies
-            self._packed = (out, (0, 5, 3, 9 if self.local_frame else -1))
-        if self.pred_opacity:
-            ret['d_opacity'] = out[:, c:c + 1]
-        return ret
-
     def forward(self, x, t, **kwargs):
-        if self._fusable(x, t):
-            return self._forward_fused(x, t)
         t_emb = self.embed_time_fn(t)
         if self.is_blender:
             t_emb = self.timenet(t_emb)
@@ -447,6 +467,11 @@ class DeformNetwork(nn.Module):
 
     def update(self, iteration, *args, **kwargs):
         return
+
+
+class DeformNetwork(_FusedNetworkMixin, _EagerDeformNetwork):
+    """Reference: utils/time_utils.py:310-458.  The dense layers run in the fused CUDA MLP on the M (<= a few thousand,
+    or M*T for the regularisers) node rows; unsupported configurations fall through to the eager layers."""
 
 
 class StaticNetwork(nn.Module):
@@ -488,16 +513,168 @@ def farthest_point_sample(xyz: torch.Tensor, npoint: int) -> torch.Tensor:
     return idx
 
 
-class ControlNodeWarp(nn.Module):
-    """Reference: utils/time_utils.py:770-1233.  Fast path = d_rot_as_res, no editing biases, no skinning/hash."""
+def landmark_interpolate(landmarks, steps, step, interpolation='log'):
+    """Piecewise schedule of the regulariser weights (utils/time_utils.py:485-503): 0 before the first step, the last
+    landmark after the last step, log- or linearly interpolated in between; a non-positive right landmark gives 0."""
+    stage = sum(1 for s_ in steps if step >= s_)
+    if stage == len(steps):
+        return max(0, landmarks[-1])
+    if stage == 0:
+        return 0
+    a, b = landmarks[stage - 1], landmarks[stage]
+    if b <= 0:
+        return 0
+    r = (step - steps[stage - 1]) / (steps[stage] - steps[stage - 1])
+    if interpolation == 'log':
+        return math.exp(math.log(a) * (1 - r) + math.log(b) * r)
+    if interpolation == 'linear':
+        return a * (1 - r) + b * r
+    raise NotImplementedError(f'Unknown interpolation type: {interpolation}')
+
+
+def knn_torch(x: torch.Tensor, y: torch.Tensor, K: int):
+    """K nearest rows of y for every row of x: (squared distances ascending (N,K), indices (N,K) int64).  Plain torch,
+    exhaustive; ties resolved towards the lower index (the published semantics of pytorch3d.ops.knn_points, which the
+    reference calls and this image does not have).  Used off the hot path only (regularisers, editing helpers)."""
+    d = ((x[:, None, :] - y[None, :, :]) ** 2).sum(-1)
+    K = min(K, y.shape[0])
+    # stable sort = lower index first among equal distances
+    order = torch.sort(d, dim=1, stable=True)
+    return order.values[:, :K], order.indices[:, :K]
+
+
+def arap_error_torch(nodes_seq: torch.Tensor, K: int = 10, radius: float = 0.1, least_edge_num: int = 3, sample_num: int = 512):
+    """As-rigid-as-possible energy of a node trajectory (T, M, 3) against its first frame: the regulariser of
+    ``ControlNodeWarp.arap_loss`` (utils/time_utils.py:1080-1089) = connectivity from the K nearest nodes of frame 0
+    (``cal_connectivity_from_points``, utils/deform_utils.py:58-113: the first ``least_edge_num`` neighbours always, the
+    others only inside ``radius``) + per-node best-fit rotation by SVD without gradient and the squared stretch of every
+    edge (``cal_arap_error`` / ``estimate_rotation``, utils/deform_utils.py:130-205; unit edge weights, at most
+    ``sample_num`` randomly drawn nodes).  Dense (M, K) formulation instead of the reference's edge lists."""
+    T, M, _ = nodes_seq.shape
+    p0 = nodes_seq[0]
+    with torch.no_grad():
+        d, idx = knn_torch(p0.detach(), p0.detach(), K + 1)
+        d, idx = d[:, 1:], idx[:, 1:]                       # drop the node itself
+        valid = torch.ones_like(d, dtype=torch.bool)
+        valid[:, least_edge_num:] = d[:, least_edge_num:] < radius ** 2
+        if M > sample_num:
+            sel = torch.randint(0, M, (sample_num,), device=p0.device)
+        else:
+            sel = torch.arange(M, device=p0.device)
+    w = valid[sel].to(p0.dtype)                              # (S, K) unit weights on existing edges
+    edges = lambda v: (v[sel][:, None, :] - v[idx[sel]]) * w[..., None]      # (S, K, 3), zero where there is no edge
+    src = edges(p0)
+    err = p0.new_zeros(())
+    for t in range(1, T):
+        tgt = edges(nodes_seq[t])
+        with torch.no_grad():
+            S = torch.bmm(src.detach().transpose(1, 2), tgt.detach() * w[..., None])          # (S, 3, 3) covariance
+            same = (src.detach() == tgt.detach()).all(dim=2).all(dim=1)
+            S[same] = 0                                       # undeformed neighbourhood -> identity rotation
+            U, sig, V = torch.svd(S)
+            R = torch.bmm(V, U.transpose(1, 2))
+            flip = torch.det(R) <= 0
+            if bool(flip.any()):
+                Um = U.clone()
+                col = torch.argmin(sig[flip], dim=1)
+                rows = torch.nonzero(flip, as_tuple=False).flatten()
+                Um[rows, :, col] *= -1
+                R[flip] = torch.bmm(V[flip], Um[flip].transpose(1, 2))
+        rigid = torch.bmm(R, src.transpose(1, 2)).transpose(1, 2)
+        err = err + (w * ((tgt - rigid) ** 2).sum(dim=2)).sum()
+    return err
+
+
+class _FastNodeWarpMixin:
+    """B200 fast path of ``ControlNodeWarp``: ``forward`` and ``cal_nn_weight`` through the fused CUDA kernels
+    (libd2gs.so).  Calls it does not cover — editing biases, skinning / hash-grid variants, external node sets — go to
+    the next class in the MRO: the reference's own ControlNodeWarp when bound to it (``bind_reference``), else the
+    stand-alone base below."""
+
+    ORDER_REFRESH = 64   # forward calls between two rebuilds of the Morton processing order
+
+    def _processing_order(self, x):
+        """Cached spatial processing order of the surfels (speed only: a stale order is still a valid permutation, the
+        centres move by a learning-rate step per iteration).  Rebuilt when the surfel count or device changes
+        (densification / pruning) and every ORDER_REFRESH calls."""
+        if not x.is_cuda:
+            return None
+        c = getattr(self, "_order_cache", None)
+        P = int(x.shape[0])
+        if c is None or c[0] != P or c[1] != x.device or c[3] >= self.ORDER_REFRESH:
+            c = [P, x.device, processing_order(x), 0]
+            object.__setattr__(self, "_order_cache", c)
+        c[3] += 1
+        return c[2]
+
+    def _fast_variant(self) -> bool:
+        return (self.d_rot_as_res and not getattr(self, "skinning", False) and not getattr(self, "use_hash", False)
+                and not getattr(self, "pred_color", False) and not getattr(self, "cached_nn_weight", False))
+
+    def cal_nn_weight(self, x, K=None, feature=None, nodes=None, gs_kernel=True, temperature=1.):
+        """Reference: utils/time_utils.py:934-967.  Returns (nn_weight (P,K), nn_dist (P,K), nn_idx (P,K) int64)."""
+        if not (gs_kernel and nodes is None and torch.is_tensor(x) and x.is_cuda and self._fast_variant()):
+            return super().cal_nn_weight(x, K=K, feature=feature, nodes=nodes, gs_kernel=gs_kernel, temperature=temperature)
+        K = self.K if K is None else K
+        M = self.nodes.shape[0]
+        zero = lambda c: torch.zeros((M, c), dtype=torch.float32, device=x.device)
+        out = node_blend(x, feature, self.nodes, self._node_radius, self._node_weight.reshape(-1) if self.with_node_weight else None,
+                         zero(3), zero(4), zero(2), None, None, K, self.hyper_dim)
+        return out["nn_weight"], out["nn_dist"], out["nn_idx"]
+
+    def forward(self, x, t, feature, motion_mask, iteration=0, is_training=True, node_trans_bias=None,
+                node_scaling_bias=None, animation_d_values=None, **kwargs):
+        if (node_trans_bias is not None or animation_d_values is not None or not torch.is_tensor(x) or not x.is_cuda
+                or not self._fast_variant()):
+            return super().forward(x, t, feature, motion_mask, iteration=iteration, is_training=is_training,
+                                   node_trans_bias=node_trans_bias, node_scaling_bias=node_scaling_bias,
+                                   animation_d_values=animation_d_values, **kwargs)
+        if t.dim() == 0:
+            t = self.expand_time(t)
+        x = x.detach()
+        net = self.network
+        if hasattr(net, '_packed'):
+            net._packed = None
+        node_attrs = self.node_deform(t=t, **kwargs)
+        packed = getattr(net, '_packed', None)
+        wl = self._node_weight.reshape(-1) if self.with_node_weight else None
+        mm = motion_mask if torch.is_tensor(motion_mask) else None
+        order = self._processing_order(x)
+        if packed is not None and t.dim() == 2 and packed[0].shape[0] == self.nodes.shape[0]:
+            net._packed = None
+            out = node_blend_packed(x, feature, self.nodes, self._node_radius, wl, packed[0], packed[1], mm, self.K, self.hyper_dim,
+                                    order=order)
+        else:
+            out = node_blend(x, feature, self.nodes, self._node_radius, wl,
+                             node_attrs['d_xyz'], node_attrs['d_rotation'], node_attrs['d_scaling'],
+                             node_attrs.get('local_rotation') if self.local_frame else None, mm, self.K, self.hyper_dim,
+                             order=order)
+        ret = {'d_xyz': out['d_xyz'], 'd_rotation': out['d_rotation'], 'd_scaling': out['d_scaling'],
+               'd_opacity': None, 'd_color': None}
+        if self.pred_opacity:
+            w, idx = out['nn_weight'], out['nn_idx']
+            ret['d_opacity'] = (node_attrs['d_opacity'][idx] * w[..., None]).sum(dim=1) * motion_mask
+        # regulariser schedule of the reference (utils/time_utils.py:1228-1232)
+        self.reg_loss = 0.
+        lam = landmark_interpolate(self.lambda_arap_landmarks, self.lambda_arap_steps, iteration)
+        if self.training and lam > 0 and is_training:
+            self.reg_loss = self.reg_loss + self.arap_loss() * lam
+        return ret
+
+
+class _StandaloneNodeWarp(nn.Module):
+    """Reference: utils/time_utils.py:770-1233 without the reference tree: constructor / bookkeeping (parameter names and
+    shapes are the state-dict contract), plain-torch versions of the calls outside the fast path.  The warm-up phase's
+    node Gaussians (``as_gaussians``), node densification and the interactive-editing branches need the reference's
+    ``scene`` package: bind to it with ``d2gs_b200.install_into_reference()`` and those members are the reference's own."""
 
     def __init__(self, is_blender, init_pcl=None, node_num=512, K=3, use_hash=False, hash_time=False,
                  enable_densify_prune=False, pred_opacity=False, pred_color=False, with_arap_loss=False,
                  with_node_weight=True, local_frame=False, d_rot_as_res=True, skinning=False, hyper_dim=2,
                  progressive_brand_time=False, max_d_scale=-1, is_scene_static=False, **kwargs):
         super().__init__()
-        if use_hash or skinning or pred_color or not d_rot_as_res:
-            raise NotImplementedError("use_hash / skinning / pred_color / d_rot_as_res=False are outside the B200 hot path")
+        if use_hash or skinning or pred_color:
+            raise NotImplementedError("use_hash / skinning / pred_color need the reference classes: d2gs_b200.install_into_reference()")
         self.K = K
         self.use_hash, self.hash_time = use_hash, hash_time
         self.enable_dp = enable_densify_prune
@@ -513,6 +690,11 @@ class ControlNodeWarp(nn.Module):
         self.is_scene_static = is_scene_static
         self.skinning = skinning
         self.with_arap_loss = with_arap_loss and not is_scene_static
+        if self.with_arap_loss:      # utils/time_utils.py:790-795
+            self.lambda_arap_landmarks = [1e-4, 1e-4, 1e-5, 1e-5, 0]
+            self.lambda_arap_steps = [0, 5000, 10000, 20000, 20001]
+        else:
+            self.lambda_arap_landmarks, self.lambda_arap_steps = [0], [0]
         if self.is_scene_static:
             self.network = StaticNetwork(return_tensors=True)
         else:
@@ -540,6 +722,9 @@ class ControlNodeWarp(nn.Module):
         return ['nodes', '_node_radius', '_node_weight'] if self.with_node_weight else ['nodes', '_node_radius']
 
     def load_state_dict(self, state_dict: Mapping[str, Any], strict: bool = True):
+        """utils/time_utils.py:845-866: node tables may change shape (densified checkpoints); ``gs_*`` entries are the
+        node Gaussians of the warm-up phase — kept (``gs_state``) and re-emitted by ``state_dict`` so a checkpoint
+        round-trips, applied to ``self.gs`` when one exists."""
         state_dict = dict(state_dict)
         for key in self.param_names:
             if key in state_dict:
@@ -549,8 +734,32 @@ class ControlNodeWarp(nn.Module):
                 else:
                     getattr(self, key).data = v
         for key in [k for k in state_dict if k.startswith('gs_')]:
-            state_dict.pop(key)   # node Gaussians of the warm-up phase are not part of the hot path
+            v = state_dict.pop(key)
+            self.gs_state[key] = v
+            if self.gs is not None:
+                try:
+                    getattr(self.gs, key[3:]).data = v
+                except Exception:
+                    setattr(self.gs, key[3:], v)
         return super().load_state_dict(state_dict=state_dict, strict=False)
+
+    @property
+    def gs_state(self):
+        d = self.__dict__.get('_gs_state')
+        if d is None:
+            d = {}
+            object.__setattr__(self, '_gs_state', d)
+        return d
+
+    def state_dict(self, *args, **kwargs):
+        sd = super().state_dict(*args, **kwargs)
+        if self.gs is not None and hasattr(self.gs, 'param_names'):
+            for name in self.gs.param_names():
+                sd['gs_' + name] = getattr(self.gs, name)
+        else:
+            for k, v in self.gs_state.items():
+                sd[k] = v
+        return sd
 
     @property
     def node_radius(self):
@@ -607,70 +816,77 @@ class ControlNodeWarp(nn.Module):
         values = self.query_network(x=nodes, t=t, **kwargs)
         return {k: (v.view(*tshape[:-1], v.shape[-1]) if v is not None else None) for k, v in values.items()}
 
-    ORDER_REFRESH = 64   # forward calls between two rebuilds of the Morton processing order
-
-    def _processing_order(self, x):
-        """Cached spatial processing order of the surfels (speed only: a stale order is still a valid permutation, the
-        centres move by a learning-rate step per iteration).  Rebuilt when the surfel count or device changes
-        (densification / pruning) and every ORDER_REFRESH calls."""
-        if not x.is_cuda:
-            return None
-        c = getattr(self, "_order_cache", None)
-        P = int(x.shape[0])
-        if c is None or c[0] != P or c[1] != x.device or c[3] >= self.ORDER_REFRESH:
-            c = [P, x.device, processing_order(x), 0]
-            object.__setattr__(self, "_order_cache", c)
-        c[3] += 1
-        return c[2]
-
     def cal_nn_weight(self, x, K=None, feature=None, nodes=None, gs_kernel=True, temperature=1.):
-        """Reference: utils/time_utils.py:934-967.  Returns (nn_weight (P,K), nn_dist (P,K), nn_idx (P,K) int64)."""
-        if not gs_kernel or nodes is not None:
-            raise NotImplementedError("softmax kernel / external node sets belong to the editing branches")
+        """Plain-torch version of utils/time_utils.py:934-967 for the calls the fused kernel does not take: CPU tensors,
+        an external node set (``nodes=``), the softmax kernel (``gs_kernel=False``)."""
+        if self.hyper_dim > 0 and feature is not None:
+            x = torch.cat([x.detach(), feature[..., :self.hyper_dim]], dim=-1)
         K = self.K if K is None else K
-        M = self.nodes.shape[0]
-        zero = lambda c: torch.zeros((M, c), dtype=torch.float32, device=x.device)
-        out = node_blend(x, feature, self.nodes, self._node_radius, self._node_weight.reshape(-1) if self.with_node_weight else None,
-                         zero(3), zero(4), zero(2), None, None, K, self.hyper_dim)
-        return out["nn_weight"], out["nn_dist"], out["nn_idx"]
+        nd = self.nodes[..., :3].detach() if nodes is None else nodes[..., :3]
+        if feature is not None:
+            nd = torch.cat([nd[..., :3].detach(), self.nodes[..., 3:]], dim=-1)
+        nn_dist, nn_idx = knn_torch(x, nd, K)
+        if not gs_kernel:
+            return torch.softmax(-nn_dist / temperature, dim=-1), nn_dist, nn_idx
+        w = torch.exp(-nn_dist / (2 * self.node_radius[nn_idx] ** 2))
+        if self.with_node_weight:
+            w = w * self.node_weight[nn_idx][..., 0]
+        w = w + 1e-7
+        return w / w.sum(dim=-1, keepdim=True), nn_dist, nn_idx
 
     def forward(self, x, t, feature, motion_mask, iteration=0, is_training=True, node_trans_bias=None,
                 node_scaling_bias=None, animation_d_values=None, **kwargs):
-        if node_trans_bias is not None or animation_d_values is not None:
-            raise NotImplementedError("interactive-editing branches (node_trans_bias / animation_d_values) are out of scope")
-        if t.dim() == 0:
-            t = self.expand_time(t)
-        x = x.detach()
-        net = self.network
-        if hasattr(net, '_packed'):
-            net._packed = None
-        node_attrs = self.node_deform(t=t, **kwargs)
-        packed = getattr(net, '_packed', None)
-        wl = self._node_weight.reshape(-1) if self.with_node_weight else None
-        mm = motion_mask if torch.is_tensor(motion_mask) else None
-        order = self._processing_order(x)
-        if packed is not None and t.dim() == 2 and packed[0].shape[0] == self.nodes.shape[0]:
-            net._packed = None
-            out = node_blend_packed(x, feature, self.nodes, self._node_radius, wl, packed[0], packed[1], mm, self.K, self.hyper_dim,
-                                    order=order)
-        else:
-            out = node_blend(x, feature, self.nodes, self._node_radius, wl,
-                             node_attrs['d_xyz'], node_attrs['d_rotation'], node_attrs['d_scaling'],
-                             node_attrs.get('local_rotation') if self.local_frame else None, mm, self.K, self.hyper_dim,
-                             order=order)
-        ret = {'d_xyz': out['d_xyz'], 'd_rotation': out['d_rotation'], 'd_scaling': out['d_scaling'],
-               'd_opacity': None, 'd_color': None}
-        if self.pred_opacity:
-            w, idx = out['nn_weight'], out['nn_idx']
-            ret['d_opacity'] = (node_attrs['d_opacity'][idx] * w[..., None]).sum(dim=1) * motion_mask
-        self.reg_loss = 0.
-        return ret
+        raise NotImplementedError(
+            "this call is outside the B200 fast path (CPU tensors, d_rot_as_res=False or the interactive-editing arguments "
+            "node_trans_bias / animation_d_values): bind to the reference classes with d2gs_b200.install_into_reference()")
 
-    def arap_loss(self, *a, **k):
-        raise NotImplementedError("ARAP regularisers (utils/deform_utils.py) are outside the hot path")
+    def arap_loss(self, t=None, delta_t=0.05, t_samp_num=2):
+        """utils/time_utils.py:1080-1089: ARAP energy of the nodes at ``t_samp_num`` random times in a window around t
+        (an (M, T, 1) time batch through ``node_deform`` -> the fused MLP runs on M*T rows)."""
+        dev = self.nodes.device
+        t = torch.rand([], device=dev) if t is None else t.squeeze() + delta_t * (torch.rand([], device=dev) - .5)
+        t_samp = torch.rand(t_samp_num, device=dev) * delta_t + t - .5 * delta_t
+        t_samp = t_samp[None, :, None].expand(self.node_num, t_samp_num, 1)
+        node_trans = self.node_deform(t=t_samp)['d_xyz']
+        nodes_t = self.nodes[:, None, :3].detach() + node_trans      # (M, T, 3)
+        return arap_error_torch(nodes_t.permute(1, 0, 2))
+
+    def elastic_loss(self, t=None, delta_t=0.005, K=2, t_samp_num=8):
+        """utils/time_utils.py:1091-1109."""
+        dev = self.nodes.device
+        t = torch.rand([], device=dev) if t is None else t.squeeze() + delta_t * (torch.rand([], device=dev) - .5)
+        t_samp = torch.rand(t_samp_num, device=dev) * delta_t + t - .5 * delta_t
+        t_samp = t_samp[None, :, None].expand(self.node_num, t_samp_num, 1)
+        nodes_t = self.nodes[:, None, :3].detach() + self.node_deform(t=t_samp)['d_xyz']
+        w, _, idx = self.cal_nn_weight(x=self.nodes[..., :3].detach(), feature=self.nodes[..., 3:], K=K + 1)
+        w, idx = w[:, 1:], idx[:, 1:]
+        var = (nodes_t[idx] - nodes_t[:, None]).norm(dim=-1).var(dim=2)
+        var = var / (var.detach() + 1e-5)
+        return (var * w).sum(dim=1).mean()
+
+    def acc_loss(self, t=None, delta_t=.005):
+        """utils/time_utils.py:1111-1122."""
+        dev = self.nodes.device
+        t = torch.rand([], device=dev) if t is None else t.squeeze() + delta_t * (torch.rand([], device=dev) - .5)
+        t3 = torch.stack([t - delta_t, t, t + delta_t])[None, :, None].expand(self.node_num, 3, 1)
+        nodes_t = self.nodes[:, None, :3].detach() + self.node_deform(t=t3)['d_xyz']
+        acc = (nodes_t[:, 0] + nodes_t[:, 2] - 2 * nodes_t[:, 1]).norm(dim=-1)
+        return (acc / (acc.detach() + 1e-5)).mean()
+
+    @property
+    def as_gaussians(self):
+        raise NotImplementedError("node Gaussians of the warm-up phase are a scene.gaussian_model.StandardGaussianModel: "
+                                  "bind to the reference tree with d2gs_b200.install_into_reference()")
 
     def densify(self, *a, **k):
-        raise NotImplementedError("node densification is outside the hot path")
+        if not self.enable_dp and not k.get('force_dp', False):
+            return                      # the reference returns silently when node densification is off (:1292-1293)
+        raise NotImplementedError("node densification edits the reference trainer's optimiser state: bind to the reference "
+                                  "classes with d2gs_b200.install_into_reference()")
+
+
+class ControlNodeWarp(_FastNodeWarpMixin, _StandaloneNodeWarp):
+    """Reference: utils/time_utils.py:770-1233.  Fast path = d_rot_as_res, no editing biases, no skinning/hash."""
 
 
 model_dict = {'mlp': DeformNetwork, 'node': ControlNodeWarp, 'static': StaticNetwork}
@@ -716,14 +932,68 @@ class DeformModel:
             return True
         return False
 
+    def densify(self, max_grad, x, x_grad, **kwargs):
+        if self.name == 'node':
+            self.deform.densify(max_grad=max_grad, optimizer=self.optimizer, x=x, x_grad=x_grad, **kwargs)
+
     def update(self, iteration):
         self.deform.update(iteration)
 
 
-def install_into_reference():
-    """Register the B200 classes into the reference's ``scene.deform_model.model_dict`` (scene/deform_model.py:10)."""
-    import scene.deform_model as ref_dm   # the reference package must be importable
-    ref_dm.model_dict['node'] = ControlNodeWarp
-    ref_dm.model_dict['mlp'] = DeformNetwork
-    ref_dm.model_dict['static'] = StaticNetwork
+# --------------------------------------------------------------------------------------------------------------
+# binding to the reference tree ("subclass of ControlNodeWarp overriding the forward fast path,
+# falling back to the reference code otherwise; registered via scene.deform_model.model_dict['node']")
+# --------------------------------------------------------------------------------------------------------------
+_BOUND = {}
+
+
+def bind_reference(time_utils_module):
+    """Build the drop-in classes ON TOP of the reference's own (``utils.time_utils``): only ``forward`` /
+    ``cal_nn_weight`` (ControlNodeWarp) and ``forward`` (DeformNetwork) are overridden, and only for the configurations
+    the CUDA kernels cover; ``arap_loss``, ``densify``, ``as_gaussians``, ``init`` (incl. the node Gaussians), the
+    editing branches, ``state_dict`` with its ``gs_*`` keys ... are inherited from the reference unchanged."""
+    key = id(time_utils_module)
+    if key in _BOUND:
+        return _BOUND[key]
+    ref = time_utils_module
+
+    class RefDeformNetwork(_FusedNetworkMixin, ref.DeformNetwork):
+        pass
+
+    class RefControlNodeWarp(_FastNodeWarpMixin, ref.ControlNodeWarp):
+        def __init__(self, *args, **kwargs):
+            super().__init__(*args, **kwargs)
+            if type(self.network) is ref.DeformNetwork:      # same parameters, fused forward
+                self.network.__class__ = RefDeformNetwork
+
+    for c, n in ((RefDeformNetwork, "DeformNetwork"), (RefControlNodeWarp, "ControlNodeWarp")):
+        c.__name__ = c.__qualname__ = n
+    out = {'mlp': RefDeformNetwork, 'node': RefControlNodeWarp, 'static': ref.StaticNetwork}
+    _BOUND[key] = out
+    return out
+
+
+def install_into_reference(patch_renderer: bool = True):
+    """Make an importable reference tree use the B200 path without editing it:
+      * ``scene.deform_model.model_dict`` (scene/deform_model.py:10) gets the classes of ``bind_reference``;
+      * if the ``gaussian_renderer`` that is importable is the REFERENCE's package (this repo's shadow package is not
+        first on sys.path), its ``render`` / ``render_flow`` are replaced by the B200 ones, so
+        ``from gaussian_renderer import render`` (train_gui.py:18, render_mesh.py:16) picks them up.
+    Returns the ``scene.deform_model`` module."""
+    import importlib
+    import importlib.util
+    tu = importlib.import_module("utils.time_utils")
+    ref_dm = importlib.import_module("scene.deform_model")
+    ref_dm.model_dict.update(bind_reference(tu))
+    if patch_renderer:
+        gr = importlib.import_module("gaussian_renderer")
+        here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        if not os.path.abspath(getattr(gr, "__file__", "") or "").startswith(here):
+            # the reference's package: load this repo's implementation under a private name and graft its entry points
+            spec = importlib.util.spec_from_file_location("d2gs_b200._gaussian_renderer",
+                                                          os.path.join(here, "gaussian_renderer", "__init__.py"))
+            ours = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(ours)
+            gr.render_reference, gr.render_flow_reference = gr.render, getattr(gr, "render_flow", None)
+            gr.render, gr.render_flow = ours.render, ours.render_flow
     return ref_dm

@@ -25,10 +25,11 @@ def views_of_rank(rank: int, world: int, n_views: int) -> List[int]:
 
 
 class _Slot:
-    __slots__ = ("view", "claimed", "dirty", "large")
+    __slots__ = ("view", "claimed", "dirty", "large", "early_group")
 
     def __init__(self, view, large):
         self.view, self.claimed, self.dirty, self.large = view, False, False, large
+        self.early_group = None      # ("default" | process group) when the slot is part of an early all-reduce
 
 
 _SLOTS = {}   # data_ptr of a parameter -> _Slot of the bucket that owns it
@@ -50,6 +51,21 @@ def claim(t: Optional[torch.Tensor], zeroed: bool) -> Optional[torch.Tensor]:
         s.view.zero_()
     s.claimed, s.dirty = True, True
     return s.view.view(t.shape)
+
+
+def reduces_early(t: Optional[torch.Tensor]) -> bool:
+    """True when the bucket slot of parameter ``t`` will be summed across ranks by the EARLY all-reduce that
+    ``grads_ready("raster")`` launches (in place, asynchronously).  From that moment the slot must not be read by the
+    rest of the backward pass: a wrapper that hands the same gradient to a second consumer (the deformation deltas of
+    ``_xyz`` / ``_rotation``) gives that consumer a private copy instead of an alias."""
+    if t is None or not _SLOTS:
+        return False
+    s = _SLOTS.get(t.data_ptr())
+    if s is None or s.early_group is None:
+        return False
+    if not (dist.is_available() and dist.is_initialized()):
+        return False
+    return dist.get_world_size(None if s.early_group == "default" else s.early_group) > 1
 
 
 _ACTIVE = []  # weak references to the direct-mode buckets, for grads_ready()
@@ -109,6 +125,7 @@ class FlatGradBucket:
             if is_early(p):
                 if self.early_begin is None:
                     self.early_begin = off
+                sl.early_group = "default"
                 self.early_slots.append(sl)
             off += pad(p.numel())
         self._early_work = None
@@ -152,6 +169,8 @@ class FlatGradBucket:
     def set_group(self, group) -> None:
         """Process group used by the early all-reduce (default group when never called)."""
         self._group = group
+        for sl in self.early_slots:
+            sl.early_group = "default" if group is None else group
 
     def _on_stage(self, stage: str) -> None:
         if stage != "raster" or not self.early_slots or self._early_work is not None:

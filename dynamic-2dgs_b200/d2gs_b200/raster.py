@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+from collections import OrderedDict
 from typing import Optional
 
 import torch
@@ -17,15 +18,36 @@ from . import _lib
 
 # (device index, P, W, H) -> last known num_rendered; sizes the binning workspace so forward is one C call
 _R_HINT: dict = {}
-# Deferred-count mode (include/d2gs.h "binning_capacity"): after `warmup` synchronous frames of a (device, P, W, H)
-# combination the forward stops reading the instance count back and bins into max-seen-count * margin slots, so the host
-# runs ahead of the device.  Counts arrive through pinned memory and are folded in by later calls; a frame that would
-# overflow its slots renders NaN and the next rasterizer call raises (the following frames use the larger count).
-_DEFERRED = {"on": True, "warmup": 4, "margin": 1.5}
-_TRACK: dict = {}          # hint key -> _CountTrack
-# (device index, P) -> zeroed (P,20) fp32 scratch the blend backward accumulates into (left zero by the library)
-_GRAD_SCRATCH: dict = {}
+# Deferred-count mode (include/d2gs.h "binning_capacity"), OPT-IN (set_deferred_count(True); always used while a CUDA graph
+# is being captured): after `warmup` synchronous frames of a (device, P, W, H) combination the forward stops reading the
+# instance count back and bins into max-seen-count * margin slots, so the host runs ahead of the device.  Counts arrive
+# through pinned memory and are folded in by later calls; a frame that would overflow its slots renders NaN and the next
+# rasterizer call raises (the following frames use the larger count).  The default is the reference's behaviour — one
+# blocking 4-byte readback per forward (rasterizer_impl.cu:281-282) — which can never overflow, whatever the camera does.
+_DEFERRED = {"on": False, "warmup": 4, "margin": 1.5}
+_TRACK: "OrderedDict" = None          # hint key -> _CountTrack (LRU, see _lru_get)
+# (device index, stream, P) -> zeroed (P,20) fp32 scratch the blend backward accumulates into (left zero by the library);
+# keyed by stream so that backward passes running concurrently on two streams never share one
+_GRAD_SCRATCH: "OrderedDict" = None
 _LAUNCH_COUNT = {"forward": 0, "backward": 0}
+_TRACK = OrderedDict()
+_GRAD_SCRATCH = OrderedDict()
+_TRACK_MAX, _SCRATCH_MAX = 64, 8
+
+
+def _lru_get(cache: OrderedDict, key, make, limit: int, on_evict=None):
+    """Least-recently-used lookup: densification changes P every few hundred iterations, so old (P, ...) entries age out
+    one at a time instead of the whole history being dropped."""
+    v = cache.get(key)
+    if v is None:
+        v = cache[key] = make()
+        while len(cache) > limit:
+            old, _ = cache.popitem(last=False)
+            if on_evict is not None:
+                on_evict(old)
+    else:
+        cache.move_to_end(key)
+    return v
 
 
 def _stream_ptr(device) -> int:
@@ -57,20 +79,21 @@ def cpu_deep_copy_tuple(input_tuple):
     return tuple(item.cpu().clone() if isinstance(item, torch.Tensor) else item for item in input_tuple)
 
 
+def _scratch_key(device: torch.device, P: int):
+    return (device.index, torch.cuda.current_stream(device).cuda_stream, P)
+
+
 def grad_scratch(device: torch.device, P: int) -> torch.Tensor:
-    key = (device.index, P)
-    t = _GRAD_SCRATCH.get(key)
-    if t is None:
-        if len(_GRAD_SCRATCH) > 8:
-            _GRAD_SCRATCH.clear()
-        t = torch.zeros((max(P, 1), 20), dtype=torch.float32, device=device)
-        _GRAD_SCRATCH[key] = t
-    return t
+    """Zeroed (P,20) accumulator of the blend backward for the CURRENT stream of `device` (kernels on one stream are
+    ordered, so one buffer per (stream, P) is never shared by two backward passes in flight)."""
+    return _lru_get(_GRAD_SCRATCH, _scratch_key(device, P),
+                    lambda: torch.zeros((max(P, 1), 20), dtype=torch.float32, device=device), _SCRATCH_MAX)
 
 
 def set_deferred_count(on: bool = True, warmup: int = 4, margin: float = 1.5) -> None:
-    """Switch the host-synchronisation-free binning mode (default on).  ``on=False`` restores the reference's behaviour:
-    one stream synchronisation per forward to read num_rendered (rasterizer_impl.cu:281-282)."""
+    """Switch the host-synchronisation-free binning mode (default OFF = the reference's behaviour: one stream
+    synchronisation per forward to read num_rendered, rasterizer_impl.cu:281-282).  Turn it on for loops whose cameras
+    keep the instance count within ``margin`` of what was seen before (bench.py does; CUDA-graph capture implies it)."""
     _DEFERRED.update(on=bool(on), warmup=int(warmup), margin=float(margin))
 
 
@@ -170,11 +193,7 @@ def raster_forward(bg, means3D, colors_precomp, opacities, scales, rotations, sc
     ctx.geom = torch.empty((gbytes,), dtype=torch.uint8, device=dev)
     ctx.img = torch.empty((ibytes,), dtype=torch.uint8, device=dev)
     hint_key = (dev.index, P, W, H)
-    track = _TRACK.get(hint_key)
-    if track is None:
-        if len(_TRACK) > 64:
-            _TRACK.clear(); _R_HINT.clear()
-        track = _TRACK[hint_key] = _CountTrack()
+    track = _lru_get(_TRACK, hint_key, _CountTrack, _TRACK_MAX, on_evict=lambda k: _R_HINT.pop(k, None))
     # CUDA-graph capture: nothing may synchronise or query, so the frame is recorded in deferred-count mode with the
     # capacity the eager frames before it established (the count still lands in pinned memory on every replay:
     # check_deferred_counts()).
@@ -327,7 +346,7 @@ def raster_backward(bg, means3D, radii, colors_precomp, scales, rotations, scale
     with torch.cuda.device(dev):
         rc = L.d2gs_raster_backward(C.byref(a), _stream_ptr(dev))
     if rc != 0:
-        _GRAD_SCRATCH.pop((dev.index, P), None)   # scratch may be dirty: never reuse it
+        _GRAD_SCRATCH.pop(_scratch_key(dev, P), None)   # scratch may be dirty: never reuse it
     _lib.check(rc, "d2gs_raster_backward")
     _LAUNCH_COUNT["backward"] += 1
     return g
@@ -452,12 +471,20 @@ class _RasterizeSurfelsRaw(torch.autograd.Function):
                             grad_out_color.float().contiguous(), grad_depth.float().contiguous(), sh_, shr_, rs.sh_degree,
                             campos, rctx, rs.debug, want=want, raw_params=True, opacities=op_, d_means3D=dx_, d_scales=ds_,
                             d_rotations=dr_, out=out)
-        from .dist import grads_ready
-        grads_ready("raster")      # the surfel-table gradients are final: buckets may start reducing them now
+        from .dist import grads_ready, reduces_early
         hd = ctx.has_delta
-        alias = lambda t: t.view_as(t)   # a second tensor object on the same memory, so autograd can adopt the first as .grad
-        return (g["dL_dmeans3D"], alias(g["dL_dmeans3D"]) if hd[0] else None, g["dL_dscales_raw"], g["dL_dscales"] if hd[1] else None,
-                g["dL_drotations"], alias(g["dL_drotations"]) if hd[2] else None, g["dL_dopacity"], g["dL_dmeans2D"],
+
+        def for_delta(grad, param):
+            # dL/d(delta) == dL/d(parameter).  Normally a second tensor object on the same memory (autograd adopts the
+            # first as .grad); but when the parameter's bucket slot is all-reduced EARLY — in place, on NCCL's stream, from
+            # grads_ready() below — the deformation backward would read it while other ranks' values are being summed in:
+            # it gets a private copy, taken before the collective is launched.
+            return grad.clone() if reduces_early(param) else grad.view_as(grad)
+        g_dxyz = for_delta(g["dL_dmeans3D"], xyz_) if hd[0] else None
+        g_drot = for_delta(g["dL_drotations"], rot_) if hd[2] else None
+        grads_ready("raster")      # the surfel-table gradients are final: buckets may start reducing them now
+        return (g["dL_dmeans3D"], g_dxyz, g["dL_dscales_raw"], g["dL_dscales"] if hd[1] else None,
+                g["dL_drotations"], g_drot, g["dL_dopacity"], g["dL_dmeans2D"],
                 g["dL_dsh"] if sh_ is not None else None, g["dL_dsh_rest"], g["dL_dcolors"], None)
 
 

@@ -1,5 +1,10 @@
-"""Drop-in replacement for the reference's ``gaussian_renderer.render`` (gaussian_renderer/__init__.py:41-219):
-same signature, same returned dict, backed by the B200 rasterizer.
+"""Drop-in replacement for the reference's ``gaussian_renderer`` package (gaussian_renderer/__init__.py):
+``render`` (:41-219) and ``render_flow`` (:222-337) with the same signatures and returned dicts, backed by the B200
+rasterizers; ``network_gui`` (gaussian_renderer/network_gui.py) and the ``GaussianModel`` re-export (:16) so that
+``from gaussian_renderer import render, network_gui, render_flow`` (train_gui.py:18) and
+``from gaussian_renderer import GaussianModel`` (render_mesh.py:22) resolve when this package shadows the reference's.
+(Alternatively leave the reference's package in place and call ``d2gs_b200.install_into_reference()``, which swaps
+``render`` / ``render_flow`` inside it.)
 
 Differences that do not change results:
   * SH coefficients are handed to the rasterizer as the two parameter tensors (DC, rest) instead of a fresh
@@ -16,6 +21,34 @@ from d2gs_b200 import raster as _raster
 from d2gs_b200 import epilogue as _epilogue
 
 _RAY_CACHE = {}
+
+
+def __getattr__(name):
+    """Lazy attributes of the reference package that live outside the hot path: ``GaussianModel`` is the reference's own
+    class (scene/gaussian_model.py, importable whenever the trainer is), ``network_gui`` the viewer socket module."""
+    if name == "GaussianModel":
+        from scene.gaussian_model import GaussianModel
+        return GaussianModel
+    if name == "network_gui":
+        import importlib
+        return importlib.import_module(__name__ + ".network_gui")
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
+
+
+def _plain_getters(pc) -> bool:
+    """The fused raw-parameter path evaluates exp(_scaling), normalize(_rotation + d), sigmoid(_opacity) inside the kernel.
+    That equals the model's getters only if the model has not overridden them: the reference's StandardGaussianModel
+    (scene/gaussian_model.py) replaces get_scaling by an isotropic mean (and has `all_the_same`), so any object whose
+    class redefines a getter relative to the base that owns `_scaling` — or that carries an `all_the_same` attribute —
+    takes the eager op sequence instead."""
+    if hasattr(pc, "all_the_same"):
+        return False
+    cls = type(pc)
+    for getter in ("get_scaling", "get_opacity", "get_rotation_bias", "get_rotation", "get_xyz"):
+        owners = [k for k in cls.__mro__ if getter in vars(k)]
+        if len(owners) > 1:        # redefined somewhere down the hierarchy
+            return False
+    return True
 
 
 def quaternion_multiply(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
@@ -129,7 +162,7 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, d_xyz, d_rotation
              and getattr(pc, "rotation_activation", torch.nn.functional.normalize) is torch.nn.functional.normalize
              and scale_const is None and d_opacity is None and d_rotation_bias is None
              and _delta_ok(d_xyz, xyz) and _delta_ok(d_scaling, pc._scaling) and _delta_ok(d_rotation, pc._rotation)
-             and pc._scaling.dim() == 2 and pc._scaling.shape[1] == 2 and not getattr(pc, "all_the_same", False))
+             and pc._scaling.dim() == 2 and pc._scaling.shape[1] == 2 and _plain_getters(pc))
     if fused:
         det = lambda t, flag: (t.detach() if flag and torch.is_tensor(t) else t)
         tz = lambda d: d if torch.is_tensor(d) else None
@@ -191,3 +224,61 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, d_xyz, d_rotation
     rets.update({'alpha': render_alpha, 'rend_normal': render_normal, 'rend_dist': render_dist, 'depth': surf_depth,
                  'surf_normal': surf_normal, 'surf_point': surf_point, "bg_color": bg})
     return rets
+
+
+def render_flow(pc, viewpoint_camera1, viewpoint_camera2, d_xyz1, d_xyz2, d_rotation1, d_scaling1, scaling_modifier=1.0,
+                compute_cov3D_python=False, scale_const=None, d_rot_as_res=True, **kwargs):
+    """Splat the per-surfel screen-space motion between (t1, camera1) and (t2, camera2): reference
+    gaussian_renderer/__init__.py:222-337 (called by train_gui.py:351 for the optical-flow loss).
+
+    The reference body unpacks four outputs from a rasterizer call — the interface of its depth/alpha 3-D Gaussian
+    rasterizer (submodules/diff-gaussian-rasterization) — while the module imports the surfel rasterizer, which returns
+    three.  Here the model decides: 3-column scales go to the 3-D drop-in (diff_gaussian_rasterization, 4 outputs); the
+    2-column scales of a surfel model go to the surfel rasterizer and ``depth`` / ``alpha`` are planes 0 / 1 of its
+    allmap (sum of w*depth, sum of w) — the same quantities the 3-D rasterizer returns."""
+    xyz = pc.get_xyz
+    screenspace_points = torch.zeros_like(xyz, dtype=xyz.dtype, requires_grad=True, device=xyz.device) + 0
+    try:
+        screenspace_points.retain_grad()
+    except Exception:
+        pass
+    tanfovx = math.tan(viewpoint_camera1.FoVx * 0.5)
+    tanfovy = math.tan(viewpoint_camera1.FoVy * 0.5)
+
+    # per-surfel flow in normalised device coordinates; centres are detached (:252), the deltas carry the gradient
+    canon = xyz.detach()
+    ones = torch.ones_like(canon[..., :1])
+    proj2 = (viewpoint_camera2 if viewpoint_camera2 is not None else viewpoint_camera1).full_proj_transform
+    uvz2 = torch.cat([canon + d_xyz2, ones], dim=-1) @ proj2
+    uvz2 = uvz2[..., :3] / uvz2[..., -1:]
+    uvz1 = torch.cat([canon + d_xyz1, ones], dim=-1) @ viewpoint_camera1.full_proj_transform
+    uvz1 = uvz1[..., :3] / uvz1[..., -1:]
+    flow = uvz2 - uvz1
+    flow = torch.cat([flow[..., :2], pc.motion_mask.expand_as(flow[..., -1:])], dim=-1)   # third channel: motion mask (:266)
+
+    means3D = xyz + d_xyz1
+    opacity = pc.get_opacity
+    base_rot = pc.get_rotation
+    if d_rot_as_res:
+        rotations = base_rot + d_rotation1
+    else:
+        rotations = base_rot if type(d_rotation1) is float else quaternion_multiply(d_rotation1, base_rot)
+    scales = torch.ones_like(pc.get_scaling) * scale_const if scale_const is not None else pc.get_scaling + d_scaling1
+    if compute_cov3D_python and scale_const is None:
+        raise NotImplementedError("compute_cov3D_python is not supported by the B200 drop-in (use the scales / rotations path)")
+    settings = dict(image_height=int(viewpoint_camera1.image_height), image_width=int(viewpoint_camera1.image_width),
+                    tanfovx=tanfovx, tanfovy=tanfovy, bg=torch.zeros_like(flow[0]), scale_modifier=scaling_modifier,
+                    viewmatrix=viewpoint_camera1.world_view_transform, projmatrix=viewpoint_camera1.full_proj_transform,
+                    sh_degree=0, campos=viewpoint_camera1.camera_center, prefiltered=False, debug=False)
+    if scales.shape[-1] == 3:
+        import diff_gaussian_rasterization as dgr
+        rendered_image, radii, rendered_depth, rendered_alpha = dgr.GaussianRasterizer(dgr.GaussianRasterizationSettings(**settings))(
+            means3D=means3D, means2D=screenspace_points, shs=None, colors_precomp=flow, opacities=opacity, scales=scales,
+            rotations=rotations, cov3D_precomp=None)
+    else:
+        rendered_image, radii, allmap = GaussianRasterizer(GaussianRasterizationSettings(**settings))(
+            means3D=means3D, means2D=screenspace_points, shs=None, colors_precomp=flow, opacities=opacity, scales=scales,
+            rotations=rotations, cov3D_precomp=None)
+        rendered_depth, rendered_alpha = allmap[0:1], allmap[1:2]
+    return {"render": rendered_image, "depth": rendered_depth, "alpha": rendered_alpha, "viewspace_points": screenspace_points,
+            "visibility_filter": radii > 0, "radii": radii}

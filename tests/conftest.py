@@ -28,5 +28,5 @@ def _fresh_binning_state():
     from d2gs_b200 import raster
     raster._TRACK.clear()
     raster._R_HINT.clear()
-    raster.set_deferred_count(True)
+    raster.set_deferred_count(False)      # the library default (the reference behaviour); tests opt in
     yield

@@ -186,3 +186,63 @@ def test_early_allreduce_of_declared_tables(tmp_path):
     path = str(tmp_path / "early.pt")
     mp.spawn(_early_worker, args=(world, _free_port(), {"path": path}), nprocs=world, join=True)
     assert torch.load(path)["launched"] == [True, True, True]      # the early collective really ran ahead of the final one
+
+
+class _TwoConsumers(torch.autograd.Function):
+    """Stand-in for _RasterizeSurfelsRaw.backward (raster.py): the gradient of a table is ALSO the gradient of a delta
+    that an earlier stage of the graph produced; the table's slot is reduced early, so the delta must not alias it."""
+
+    @staticmethod
+    def forward(ctx, table, delta):
+        ctx.save_for_backward(table.detach())
+        ctx.delta = delta.detach()
+        return ((table + delta) ** 2).sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        (table,) = ctx.saved_tensors
+        out = ddist.claim(table, zeroed=False)
+        torch.mul(table + ctx.delta, 2.0 * g, out=out)
+        g_delta = out.clone() if ddist.reduces_early(table) else out.view_as(out)
+        ddist.grads_ready("raster")                     # launches the in-place early all-reduce of `out`
+        return out, g_delta
+
+
+def _alias_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    table = torch.nn.Parameter(torch.randn(50, 3))
+    net = torch.nn.Parameter(torch.randn(3))              # "deformation network": consumes the delta's gradient downstream
+    b = ddist.FlatGradBucket([net, table], early=[table])
+    assert ddist.reduces_early(table) and not ddist.reduces_early(net)
+    b.zero()
+    delta = net[None, :].expand(50, 3) * 0.5              # d(delta)/d(net) consumes the LOCAL gradient of the table, downstream
+    scale = float(rank + 1)
+    (scale * _TwoConsumers.apply(table, delta)).backward()
+    b.all_reduce()
+    # the downstream consumer must have seen the LOCAL table gradient: the all-reduced net gradient is the sum of the
+    # per-rank contributions computed independently (were it fed from the slot while it is being reduced, rank r could
+    # see the other ranks' values as well and the total would come out too large)
+    tot = sum(2.0 * (r + 1) for r in range(world))
+    want_table = tot * (table.data + delta.detach())
+    assert torch.allclose(table.grad, want_table, rtol=1e-5)
+    assert torch.allclose(net.grad, 0.5 * want_table.sum(0), rtol=1e-5)
+    if rank == 0:
+        torch.save({"ok": True}, out["path"])
+    dist.destroy_process_group()
+
+
+def test_early_reduced_slot_is_never_aliased_downstream(tmp_path):
+    """with N > 1 the gradient handed to the deformation deltas must be a private copy, taken before the
+    early all-reduce starts summing other ranks' values into the parameter's bucket slot."""
+    params = _model()
+    b = ddist.FlatGradBucket(params, early=[params[1]])
+    try:
+        assert not ddist.reduces_early(params[1])          # no process group: nothing is reduced, aliasing is safe
+    finally:
+        b.detach()
+    world = 2
+    path = str(tmp_path / "alias.pt")
+    mp.spawn(_alias_worker, args=(world, _free_port(), {"path": path}), nprocs=world, join=True)
+    assert torch.load(path)["ok"]
