@@ -157,6 +157,7 @@ class Workload:
         self.gt_dev = self.gt_host.to(device)
         self.use_deform = cfg["n_nodes"] > 0
         self.loss_kind = "synthetic"
+        self.keep_stats = False
         self.deform_parameters = lambda: []
 
 
@@ -196,7 +197,8 @@ def step_ours(wl: Workload, cam, gt, gt_ready=None):
     else:
         d_xyz, d_rot, d_scale = 0.0, 0.0, 0.0
     out = render(cam, pc, wl.pipe, wl.bg, d_xyz, d_rot, d_scale)
-    wl.last_out = out
+    if wl.keep_stats:      # only what the training tail reads; holding `out` would keep the step's autograd graph alive
+        wl.last_out = {"viewspace_points": out["viewspace_points"], "visibility_filter": out["visibility_filter"], "radii": out["radii"]}
     if gt_ready is not None:
         torch.cuda.current_stream().wait_event(gt_ready)     # the target image arrives on the copy stream
     if wl.loss_kind == "train":
@@ -284,7 +286,8 @@ def step_reference(wl: Workload, cam, gt, gt_ready=None):
             else:
                 d_xyz, d_rot, d_scale = 0.0, 0.0, 0.0
         out = rp.render_reference(wl.ref_mod, cam, pc, wl.bg, d_xyz, d_rot, d_scale)
-        wl.last_out = out
+        if wl.keep_stats:
+            wl.last_out = {"viewspace_points": out["viewspace_points"], "visibility_filter": out["visibility_filter"], "radii": out["radii"]}
         if gt_ready is not None:
             torch.cuda.current_stream().wait_event(gt_ready)
         if wl.loss_kind == "train":
@@ -484,6 +487,7 @@ def main():
     from d2gs_b200 import model as mdl
     wl = Workload(args.config, device, args.impl)
     wl.loss_kind = args.loss
+    wl.keep_stats = bool(args.train)
     cfg = wl.cfg
 
     impl_note = None

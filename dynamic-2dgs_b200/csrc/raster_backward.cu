@@ -21,8 +21,13 @@ namespace d2gs {
 constexpr int BWD_BATCH = D2GS_BWD_BATCH;   // instances staged per round
 // Each 16x16 tile is worked on by TWO CTAs of 4 warps (rows 0-7 / 8-15, blockIdx.z): barriers then wait for the
 // slowest of 4 patches instead of 8, and six small CTAs per SM interleave where three large ones stalled together.
-constexpr int BWD_THREADS = TILE_PIX / 2;
-constexpr int NWARP = BWD_THREADS / 32;
+#ifndef D2GS_BWD_WARPS
+#define D2GS_BWD_WARPS 4
+#endif
+constexpr int NWARP = D2GS_BWD_WARPS;            // warps (8x4 pixel patches) per CTA: 4, 2 or 1
+constexpr int BWD_THREADS = 32 * NWARP;
+constexpr int BWD_Z = 8 / NWARP;                 // CTAs per 16x16 tile (blockIdx.z)
+constexpr int BWD_SPT = (D2GS_BWD_BATCH + BWD_THREADS - 1) / BWD_THREADS;   // staging slots per thread
 constexpr int ACC_STRIDE = 19;   // 18 components, odd stride keeps the flush free of bank conflicts
 constexpr unsigned FULL = 0xffffffffu;
 // per-warp reduction scratch: RED_ROWS rows of RED_STRIDE floats.  A row holds one contributing lane's 18 components in
@@ -117,24 +122,36 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_MINBLOCKS) blend_bwd_ker
   float Q = T_final * bg_dot_dpixel;   // see "ONE running scalar" below
 
   const int rounds = (len + BWD_BATCH - 1) / BWD_BATCH;
-  // instance id of this thread's slot in batch bi (back to front: slot t holds list position len-1-(bi*B+t))
-  auto slot_id = [&](int bi) -> uint32_t {
+  // instance ids of this thread's slots in batch bi (back to front: slot t holds list position len-1-(bi*B+t))
+  struct Ids { uint32_t v[BWD_SPT]; };
+  auto slot_id = [&](int bi) -> Ids {
+    Ids r;
     const int nb = min(BWD_BATCH, (int)len - bi * BWD_BATCH);
-    return (bi < rounds && tid < nb) ? __ldg(&point_list[range.x + (len - 1 - (uint32_t)(bi * BWD_BATCH + tid))]) : 0xffffffffu;
-  };
-  // stage batch bi into buffer buf with cp.async; `id` was fetched one iteration earlier so no load latency is exposed
-  auto stage = [&](int bi, int buf, uint32_t id) {
-    if (id != 0xffffffffu) {
-      s_id[buf * BWD_BATCH + tid] = id;
-      const float4* r4 = reinterpret_cast<const float4*>(rec + id);
-      const uint32_t dst = sq_base + (uint32_t)buf * (uint32_t)BWD_SMEM_Q1 + ((uint32_t)tid << 4);
 #pragma unroll
-      for (int q = 0; q < REC_QUADS; q++) cp_async16(dst + q * QS, r4 + q);
+    for (int k = 0; k < BWD_SPT; k++) {
+      const int t = tid + k * BWD_THREADS;
+      r.v[k] = (bi < rounds && t < nb) ? __ldg(&point_list[range.x + (len - 1 - (uint32_t)(bi * BWD_BATCH + t))]) : 0xffffffffu;
+    }
+    return r;
+  };
+  // stage batch bi into buffer buf with cp.async; the ids were fetched one iteration earlier so no load latency is exposed
+  auto stage = [&](int bi, int buf, const Ids& ids) {
+#pragma unroll
+    for (int k = 0; k < BWD_SPT; k++) {
+      const uint32_t id = ids.v[k];
+      const int t = tid + k * BWD_THREADS;
+      if (id != 0xffffffffu) {
+        s_id[buf * BWD_BATCH + t] = id;
+        const float4* r4 = reinterpret_cast<const float4*>(rec + id);
+        const uint32_t dst = sq_base + (uint32_t)buf * (uint32_t)BWD_SMEM_Q1 + ((uint32_t)t << 4);
+#pragma unroll
+        for (int q = 0; q < REC_QUADS; q++) cp_async16(dst + q * QS, r4 + q);
+      }
     }
     cp_async_commit();
   };
   stage(0, 0, slot_id(0));
-  uint32_t pre_id = slot_id(1);
+  Ids pre_id = slot_id(1);
   int remaining = (int)len;
   for (int i = 0; i < rounds; i++, remaining -= BWD_BATCH) {
     const int n = min(BWD_BATCH, remaining);
@@ -180,24 +197,26 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_MINBLOCKS) blend_bwd_ker
         if (!inside || contributor >= last_contributor) break;
         const float4 a = lds128(sb0 + off), b = lds128(sb1 + off), c = lds128(sb2 + off);
         const float3 Tu = {a.x, a.y, a.z}, Tv = {a.w, b.x, b.y}, Tw = {b.z, b.w, c.x};
-        const float3 k = {-Tu.x + pixf.x * Tw.x, -Tu.y + pixf.x * Tw.y, -Tu.z + pixf.x * Tw.z};
-        const float3 l = {-Tv.x + pixf.y * Tw.x, -Tv.y + pixf.y * Tw.y, -Tv.z + pixf.y * Tw.z};
-        const float3 p = {k.y * l.z - k.z * l.y, k.z * l.x - k.x * l.z, k.x * l.y - k.y * l.x};
-        const float2 d = {c.y - pixf.x, c.z - pixf.y};
-        const float rho2d = 2.0f * (d.x * d.x + d.y * d.y);
+        // same pinned roundings as blend_fwd_kernel: the set of contributing pairs must be the forward's, bit for bit
+        const float3 k = {__fmaf_rn(pixf.x, Tw.x, -Tu.x), __fmaf_rn(pixf.x, Tw.y, -Tu.y), __fmaf_rn(pixf.x, Tw.z, -Tu.z)};
+        const float3 l = {__fmaf_rn(pixf.y, Tw.x, -Tv.x), __fmaf_rn(pixf.y, Tw.y, -Tv.y), __fmaf_rn(pixf.y, Tw.z, -Tv.z)};
+        const float3 p = {__fmaf_rn(k.y, l.z, -__fmul_rn(k.z, l.y)), __fmaf_rn(k.z, l.x, -__fmul_rn(k.x, l.z)),
+                          __fmaf_rn(k.x, l.y, -__fmul_rn(k.y, l.x))};
+        const float2 d = {__fsub_rn(c.y, pixf.x), __fsub_rn(c.z, pixf.y)};
+        const float rho2d = 2.0f * __fmaf_rn(d.x, d.x, __fmul_rn(d.y, d.y));
         if (pair_rejected(p.x, p.y, p.z, rho2d, c.w)) break;   // alpha < 1/255 for certain
         if (p.z == 0.0f) break;
-        const float2 s = {p.x / p.z, p.y / p.z};
-        const float rho3d = (s.x * s.x + s.y * s.y);
+        const float2 s = {__fdiv_rn(p.x, p.z), __fdiv_rn(p.y, p.z)};
+        const float rho3d = __fmaf_rn(s.x, s.x, __fmul_rn(s.y, s.y));
         const float rho = fminf(rho3d, rho2d);
-        const float c_d = (rho3d <= rho2d) ? (s.x * Tw.x + s.y * Tw.y) + Tw.z : Tw.z;
+        const float c_d = (rho3d <= rho2d) ? __fadd_rn(Tw.z, __fmaf_rn(Tw.x, s.x, __fmul_rn(Tw.y, s.y))) : Tw.z;
         if (c_d < 0.2f) break;
         const float power = -0.5f * rho;
         if (power > 0.0f) break;
         const float G = expf(power);
         const float4 col = lds128(sb4 + off);   // rgb + opacity
         const float opac = col.w;
-        const float alpha = fminf(0.99f, opac * G);
+        const float alpha = fminf(0.99f, __fmul_rn(opac, G));
         if (alpha < 1.0f / 255.0f) break;
         const float4 nrm = lds128(sb3 + off);
         const float normal[3] = {nrm.x, nrm.y, nrm.z};
@@ -223,19 +242,21 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_MINBLOCKS) blend_bwd_ker
         }
         E = fmaf(c_d, dL_ddepth, E);
         float dL_dz = 0.0f, dL_dweight = 0.f;
-        // depth mapped to [0,1]; fp32 here (gradients are compared to 1e-4, not bit-wise)
+        // depth mapped to [0,1]: the reference's float, bit for bit (mapped_depth) — the weight gradient below is a
+        // difference of nearly equal terms and amplifies a last-bit change of m_d by ~1e3
         const float inv_d = __fdividef(1.0f, c_d);
-        const float m_d = (1.0f - 0.2f * inv_d) * 1.002004008016032f;       // same fp32 form as the forward
+        const float m_d = mapped_depth(c_d);
         const float dmd_dd = 0.2004008016032064f * inv_d * inv_d;            // near*far/(far-near) / d^2
         if (contributor == (uint32_t)(median_contributor - 1)) {
           dL_dz += dL_dmedian_depth;
           dL_dweight += dL_dmax_dweight;
         }
-        dL_dweight += (final_D2 + m_d * m_d * final_A - 2 * m_d * final_D) * dL_dreg;
+        // (final_D2 + m^2 A - 2 m D) * dL_dreg with the reference build's roundings (backward.cu:362)
+        dL_dweight = __fmaf_rn(dL_dreg, __fmaf_rn(__fadd_rn(m_d, m_d), -final_D, __fmaf_rn(final_A, __fmul_rn(m_d, m_d), final_D2)), dL_dweight);
         E += dL_dweight;
         const float dL_dalpha = T * E - Q * inv_1ma;
         Q = fmaf(w, E, Q);
-        const float dL_dmd = 2.0f * w * (m_d * final_A - final_D) * dL_dreg;
+        const float dL_dmd = 2.0f * w * __fmaf_rn(final_A, m_d, -final_D) * dL_dreg;
         dL_dz += dL_dmd * dmd_dd;
 
         const float dL_dG = opac * dL_dalpha;
@@ -332,7 +353,7 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_MINBLOCKS) blend_bwd_ker
 void launch_blend_bwd(const BwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
                       const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, const float* dL_dothers,
                       float* grad_rec, int cull, cudaStream_t s) {
-  dim3 grid(p.gx, p.gy, 2);
+  dim3 grid(p.gx, p.gy, BWD_Z);
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES);

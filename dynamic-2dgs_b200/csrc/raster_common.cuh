@@ -178,9 +178,16 @@ __device__ __forceinline__ v3 cross3(v3 a, v3 b) {
   return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
 struct m3 { v3 c0, c1, c2; };   // columns
+// matrix * vector with the roundings of the reference build's glm product (m0*x + m1*y + m2*z compiles to
+// fma(m2, z, fma(m0, x, rn(m1*y))) there): pinned, because left to the compiler the SAME source line was contracted one
+// way for the second homography column and another way for the first (found at BASELINE sizes in round 2: the first
+// column of transMat differed from the reference in the last bits for ~10 % of the surfels).
+__device__ __forceinline__ float mad3_glm(float a0, float b0, float a1, float b1, float a2, float b2) {
+  return __fmaf_rn(a2, b2, __fmaf_rn(a0, b0, __fmul_rn(a1, b1)));
+}
 __device__ __forceinline__ v3 operator*(const m3& m, v3 v) {
-  return {m.c0.x * v.x + m.c1.x * v.y + m.c2.x * v.z, m.c0.y * v.x + m.c1.y * v.y + m.c2.y * v.z,
-          m.c0.z * v.x + m.c1.z * v.y + m.c2.z * v.z};
+  return {mad3_glm(m.c0.x, v.x, m.c1.x, v.y, m.c2.x, v.z), mad3_glm(m.c0.y, v.x, m.c1.y, v.y, m.c2.y, v.z),
+          mad3_glm(m.c0.z, v.x, m.c1.z, v.y, m.c2.z, v.z)};
 }
 __device__ __forceinline__ m3 transpose3(const m3& m) {
   return {{m.c0.x, m.c1.x, m.c2.x}, {m.c0.y, m.c1.y, m.c2.y}, {m.c0.z, m.c1.z, m.c2.z}};
@@ -189,13 +196,50 @@ __device__ __forceinline__ m3 transpose3(const m3& m) {
 __device__ __forceinline__ m3 view_rot(const float* v) {
   return {{v[0], v[1], v[2]}, {v[4], v[5], v[6]}, {v[8], v[9], v[10]}};
 }
-// unit-quaternion (w,x,y,z) -> rotation, columns (reference: auxiliary.h:188-210)
+// unit-quaternion (w,x,y,z) -> rotation, columns (reference: auxiliary.h:188-210).
+// Every rounding is pinned to what the reference build executes (its SASS shares y*y and z*z between the three diagonal
+// entries: 1-2(yy+zz) adds two ROUNDED squares, the other two fuse x*x into the addition), so the homography
+// rows — and with them every alpha of the blend — come out bit-identical; left to the compiler, the first column differed
+// in the last bit for ~10 % of the surfels (found by the live comparison at BASELINE sizes, round 2).
 __device__ __forceinline__ m3 quat_to_rot(float4 q) {
-  float s = rsqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
-  float w = q.x * s, x = q.y * s, y = q.z * s, z = q.w * s;
-  return {{1.f - 2.f * (y * y + z * z), 2.f * (x * y + w * z), 2.f * (x * z - w * y)},
-          {2.f * (x * y - w * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z + w * x)},
-          {2.f * (x * z + w * y), 2.f * (y * z - w * x), 1.f - 2.f * (x * x + y * y)}};
+  const float s = rsqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+  const float w = __fmul_rn(q.x, s), x = __fmul_rn(q.y, s), y = __fmul_rn(q.z, s), z = __fmul_rn(q.w, s);
+  const float wz = __fmul_rn(w, z), wy = __fmul_rn(w, y), wx = __fmul_rn(w, x);
+  const float yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+  const float d0 = __fadd_rn(yy, zz), d1 = __fmaf_rn(x, x, zz), d2 = __fmaf_rn(x, x, yy);
+  const float xy_p = __fmaf_rn(x, y, wz), xy_m = __fmaf_rn(x, y, -wz);
+  const float yz_p = __fmaf_rn(y, z, wx), yz_m = __fmaf_rn(y, z, -wx);
+  const float xz_p = __fmaf_rn(x, z, wy), xz_m = __fmaf_rn(x, z, -wy);
+  return {{__fsub_rn(1.f, __fadd_rn(d0, d0)), __fadd_rn(xy_p, xy_p), __fadd_rn(xz_m, xz_m)},
+          {__fadd_rn(xy_m, xy_m), __fsub_rn(1.f, __fadd_rn(d1, d1)), __fadd_rn(yz_p, yz_p)},
+          {__fadd_rn(xz_p, xz_p), __fadd_rn(yz_m, yz_m), __fsub_rn(1.f, __fadd_rn(d2, d2))}};
+}
+
+// Depth mapped to [0,1] between the near and far planes for the distortion bookkeeping.  The reference evaluates
+//   (FAR*d - FAR*NEAR) / ((FAR-NEAR)*d)   in DOUBLE (its macros are double literals, forward.cu:399, backward.cu:352) and
+// rounds to float.  The distortion terms m*m*A + dist2 - 2*m*dist1 cancel to ~1e-3 of their operands, so a last-bit
+// difference in m shows up as a 1e-3 relative difference of the distortion map: m has to be the reference's float
+// exactly.  Instead of a double division per contributing (pixel, surfel) pair (14 half-rate DFMAs), m = a - b/d with
+// a = 100/99.8, b = 20/99.8 is evaluated in float-float arithmetic (error < 2^-44) and rounded once; when the result lies
+// within 2^-14 ulp of a rounding boundary — one evaluation in ~10^4 — the double expression itself decides.
+static __device__ __noinline__ float mapped_depth_double(float d) {
+  return (float)((D2GS_FAR_PLANE * d - D2GS_FAR_PLANE * D2GS_NEAR_PLANE) / ((D2GS_FAR_PLANE - D2GS_NEAR_PLANE) * d));
+}
+__device__ __forceinline__ float mapped_depth(float d) {
+  constexpr double C = D2GS_FAR_PLANE - D2GS_NEAR_PLANE;
+  constexpr double A = D2GS_FAR_PLANE / C, B = (D2GS_FAR_PLANE * D2GS_NEAR_PLANE) / C;
+  constexpr float a_hi = (float)A, a_lo = (float)(A - (double)a_hi), b_hi = (float)B, b_lo = (float)(B - (double)b_hi);
+  const float q_hi = __fdiv_rn(b_hi, d);
+  const float r = __fmaf_rn(-q_hi, d, b_hi);                    // exact remainder of the rounded quotient
+  const float q_lo = __fdividef(__fadd_rn(r, b_lo), d);
+  const float s = __fsub_rn(a_hi, q_hi);                        // a_hi >= q_hi for every depth behind the near plane
+  const float e = __fsub_rn(__fsub_rn(a_hi, s), q_hi);          // Fast2Sum: exact rounding error of s
+  const float t = __fadd_rn(e, __fsub_rn(a_lo, q_lo));
+  const float m = __fadd_rn(s, t);
+  // distance of |t| from half an ulp of s, relative to that half ulp
+  const float h = __int_as_float((__float_as_int(s) & 0x7f800000) - (24 << 23));
+  if (!(fabsf(fabsf(t) - h) > h * 6.1035156e-5f) || !(s > 1e-30f)) return mapped_depth_double(d);
+  return m;
 }
 
 // ---- launch-side argument blocks ----------------------------------------------------------------------

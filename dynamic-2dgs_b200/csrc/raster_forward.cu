@@ -250,7 +250,13 @@ void launch_ranges_deferred(uint32_t capacity, const uint32_t* status, const uin
 constexpr int BLEND_BATCH = D2GS_FWD_BATCH;   // instances per staged batch (double buffered)
 // Two CTAs of 4 warps per 16x16 tile (rows 0-7 / 8-15, blockIdx.z): barriers wait for 4 patches instead of 8, a half
 // tile whose pixels are all saturated stops on its own, and eight small CTAs per SM interleave.
-constexpr int FWD_THREADS = TILE_PIX / 2;
+#ifndef D2GS_FWD_WARPS
+#define D2GS_FWD_WARPS 4
+#endif
+constexpr int FWD_NWARP = D2GS_FWD_WARPS;        // warps (8x4 pixel patches) per CTA: 4, 2 or 1
+constexpr int FWD_THREADS = 32 * FWD_NWARP;
+constexpr int FWD_Z = 8 / FWD_NWARP;             // CTAs per 16x16 tile (blockIdx.z)
+constexpr int FWD_SPT = (D2GS_FWD_BATCH + FWD_THREADS - 1) / FWD_THREADS;   // staging slots per thread
 
 __device__ __forceinline__ void pixel_of_thread(int tid, int& lx, int& ly) {
   const int w = tid >> 5, l = tid & 31;
@@ -280,7 +286,7 @@ __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_ker
   const float2 pixf = {(float)pix_x + 0.5f, (float)pix_y + 0.5f};
   bool done = !inside;
   // pixel-centre bounds of this warp's patch
-  const int wq = (tid >> 5) + (FWD_THREADS / 32) * (int)blockIdx.z;
+  const int wq = (tid >> 5) + FWD_NWARP * (int)blockIdx.z;
   const float pcx0 = (float)(blockIdx.x * TILE_X + ((wq & 1) << 3)) + 0.5f, pcx1 = pcx0 + 7.0f;
   const float pcy0 = (float)(blockIdx.y * TILE_Y + ((wq >> 1) << 2)) + 0.5f, pcy1 = pcy0 + 3.0f;
 
@@ -298,22 +304,33 @@ __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_ker
   float dist1 = 0.f, dist2 = 0.f, distortion = 0.f;
   float median_depth = 0.f, median_weight = 0.f;
 
-  // instance id of this thread's slot in batch bi; fetched one batch ahead of the cp.async that needs it
-  auto slot_id = [&](int bi) -> uint32_t {
-    const uint32_t pos = range.x + (uint32_t)(bi * BLEND_BATCH + tid);
-    return (bi < rounds && tid < BLEND_BATCH && pos < range.y) ? __ldg(&point_list[pos]) : 0xffffffffu;
-  };
-  auto stage = [&](int buf, uint32_t id) {
-    if (id != 0xffffffffu) {
-      const float4* r4 = reinterpret_cast<const float4*>(rec + id);
-      const uint32_t dst = sq_base + (uint32_t)buf * BUF + ((uint32_t)tid << 4);
+  // instance ids of this thread's slots in batch bi; fetched one batch ahead of the cp.async that needs them
+  struct Ids { uint32_t v[FWD_SPT]; };
+  auto slot_id = [&](int bi) -> Ids {
+    Ids r;
 #pragma unroll
-      for (int q = 0; q < REC_QUADS; q++) cp_async16(dst + q * QS, r4 + q);
+    for (int k = 0; k < FWD_SPT; k++) {
+      const int t = tid + k * FWD_THREADS;
+      const uint32_t pos = range.x + (uint32_t)(bi * BLEND_BATCH + t);
+      r.v[k] = (bi < rounds && t < BLEND_BATCH && pos < range.y) ? __ldg(&point_list[pos]) : 0xffffffffu;
+    }
+    return r;
+  };
+  auto stage = [&](int buf, const Ids& ids) {
+#pragma unroll
+    for (int k = 0; k < FWD_SPT; k++) {
+      const uint32_t id = ids.v[k];
+      if (id != 0xffffffffu) {
+        const float4* r4 = reinterpret_cast<const float4*>(rec + id);
+        const uint32_t dst = sq_base + (uint32_t)buf * BUF + ((uint32_t)(tid + k * FWD_THREADS) << 4);
+#pragma unroll
+        for (int q = 0; q < REC_QUADS; q++) cp_async16(dst + q * QS, r4 + q);
+      }
     }
     cp_async_commit();
   };
   stage(0, slot_id(0));
-  uint32_t pre_id = slot_id(1);
+  Ids pre_id = slot_id(1);
   for (int i = 0; i < rounds; i++, toDo -= BLEND_BATCH) {
     // every warp has left batch i-1 (so its buffer may be refilled) — and if all pixels are finished the tile is done
     if (__syncthreads_count(done) == FWD_THREADS) break;
@@ -354,48 +371,55 @@ __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_ker
       const uint32_t off = (uint32_t)j << 4;
       const float4 a = lds128(sb0 + off), b = lds128(sb1 + off), c = lds128(sb2 + off);
       const float3 Tu = {a.x, a.y, a.z}, Tv = {a.w, b.x, b.y}, Tw = {b.z, b.w, c.x};
-      // ray / splat intersection: two planes through the pixel, their cross product is the homogeneous hit point
-      const float3 k = {-Tu.x + pixf.x * Tw.x, -Tu.y + pixf.x * Tw.y, -Tu.z + pixf.x * Tw.z};
-      const float3 l = {-Tv.x + pixf.y * Tw.x, -Tv.y + pixf.y * Tw.y, -Tv.z + pixf.y * Tw.z};
-      const float3 p = {k.y * l.z - k.z * l.y, k.z * l.x - k.x * l.z, k.x * l.y - k.y * l.x};
-      const float2 dd = {c.y - pixf.x, c.z - pixf.y};
+      // ray / splat intersection: two planes through the pixel, their cross product is the homogeneous hit point.
+      // Roundings pinned (intrinsics) to the instruction sequence of the reference build: every alpha — and with it
+      // n_contrib, the saturation test and the median — must come out bit-identical (forward.cu:357-398).
+      const float3 k = {__fmaf_rn(pixf.x, Tw.x, -Tu.x), __fmaf_rn(pixf.x, Tw.y, -Tu.y), __fmaf_rn(pixf.x, Tw.z, -Tu.z)};
+      const float3 l = {__fmaf_rn(pixf.y, Tw.x, -Tv.x), __fmaf_rn(pixf.y, Tw.y, -Tv.y), __fmaf_rn(pixf.y, Tw.z, -Tv.z)};
+      const float3 p = {__fmaf_rn(k.y, l.z, -__fmul_rn(k.z, l.y)), __fmaf_rn(k.z, l.x, -__fmul_rn(k.x, l.z)),
+                        __fmaf_rn(k.x, l.y, -__fmul_rn(k.y, l.x))};
+      const float2 dd = {__fsub_rn(c.y, pixf.x), __fsub_rn(c.z, pixf.y)};
       // 1/FilterSize^2 * r^2 evaluated in double and rounded equals 2*r^2 in float exactly
-      const float rho2d = 2.0f * (dd.x * dd.x + dd.y * dd.y);
+      const float rho2d = 2.0f * __fmaf_rn(dd.x, dd.x, __fmul_rn(dd.y, dd.y));
       if (pair_rejected(p.x, p.y, p.z, rho2d, c.w)) continue;   // alpha < 1/255 for certain
       if (p.z == 0.0f) continue;
-      const float2 s = {p.x / p.z, p.y / p.z};
-      const float rho3d = (s.x * s.x + s.y * s.y);
+      const float2 s = {__fdiv_rn(p.x, p.z), __fdiv_rn(p.y, p.z)};
+      const float rho3d = __fmaf_rn(s.x, s.x, __fmul_rn(s.y, s.y));
       const float rho = fminf(rho3d, rho2d);
-      const float depth = (rho3d <= rho2d) ? (s.x * Tw.x + s.y * Tw.y) + Tw.z : Tw.z;
+      const float depth = (rho3d <= rho2d) ? __fadd_rn(Tw.z, __fmaf_rn(Tw.x, s.x, __fmul_rn(Tw.y, s.y))) : Tw.z;
       if (depth < 0.2f) continue;   // (double)depth < 0.2 <=> depth < 0.2f
       const float power = -0.5f * rho;
       if (power > 0.0f) continue;
       const float4 col = lds128(sb4 + off);   // rgb + opacity
-      const float alpha = fminf(0.99f, col.w * expf(power));
+      const float alpha = fminf(0.99f, __fmul_rn(col.w, expf(power)));
       if (alpha < 1.0f / 255.0f) continue;
-      const float test_T = T * (1 - alpha);
+      const float test_T = __fmul_rn(T, __fsub_rn(1.f, alpha));
       if (test_T < 0.0001f) {
         done = true;
         continue;
       }
       const uint32_t contributor = cbase + (uint32_t)j;
       const float4 nrm = lds128(sb3 + off);
-      // distortion bookkeeping: depth mapped to [0,1] between the near and far planes,
-      // (far*d - far*near) / ((far-near)*d) == (1 - near/d) * far/(far-near), evaluated in fp32
-      const float A = 1 - T;
-      const float md = (1.0f - 0.2f / depth) * 1.002004008016032f;
-      const float error = md * md * A + dist2 - 2 * md * dist1;
-      distortion += error * alpha * T;
+      // distortion bookkeeping (forward.cu:399-421): every accumulator is fma(T, value*alpha, acc) like the reference
+      const float A = __fsub_rn(1.f, T);
+      const float md = mapped_depth(depth);
+      const float md2 = __fmul_rn(md, md);
+      const float error = __fmaf_rn(-dist1, __fadd_rn(md, md), __fmaf_rn(A, md2, dist2));
+      distortion = __fmaf_rn(T, __fmul_rn(alpha, error), distortion);
       if (T > 0.5f) {
         median_depth = depth;
-        median_weight = alpha * T;
+        median_weight = __fmul_rn(T, alpha);
         median_contributor = contributor;
       }
-      N[0] += nrm.x * alpha * T; N[1] += nrm.y * alpha * T; N[2] += nrm.z * alpha * T;
-      Dacc += depth * alpha * T;
-      dist1 += md * alpha * T;
-      dist2 += md * md * alpha * T;
-      C[0] += col.x * alpha * T; C[1] += col.y * alpha * T; C[2] += col.z * alpha * T;
+      N[0] = __fmaf_rn(T, __fmul_rn(nrm.x, alpha), N[0]);
+      N[1] = __fmaf_rn(T, __fmul_rn(nrm.y, alpha), N[1]);
+      N[2] = __fmaf_rn(T, __fmul_rn(nrm.z, alpha), N[2]);
+      Dacc = __fmaf_rn(T, __fmul_rn(depth, alpha), Dacc);
+      dist1 = __fmaf_rn(T, __fmul_rn(alpha, md), dist1);
+      dist2 = __fmaf_rn(T, __fmul_rn(alpha, md2), dist2);
+      C[0] = __fmaf_rn(T, __fmul_rn(col.x, alpha), C[0]);
+      C[1] = __fmaf_rn(T, __fmul_rn(col.y, alpha), C[1]);
+      C[2] = __fmaf_rn(T, __fmul_rn(col.z, alpha), C[2]);
       T = test_T;
       last_contributor = contributor;
       }
@@ -413,9 +437,9 @@ __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_ker
     // deferred-count mode: a frame whose instance count exceeded the binning capacity is never silently wrong
     const bool poisoned = status != nullptr && status[1] != 0u;
     const float qnan = __int_as_float(0x7fc00000);
-    out_color[0 * HW + pix_id] = poisoned ? qnan : C[0] + T * bg[0];
-    out_color[1 * HW + pix_id] = poisoned ? qnan : C[1] + T * bg[1];
-    out_color[2 * HW + pix_id] = poisoned ? qnan : C[2] + T * bg[2];
+    out_color[0 * HW + pix_id] = poisoned ? qnan : __fmaf_rn(T, bg[0], C[0]);
+    out_color[1 * HW + pix_id] = poisoned ? qnan : __fmaf_rn(T, bg[1], C[1]);
+    out_color[2 * HW + pix_id] = poisoned ? qnan : __fmaf_rn(T, bg[2], C[2]);
     out_others[0 * HW + pix_id] = Dacc;
     out_others[1 * HW + pix_id] = 1 - T;
     out_others[2 * HW + pix_id] = N[0];
@@ -430,7 +454,7 @@ __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_ker
 void launch_blend_fwd(const FwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
                       float* final_T, uint32_t* n_contrib, float* out_color, float* out_others, int cull,
                       const uint32_t* status, cudaStream_t s) {
-  dim3 grid(p.gx, p.gy, 2);
+  dim3 grid(p.gx, p.gy, FWD_Z);
   blend_fwd_kernel<<<grid, FWD_THREADS, 0, s>>>(ranges, point_list, p.W, p.H, rec, p.bg, final_T, n_contrib, out_color,
                                             out_others, cull, status);
 }

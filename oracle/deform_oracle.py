@@ -112,6 +112,13 @@ def knn_points(x: torch.Tensor, nodes: torch.Tensor, K: int, mode: str = "exact"
         d2 = ((x * x).sum(1, keepdim=True) + (nodes * nodes).sum(1)[None, :] - 2.0 * (x @ nodes.T)).clamp_min(0)
         dist, idx = torch.topk(d2, K, dim=1, largest=False, sorted=True)
         return dist, idx
+    if x.shape[0] * nodes.shape[0] * x.shape[1] > (1 << 28):
+        # same selection at BASELINE sizes without materialising P*M*D at once: indices chunk by chunk (no gradient
+        # flows through a selection), then the K distances recomputed with the same explicit arithmetic
+        with torch.no_grad():
+            order = torch.cat([torch.sort(((x[s:s + 8192, None, :] - nodes[None, :, :]) ** 2).sum(-1), dim=1, stable=True).indices[:, :K]
+                               for s in range(0, x.shape[0], 8192)])
+        return ((x[:, None, :] - nodes[order]) ** 2).sum(-1), order
     d2 = ((x[:, None, :] - nodes[None, :, :]) ** 2).sum(-1)   # explicit: cdist()**2 is not bit-identical
     order = torch.sort(d2, dim=1, stable=True).indices[:, :K]
     return torch.gather(d2, 1, order), order

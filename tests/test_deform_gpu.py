@@ -390,7 +390,7 @@ def test_render_dropin_matches_reference_pipeline(cfg_name, cam_index, n_cams, c
         else:
             net = {k[len("network."):]: v for k, v in dm.deform.named_parameters() if k.startswith("network.")}
             d = rp.deform_reference(net, dm.deform.nodes, dm.deform._node_radius, dm.deform._node_weight, pc.get_xyz.detach(), cam.fid,
-                                    pc.feature, pc.motion_mask, 4, 8, local_frame=True, knn_mode="exact" if cfg["P"] <= 50_000 else "mm")
+                                    pc.feature, pc.motion_mask, 4, 8, local_frame=True, knn_mode="exact")
             if perturb:
                 gp = torch.Generator().manual_seed(7)
                 d = {k: d[k] * (1.0 + perturb * torch.randn(d[k].shape, generator=gp).to(dev)) for k in ("d_xyz", "d_rotation", "d_scaling")}
@@ -425,14 +425,20 @@ def test_render_dropin_matches_reference_pipeline(cfg_name, cam_index, n_cams, c
     assert set(o_out) == set(r_out)
     # the deformation deltas agree to ~1e-6 (different fp32 summation order than the eager blend), so a handful of
     # radii may flip by one pixel; the rasterizer itself is bit-exact on identical inputs (test_raster_gpu.py)
-    assert (o_out["radii"] != r_out["radii"]).mean() < 2e-3
-    assert (o_out["visibility_filter"] != r_out["visibility_filter"]).mean() < 2e-3
+    # (the reference's screen-space extent is sqrt(centre^2 - sum f T^2): at 800x800 that cancels ~4 000-fold, so the flip
+    # rate grows with the image size — the yardstick is the reference against itself with 1e-6-perturbed deformation)
+    pr_out, p_g, p_vs = run(False, perturb=1e-6)
+    flip_floor = float((pr_out["radii"] != r_out["radii"]).mean())
+    assert (o_out["radii"] != r_out["radii"]).mean() < max(2e-3, 2 * flip_floor), flip_floor
+    assert (o_out["visibility_filter"] != r_out["visibility_filter"]).mean() < max(2e-3, 2 * flip_floor)
     for k in keys + ("surf_point",):
-        # the distortion map is a variance-like difference of nearly equal sums: the 1e-6 differences between the two
-        # deformation implementations are amplified ~1e3x there (same for the reference run twice with perturbed inputs)
-        tol = 2e-2 if k == "rend_dist" else (5e-3 if k == "surf_normal" else 1e-4)
-        assert util.rel_err(o_out[k], r_out[k]) < tol, (k, util.rel_err(o_out[k], r_out[k]))
-    assert util.rel_err(o_vs, r_vs) < 5e-2      # densification statistic: a sum of large cancelling terms, sensitive to the 1e-6 deform differences
+        # 1e-4, or — for the maps that amplify input differences (the distortion map is a variance-like difference of nearly
+        # equal sums, the depth normals are finite differences) — 3x what the REFERENCE shows against itself when its
+        # deformation outputs are perturbed by 1e-6, the size of the difference between the two deformation implementations
+        floor = util.rel_err(pr_out[k], r_out[k])
+        assert util.rel_err(o_out[k], r_out[k]) < max(1e-4, 3 * floor), (k, util.rel_err(o_out[k], r_out[k]), floor)
+    # densification statistic: a sum of large cancelling terms, same yardstick
+    assert util.rel_err(o_vs, r_vs) < max(1e-3, 3 * util.rel_err(p_vs, r_vs)), (util.rel_err(o_vs, r_vs), util.rel_err(p_vs, r_vs))
     assert set(o_g) == set(r_g), set(o_g) ^ set(r_g)
     # Noise floor: our fused deformation and the eager one differ by ~1e-6 relative in d_xyz / d_rotation / d_scaling
     # (fp32 summation order).  That flips the radius or visibility of up to 0.2 % of the surfels (asserted above) and the
@@ -440,7 +446,6 @@ def test_render_dropin_matches_reference_pipeline(cfg_name, cam_index, n_cams, c
     # deformation outputs perturbed by 1e-6: our deviation must stay within a few of those floors.
     # (`feature` additionally has an analytically ~zero gradient here - all nodes share one radius, so the normalised
     # weights are invariant to the common shift of the K distances - hence the absolute term.)
-    _, p_g, _ = run(False, perturb=1e-6)
     scale = max(float(np.linalg.norm(v)) for v in r_g.values())
     report = {}
     for n in o_g:
@@ -472,11 +477,21 @@ def test_render_gradients_incl_distortion_and_normal_match_reference(cfg_name, c
     outputs (computed once by the B200 deform path, as leaf tensors), so nothing but render() differs:
     render() here vs the reference render() sequence around the unmodified reference extension.  Loss = the training loss
     itself (L1 + D-SSIM + lambda_normal * normal consistency + lambda_dist * distortion) plus seeded random weights on
-    every returned map.  Maps 1e-4, gradients w.r.t. every surfel table AND the three deformation outputs <= 5e-4
-    norm-wise (stated floor: the reference extension's own run-to-run spread from atomic ordering is ~2e-6)."""
+    every returned map.
+
+    (A) eager activations in front of our rasterizer (gaussian_renderer.FUSED_ACTIVATIONS = False): the rasterizer inputs
+        are then bit-identical to the reference's, and so must be EVERY map it returns — colour, alpha, normals, median
+        depth, distortion — bit for bit; gradients w.r.t. every surfel table and the three deformation outputs <= 5e-4
+        norm-wise (the reference sums its atomics in nondeterministic order: its own run-to-run spread is ~2e-6).
+    (B) the shipped fused-activation path (exp / sigmoid / normalize inside the per-surfel kernel): its activations differ
+        from torch's in the last bit, and the reference's distortion map is a sum of differences of nearly equal numbers
+        (m^2 A + D2 - 2 m D), which amplifies a 1-ulp input change to ~1e-3 of the map — in the reference itself: the
+        stated floor is the reference run against ITSELF with its rasterizer inputs perturbed by 1 ulp (6e-8 relative).
+        Maps 1e-4 (rend_dist: 3 x floor), gradients <= 5e-4 |g| + 4 x floor."""
     ref = util.load_reference_ext()
     if ref is None:
         pytest.skip("oracle/_ref not available")
+    import gaussian_renderer
     from d2gs_b200 import deform as dfm, model as mdl, synthetic as syn
     from gaussian_renderer import render
     from oracle import loss_oracle as lo
@@ -502,13 +517,21 @@ def test_render_gradients_incl_distortion_and_normal_match_reference(cfg_name, c
     gen = torch.Generator().manual_seed(11)
     wts = {}
 
-    def run(ours: bool):
+    def run(ours: bool, fused: bool = True, ulp_noise: bool = False):
         pc = mdl.SurfelModel(sc, dev)
         d = {k: v.clone().requires_grad_(True) for k, v in deltas.items()}
+        dd = d
+        if ulp_noise:       # +-1 ulp on what the rasterizer sees: the conditioning yardstick of (B)
+            gp = torch.Generator().manual_seed(5)
+            dd = {k: v * (1.0 + 6e-8 * torch.randn(v.shape, generator=gp).to(dev)) for k, v in d.items()}
         if ours:
-            out = render(cam, pc, mdl.PipelineParams(), bg, d["d_xyz"], d["d_rotation"], d["d_scaling"])
+            gaussian_renderer.FUSED_ACTIVATIONS = fused
+            try:
+                out = render(cam, pc, mdl.PipelineParams(), bg, dd["d_xyz"], dd["d_rotation"], dd["d_scaling"])
+            finally:
+                gaussian_renderer.FUSED_ACTIVATIONS = True
         else:
-            out = rp.render_reference(ref, cam, pc, bg, d["d_xyz"], d["d_rotation"], d["d_scaling"])
+            out = rp.render_reference(ref, cam, pc, bg, dd["d_xyz"], dd["d_rotation"], dd["d_scaling"])
         loss = lo.surfel_loss(out["render"], gt, out["rend_normal"], out["surf_normal"], out["rend_dist"], 0.2, 0.02, 1000.0)[0]
         for k in keys:
             if k not in wts:
@@ -519,17 +542,32 @@ def test_render_gradients_incl_distortion_and_normal_match_reference(cfg_name, c
         grads = {n: p_.grad.detach().cpu().numpy().copy() for n, p_ in pc.named_parameters() if p_.grad is not None}
         grads.update({k: v.grad.detach().cpu().numpy().copy() for k, v in d.items()})
         grads["viewspace_points"] = out["viewspace_points"].grad.detach().cpu().numpy().copy()
-        return {k: out[k].detach().cpu().numpy() for k in keys + ("surf_point", "radii")}, grads, float(loss)
+        return {k: out[k].detach().cpu().numpy() for k in keys + ("surf_point", "radii")}, grads, float(loss.detach())
 
-    o_out, o_g, o_l = run(True)
     r_out, r_g, r_l = run(False)
-    assert np.array_equal(o_out["radii"], r_out["radii"])            # identical inputs: the integer stages are bit-exact
-    for k in keys + ("surf_point",):
-        e = util.rel_err(o_out[k], r_out[k])
-        assert e < 1e-4, (k, e)
-    assert abs(o_l - r_l) <= 1e-5 * abs(r_l)
-    assert set(o_g) == set(r_g), set(o_g) ^ set(r_g)
+    # ---- (A) identical rasterizer inputs: bit-identical maps, gradients to atomic-ordering accuracy
+    a_out, a_g, a_l = run(True, fused=False)
+    for k in keys + ("surf_point", "radii"):
+        assert np.array_equal(a_out[k], r_out[k]), (k, util.rel_err(a_out[k], r_out[k]))
+    assert a_l == r_l
+    assert set(a_g) == set(r_g), set(a_g) ^ set(r_g)
     for n in r_g:
-        e = util.rel_err(o_g[n].reshape(r_g[n].shape), r_g[n])
+        e = util.rel_err(a_g[n].reshape(r_g[n].shape), r_g[n])
         assert e < 5e-4, (n, e)
     assert float(np.abs(r_g["d_scaling"]).max()) > 0 and float(np.abs(r_out["rend_dist"]).max()) > 0
+    # ---- (B) fused activations against the floor of the reference's own conditioning
+    p_out, p_g, _ = run(False, ulp_noise=True)
+    o_out, o_g, o_l = run(True, fused=True)
+    assert (o_out["radii"] != r_out["radii"]).mean() <= max(1e-4, 3 * (p_out["radii"] != r_out["radii"]).mean())
+    for k in keys + ("surf_point",):
+        e, floor = util.rel_err(o_out[k], r_out[k]), util.rel_err(p_out[k], r_out[k])
+        assert e < max(1e-4, 3 * floor), (k, e, floor)
+    assert abs(o_l - r_l) <= 1e-4 * abs(r_l)
+    scale = max(float(np.linalg.norm(v)) for v in r_g.values())
+    bad = {}
+    for n in r_g:
+        err = float(np.linalg.norm(o_g[n].reshape(r_g[n].shape).astype(np.float64) - r_g[n]))
+        floor = float(np.linalg.norm(p_g[n].astype(np.float64) - r_g[n]))
+        if err > 5e-4 * float(np.linalg.norm(r_g[n])) + 4.0 * floor + 1e-7 * scale:
+            bad[n] = (err, floor, float(np.linalg.norm(r_g[n])))
+    assert not bad, bad

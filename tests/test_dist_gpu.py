@@ -1,0 +1,84 @@
+"""2-GPU (NCCL) check of the view-sharded step: the all-reduced gradients with the EARLY all-reduce of the surfel tables
+must equal those of the plain single all-reduce at the end — in particular the deformation-network / node gradients,
+which are computed downstream of dL/dxyz and dL/drotation while the early collective is already summing those tables
+across ranks (the deltas must not alias an early bucket slot).  Skipped on boxes with one GPU
+(run with `gpurun --gpus 2`)."""
+import os
+import socket
+
+import pytest
+import torch
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, path):
+    import numpy as np
+    import torch.distributed as dist
+    from d2gs_b200 import deform as dfm, dist as ddist, model as mdl, synthetic as syn
+    from gaussian_renderer import render
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    cfg = syn.CONFIGS["T1"]
+    sc = syn.make_scene(cfg["P"], cfg["seed"], cfg["s_med"], n_nodes=cfg["n_nodes"], hyper_dim=8)
+    cams = syn.fibonacci_cameras(8, cfg["W"], cfg["H"])
+    results = {}
+    for early_on in (False, True):
+        torch.manual_seed(0)
+        pc = mdl.SurfelModel(sc, dev)
+        dm = dfm.DeformModel(deform_type="node", is_blender=True, K=4, hyper_dim=8, node_num=cfg["n_nodes"], local_frame=True)
+        with torch.no_grad():
+            dm.deform.nodes.copy_(torch.as_tensor(sc.nodes, device=dev))
+            dm.deform._node_radius.copy_(torch.as_tensor(sc.node_radius, device=dev))
+            for h in (dm.deform.network.gaussian_warp, dm.deform.network.gaussian_rotation, dm.deform.network.local_rotation):
+                h.weight.mul_(1e3)
+        params = list(pc.raster_parameters()) + [p for p in dm.deform.parameters() if p.requires_grad]
+        early = [p for p in pc.raster_parameters() if p is not pc.feature]
+        bucket = ddist.FlatGradBucket(params, large_numel=1 << 12, early=early if early_on else None)
+        assert ddist.reduces_early(pc._xyz) == early_on
+        g = torch.Generator().manual_seed(3)
+        w = (torch.randn((3, cfg["H"], cfg["W"]), generator=g) / (cfg["H"] * cfg["W"])).to(dev)
+        wd = (torch.randn((1, cfg["H"], cfg["W"]), generator=g) / (cfg["H"] * cfg["W"])).to(dev)
+        acc = None
+        for step in range(3):                       # several steps: a race would show up nondeterministically
+            bucket.zero()
+            cam = mdl.ViewCamera(cams[ddist.view_for(step, rank, world, 8)], dev)
+            d = dm.step(pc.get_xyz.detach(), dm.deform.expand_time(cam.fid), feature=pc.feature, motion_mask=pc.motion_mask)
+            out = render(cam, pc, mdl.PipelineParams(), torch.zeros(3, device=dev), d["d_xyz"], d["d_rotation"], d["d_scaling"])
+            ((out["render"] * w).sum() + (out["depth"] * wd).sum() + (out["rend_normal"] * w).sum()).backward()
+            launched = bucket._early_work is not None
+            assert launched == early_on
+            bucket.all_reduce()
+            torch.cuda.synchronize(dev)
+            acc = bucket.flat.clone() if acc is None else acc + bucket.flat
+        names = {id(p): n for n, p in list(pc.named_parameters()) + list(dm.deform.named_parameters())}
+        results[early_on] = {names[id(p)]: p.grad.detach().cpu().numpy().copy() for p in bucket.params}
+        results[early_on]["__acc__"] = acc.cpu().numpy()
+        bucket.detach()
+    if rank == 0:
+        bad = {}
+        for n in results[False]:
+            a, b = results[True][n], results[False][n]
+            e = float(np.linalg.norm(a.astype(np.float64) - b) / max(float(np.linalg.norm(b)), 1e-30))
+            if e > 1e-4:      # atomic ordering only; a race contaminates the network gradients at O(1)
+                bad[n] = e
+        torch.save({"bad": bad, "n": len(results[False])}, path)
+    dist.destroy_process_group()
+
+
+def test_early_allreduce_matches_single_allreduce_on_two_gpus(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    path = str(tmp_path / "r.pt")
+    mp.spawn(_worker, args=(2, _free_port(), path), nprocs=2, join=True)
+    got = torch.load(path)
+    assert got["n"] > 20 and not got["bad"], got["bad"]
