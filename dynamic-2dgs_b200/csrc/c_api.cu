@@ -48,6 +48,7 @@ static bool g_profile = false;
 int g_deform_bwd_smem = 1;  // node-gradient accumulation of deform_bwd: 1 = per-CTA shared accumulators, 0 = global reductions
 int g_knn_filter = 1;       // warp-level candidate filter of the K-nearest-node search (0: every node is visited; same results)
 static int g_tile_sort = 1;   // binning: 0 = global radix sort of (tile | depth) keys, 1 = per-tile buckets + segmented sort (same lists)
+static int g_tile_order = 1;  // blend CTAs visit tiles longest list first (scheduling only; set before the forward of a frame)
 static int g_cull = 1;   // warp-level cull boxes in the blend kernels (tests switch it off to prove it changes nothing)
 static std::vector<StageRec> g_recs;
 static std::vector<cudaEvent_t> g_free_events;
@@ -92,6 +93,7 @@ ImgLayout img_layout(int W, int H) {
   L.tile_count = o; o = align_up(o + 4 * tiles);
   L.seg_begin = o; o = align_up(o + 4 * tiles);
   L.seg_end = o; o = align_up(o + 4 * tiles);
+  L.tile_order = o; o = align_up(o + 4 * tiles);
   L.total = o + 256;
   return L;
 }
@@ -144,6 +146,7 @@ int d2gs_set_option(const char* name, int value) {
   if (std::strcmp(name, "deform_bwd_smem") == 0) { g_deform_bwd_smem = value != 0; return D2GS_OK; }
   if (std::strcmp(name, "knn_filter") == 0) { g_knn_filter = value != 0; return D2GS_OK; }
   if (std::strcmp(name, "tile_sort") == 0) { g_tile_sort = value != 0; return D2GS_OK; }
+  if (std::strcmp(name, "tile_order") == 0) { g_tile_order = value != 0; return D2GS_OK; }
   return fail(D2GS_ERR_INVALID_ARG, std::string("unknown option ") + name);
 }
 
@@ -245,6 +248,7 @@ int d2gs_raster_forward(const D2gsRasterFwdArgs* a, void* stream_) {
   uint32_t* tile_count = (uint32_t*)(ib + IL.tile_count);
   uint32_t* seg_begin = (uint32_t*)(ib + IL.seg_begin);
   uint32_t* big_list = (uint32_t*)(ib + IL.seg_end);
+  uint32_t* tile_order = g_tile_order ? (uint32_t*)(ib + IL.tile_order) : nullptr;
   if (deferred && a->binning_capacity > 0xffffffffll) return fail(D2GS_ERR_INVALID_ARG, "binning_capacity exceeds 2^32-1 instances");
   uint4* tile_box = (uint4*)(gb + GL.tile_box);
   p.tile_box = tile_sort ? tile_box : nullptr;
@@ -255,7 +259,7 @@ int d2gs_raster_forward(const D2gsRasterFwdArgs* a, void* stream_) {
       // per-tile counters -> ranges, instance total and overflow flag (no per-surfel scan)
       StageTimer t(ST_SCAN, stream);
       launch_tile_count(P, tile_box, p.gx, p.gy, tile_count, stream);
-      launch_tile_scan(tiles, deferred ? (uint32_t)a->binning_capacity : 0xffffffffu, tile_count, seg_begin, ranges, big_list, status, stream);
+      launch_tile_scan(tiles, deferred ? (uint32_t)a->binning_capacity : 0xffffffffu, tile_count, seg_begin, ranges, big_list, status, tile_order, stream);
     } else {
       size_t tmp = GL.scan_temp_bytes;
       StageTimer t(ST_SCAN, stream);
@@ -318,12 +322,13 @@ int d2gs_raster_forward(const D2gsRasterFwdArgs* a, void* stream_) {
   { StageTimer t(ST_RANGES, stream);
     D2GS_CUDA_OK(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)p.gx * p.gy, stream));
     if (deferred) launch_ranges_deferred((uint32_t)R, status, keys_sorted, ranges, stream);
-    else launch_ranges(R, keys_sorted, ranges, stream); }
+    else launch_ranges(R, keys_sorted, ranges, stream);
+    if (tile_order) launch_tile_order(tiles, ranges, tile_order, stream); }
   D2GS_STAGE("ranges", a->debug, stream);
   }
   { StageTimer t(ST_BLEND_F, stream);
     launch_blend_fwd(p, ranges, point_list, rec, final_T, n_contrib, a->out_color, a->out_others, g_cull,
-                     deferred ? status : nullptr, stream); }
+                     deferred ? status : nullptr, tile_order, stream); }
   D2GS_STAGE("blend", a->debug, stream);
   return D2GS_OK;
 }
@@ -373,7 +378,7 @@ int d2gs_raster_backward(const D2gsRasterBwdArgs* a, void* stream_) {
   if (a->num_rendered > 0) {
     { StageTimer t(ST_BLEND_B, stream);
       launch_blend_bwd(p, ranges, point_list, rec, final_T, n_contrib, a->dL_dout_color, a->dL_dout_others,
-                       a->grad_scratch, g_cull, stream); }
+                       a->grad_scratch, g_cull, g_tile_order ? (const uint32_t*)(ib + IL.tile_order) : nullptr, stream); }
     D2GS_STAGE("blend_bwd", a->debug, stream);
   }
   { StageTimer t(ST_PRE_B, stream);

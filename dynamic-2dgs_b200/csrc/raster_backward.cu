@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_MINBLOCKS) blend_bwd_ker
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
     const float* __restrict__ bg, const SurfelRec* __restrict__ rec, const float* __restrict__ final_Ts,
     const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
-    const float* __restrict__ dL_dothers, float* __restrict__ grad_rec, int cull) {
+    const float* __restrict__ dL_dothers, float* __restrict__ grad_rec, int cull,
+    const uint32_t* __restrict__ tile_order, uint32_t gx) {
   extern __shared__ __align__(16) unsigned char bwd_smem[];
   float* s_acc = reinterpret_cast<float*>(bwd_smem + BWD_SMEM_Q);        // [warp][slot][ACC_STRIDE]
   float* s_red = reinterpret_cast<float*>(bwd_smem + BWD_SMEM_Q + BWD_SMEM_ACC);        // [warp][RED_ROWS][RED_STRIDE]
@@ -64,17 +65,21 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_MINBLOCKS) blend_bwd_ker
   uint32_t* s_max = s_id + 2 * BWD_BATCH;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int gwarp = warp + NWARP * (int)blockIdx.z;      // patch index inside the tile (0..7)
+  // 1-D grid, longest tile lists first (see blend_fwd_kernel)
+  const uint32_t sub = blockIdx.x % BWD_Z;
+  const uint32_t tile = tile_order ? __ldg(tile_order + blockIdx.x / BWD_Z) : blockIdx.x / BWD_Z;
+  const uint32_t tile_x = tile % gx, tile_y = tile / gx;
+  const int gwarp = warp + NWARP * (int)sub;      // patch index inside the tile (0..7)
   int lx, ly;
-  pixel_of_thread_b(tid + BWD_THREADS * (int)blockIdx.z, lx, ly);
-  const uint32_t pix_x = blockIdx.x * TILE_X + lx, pix_y = blockIdx.y * TILE_Y + ly;
+  pixel_of_thread_b(tid + BWD_THREADS * (int)sub, lx, ly);
+  const uint32_t pix_x = tile_x * TILE_X + lx, pix_y = tile_y * TILE_Y + ly;
   const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
   const uint32_t pix_id = W * pix_y + pix_x;
   const size_t HW = (size_t)H * W;
   const float2 pixf = {(float)pix_x + 0.5f, (float)pix_y + 0.5f};
-  const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
-  const float pcx0 = (float)(blockIdx.x * TILE_X + ((gwarp & 1) << 3)) + 0.5f, pcx1 = pcx0 + 7.0f;
-  const float pcy0 = (float)(blockIdx.y * TILE_Y + ((gwarp >> 1) << 2)) + 0.5f, pcy1 = pcy0 + 3.0f;
+  const uint2 range = ranges[tile];
+  const float pcx0 = (float)(tile_x * TILE_X + ((gwarp & 1) << 3)) + 0.5f, pcx1 = pcx0 + 7.0f;
+  const float pcy0 = (float)(tile_y * TILE_Y + ((gwarp >> 1) << 2)) + 0.5f, pcy1 = pcy0 + 3.0f;
   const uint32_t sq_base = smem_addr(bwd_smem);
   constexpr uint32_t QS = 16u * BWD_BATCH;   // bytes per staged quad plane
   float* my_acc = s_acc + (size_t)warp * BWD_BATCH * ACC_STRIDE;
@@ -352,8 +357,8 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_MINBLOCKS) blend_bwd_ker
 
 void launch_blend_bwd(const BwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
                       const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, const float* dL_dothers,
-                      float* grad_rec, int cull, cudaStream_t s) {
-  dim3 grid(p.gx, p.gy, BWD_Z);
+                      float* grad_rec, int cull, const uint32_t* tile_order, cudaStream_t s) {
+  const uint32_t grid = p.gx * p.gy * BWD_Z;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES);
@@ -362,7 +367,7 @@ void launch_blend_bwd(const BwdParams& p, const uint2* ranges, const uint32_t* p
     configured = true;
   }
   blend_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM_BYTES, s>>>(ranges, point_list, p.W, p.H, p.bg, rec, final_T, n_contrib, dL_dpix,
-                                            dL_dothers, grad_rec, cull);
+                                            dL_dothers, grad_rec, cull, tile_order, p.gx);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -274,23 +274,28 @@ __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_ker
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
     const SurfelRec* __restrict__ rec, const float* __restrict__ bg, float* __restrict__ final_T,
     uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, float* __restrict__ out_others, int cull,
-    const uint32_t* __restrict__ status) {
+    const uint32_t* __restrict__ status, const uint32_t* __restrict__ tile_order, uint32_t gx) {
   __shared__ float4 s_q[2][REC_QUADS][BLEND_BATCH];
 
   const int tid = threadIdx.x;
+  // 1-D grid: CTA b works on sub-tile b % FWD_Z of the (b / FWD_Z)-th LONGEST tile list, so the in-order CTA dispatch
+  // starts the long lists first and the empty tiles fill the tail of the kernel
+  const uint32_t sub = blockIdx.x % FWD_Z;
+  const uint32_t tile = tile_order ? __ldg(tile_order + blockIdx.x / FWD_Z) : blockIdx.x / FWD_Z;
+  const uint32_t tile_x = tile % gx, tile_y = tile / gx;
   int lx, ly;
-  pixel_of_thread(tid + FWD_THREADS * (int)blockIdx.z, lx, ly);
-  const uint32_t pix_x = blockIdx.x * TILE_X + lx, pix_y = blockIdx.y * TILE_Y + ly;
+  pixel_of_thread(tid + FWD_THREADS * (int)sub, lx, ly);
+  const uint32_t pix_x = tile_x * TILE_X + lx, pix_y = tile_y * TILE_Y + ly;
   const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
   const uint32_t pix_id = W * pix_y + pix_x;
   const float2 pixf = {(float)pix_x + 0.5f, (float)pix_y + 0.5f};
   bool done = !inside;
   // pixel-centre bounds of this warp's patch
-  const int wq = (tid >> 5) + FWD_NWARP * (int)blockIdx.z;
-  const float pcx0 = (float)(blockIdx.x * TILE_X + ((wq & 1) << 3)) + 0.5f, pcx1 = pcx0 + 7.0f;
-  const float pcy0 = (float)(blockIdx.y * TILE_Y + ((wq >> 1) << 2)) + 0.5f, pcy1 = pcy0 + 3.0f;
+  const int wq = (tid >> 5) + FWD_NWARP * (int)sub;
+  const float pcx0 = (float)(tile_x * TILE_X + ((wq & 1) << 3)) + 0.5f, pcx1 = pcx0 + 7.0f;
+  const float pcy0 = (float)(tile_y * TILE_Y + ((wq >> 1) << 2)) + 0.5f, pcy1 = pcy0 + 3.0f;
 
-  const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
+  const uint2 range = ranges[tile];
   const int rounds = (range.y - range.x + BLEND_BATCH - 1) / BLEND_BATCH;
   int toDo = range.y - range.x;
   const uint32_t sq_base = smem_addr(&s_q[0][0][0]);
@@ -453,10 +458,10 @@ __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_ker
 
 void launch_blend_fwd(const FwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
                       float* final_T, uint32_t* n_contrib, float* out_color, float* out_others, int cull,
-                      const uint32_t* status, cudaStream_t s) {
-  dim3 grid(p.gx, p.gy, FWD_Z);
+                      const uint32_t* status, const uint32_t* tile_order, cudaStream_t s) {
+  const uint32_t grid = p.gx * p.gy * FWD_Z;
   blend_fwd_kernel<<<grid, FWD_THREADS, 0, s>>>(ranges, point_list, p.W, p.H, rec, p.bg, final_T, n_contrib, out_color,
-                                            out_others, cull, status);
+                                            out_others, cull, status, tile_order, p.gx);
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,

@@ -48,11 +48,48 @@ __global__ void __launch_bounds__(256) tile_count_kernel(int P, const uint4* __r
   }
 }
 
+// One CTA (1024 threads): tile ids by decreasing list length.  Counting sort over 256 length classes (class = length / 16,
+// capped): histogram -> exclusive scan from the longest class down -> scatter.  The order inside a class is whatever the
+// atomics produce; it only steers scheduling, never results.
+constexpr int ORDER_CLASSES = 256;
+__device__ __forceinline__ void order_tiles_by_length(uint32_t tiles, const uint2* ranges, uint32_t* __restrict__ order,
+                                                      uint32_t* s_hist /*[ORDER_CLASSES]*/) {
+  for (int c = threadIdx.x; c < ORDER_CLASSES; c += blockDim.x) s_hist[c] = 0u;
+  __syncthreads();
+  auto cls = [](uint2 r) { return min((uint32_t)ORDER_CLASSES - 1u, (r.y - r.x) >> 4); };
+  for (uint32_t t = threadIdx.x; t < tiles; t += blockDim.x) atomicAdd(s_hist + cls(ranges[t]), 1u);
+  __syncthreads();
+  if (threadIdx.x < 32) {      // exclusive scan in descending class order: 8 classes per lane
+    const int lane = threadIdx.x;
+    uint32_t loc[8], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { loc[i] = s_hist[ORDER_CLASSES - 1 - (lane * 8 + i)]; sum += loc[i]; }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t n = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += n;
+    }
+    uint32_t run = inc - sum;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { s_hist[ORDER_CLASSES - 1 - (lane * 8 + i)] = run; run += loc[i]; }
+  }
+  __syncthreads();
+  for (uint32_t t = threadIdx.x; t < tiles; t += blockDim.x) order[atomicAdd(s_hist + cls(ranges[t]), 1u)] = t;
+}
+
+__global__ void __launch_bounds__(1024) tile_order_kernel(uint32_t tiles, const uint2* __restrict__ ranges, uint32_t* __restrict__ order) {
+  __shared__ uint32_t s_hist[ORDER_CLASSES];
+  order_tiles_by_length(tiles, ranges, order, s_hist);
+}
+
 // one CTA: exclusive scan of the tile counters (chunks of 1024 with a running carry)
 __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t tiles, uint32_t capacity, uint32_t* __restrict__ tile_count,
                                                          uint32_t* __restrict__ seg_begin, uint2* __restrict__ ranges,
-                                                         uint32_t* __restrict__ big_list, uint32_t* __restrict__ status) {
+                                                         uint32_t* __restrict__ big_list, uint32_t* __restrict__ status,
+                                                         uint32_t* __restrict__ tile_order) {
   __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_hist[ORDER_CLASSES];
   __shared__ uint32_t s_carry, s_nbig;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) { s_carry = 0; s_nbig = 0; }
@@ -106,6 +143,10 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t tiles, uint32_
     __syncthreads();
   }
   if (threadIdx.x == 0) status[2] = s_nbig;
+  if (tile_order) {
+    __syncthreads();               // this CTA wrote every range: visible to all its threads after the barrier
+    order_tiles_by_length(tiles, ranges, tile_order, s_hist);
+  }
 }
 
 __global__ void __launch_bounds__(256) tile_scatter_kernel(int P, const uint4* __restrict__ tile_box, uint32_t gx, uint32_t gy,
@@ -269,8 +310,11 @@ void launch_tile_count(int P, const uint4* tile_box, uint32_t gx, uint32_t gy, u
   tile_count_kernel<<<persistent_grid(P), 256, smem, s>>>(P, tile_box, gx, gy, tile_count);
 }
 void launch_tile_scan(uint32_t tiles, uint32_t capacity, uint32_t* tile_count, uint32_t* seg_begin, uint2* ranges, uint32_t* big_list,
-                      uint32_t* status, cudaStream_t s) {
-  tile_scan_kernel<<<1, 1024, 0, s>>>(tiles, capacity, tile_count, seg_begin, ranges, big_list, status);
+                      uint32_t* status, uint32_t* tile_order, cudaStream_t s) {
+  tile_scan_kernel<<<1, 1024, 0, s>>>(tiles, capacity, tile_count, seg_begin, ranges, big_list, status, tile_order);
+}
+void launch_tile_order(uint32_t tiles, const uint2* ranges, uint32_t* tile_order, cudaStream_t s) {
+  tile_order_kernel<<<1, 1024, 0, s>>>(tiles, ranges, tile_order);
 }
 void launch_tile_scatter(int P, const uint4* tile_box, uint32_t gx, uint32_t gy, const uint32_t* seg_begin, uint32_t* cursor,
                          const uint32_t* status, uint64_t* keys, cudaStream_t s) {

@@ -74,6 +74,9 @@ if __name__ == "__main__":
             libs.append(args[i]); i += 1
     for lib in libs:
         env = dict(os.environ)
+        lib, _, opts = lib.partition("@")          # "default@tile_order=0": D2GS_OPTIONS for that run
+        if opts:
+            env["D2GS_OPTIONS"] = opts
         if lib == "default":
             env.pop("D2GS_LIB", None)
         else:
@@ -86,6 +89,6 @@ if __name__ == "__main__":
             continue
         d = json.loads(line[0][8:])
         s = d["stages_ms"]
-        print(f"{os.path.basename(lib):44s} fwd {s.get('blend_fwd')} bwd {s.get('blend_bwd')} pre_f {s.get('preprocess_fwd')} pre_b {s.get('preprocess_bwd')} "
+        print(f"{os.path.basename(lib) + ('@' + opts if opts else ''):44s} fwd {s.get('blend_fwd')} bwd {s.get('blend_bwd')} pre_f {s.get('preprocess_fwd')} pre_b {s.get('preprocess_bwd')} "
               f"scan {s.get('scan')} dup {s.get('duplicate')} sort {s.get('sort')} frame {d['total_ms_per_frame']:.3f}  chk {['%.7g' % c for c in d['checksum']]}",
               flush=True)

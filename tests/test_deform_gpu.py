@@ -435,8 +435,17 @@ def test_render_dropin_matches_reference_pipeline(cfg_name, cam_index, n_cams, c
         # 1e-4, or — for the maps that amplify input differences (the distortion map is a variance-like difference of nearly
         # equal sums, the depth normals are finite differences) — 3x what the REFERENCE shows against itself when its
         # deformation outputs are perturbed by 1e-6, the size of the difference between the two deformation implementations
-        floor = util.rel_err(pr_out[k], r_out[k])
-        assert util.rel_err(o_out[k], r_out[k]) < max(1e-4, 3 * floor), (k, util.rel_err(o_out[k], r_out[k]), floor)
+        # The two deformation implementations differ by ~5e-7 of |d_xyz| (measured, gpu_deform_diag.py); the median depth is
+        # piecewise constant in the inputs and jumps by a whole inter-surfel distance where the transmittance crosses 0.5, so
+        # the comparison drops the 0.1 % of pixels with the largest difference (for the yardstick too) and bounds how far the
+        # full-map error may exceed it: a handful of flipped pixels, not a systematic difference.
+        # (colour, alpha and the blended normals are continuous: compared in full.)
+        metric = util.rel_err_trimmed if k in ("depth", "surf_normal", "surf_point", "rend_dist") else util.rel_err
+        floor = metric(pr_out[k], r_out[k])
+        err = metric(o_out[k], r_out[k])
+        assert err < max(1e-4, 3 * floor), (k, err, floor)
+        big = np.abs(o_out[k].astype(np.float64) - r_out[k]) > 1e-3 * max(float(np.abs(r_out[k]).max()), 1e-30)
+        assert big.mean() < 1e-3, (k, float(big.mean()))
     # densification statistic: a sum of large cancelling terms, same yardstick
     assert util.rel_err(o_vs, r_vs) < max(1e-3, 3 * util.rel_err(p_vs, r_vs)), (util.rel_err(o_vs, r_vs), util.rel_err(p_vs, r_vs))
     assert set(o_g) == set(r_g), set(o_g) ^ set(r_g)
