@@ -49,6 +49,7 @@ int g_deform_bwd_smem = 1;  // node-gradient accumulation of deform_bwd: 1 = per
 int g_knn_filter = 1;       // warp-level candidate filter of the K-nearest-node search (0: every node is visited; same results)
 static int g_tile_sort = 1;   // binning: 0 = global radix sort of (tile | depth) keys, 1 = per-tile buckets + segmented sort (same lists)
 static int g_tile_order = 1;  // blend CTAs visit tiles longest list first (scheduling only; set before the forward of a frame)
+static int g_lane_walk = 3;   // bit 0: forward blend, bit 1: backward blend walk per-lane hit lists (A/B switch; same results)
 static int g_cull = 1;   // warp-level cull boxes in the blend kernels (tests switch it off to prove it changes nothing)
 static std::vector<StageRec> g_recs;
 static std::vector<cudaEvent_t> g_free_events;
@@ -146,6 +147,7 @@ int d2gs_set_option(const char* name, int value) {
   if (std::strcmp(name, "deform_bwd_smem") == 0) { g_deform_bwd_smem = value != 0; return D2GS_OK; }
   if (std::strcmp(name, "knn_filter") == 0) { g_knn_filter = value != 0; return D2GS_OK; }
   if (std::strcmp(name, "tile_sort") == 0) { g_tile_sort = value != 0; return D2GS_OK; }
+  if (std::strcmp(name, "lane_walk") == 0) { g_lane_walk = value; return D2GS_OK; }
   if (std::strcmp(name, "tile_order") == 0) { g_tile_order = value != 0; return D2GS_OK; }
   return fail(D2GS_ERR_INVALID_ARG, std::string("unknown option ") + name);
 }
@@ -328,7 +330,7 @@ int d2gs_raster_forward(const D2gsRasterFwdArgs* a, void* stream_) {
   }
   { StageTimer t(ST_BLEND_F, stream);
     launch_blend_fwd(p, ranges, point_list, rec, final_T, n_contrib, a->out_color, a->out_others, g_cull,
-                     deferred ? status : nullptr, tile_order, stream); }
+                     deferred ? status : nullptr, tile_order, g_lane_walk & 1, stream); }
   D2GS_STAGE("blend", a->debug, stream);
   return D2GS_OK;
 }
@@ -378,7 +380,8 @@ int d2gs_raster_backward(const D2gsRasterBwdArgs* a, void* stream_) {
   if (a->num_rendered > 0) {
     { StageTimer t(ST_BLEND_B, stream);
       launch_blend_bwd(p, ranges, point_list, rec, final_T, n_contrib, a->dL_dout_color, a->dL_dout_others,
-                       a->grad_scratch, g_cull, g_tile_order ? (const uint32_t*)(ib + IL.tile_order) : nullptr, stream); }
+                       a->grad_scratch, g_cull, g_tile_order ? (const uint32_t*)(ib + IL.tile_order) : nullptr,
+                       (g_lane_walk >> 1) & 1, stream); }
     D2GS_STAGE("blend_bwd", a->debug, stream);
   }
   { StageTimer t(ST_PRE_B, stream);

@@ -355,16 +355,340 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_MINBLOCKS) blend_bwd_ker
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Lane-walk variant of the backward blend (default; see blend_fwd_lw_kernel).  Per warp and chunk of survivors:
+//   phase 1  all lanes run the exact prefilter for every cull-box survivor (broadcast LDS.128); the ballot of the
+//            passing lanes is the survivor's hit mask: it reserves popc(mask) rows of the warp's gradient scratch and
+//            each lane keeps ITS hits as bits (ordinal of the survivor in the chunk) of a 64-bit mask;
+//   phase 2  every lane walks its own hits back to front (lanes work on different surfels at the same time: ~18-20
+//            active lanes instead of ~9), runs the compositing gradient with the running scalars T, Q of its pixel and
+//            writes its 18 components as row  rowbase(survivor) + rank(lane in the hit mask);
+//   phase 3  per survivor, 18 lanes sum one column each over its rows and issue ONE global reduction per
+//            (patch, surfel, component).  No per-warp accumulators, no CTA-wide flush, no second barrier per batch.
+// Same float operations per (pixel, surfel) pair as blend_bwd_kernel; only the order of the gradient sums differs.
+// ------------------------------------------------------------------------------------------------------------
+#ifndef D2GS_BWD_LW_ROWS
+#define D2GS_BWD_LW_ROWS 128
+#endif
+constexpr int LW_ROWS = D2GS_BWD_LW_ROWS;      // gradient rows per warp (80 B each)
+constexpr int LW_ORD = 64;                      // survivors per chunk (two 32-bit hit masks per lane)
+constexpr size_t LWB_SMEM_Q = 2 * BWD_SMEM_Q1;
+constexpr size_t LWB_SMEM_ROWS = sizeof(float) * NWARP * LW_ROWS * RED_STRIDE;
+constexpr size_t LWB_SMEM_META = sizeof(uint2) * NWARP * LW_ORD;       // {hit mask, first row | slot << 16}
+constexpr size_t LWB_SMEM_BYTES = LWB_SMEM_Q + LWB_SMEM_ROWS + LWB_SMEM_META + sizeof(uint32_t) * (2 * BWD_BATCH + NWARP);
+
+#ifndef D2GS_BWD_LW_MINBLOCKS
+#define D2GS_BWD_LW_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_LW_MINBLOCKS) blend_bwd_lw_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
+    const float* __restrict__ bg, const SurfelRec* __restrict__ rec, const float* __restrict__ final_Ts,
+    const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
+    const float* __restrict__ dL_dothers, float* __restrict__ grad_rec, int cull,
+    const uint32_t* __restrict__ tile_order, uint32_t gx) {
+  extern __shared__ __align__(16) unsigned char bwd_smem[];
+  float* s_rows = reinterpret_cast<float*>(bwd_smem + LWB_SMEM_Q);                          // [warp][LW_ROWS][RED_STRIDE]
+  uint2* s_meta = reinterpret_cast<uint2*>(bwd_smem + LWB_SMEM_Q + LWB_SMEM_ROWS);          // [warp][LW_ORD]
+  uint32_t* s_id = reinterpret_cast<uint32_t*>(bwd_smem + LWB_SMEM_Q + LWB_SMEM_ROWS + LWB_SMEM_META);   // [2][BWD_BATCH]
+  uint32_t* s_max = s_id + 2 * BWD_BATCH;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t sub = blockIdx.x % BWD_Z;
+  const uint32_t tile = tile_order ? __ldg(tile_order + blockIdx.x / BWD_Z) : blockIdx.x / BWD_Z;
+  const uint32_t tile_x = tile % gx, tile_y = tile / gx;
+  const int gwarp = warp + NWARP * (int)sub;
+  int lx, ly;
+  pixel_of_thread_b(tid + BWD_THREADS * (int)sub, lx, ly);
+  const uint32_t pix_x = tile_x * TILE_X + lx, pix_y = tile_y * TILE_Y + ly;
+  const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
+  const uint32_t pix_id = W * pix_y + pix_x;
+  const size_t HW = (size_t)H * W;
+  const float2 pixf = {(float)pix_x + 0.5f, (float)pix_y + 0.5f};
+  const uint2 range = ranges[tile];
+  const float pcx0 = (float)(tile_x * TILE_X + ((gwarp & 1) << 3)) + 0.5f, pcx1 = pcx0 + 7.0f;
+  const float pcy0 = (float)(tile_y * TILE_Y + ((gwarp >> 1) << 2)) + 0.5f, pcy1 = pcy0 + 3.0f;
+  const uint32_t sq_base = smem_addr(bwd_smem);
+  constexpr uint32_t QS = 16u * BWD_BATCH;
+  const uint32_t lanes_below = (1u << lane) - 1u;
+  const uint32_t rows_w = smem_addr(s_rows + (size_t)warp * LW_ROWS * RED_STRIDE);
+  const uint32_t rows_col = rows_w + 4u * (uint32_t)lane;
+  const uint32_t meta_w = smem_addr(s_meta + (size_t)warp * LW_ORD);
+  // GradRec slot of column `lane` (rows are written in accumulator-slot order, see the row stores below)
+  float* const grad_col = grad_rec + lane;
+
+  const float T_final = inside ? final_Ts[pix_id] : 0;
+  float T = T_final;
+  const uint32_t last_contributor = inside ? n_contrib[pix_id] : 0;
+  const int median_contributor = inside ? (int)n_contrib[pix_id + HW] : 0;
+  {
+    const uint32_t m = __reduce_max_sync(FULL, last_contributor);
+    if (lane == 0) s_max[warp] = m;
+  }
+  __syncthreads();
+  uint32_t len = 0;
+#pragma unroll
+  for (int i = 0; i < NWARP; i++) len = max(len, s_max[i]);
+  len = min(len, range.y - range.x);
+  if (len == 0) return;
+
+  float dL_dpixel[3] = {0.f, 0.f, 0.f}, dL_dnormal2D[3] = {0.f, 0.f, 0.f};
+  float dL_ddepth = 0.f, dL_daccum = 0.f, dL_dreg = 0.f, dL_dmedian_depth = 0.f, dL_dmax_dweight = 0.f;
+  if (inside) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) dL_dpixel[ch] = dL_dpixels[ch * HW + pix_id];
+    dL_ddepth = dL_dothers[0 * HW + pix_id];
+    dL_daccum = dL_dothers[1 * HW + pix_id];
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) dL_dnormal2D[ch] = dL_dothers[(2 + ch) * HW + pix_id];
+    dL_dmedian_depth = dL_dothers[5 * HW + pix_id];
+    dL_dreg = dL_dothers[6 * HW + pix_id];
+    dL_dmax_dweight = dL_dothers[7 * HW + pix_id];
+  }
+  const float final_D = inside ? final_Ts[pix_id + HW] : 0;
+  const float final_D2 = inside ? final_Ts[pix_id + 2 * HW] : 0;
+  const float final_A = 1 - T_final;
+  const float bg_dot_dpixel = bg[0] * dL_dpixel[0] + bg[1] * dL_dpixel[1] + bg[2] * dL_dpixel[2];
+  float Q = T_final * bg_dot_dpixel;
+
+  const int rounds = (len + BWD_BATCH - 1) / BWD_BATCH;
+  struct Ids { uint32_t v[BWD_SPT]; };
+  auto slot_id = [&](int bi) -> Ids {
+    Ids r;
+    const int nb = min(BWD_BATCH, (int)len - bi * BWD_BATCH);
+#pragma unroll
+    for (int k = 0; k < BWD_SPT; k++) {
+      const int t = tid + k * BWD_THREADS;
+      r.v[k] = (bi < rounds && t < nb) ? __ldg(&point_list[range.x + (len - 1 - (uint32_t)(bi * BWD_BATCH + t))]) : 0xffffffffu;
+    }
+    return r;
+  };
+  auto stage = [&](int bi, int buf, const Ids& ids) {
+#pragma unroll
+    for (int k = 0; k < BWD_SPT; k++) {
+      const uint32_t id = ids.v[k];
+      const int t = tid + k * BWD_THREADS;
+      if (id != 0xffffffffu) {
+        s_id[buf * BWD_BATCH + t] = id;
+        const float4* r4 = reinterpret_cast<const float4*>(rec + id);
+        const uint32_t dst = sq_base + (uint32_t)buf * (uint32_t)BWD_SMEM_Q1 + ((uint32_t)t << 4);
+#pragma unroll
+        for (int q = 0; q < REC_QUADS; q++) cp_async16(dst + q * QS, r4 + q);
+      }
+    }
+    cp_async_commit();
+  };
+  stage(0, 0, slot_id(0));
+  Ids pre_id = slot_id(1);
+  int remaining = (int)len;
+  for (int i = 0; i < rounds; i++, remaining -= BWD_BATCH) {
+    const int n = min(BWD_BATCH, remaining);
+    const int buf = i & 1;
+    // buffer buf^1 was last read in batch i-1: every warp has to be past it before it is refilled
+    __syncthreads();
+    if (i + 1 < rounds) {
+      stage(i + 1, buf ^ 1, pre_id);
+      pre_id = slot_id(i + 2);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const uint32_t sb0 = sq_base + (uint32_t)buf * (uint32_t)BWD_SMEM_Q1;
+    const uint32_t sb1 = sb0 + QS, sb2 = sb0 + 2 * QS, sb3 = sb0 + 3 * QS, sb4 = sb0 + 4 * QS, sb5 = sb0 + 5 * QS;
+    const uint32_t* cur_id = s_id + buf * BWD_BATCH;
+    const uint32_t pos0 = len - 1 - (uint32_t)(i * BWD_BATCH);      // list position of staged slot 0 (slot j: pos0 - j)
+
+    uint32_t keepmask[BWD_WORDS];
+#pragma unroll
+    for (int w = 0; w < BWD_WORDS; w++) {
+      const int jj = w * 32 + lane;
+      bool keep = jj < n;
+      if (keep && cull) {
+        const float4 bb = lds128(sb5 + ((uint32_t)jj << 4));
+        keep = !(bb.z < pcx0 || bb.x > pcx1 || bb.w < pcy0 || bb.y > pcy1);
+      }
+      keepmask[w] = __ballot_sync(FULL, keep);
+    }
+    int w = 0;
+    uint32_t m = keepmask[0];
+    while (true) {
+      // ---- phase 1: exact prefilter on all lanes, rows reserved per survivor, per-lane hit masks
+      uint32_t hit_lo = 0u, hit_hi = 0u;
+      int ord = 0, rows_used = 0;
+      while (ord < LW_ORD && rows_used <= LW_ROWS - 32) {
+        if (m == 0u) {
+          if (++w >= BWD_WORDS) break;
+#pragma unroll
+          for (int q = 1; q < BWD_WORDS; q++) if (w == q) m = keepmask[q];
+          continue;
+        }
+        const int j = w * 32 + (__ffs(m) - 1);
+        m &= m - 1u;
+        bool pass = inside && (pos0 - (uint32_t)j) < last_contributor;
+        const uint32_t off = (uint32_t)j << 4;
+        const float4 a = lds128(sb0 + off), b = lds128(sb1 + off), c = lds128(sb2 + off);
+        const float3 k = {__fmaf_rn(pixf.x, b.z, -a.x), __fmaf_rn(pixf.x, b.w, -a.y), __fmaf_rn(pixf.x, c.x, -a.z)};
+        const float3 l = {__fmaf_rn(pixf.y, b.z, -a.w), __fmaf_rn(pixf.y, b.w, -b.x), __fmaf_rn(pixf.y, c.x, -b.y)};
+        const float3 p = {__fmaf_rn(k.y, l.z, -__fmul_rn(k.z, l.y)), __fmaf_rn(k.z, l.x, -__fmul_rn(k.x, l.z)),
+                          __fmaf_rn(k.x, l.y, -__fmul_rn(k.y, l.x))};
+        const float2 d = {__fsub_rn(c.y, pixf.x), __fsub_rn(c.z, pixf.y)};
+        const float rho2d = 2.0f * __fmaf_rn(d.x, d.x, __fmul_rn(d.y, d.y));
+        pass = pass && !pair_rejected(p.x, p.y, p.z, rho2d, c.w) && p.z != 0.0f;
+        const uint32_t hm = __ballot_sync(FULL, pass);
+        if (hm == 0u) continue;
+        const uint32_t bit = pass ? 1u : 0u;
+        if (ord < 32) hit_lo |= bit << ord; else hit_hi |= bit << (ord - 32);
+        if (lane == 0)
+          asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(meta_w + 8u * (uint32_t)ord), "r"(hm),
+                       "r"((uint32_t)rows_used | ((uint32_t)j << 16)) : "memory");
+        rows_used += __popc(hm);
+        ord++;
+      }
+      if (ord > 0) {
+        __syncwarp();
+        // ---- phase 2: every lane walks its own hits (increasing ordinal = back to front)
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+          uint32_t mine = half ? hit_hi : hit_lo;
+          const uint32_t mbase = meta_w + 256u * (uint32_t)half;
+          while (mine != 0u) {
+            const uint32_t o = (uint32_t)(__ffs(mine) - 1);
+            mine &= mine - 1u;
+            uint32_t hm, rj;
+            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(hm), "=r"(rj) : "r"(mbase + 8u * o));
+            const uint32_t j = rj >> 16;
+            const uint32_t row = (rj & 0xffffu) + (uint32_t)__popc(hm & lanes_below);
+            const uint32_t contributor = pos0 - j;
+            const uint32_t off = j << 4;
+            float g[16];
+            float gm0 = 0.f, gm1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 16; q++) g[q] = 0.f;
+            do {
+              const float4 a = lds128(sb0 + off), b = lds128(sb1 + off), c = lds128(sb2 + off);
+              const float3 Tw = {b.z, b.w, c.x};
+              const float3 k = {__fmaf_rn(pixf.x, b.z, -a.x), __fmaf_rn(pixf.x, b.w, -a.y), __fmaf_rn(pixf.x, c.x, -a.z)};
+              const float3 l = {__fmaf_rn(pixf.y, b.z, -a.w), __fmaf_rn(pixf.y, b.w, -b.x), __fmaf_rn(pixf.y, c.x, -b.y)};
+              const float3 p = {__fmaf_rn(k.y, l.z, -__fmul_rn(k.z, l.y)), __fmaf_rn(k.z, l.x, -__fmul_rn(k.x, l.z)),
+                                __fmaf_rn(k.x, l.y, -__fmul_rn(k.y, l.x))};
+              const float2 d = {__fsub_rn(c.y, pixf.x), __fsub_rn(c.z, pixf.y)};
+              const float rho2d = 2.0f * __fmaf_rn(d.x, d.x, __fmul_rn(d.y, d.y));
+              const float2 s = {__fdiv_rn(p.x, p.z), __fdiv_rn(p.y, p.z)};
+              const float rho3d = __fmaf_rn(s.x, s.x, __fmul_rn(s.y, s.y));
+              const float rho = fminf(rho3d, rho2d);
+              const float c_d = (rho3d <= rho2d) ? __fadd_rn(Tw.z, __fmaf_rn(Tw.x, s.x, __fmul_rn(Tw.y, s.y))) : Tw.z;
+              if (c_d < 0.2f) break;
+              const float power = -0.5f * rho;
+              if (power > 0.0f) break;
+              const float G = expf(power);
+              const float4 col = lds128(sb4 + off);
+              const float opac = col.w;
+              const float alpha = fminf(0.99f, __fmul_rn(opac, G));
+              if (alpha < 1.0f / 255.0f) break;
+              const float4 nrm = lds128(sb3 + off);
+              const float normal[3] = {nrm.x, nrm.y, nrm.z};
+              const float color[3] = {col.x, col.y, col.z};
+              // compositing gradient with the running scalars T, Q (see blend_bwd_kernel)
+              const float inv_1ma = __fdividef(1.0f, 1.f - alpha);
+              T = T * inv_1ma;
+              const float wgt = alpha * T;
+              float E = dL_daccum;
+#pragma unroll
+              for (int ch = 0; ch < 3; ch++) {
+                E = fmaf(color[ch], dL_dpixel[ch], E);
+                E = fmaf(normal[ch], dL_dnormal2D[ch], E);
+                g[13 + ch] = wgt * dL_dpixel[ch];
+                g[9 + ch] = wgt * dL_dnormal2D[ch];
+              }
+              E = fmaf(c_d, dL_ddepth, E);
+              float dL_dz = 0.0f, dL_dweight = 0.f;
+              const float inv_d = __fdividef(1.0f, c_d);
+              const float m_d = mapped_depth(c_d);
+              const float dmd_dd = 0.2004008016032064f * inv_d * inv_d;
+              if (contributor == (uint32_t)(median_contributor - 1)) {
+                dL_dz += dL_dmedian_depth;
+                dL_dweight += dL_dmax_dweight;
+              }
+              dL_dweight = __fmaf_rn(dL_dreg, __fmaf_rn(__fadd_rn(m_d, m_d), -final_D, __fmaf_rn(final_A, __fmul_rn(m_d, m_d), final_D2)), dL_dweight);
+              E += dL_dweight;
+              const float dL_dalpha = T * E - Q * inv_1ma;
+              Q = fmaf(wgt, E, Q);
+              const float dL_dmd = 2.0f * wgt * __fmaf_rn(final_A, m_d, -final_D) * dL_dreg;
+              dL_dz += dL_dmd * dmd_dd;
+              const float dL_dG = opac * dL_dalpha;
+              dL_dz += wgt * dL_ddepth;
+              if (rho3d <= rho2d) {
+                const float2 dL_ds = {dL_dG * -G * s.x + dL_dz * Tw.x, dL_dG * -G * s.y + dL_dz * Tw.y};
+                const float inv_pz = __fdividef(1.0f, p.z);
+                const float dsx_pz = dL_ds.x * inv_pz, dsy_pz = dL_ds.y * inv_pz;
+                const float3 dL_dp = {dsx_pz, dsy_pz, -(dsx_pz * s.x + dsy_pz * s.y)};
+                const float3 dL_dk = {l.y * dL_dp.z - l.z * dL_dp.y, l.z * dL_dp.x - l.x * dL_dp.z, l.x * dL_dp.y - l.y * dL_dp.x};
+                const float3 dL_dl = {dL_dp.y * k.z - dL_dp.z * k.y, dL_dp.z * k.x - dL_dp.x * k.z, dL_dp.x * k.y - dL_dp.y * k.x};
+                g[0] = -dL_dk.x; g[1] = -dL_dk.y; g[2] = -dL_dk.z;
+                g[3] = -dL_dl.x; g[4] = -dL_dl.y; g[5] = -dL_dl.z;
+                g[6] = pixf.x * dL_dk.x + pixf.y * dL_dl.x + dL_dz * s.x;
+                g[7] = pixf.x * dL_dk.y + pixf.y * dL_dl.y + dL_dz * s.y;
+                g[8] = pixf.x * dL_dk.z + pixf.y * dL_dl.z + dL_dz;
+              } else {
+                gm0 = dL_dG * (-G * 2.0f * d.x);
+                gm1 = dL_dG * (-G * 2.0f * d.y);
+                g[8] = dL_dz;
+              }
+              g[12] = G * dL_dalpha;
+            } while (0);
+            // row in accumulator-slot order: 0..8 transMat | 9,10 mean2D | 11..13 normal | 14 opacity | 15..17 colour
+            // (a pair the later tests dropped writes a row of zeros: its row was reserved by the prefilter ballot)
+            const uint32_t dst = rows_w + row * (RED_STRIDE * 4);
+            sts128(dst, g[0], g[1], g[2], g[3]);
+            sts128(dst + 16, g[4], g[5], g[6], g[7]);
+            sts128(dst + 32, g[8], gm0, gm1, g[9]);
+            sts128(dst + 48, g[10], g[11], g[12], g[13]);
+            sts64(dst + 64, g[14], g[15]);
+          }
+        }
+        __syncwarp();
+        // ---- phase 3: column sums per survivor, one global reduction per (patch, surfel, component)
+#pragma unroll 1
+        for (int o = 0; o < ord; o++) {
+          uint32_t hm, rj;
+          asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(hm), "=r"(rj) : "r"(meta_w + 8u * (uint32_t)o));
+          const int nr = __popc(hm);
+          uint32_t ad = rows_col + (rj & 0xffffu) * (RED_STRIDE * 4);
+          float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+          int r = 0;
+          for (; r + 4 <= nr; r += 4, ad += 4 * RED_STRIDE * 4) {
+            t0 += lds32(ad); t1 += lds32(ad + RED_STRIDE * 4); t2 += lds32(ad + 2 * RED_STRIDE * 4); t3 += lds32(ad + 3 * RED_STRIDE * 4);
+          }
+          if (r + 2 <= nr) { t0 += lds32(ad); t1 += lds32(ad + RED_STRIDE * 4); ad += 2 * RED_STRIDE * 4; r += 2; }
+          if (r < nr) t2 += lds32(ad);
+          const float tot = (t0 + t1) + (t2 + t3);
+          if (lane < RED_COMPS && tot != 0.f) atomicAdd(grad_col + (size_t)cur_id[rj >> 16] * GRAD_REC_FLOATS, tot);
+        }
+        __syncwarp();     // rows and meta are rewritten by the next chunk
+      }
+      if (w >= BWD_WORDS) break;
+    }
+  }
+}
+
 void launch_blend_bwd(const BwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
                       const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, const float* dL_dothers,
-                      float* grad_rec, int cull, const uint32_t* tile_order, cudaStream_t s) {
+                      float* grad_rec, int cull, const uint32_t* tile_order, int lane_walk, cudaStream_t s) {
   const uint32_t grid = p.gx * p.gy * BWD_Z;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES);
     // five CTAs of 37.4 KB (+1 KB each reserved by the system) need a large shared-memory carve-out
     cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(blend_bwd_lw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LWB_SMEM_BYTES);
+    cudaFuncSetAttribute(blend_bwd_lw_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
+  }
+  if (lane_walk) {
+    blend_bwd_lw_kernel<<<grid, BWD_THREADS, LWB_SMEM_BYTES, s>>>(ranges, point_list, p.W, p.H, p.bg, rec, final_T, n_contrib,
+                                                                 dL_dpix, dL_dothers, grad_rec, cull, tile_order, p.gx);
+    return;
   }
   blend_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM_BYTES, s>>>(ranges, point_list, p.W, p.H, p.bg, rec, final_T, n_contrib, dL_dpix,
                                             dL_dothers, grad_rec, cull, tile_order, p.gx);

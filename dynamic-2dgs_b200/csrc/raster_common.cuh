@@ -322,7 +322,7 @@ void launch_ranges_deferred(uint32_t capacity, const uint32_t* status, const uin
 // `status` (may be NULL): when status[1] != 0 the binning overflowed and the colour planes are poisoned with NaN
 void launch_blend_fwd(const FwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
                       float* final_T, uint32_t* n_contrib, float* out_color, float* out_others, int cull,
-                      const uint32_t* status, const uint32_t* tile_order, cudaStream_t s);
+                      const uint32_t* status, const uint32_t* tile_order, int lane_walk, cudaStream_t s);
 
 struct BwdParams {
   int P, D, M, W, H;
@@ -347,7 +347,7 @@ struct BwdParams {
 };
 void launch_blend_bwd(const BwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
                       const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, const float* dL_dothers,
-                      float* grad_rec, int cull, const uint32_t* tile_order, cudaStream_t s);
+                      float* grad_rec, int cull, const uint32_t* tile_order, int lane_walk, cudaStream_t s);
 void launch_preprocess_bwd(const BwdParams& p, const SurfelRec* rec, const uint8_t* clamped, const int* radii,
                            float* grad_rec, float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
                            float* dL_dmeans3D, float* dL_dtransMat, float* dL_dsh, float* dL_dsh_rest,

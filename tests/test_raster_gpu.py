@@ -299,6 +299,38 @@ def test_warp_cull_boxes_change_nothing(cfg, s_med, cam_pos, cuda_device):
     assert float(a["allmap"][1].detach().max()) > 0.5      # the view actually shows the object
 
 
+@pytest.mark.parametrize("cfg,s_med,cam_pos,cam_index", [("T1", None, None, 3), ("T1", 0.05, None, 3), ("T1", 0.02, (0.3, 0.2, 0.1), 3),
+                                                        ("T0", 0.15, (0.0, 0.9, 0.0), 3), ("C3", None, None, 17)])
+def test_lane_walk_blend_is_identical(cfg, s_med, cam_pos, cam_index, cuda_device):
+    """The default blend kernels let every lane walk its OWN list of prefilter hits (lanes of a warp work on different
+    surfels at the same time); `lane_walk = 0` selects the kernels where a warp visits one surfel at a time.  Per pixel
+    the surfels are consumed in the same order with the same float operations: images, n_contrib and final_T must be
+    bit-identical (small and huge splats, camera inside the object, benchmark size); gradients differ only by the order
+    of the floating-point sums."""
+    from d2gs_b200 import _lib, raster, synthetic as syn
+    n_cams = 100 if cfg.startswith("C") else 8
+    act, kw = util.raster_inputs(cfg, s_med=s_med, cam_index=cam_index, n_cams=n_cams)
+    if cam_pos is not None:
+        c = syn.look_at_camera(cam_pos, kw["image_width"], kw["image_height"], target=(0.0, 0.0, 0.0))
+        kw.update(viewmatrix=c.world_view_transform, projmatrix=c.full_proj_transform, campos=c.camera_center)
+    gc, go = util.upstream_grads(kw["image_height"], kw["image_width"], seed=8)
+    res = {}
+    try:
+        for lw in (3, 0):
+            _lib.set_option("lane_walk", lw)
+            o = run_ours(act, kw, cuda_device, gc, go)
+            res[lw] = (o, raster.export_state(o["ctx"]))
+    finally:
+        _lib.set_option("lane_walk", 3)
+    (a, sa), (b, sb) = res[3], res[0]
+    assert a["ctx"].num_rendered == b["ctx"].num_rendered > 0
+    assert torch.equal(a["color"], b["color"]) and torch.equal(a["allmap"], b["allmap"])
+    assert torch.equal(sa["n_contrib"], sb["n_contrib"]) and torch.equal(sa["final_T"], sb["final_T"])
+    for k in ("means3D", "shs", "scales", "rotations", "opacities"):
+        assert util.rel_err(np_(a["ins"][k].grad), np_(b["ins"][k].grad)) < 2e-5, k
+    assert float(a["allmap"][1].detach().max()) > 0.5
+
+
 def test_debug_mode_and_repeatability(cuda_device):
     act, kw = util.raster_inputs("T0")
     gc, go = util.upstream_grads(kw["image_height"], kw["image_width"], seed=4)
