@@ -495,13 +495,27 @@ __device__ __forceinline__ void warp_transpose_reduce32(float (&g)[32], int lane
 // 32-value transposed butterfly sums the rows, and lanes 0..NG-1 issue ONE global reduction each.  92 shared-memory CAS
 // loops per surfel become ~9 x NG fire-and-forget REDs per warp, and the node attributes are warp-uniform loads.
 // A warp whose surfels are not coherent (more than MAX_DISTINCT different nearest nodes) falls back to per-lane REDs.
-template <int K>
+// HMAX: capacity of the hyper-coordinate loops (8 when hyper_dim <= 8 — the trainer's setting — else 16): the loops are
+// fully unrolled and predicated, so half the capacity is half their instructions and registers.
+template <int K, int HMAX>
 __global__ void __launch_bounds__(256, 3) deform_bwd_coherent_kernel(DeformBwdP a) {
-  constexpr int HMAX = MAX_D - 3;
   constexpr int MAX_DISTINCT = 12;
   const int NG = NG_FIXED + a.hyper;
   const int nstride = 3 + a.hyper;
   const int lane = threadIdx.x & 31;
+  // destination of gradient component `lane` of node m: flush_base + flush_stride * m (resolved once, not per flush)
+  float* flush_base = nullptr;
+  int flush_stride = 0;
+  {
+    const int c = lane;
+    if (c < 3) { flush_base = a.d_trans + c; flush_stride = a.st_t; }
+    else if (c < 7) { flush_base = a.d_rot + (c - 3); flush_stride = a.st_r; }
+    else if (c < 9) { flush_base = a.d_scale + (c - 7); flush_stride = a.st_s; }
+    else if (c < 13) { if (a.d_local_rot) { flush_base = a.d_local_rot + (c - 9); flush_stride = a.st_l; } }
+    else if (c == 13) { flush_base = a.d_radius_log; flush_stride = 1; }
+    else if (c == 14) { if (a.d_weight_logit) { flush_base = a.d_weight_logit; flush_stride = 1; } }
+    else if (c < NG) { flush_base = a.d_nodes + 3 + (c - NG_FIXED); flush_stride = nstride; }
+  }
   auto dst_of = [&](int m, int c) -> float* {
     if (c < 3) return a.d_trans + a.st_t * m + c;
     if (c < 7) return a.d_rot + a.st_r * m + (c - 3);
@@ -683,7 +697,7 @@ __global__ void __launch_bounds__(256, 3) deform_bwd_coherent_kernel(DeformBwdP 
     float g[32];
     pair_row(mm, w, duk, dk, g);
     warp_transpose_reduce32(g, lane);
-    if (lane < NG && g[0] != 0.f) { float* q = dst_of(mm, lane); if (q) atomicAdd(q, g[0]); }
+    if (flush_base != nullptr && g[0] != 0.f) atomicAdd(flush_base + (size_t)flush_stride * mm, g[0]);
   }
 }
 
@@ -763,14 +777,14 @@ int deform_backward_launch(const DeformBwdHost& h, cudaStream_t s, const char** 
   if (h.order && NG_FIXED + h.hyper <= 32) {
     const int grid = (h.P + 255) / 256;
     switch (h.K) {
-      case 1: deform_bwd_coherent_kernel<1><<<grid, 256, 0, s>>>(a); break;
-      case 2: deform_bwd_coherent_kernel<2><<<grid, 256, 0, s>>>(a); break;
-      case 3: deform_bwd_coherent_kernel<3><<<grid, 256, 0, s>>>(a); break;
-      case 4: deform_bwd_coherent_kernel<4><<<grid, 256, 0, s>>>(a); break;
-      case 5: deform_bwd_coherent_kernel<5><<<grid, 256, 0, s>>>(a); break;
-      case 6: deform_bwd_coherent_kernel<6><<<grid, 256, 0, s>>>(a); break;
-      case 7: deform_bwd_coherent_kernel<7><<<grid, 256, 0, s>>>(a); break;
-      default: deform_bwd_coherent_kernel<8><<<grid, 256, 0, s>>>(a); break;
+      case 1: if (a.hyper <= 8) deform_bwd_coherent_kernel<1, 8><<<grid, 256, 0, s>>>(a); else deform_bwd_coherent_kernel<1, MAX_D - 3><<<grid, 256, 0, s>>>(a); break;
+      case 2: if (a.hyper <= 8) deform_bwd_coherent_kernel<2, 8><<<grid, 256, 0, s>>>(a); else deform_bwd_coherent_kernel<2, MAX_D - 3><<<grid, 256, 0, s>>>(a); break;
+      case 3: if (a.hyper <= 8) deform_bwd_coherent_kernel<3, 8><<<grid, 256, 0, s>>>(a); else deform_bwd_coherent_kernel<3, MAX_D - 3><<<grid, 256, 0, s>>>(a); break;
+      case 4: if (a.hyper <= 8) deform_bwd_coherent_kernel<4, 8><<<grid, 256, 0, s>>>(a); else deform_bwd_coherent_kernel<4, MAX_D - 3><<<grid, 256, 0, s>>>(a); break;
+      case 5: if (a.hyper <= 8) deform_bwd_coherent_kernel<5, 8><<<grid, 256, 0, s>>>(a); else deform_bwd_coherent_kernel<5, MAX_D - 3><<<grid, 256, 0, s>>>(a); break;
+      case 6: if (a.hyper <= 8) deform_bwd_coherent_kernel<6, 8><<<grid, 256, 0, s>>>(a); else deform_bwd_coherent_kernel<6, MAX_D - 3><<<grid, 256, 0, s>>>(a); break;
+      case 7: if (a.hyper <= 8) deform_bwd_coherent_kernel<7, 8><<<grid, 256, 0, s>>>(a); else deform_bwd_coherent_kernel<7, MAX_D - 3><<<grid, 256, 0, s>>>(a); break;
+      default: if (a.hyper <= 8) deform_bwd_coherent_kernel<8, 8><<<grid, 256, 0, s>>>(a); else deform_bwd_coherent_kernel<8, MAX_D - 3><<<grid, 256, 0, s>>>(a); break;
     }
     return 0;
   }

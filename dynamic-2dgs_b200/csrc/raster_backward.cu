@@ -369,17 +369,17 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_MINBLOCKS) blend_bwd_ker
 // Same float operations per (pixel, surfel) pair as blend_bwd_kernel; only the order of the gradient sums differs.
 // ------------------------------------------------------------------------------------------------------------
 #ifndef D2GS_BWD_LW_ROWS
-#define D2GS_BWD_LW_ROWS 128
+#define D2GS_BWD_LW_ROWS 64
 #endif
 constexpr int LW_ROWS = D2GS_BWD_LW_ROWS;      // gradient rows per warp (80 B each)
-constexpr int LW_ORD = 64;                      // survivors per chunk (two 32-bit hit masks per lane)
+constexpr int LW_ORD = 32;                      // survivors per chunk (one 32-bit hit mask per lane)
 constexpr size_t LWB_SMEM_Q = 2 * BWD_SMEM_Q1;
 constexpr size_t LWB_SMEM_ROWS = sizeof(float) * NWARP * LW_ROWS * RED_STRIDE;
 constexpr size_t LWB_SMEM_META = sizeof(uint2) * NWARP * LW_ORD;       // {hit mask, first row | slot << 16}
 constexpr size_t LWB_SMEM_BYTES = LWB_SMEM_Q + LWB_SMEM_ROWS + LWB_SMEM_META + sizeof(uint32_t) * (2 * BWD_BATCH + NWARP);
 
 #ifndef D2GS_BWD_LW_MINBLOCKS
-#define D2GS_BWD_LW_MINBLOCKS 4
+#define D2GS_BWD_LW_MINBLOCKS 6
 #endif
 __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_LW_MINBLOCKS) blend_bwd_lw_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
@@ -412,10 +412,7 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_LW_MINBLOCKS) blend_bwd_
   constexpr uint32_t QS = 16u * BWD_BATCH;
   const uint32_t lanes_below = (1u << lane) - 1u;
   const uint32_t rows_w = smem_addr(s_rows + (size_t)warp * LW_ROWS * RED_STRIDE);
-  const uint32_t rows_col = rows_w + 4u * (uint32_t)lane;
   const uint32_t meta_w = smem_addr(s_meta + (size_t)warp * LW_ORD);
-  // GradRec slot of column `lane` (rows are written in accumulator-slot order, see the row stores below)
-  float* const grad_col = grad_rec + lane;
 
   const float T_final = inside ? final_Ts[pix_id] : 0;
   float T = T_final;
@@ -514,9 +511,9 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_LW_MINBLOCKS) blend_bwd_
     uint32_t m = keepmask[0];
     while (true) {
       // ---- phase 1: exact prefilter on all lanes, rows reserved per survivor, per-lane hit masks
-      uint32_t hit_lo = 0u, hit_hi = 0u;
+      uint32_t mine = 0u;
       int ord = 0, rows_used = 0;
-      while (ord < LW_ORD && rows_used <= LW_ROWS - 32) {
+      while (ord < LW_ORD) {
         if (m == 0u) {
           if (++w >= BWD_WORDS) break;
 #pragma unroll
@@ -524,7 +521,6 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_LW_MINBLOCKS) blend_bwd_
           continue;
         }
         const int j = w * 32 + (__ffs(m) - 1);
-        m &= m - 1u;
         bool pass = inside && (pos0 - (uint32_t)j) < last_contributor;
         const uint32_t off = (uint32_t)j << 4;
         const float4 a = lds128(sb0 + off), b = lds128(sb1 + off), c = lds128(sb2 + off);
@@ -536,22 +532,22 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_LW_MINBLOCKS) blend_bwd_
         const float rho2d = 2.0f * __fmaf_rn(d.x, d.x, __fmul_rn(d.y, d.y));
         pass = pass && !pair_rejected(p.x, p.y, p.z, rho2d, c.w) && p.z != 0.0f;
         const uint32_t hm = __ballot_sync(FULL, pass);
+        const int nh = __popc(hm);
+        if (rows_used + nh > LW_ROWS) break;     // does not fit any more: it opens the next chunk (its bit stays in m)
+        m &= m - 1u;
         if (hm == 0u) continue;
-        const uint32_t bit = pass ? 1u : 0u;
-        if (ord < 32) hit_lo |= bit << ord; else hit_hi |= bit << (ord - 32);
+        mine |= (pass ? 1u : 0u) << ord;
         if (lane == 0)
           asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(meta_w + 8u * (uint32_t)ord), "r"(hm),
                        "r"((uint32_t)rows_used | ((uint32_t)j << 16)) : "memory");
-        rows_used += __popc(hm);
+        rows_used += nh;
         ord++;
       }
       if (ord > 0) {
         __syncwarp();
         // ---- phase 2: every lane walks its own hits (increasing ordinal = back to front)
-#pragma unroll 1
-        for (int half = 0; half < 2; half++) {
-          uint32_t mine = half ? hit_hi : hit_lo;
-          const uint32_t mbase = meta_w + 256u * (uint32_t)half;
+        {
+          const uint32_t mbase = meta_w;
           while (mine != 0u) {
             const uint32_t o = (uint32_t)(__ffs(mine) - 1);
             mine &= mine - 1u;
@@ -648,22 +644,26 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_LW_MINBLOCKS) blend_bwd_
           }
         }
         __syncwarp();
-        // ---- phase 3: column sums per survivor, one global reduction per (patch, surfel, component)
-#pragma unroll 1
-        for (int o = 0; o < ord; o++) {
+        // ---- phase 3: every lane sums ONE (survivor, group of 4 components) over the survivor's rows (LDS.128) and
+        // issues one 16-byte global reduction: 5 lanes per survivor, ~6 survivors per pass of the warp
+        for (int t = lane; t < 5 * ord; t += 32) {
+          const int o = t / 5, gq = t - 5 * o;
           uint32_t hm, rj;
           asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(hm), "=r"(rj) : "r"(meta_w + 8u * (uint32_t)o));
-          const int nr = __popc(hm);
-          uint32_t ad = rows_col + (rj & 0xffffu) * (RED_STRIDE * 4);
-          float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-          int r = 0;
-          for (; r + 4 <= nr; r += 4, ad += 4 * RED_STRIDE * 4) {
-            t0 += lds32(ad); t1 += lds32(ad + RED_STRIDE * 4); t2 += lds32(ad + 2 * RED_STRIDE * 4); t3 += lds32(ad + 3 * RED_STRIDE * 4);
+          int nr = __popc(hm);
+          uint32_t ad = rows_w + (rj & 0xffffu) * (RED_STRIDE * 4) + 16u * (uint32_t)gq;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (; nr >= 2; nr -= 2, ad += 2 * RED_STRIDE * 4) {
+            const float4 u = lds128(ad), v = lds128(ad + RED_STRIDE * 4);
+            acc.x += u.x + v.x; acc.y += u.y + v.y; acc.z += u.z + v.z; acc.w += u.w + v.w;
           }
-          if (r + 2 <= nr) { t0 += lds32(ad); t1 += lds32(ad + RED_STRIDE * 4); ad += 2 * RED_STRIDE * 4; r += 2; }
-          if (r < nr) t2 += lds32(ad);
-          const float tot = (t0 + t1) + (t2 + t3);
-          if (lane < RED_COMPS && tot != 0.f) atomicAdd(grad_col + (size_t)cur_id[rj >> 16] * GRAD_REC_FLOATS, tot);
+          if (nr) {
+            const float4 u = lds128(ad);
+            acc.x += u.x; acc.y += u.y; acc.z += u.z; acc.w += u.w;
+          }
+          if (gq == 4) { acc.z = 0.f; acc.w = 0.f; }      // floats 18, 19 of a row are padding (never written)
+          if (acc.x != 0.f || acc.y != 0.f || acc.z != 0.f || acc.w != 0.f)
+            atomicAdd(reinterpret_cast<float4*>(grad_rec + (size_t)cur_id[rj >> 16] * GRAD_REC_FLOATS) + gq, acc);
         }
         __syncwarp();     // rows and meta are rewritten by the next chunk
       }

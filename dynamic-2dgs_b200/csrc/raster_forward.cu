@@ -469,7 +469,10 @@ __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_ker
 // Per pixel the instances are still consumed strictly in list order with the same float operations, so every output
 // is bit-identical to blend_fwd_kernel (and to the reference where that one is).
 // ------------------------------------------------------------------------------------------------------------
-constexpr int LW_CHUNK = 64;    // cull-box survivors per phase-1/phase-2 round (two 32-bit masks per lane)
+#ifndef D2GS_FWD_LW_CHUNK
+#define D2GS_FWD_LW_CHUNK 32
+#endif
+constexpr int LW_CHUNK = D2GS_FWD_LW_CHUNK;    // cull-box survivors per phase-1/phase-2 round (one or two 32-bit masks per lane)
 __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_lw_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
     const SurfelRec* __restrict__ rec, const float* __restrict__ bg, float* __restrict__ final_T,
@@ -587,7 +590,7 @@ __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_lw_
         const float rho2d = 2.0f * __fmaf_rn(dd.x, dd.x, __fmul_rn(dd.y, dd.y));
         const bool pass = !pair_rejected(p.x, p.y, p.z, rho2d, c.w) && p.z != 0.0f;
         const uint32_t bit = pass ? 1u : 0u;
-        if (ord < 32) hit_lo |= bit << ord; else hit_hi |= bit << (ord - 32);
+        if (LW_CHUNK <= 32 || ord < 32) hit_lo |= bit << ord; else hit_hi |= bit << (ord - 32);
         if (lane == 0) asm volatile("st.shared.u8 [%0], %1;" ::"r"(slot_base + (uint32_t)ord), "r"(j) : "memory");
         ord++;
       }
@@ -595,7 +598,7 @@ __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_lw_
       __syncwarp();
       // ---- phase 2: every lane consumes its own hits in list order
 #pragma unroll 1
-      for (int half = 0; half < 2; half++) {
+      for (int half = 0; half < (LW_CHUNK + 31) / 32; half++) {
         uint32_t mine = half ? hit_hi : hit_lo;
         const uint32_t sbase = slot_base + 32u * (uint32_t)half;
         while (mine != 0u && !done) {

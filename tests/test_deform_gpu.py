@@ -562,8 +562,9 @@ def test_render_gradients_incl_distortion_and_normal_match_reference(cfg_name, c
     # reference runs ~40 eager kernels with a matmul and torch.inverse: same formulas, last-bit differences (<= 1e-6).
     for k in ("render", "alpha", "rend_dist", "radii"):
         assert np.array_equal(a_out[k], r_out[k]), (k, util.rel_err(a_out[k], r_out[k]))
-    for k in ("rend_normal", "depth", "surf_normal", "surf_point"):
-        assert util.rel_err(a_out[k], r_out[k]) < 1e-6, (k, util.rel_err(a_out[k], r_out[k]))
+    # (surf_normal: central differences of unprojected points ~1e-3 apart amplify those last-bit differences ~100-fold.)
+    for k, tol in (("rend_normal", 1e-6), ("depth", 1e-6), ("surf_point", 1e-6), ("surf_normal", 1e-4)):
+        assert util.rel_err(a_out[k], r_out[k]) < tol, (k, util.rel_err(a_out[k], r_out[k]))
     assert abs(a_l - r_l) <= 1e-6 * abs(r_l), (a_l, r_l)
     assert set(a_g) == set(r_g), set(a_g) ^ set(r_g)
     for n in r_g:
