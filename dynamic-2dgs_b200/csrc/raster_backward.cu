@@ -43,6 +43,12 @@ constexpr size_t BWD_SMEM_ACC = sizeof(float) * NWARP * BWD_BATCH * ACC_STRIDE; 
 constexpr size_t BWD_SMEM_RED = sizeof(float) * NWARP * RED_ROWS * RED_STRIDE;         // per-warp reduction scratch
 constexpr size_t BWD_SMEM_BYTES = BWD_SMEM_Q + BWD_SMEM_ACC + BWD_SMEM_RED + sizeof(uint32_t) * (2 * BWD_BATCH + NWARP);
 
+// MUFU.RCP without the range scaling of __fdividef (6 instructions less): for operands far from the denormal range
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ void pixel_of_thread_b(int tid, int& lx, int& ly) {
   const int w = tid >> 5, l = tid & 31;
   lx = ((w & 1) << 3) | (l & 7);
@@ -371,6 +377,9 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_MINBLOCKS) blend_bwd_ker
 #ifndef D2GS_BWD_LW_ROWS
 #define D2GS_BWD_LW_ROWS 64
 #endif
+#ifndef D2GS_BWD_LW_P3
+#define D2GS_BWD_LW_P3 5
+#endif
 constexpr int LW_ROWS = D2GS_BWD_LW_ROWS;      // gradient rows per warp (80 B each)
 constexpr int LW_ORD = 32;                      // survivors per chunk (one 32-bit hit mask per lane)
 constexpr size_t LWB_SMEM_Q = 2 * BWD_SMEM_Q1;
@@ -386,7 +395,8 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_LW_MINBLOCKS) blend_bwd_
     const float* __restrict__ bg, const SurfelRec* __restrict__ rec, const float* __restrict__ final_Ts,
     const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
     const float* __restrict__ dL_dothers, float* __restrict__ grad_rec, int cull,
-    const uint32_t* __restrict__ tile_order, uint32_t gx) {
+    const uint32_t* __restrict__ tile_order, uint32_t gx, const uint32_t* __restrict__ hit_mask,
+    const uint32_t* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char bwd_smem[];
   float* s_rows = reinterpret_cast<float*>(bwd_smem + LWB_SMEM_Q);                          // [warp][LW_ROWS][RED_STRIDE]
   uint2* s_meta = reinterpret_cast<uint2*>(bwd_smem + LWB_SMEM_Q + LWB_SMEM_ROWS);          // [warp][LW_ORD]
@@ -413,6 +423,9 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_LW_MINBLOCKS) blend_bwd_
   const uint32_t lanes_below = (1u << lane) - 1u;
   const uint32_t rows_w = smem_addr(s_rows + (size_t)warp * LW_ROWS * RED_STRIDE);
   const uint32_t meta_w = smem_addr(s_meta + (size_t)warp * LW_ORD);
+  // hit masks of the forward pass (ballots of the exact prefilter), if the forward of this frame wrote them
+  const uint32_t* const hm_row = (hit_mask != nullptr && status != nullptr && __ldg(status + 3) == HIT_MASK_MAGIC)
+                                     ? hit_mask + (size_t)range.x * 8u + (size_t)gwarp * (range.y - range.x) : nullptr;
 
   const float T_final = inside ? final_Ts[pix_id] : 0;
   float T = T_final;
@@ -481,6 +494,15 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_LW_MINBLOCKS) blend_bwd_
   for (int i = 0; i < rounds; i++, remaining -= BWD_BATCH) {
     const int n = min(BWD_BATCH, remaining);
     const int buf = i & 1;
+    // forward hit masks of this batch's slots (lane L: slots L, L + 32, ...), fetched ahead of the staging barrier
+    uint32_t fmask[BWD_WORDS];
+    if (hm_row) {
+#pragma unroll
+      for (int q = 0; q < BWD_WORDS; q++) {
+        const int jj = q * 32 + lane;
+        fmask[q] = jj < n ? __ldg(hm_row + (len - 1 - (uint32_t)(i * BWD_BATCH + jj))) : 0u;
+      }
+    }
     // buffer buf^1 was last read in batch i-1: every warp has to be past it before it is refilled
     __syncthreads();
     if (i + 1 < rounds) {
@@ -522,6 +544,14 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_LW_MINBLOCKS) blend_bwd_
         }
         const int j = w * 32 + (__ffs(m) - 1);
         bool pass = inside && (pos0 - (uint32_t)j) < last_contributor;
+        if (hm_row) {
+          // the forward's ballot of the exact prefilter replaces ~45 instructions of intersection arithmetic
+          uint32_t fm = fmask[0];
+#pragma unroll
+          for (int q = 1; q < BWD_WORDS; q++) if (w == q) fm = fmask[q];
+          fm = __shfl_sync(FULL, fm, j & 31);
+          pass = pass && ((fm >> lane) & 1u);
+        } else {
         const uint32_t off = (uint32_t)j << 4;
         const float4 a = lds128(sb0 + off), b = lds128(sb1 + off), c = lds128(sb2 + off);
         const float3 k = {__fmaf_rn(pixf.x, b.z, -a.x), __fmaf_rn(pixf.x, b.w, -a.y), __fmaf_rn(pixf.x, c.x, -a.z)};
@@ -531,6 +561,7 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_LW_MINBLOCKS) blend_bwd_
         const float2 d = {__fsub_rn(c.y, pixf.x), __fsub_rn(c.z, pixf.y)};
         const float rho2d = 2.0f * __fmaf_rn(d.x, d.x, __fmul_rn(d.y, d.y));
         pass = pass && !pair_rejected(p.x, p.y, p.z, rho2d, c.w) && p.z != 0.0f;
+        }
         const uint32_t hm = __ballot_sync(FULL, pass);
         const int nh = __popc(hm);
         if (rows_used + nh > LW_ROWS) break;     // does not fit any more: it opens the next chunk (its bit stays in m)
@@ -586,7 +617,7 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_LW_MINBLOCKS) blend_bwd_
               const float normal[3] = {nrm.x, nrm.y, nrm.z};
               const float color[3] = {col.x, col.y, col.z};
               // compositing gradient with the running scalars T, Q (see blend_bwd_kernel)
-              const float inv_1ma = __fdividef(1.0f, 1.f - alpha);
+              const float inv_1ma = rcp_fast(1.f - alpha);          // 1 - alpha in [0.01, 1]
               T = T * inv_1ma;
               const float wgt = alpha * T;
               float E = dL_daccum;
@@ -599,7 +630,7 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_LW_MINBLOCKS) blend_bwd_
               }
               E = fmaf(c_d, dL_ddepth, E);
               float dL_dz = 0.0f, dL_dweight = 0.f;
-              const float inv_d = __fdividef(1.0f, c_d);
+              const float inv_d = rcp_fast(c_d);                     // c_d >= 0.2
               const float m_d = mapped_depth(c_d);
               const float dmd_dd = 0.2004008016032064f * inv_d * inv_d;
               if (contributor == (uint32_t)(median_contributor - 1)) {
@@ -616,7 +647,7 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_LW_MINBLOCKS) blend_bwd_
               dL_dz += wgt * dL_ddepth;
               if (rho3d <= rho2d) {
                 const float2 dL_ds = {dL_dG * -G * s.x + dL_dz * Tw.x, dL_dG * -G * s.y + dL_dz * Tw.y};
-                const float inv_pz = __fdividef(1.0f, p.z);
+                const float inv_pz = rcp_fast(p.z);
                 const float dsx_pz = dL_ds.x * inv_pz, dsy_pz = dL_ds.y * inv_pz;
                 const float3 dL_dp = {dsx_pz, dsy_pz, -(dsx_pz * s.x + dsy_pz * s.y)};
                 const float3 dL_dk = {l.y * dL_dp.z - l.z * dL_dp.y, l.z * dL_dp.x - l.x * dL_dp.z, l.x * dL_dp.y - l.y * dL_dp.x};
@@ -644,6 +675,35 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_LW_MINBLOCKS) blend_bwd_
           }
         }
         __syncwarp();
+#if D2GS_BWD_LW_P3 == 4
+        // ---- phase 3: every lane sums ONE (survivor, quarter row) over the survivor's rows — components 4g..4g+3 with one
+        // LDS.128 and component 16 + (g & 1) with one LDS.32 per row — and issues one 16-byte global reduction (plus a scalar one
+        // for g < 2): 4 lanes per survivor, up to 8 survivors per pass of the warp
+        for (int t = lane; t < 4 * ord; t += 32) {
+          const int o = t >> 2, gq = t & 3;
+          uint32_t hm, rj;
+          asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(hm), "=r"(rj) : "r"(meta_w + 8u * (uint32_t)o));
+          int nr = __popc(hm);
+          uint32_t ad = rows_w + (rj & 0xffffu) * (RED_STRIDE * 4) + 16u * (uint32_t)gq;
+          const uint32_t sgl = 64u + 4u * (uint32_t)(gq & 1) - 16u * (uint32_t)gq;     // offset of the single from `ad`
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          float acc1 = 0.f;
+          for (; nr >= 2; nr -= 2, ad += 2 * RED_STRIDE * 4) {
+            const float4 u = lds128(ad), v = lds128(ad + RED_STRIDE * 4);
+            const float u1 = lds32(ad + sgl), v1 = lds32(ad + sgl + RED_STRIDE * 4);
+            acc.x += u.x + v.x; acc.y += u.y + v.y; acc.z += u.z + v.z; acc.w += u.w + v.w;
+            acc1 += u1 + v1;
+          }
+          if (nr) {
+            const float4 u = lds128(ad);
+            acc1 += lds32(ad + sgl);
+            acc.x += u.x; acc.y += u.y; acc.z += u.z; acc.w += u.w;
+          }
+          float* dst = grad_rec + (size_t)cur_id[rj >> 16] * GRAD_REC_FLOATS;
+          if (acc.x != 0.f || acc.y != 0.f || acc.z != 0.f || acc.w != 0.f) atomicAdd(reinterpret_cast<float4*>(dst) + gq, acc);
+          if (gq < 2 && acc1 != 0.f) atomicAdd(dst + 16 + gq, acc1);
+        }
+#else
         // ---- phase 3: every lane sums ONE (survivor, group of 4 components) over the survivor's rows (LDS.128) and
         // issues one 16-byte global reduction: 5 lanes per survivor, ~6 survivors per pass of the warp
         for (int t = lane; t < 5 * ord; t += 32) {
@@ -665,6 +725,7 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_LW_MINBLOCKS) blend_bwd_
           if (acc.x != 0.f || acc.y != 0.f || acc.z != 0.f || acc.w != 0.f)
             atomicAdd(reinterpret_cast<float4*>(grad_rec + (size_t)cur_id[rj >> 16] * GRAD_REC_FLOATS) + gq, acc);
         }
+#endif
         __syncwarp();     // rows and meta are rewritten by the next chunk
       }
       if (w >= BWD_WORDS) break;
@@ -674,7 +735,8 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_LW_MINBLOCKS) blend_bwd_
 
 void launch_blend_bwd(const BwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
                       const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, const float* dL_dothers,
-                      float* grad_rec, int cull, const uint32_t* tile_order, int lane_walk, cudaStream_t s) {
+                      float* grad_rec, int cull, const uint32_t* tile_order, int lane_walk, const uint32_t* hit_mask,
+                      const uint32_t* status, cudaStream_t s) {
   const uint32_t grid = p.gx * p.gy * BWD_Z;
   static bool configured = false;
   if (!configured) {
@@ -687,7 +749,7 @@ void launch_blend_bwd(const BwdParams& p, const uint2* ranges, const uint32_t* p
   }
   if (lane_walk) {
     blend_bwd_lw_kernel<<<grid, BWD_THREADS, LWB_SMEM_BYTES, s>>>(ranges, point_list, p.W, p.H, p.bg, rec, final_T, n_contrib,
-                                                                 dL_dpix, dL_dothers, grad_rec, cull, tile_order, p.gx);
+                                                                 dL_dpix, dL_dothers, grad_rec, cull, tile_order, p.gx, hit_mask, status);
     return;
   }
   blend_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM_BYTES, s>>>(ranges, point_list, p.W, p.H, p.bg, rec, final_T, n_contrib, dL_dpix,
@@ -746,7 +808,10 @@ __device__ __forceinline__ void store_sh_chunk(const BwdParams& p, float* dL_dsh
 
 constexpr int SH_WARP_FLOATS = 32 * 45 + 32 * 3;   // per-warp staging of the split SH layout: rest block + DC block
 
-__global__ void __launch_bounds__(256, 3) preprocess_bwd_kernel(
+#ifndef D2GS_PREB_MINBLOCKS
+#define D2GS_PREB_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(256, D2GS_PREB_MINBLOCKS) preprocess_bwd_kernel(
     BwdParams p, const SurfelRec* __restrict__ rec, const uint8_t* __restrict__ clamped,
     const int* __restrict__ radii, float* __restrict__ grad_rec, float* __restrict__ dL_dmeans2D,
     float* __restrict__ dL_dcolors, float* __restrict__ dL_dopacity, float* __restrict__ dL_dmeans3D,
@@ -763,7 +828,16 @@ __global__ void __launch_bounds__(256, 3) preprocess_bwd_kernel(
   float* wdc = wrest + 32 * 45;
   const int wbase = idx - lane;                       // first surfel of this warp
   const int nsurf = min(32, p.P - wbase);             // <= 0 for a warp past the end
-  if (staged && nsurf > 0) {
+  // The copy is asynchronous (LDGSTS, no registers): it is in flight while the thread loads its gradient record and
+  // projected record and runs the homography part; the wait sits in front of the SH part.
+  const bool async_stage = staged && nsurf == 32 && ((reinterpret_cast<uintptr_t>(p.shs) & 15) == 0);
+  if (async_stage) {
+    const float4* src = reinterpret_cast<const float4*>(p.sh_rest + (size_t)wbase * 45);
+    const uint32_t d0 = smem_addr(wrest);
+    for (int v = lane; v < 360; v += 32) cp_async16(d0 + 16u * (uint32_t)v, src + v);
+    if (lane < 24) cp_async16(smem_addr(wdc) + 16u * (uint32_t)lane, reinterpret_cast<const float4*>(p.shs + (size_t)wbase * 3) + lane);
+    cp_async_commit();
+  } else if (staged && nsurf > 0) {
     const int nrest = nsurf * 45, nvec = nrest >> 2;
     const float4* src = reinterpret_cast<const float4*>(p.sh_rest + (size_t)wbase * 45);
     for (int v = lane; v < nvec; v += 32) reinterpret_cast<float4*>(wrest)[v] = __ldg(src + v);
@@ -862,6 +936,11 @@ __global__ void __launch_bounds__(256, 3) preprocess_bwd_kernel(
     dopacity = gr[G_OPA];
     if (p.raw) dopacity *= act.opacity * (1.0f - act.opacity);
 
+  }
+  // every lane of the warp (visible or not) waits for ITS copies, then the warp barrier publishes them to the other lanes
+  // (a warp in async_stage mode is full, so all 32 lanes are here)
+  if (async_stage) { cp_async_wait<0>(); __syncwarp(); }
+  if (visible) {
     // (3) colour -> SH coefficients and view direction
     if (p.shs != nullptr) {
       const v3 pw = p.raw ? act.pw : v3{p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]};

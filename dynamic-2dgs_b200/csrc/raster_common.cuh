@@ -61,7 +61,7 @@ struct ImgLayout {
   size_t ranges, final_T, n_contrib, tile_count, seg_begin, seg_end, tile_order, total;
 };
 struct BinLayout {
-  size_t keys_unsorted, keys_sorted, vals_unsorted, point_list, sort_temp, total;
+  size_t keys_unsorted, keys_sorted, vals_unsorted, point_list, sort_temp, hit_mask, total;
   size_t sort_temp_bytes;
 };
 constexpr int TILE_SORT_MAX_TILES = 24576;   // per-tile binning keeps two counters per tile in shared memory (192 KB at the limit)
@@ -265,6 +265,8 @@ struct FwdParams {
   const float* d_scales;
   const float* d_rotations;
   uint4* tile_box;         // optional (P): {x0 | x1 << 16, y0 | y1 << 16, depth bits, 0} of the tile rectangle, all zero when culled
+  uint32_t* frame_flag;    // optional: status[3], set to `frame_flag_value` by the per-surfel kernel (hit-mask handshake)
+  uint32_t frame_flag_value;
 };
 
 // Activated surfel parameters from the raw ones, op for op what the eager glue computes
@@ -322,7 +324,12 @@ void launch_ranges_deferred(uint32_t capacity, const uint32_t* status, const uin
 // `status` (may be NULL): when status[1] != 0 the binning overflowed and the colour planes are poisoned with NaN
 void launch_blend_fwd(const FwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
                       float* final_T, uint32_t* n_contrib, float* out_color, float* out_others, int cull,
-                      const uint32_t* status, const uint32_t* tile_order, int lane_walk, cudaStream_t s);
+                      const uint32_t* status, const uint32_t* tile_order, int lane_walk, uint32_t* hit_mask, cudaStream_t s);
+// Hit masks handed from the lane-walk forward to the lane-walk backward: one 32-bit word per (list position, 8x4 patch) —
+// the ballot of the exact prefilter over the patch's pixels.  Stored patch-major inside a tile's list segment:
+//   hit_mask[8 * range.x + patch * (range.y - range.x) + position]        (only cull-box survivors are written)
+// status[3] == HIT_MASK_MAGIC tells the backward that the forward of this frame wrote them.
+constexpr uint32_t HIT_MASK_MAGIC = 0x4b53414du;
 
 struct BwdParams {
   int P, D, M, W, H;
@@ -347,7 +354,8 @@ struct BwdParams {
 };
 void launch_blend_bwd(const BwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
                       const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, const float* dL_dothers,
-                      float* grad_rec, int cull, const uint32_t* tile_order, int lane_walk, cudaStream_t s);
+                      float* grad_rec, int cull, const uint32_t* tile_order, int lane_walk, const uint32_t* hit_mask,
+                      const uint32_t* status, cudaStream_t s);
 void launch_preprocess_bwd(const BwdParams& p, const SurfelRec* rec, const uint8_t* clamped, const int* radii,
                            float* grad_rec, float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
                            float* dL_dmeans3D, float* dL_dtransMat, float* dL_dsh, float* dL_dsh_rest,

@@ -39,10 +39,35 @@ __device__ __forceinline__ void load_sh(const FwdParams& p, int idx, int ncoef, 
   }
 }
 
+constexpr int SHF_WARP_FLOATS = 32 * 45 + 32 * 3;   // per-warp staging of the split SH layout: rest block + DC block
+
 __global__ void __launch_bounds__(256, 3) preprocess_fwd_kernel(FwdParams p, SurfelRec* __restrict__ rec,
                                                              uint8_t* __restrict__ clamped, int* __restrict__ radii,
-                                                             uint32_t* __restrict__ tiles_touched) {
+                                                             uint32_t* __restrict__ tiles_touched, const bool staged) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  // Split SH layout (DC (P,1,3) + rest (P,15,3), the trainer's parameters): the 32 surfels of a warp own one contiguous
+  // 5760-B block of `rest` and 384 B of DC.  The warp copies both to shared memory with 16-byte asynchronous copies
+  // (LDGSTS: coalesced, no staging registers); each thread then reads its 48 coefficients at a 45-word stride
+  // (conflict-free) instead of issuing 48 scalar global loads at a 180-B stride (lg_throttle 8.3 in profiles/ncu_r1i.md).
+  // The wait sits right here, before any lane can leave the kernel: a lane that returned early would never publish its
+  // copies.  (The projection code below is textually the round-1 kernel: its FMA contraction is part of the bit-exact
+  // contract with the reference build, so it is not restructured around the copy.)
+  extern __shared__ float s_shf[];
+  const int lane = threadIdx.x & 31;
+  float* wrest = s_shf + (threadIdx.x >> 5) * SHF_WARP_FLOATS;
+  float* wdc = wrest + 32 * 45;
+  const int wbase = idx - lane;
+  const bool async_stage = staged && wbase + 32 <= p.P;
+  if (async_stage) {
+    const float4* src = reinterpret_cast<const float4*>(p.sh_rest + (size_t)wbase * 45);
+    const uint32_t d0 = smem_addr(wrest);
+    for (int v = lane; v < 360; v += 32) cp_async16(d0 + 16u * (uint32_t)v, src + v);
+    if (lane < 24) cp_async16(smem_addr(wdc) + 16u * (uint32_t)lane, reinterpret_cast<const float4*>(p.shs + (size_t)wbase * 3) + lane);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+  }
+  if (idx == 0 && p.frame_flag) *p.frame_flag = p.frame_flag_value;
   if (idx >= p.P) return;
   radii[idx] = 0;
   tiles_touched[idx] = 0;
@@ -117,7 +142,13 @@ __global__ void __launch_bounds__(256, 3) preprocess_fwd_kernel(FwdParams p, Sur
     dir = dir / sqrtf(dot3(dir, dir));
     float sh[48];
     const int ncoef = (p.D + 1) * (p.D + 1);
-    load_sh(p, idx, ncoef, sh);
+    if (async_stage) {
+#pragma unroll
+      for (int i = 0; i < 48; i++)
+        if (i < ncoef * 3) sh[i] = (i < 3) ? wdc[lane * 3 + i] : wrest[lane * 45 + (i - 3)];
+    } else {
+      load_sh(p, idx, ncoef, sh);
+    }
     v3 res = eval_sh(p.D, dir, sh);
     res.x += 0.5f; res.y += 0.5f; res.z += 0.5f;
     clamped[idx] = (uint8_t)((res.x < 0 ? 1 : 0) | (res.y < 0 ? 2 : 0) | (res.z < 0 ? 4 : 0));
@@ -144,7 +175,15 @@ __global__ void __launch_bounds__(256, 3) preprocess_fwd_kernel(FwdParams p, Sur
 void launch_preprocess_fwd(const FwdParams& p, SurfelRec* rec, uint8_t* clamped, int* radii, uint32_t* tiles_touched,
                            cudaStream_t s) {
   if (p.P == 0) return;
-  preprocess_fwd_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p, rec, clamped, radii, tiles_touched);
+  const auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool staged = p.colors_precomp == nullptr && p.shs && p.sh_rest && p.M == 16 && al16(p.sh_rest) && al16(p.shs);
+  const size_t smem = staged ? sizeof(float) * SHF_WARP_FLOATS * 8 : 0;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(preprocess_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * SHF_WARP_FLOATS * 8));
+    configured = true;
+  }
+  preprocess_fwd_kernel<<<(p.P + 255) / 256, 256, smem, s>>>(p, rec, clamped, radii, tiles_touched, staged);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -477,7 +516,8 @@ __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_lw_
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
     const SurfelRec* __restrict__ rec, const float* __restrict__ bg, float* __restrict__ final_T,
     uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, float* __restrict__ out_others, int cull,
-    const uint32_t* __restrict__ status, const uint32_t* __restrict__ tile_order, uint32_t gx) {
+    const uint32_t* __restrict__ status, const uint32_t* __restrict__ tile_order, uint32_t gx,
+    uint32_t* __restrict__ hit_mask) {
   __shared__ float4 s_q[2][REC_QUADS][BLEND_BATCH];
   __shared__ uint8_t s_slot[FWD_NWARP][LW_CHUNK];
 
@@ -503,6 +543,8 @@ __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_lw_
   const uint32_t slot_base = smem_addr(&s_slot[tid >> 5][0]);
   constexpr uint32_t QS = 16u * BLEND_BATCH;
   constexpr uint32_t BUF = QS * REC_QUADS;
+  // this patch's row of the tile's hit-mask segment (see raster_common.cuh)
+  uint32_t* const hm_row = hit_mask ? hit_mask + (size_t)range.x * 8u + (size_t)wq * (range.y - range.x) : nullptr;
 
   float T = 1.0f;
   uint32_t last_contributor = 0, median_contributor = 0;
@@ -589,6 +631,10 @@ __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_lw_
         const float2 dd = {__fsub_rn(c.y, pixf.x), __fsub_rn(c.z, pixf.y)};
         const float rho2d = 2.0f * __fmaf_rn(dd.x, dd.x, __fmul_rn(dd.y, dd.y));
         const bool pass = !pair_rejected(p.x, p.y, p.z, rho2d, c.w) && p.z != 0.0f;
+        if (hm_row) {      // the backward reads the ballot instead of repeating the prefilter
+          const uint32_t hm = __ballot_sync(0xffffffffu, pass);
+          if (lane == 0) hm_row[i * BLEND_BATCH + j] = hm;
+        }
         const uint32_t bit = pass ? 1u : 0u;
         if (LW_CHUNK <= 32 || ord < 32) hit_lo |= bit << ord; else hit_hi |= bit << (ord - 32);
         if (lane == 0) asm volatile("st.shared.u8 [%0], %1;" ::"r"(slot_base + (uint32_t)ord), "r"(j) : "memory");
@@ -686,11 +732,11 @@ __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_lw_
 
 void launch_blend_fwd(const FwdParams& p, const uint2* ranges, const uint32_t* point_list, const SurfelRec* rec,
                       float* final_T, uint32_t* n_contrib, float* out_color, float* out_others, int cull,
-                      const uint32_t* status, const uint32_t* tile_order, int lane_walk, cudaStream_t s) {
+                      const uint32_t* status, const uint32_t* tile_order, int lane_walk, uint32_t* hit_mask, cudaStream_t s) {
   const uint32_t grid = p.gx * p.gy * FWD_Z;
   if (lane_walk) {
     blend_fwd_lw_kernel<<<grid, FWD_THREADS, 0, s>>>(ranges, point_list, p.W, p.H, rec, p.bg, final_T, n_contrib, out_color,
-                                                     out_others, cull, status, tile_order, p.gx);
+                                                     out_others, cull, status, tile_order, p.gx, hit_mask);
     return;
   }
   blend_fwd_kernel<<<grid, FWD_THREADS, 0, s>>>(ranges, point_list, p.W, p.H, rec, p.bg, final_T, n_contrib, out_color,
