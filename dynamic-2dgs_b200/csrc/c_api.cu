@@ -49,7 +49,8 @@ int g_deform_bwd_smem = 1;  // node-gradient accumulation of deform_bwd: 1 = per
 int g_knn_filter = 1;       // warp-level candidate filter of the K-nearest-node search (0: every node is visited; same results)
 static int g_tile_sort = 1;   // binning: 0 = global radix sort of (tile | depth) keys, 1 = per-tile buckets + segmented sort (same lists)
 static int g_tile_order = 1;  // blend CTAs visit tiles longest list first (scheduling only; set before the forward of a frame)
-static int g_lane_walk = 3;   // bit 0: forward blend, bit 1: backward blend walk per-lane hit lists (A/B switch; same results)
+static int g_lane_walk = 7;   // bit 0: forward blend, bit 1: backward blend walk per-lane hit lists; bit 2: the forward hands its
+                              // prefilter ballots to the backward (A/B switches; same results)
 static int g_cull = 1;   // warp-level cull boxes in the blend kernels (tests switch it off to prove it changes nothing)
 static std::vector<StageRec> g_recs;
 static std::vector<cudaEvent_t> g_free_events;
@@ -112,6 +113,7 @@ BinLayout bin_layout(int64_t R) {
                                   (uint32_t*)nullptr, (int)n);
   L.sort_temp_bytes = tmp;
   L.sort_temp = o; o = align_up(o + tmp);
+  L.hit_mask = o; o = align_up(o + 32 * n);     // one 32-bit prefilter ballot per (instance, 8x4 patch of its tile)
   L.total = o + 256;
   return L;
 }
@@ -254,6 +256,11 @@ int d2gs_raster_forward(const D2gsRasterFwdArgs* a, void* stream_) {
   if (deferred && a->binning_capacity > 0xffffffffll) return fail(D2GS_ERR_INVALID_ARG, "binning_capacity exceeds 2^32-1 instances");
   uint4* tile_box = (uint4*)(gb + GL.tile_box);
   p.tile_box = tile_sort ? tile_box : nullptr;
+  // hit-mask handshake with the backward: the per-surfel kernel stamps status[3] (every frame, so a frame rendered with
+  // another setting never leaves a stale stamp behind)
+  const bool write_masks = (g_lane_walk & 1) && (g_lane_walk & 4);
+  p.frame_flag = status + 3;
+  p.frame_flag_value = write_masks ? HIT_MASK_MAGIC : 0u;
   if (!a->resume) {
     { StageTimer t(ST_PRE, stream); launch_preprocess_fwd(p, rec, clamped, a->radii, tiles_touched, stream); }
     D2GS_STAGE("preprocess", a->debug, stream);
@@ -330,7 +337,8 @@ int d2gs_raster_forward(const D2gsRasterFwdArgs* a, void* stream_) {
   }
   { StageTimer t(ST_BLEND_F, stream);
     launch_blend_fwd(p, ranges, point_list, rec, final_T, n_contrib, a->out_color, a->out_others, g_cull,
-                     deferred ? status : nullptr, tile_order, g_lane_walk & 1, stream); }
+                     deferred ? status : nullptr, tile_order, g_lane_walk & 1,
+                     write_masks ? (uint32_t*)(bb + BL.hit_mask) : nullptr, stream); }
   D2GS_STAGE("blend", a->debug, stream);
   return D2GS_OK;
 }
@@ -381,7 +389,8 @@ int d2gs_raster_backward(const D2gsRasterBwdArgs* a, void* stream_) {
     { StageTimer t(ST_BLEND_B, stream);
       launch_blend_bwd(p, ranges, point_list, rec, final_T, n_contrib, a->dL_dout_color, a->dL_dout_others,
                        a->grad_scratch, g_cull, g_tile_order ? (const uint32_t*)(ib + IL.tile_order) : nullptr,
-                       (g_lane_walk >> 1) & 1, stream); }
+                       (g_lane_walk >> 1) & 1, (g_lane_walk & 4) ? (const uint32_t*)(bb + BL.hit_mask) : nullptr,
+                       (const uint32_t*)(gb + GL.status), stream); }
     D2GS_STAGE("blend_bwd", a->debug, stream);
   }
   { StageTimer t(ST_PRE_B, stream);

@@ -84,29 +84,75 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory"); }
 
+// Thread-block clusters: the CTAs of a cluster need the SAME weights at the same time, so ONE bulk copy per chunk,
+// issued by the cluster's rank-0 CTA with .multicast::cluster, lands in the ring stage of every CTA of the cluster and
+// signals each CTA's own "full" mbarrier.  L2 -> SM traffic drops from (CTAs x 2.1 MB) to (clusters x 2.1 MB): at
+// 128 CTAs the per-CTA streams added up to 270 MB per pass through an L2 that delivers ~12 TB/s — the floor of the
+// un-clustered kernel was ~22 us whatever the math did.
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok, spins = 0;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 28)) __trap();
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+
+// Barriers per CTA: full[STAGES] (count 1: the local producer's arrive.expect_tx; the bytes come from rank 0's multicast),
+// empty[STAGES] (count 8: this CTA's consumer warps), cempty[STAGES] (count 8 x cluster size; only rank 0's copy is used:
+// every consumer warp of the cluster arrives on it remotely, and rank 0's producer waits on it before it overwrites the
+// stage in ALL CTAs).
 struct Ring {
-  uint32_t stage0, stage_bytes, full0, empty0;   // shared-window addresses
-  int g;                                         // running chunk counter (same sequence on both sides)
+  uint32_t stage0, stage_bytes, full0, empty0, cempty0;   // shared-window addresses
+  uint32_t rank, csize, cempty_rank0;                     // cluster rank / size, rank 0's cempty[0] as a cluster address
+  int g;                                                  // running chunk counter (same sequence on both sides)
   __device__ __forceinline__ uint32_t stage(int st) const { return stage0 + (uint32_t)st * stage_bytes; }
   __device__ __forceinline__ uint32_t full(int st) const { return full0 + 8u * st; }
   __device__ __forceinline__ uint32_t empty(int st) const { return empty0 + 8u * st; }
+  __device__ __forceinline__ uint32_t cempty(int st) const { return cempty0 + 8u * st; }
 };
 __device__ __forceinline__ void ring_setup(Ring& r, unsigned char* stages, uint32_t stage_bytes, uint64_t* bars, int tid) {
   r.stage0 = smem_addr(stages); r.stage_bytes = stage_bytes;
-  r.full0 = smem_addr(bars); r.empty0 = smem_addr(bars + STAGES); r.g = 0;
+  r.full0 = smem_addr(bars); r.empty0 = smem_addr(bars + STAGES); r.cempty0 = smem_addr(bars + 2 * STAGES); r.g = 0;
+  r.rank = cluster_rank(); r.csize = cluster_size();
+  r.cempty_rank0 = map_to_rank(r.cempty0, 0);
   if (tid == 0) {
-    for (int i = 0; i < STAGES; i++) { mbar_init(r.full(i), 1); mbar_init(r.empty(i), CONSUMERS / 32); }
+    for (int i = 0; i < STAGES; i++) {
+      mbar_init(r.full(i), 1); mbar_init(r.empty(i), CONSUMERS / 32); mbar_init(r.cempty(i), (CONSUMERS / 32) * r.csize);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  __syncthreads();
+  cluster_sync_all();      // every CTA's barriers are initialised before any remote arrive / multicast can reach them
 }
-// producer side: one chunk
+// producer side (one thread per CTA): one chunk
 __device__ __forceinline__ void ring_push(Ring& r, const void* src, uint32_t bytes) {
   const int st = r.g % STAGES; const uint32_t par = (uint32_t)(r.g / STAGES) & 1u;
-  mbar_wait(r.empty(st), par ^ 1u);
-  mbar_expect_tx(r.full(st), bytes);
-  bulk_g2s(r.stage(st), src, bytes, r.full(st));
+  mbar_wait(r.empty(st), par ^ 1u);              // this CTA's consumers have left the stage
+  mbar_expect_tx(r.full(st), bytes);             // arm the local "full" barrier for the multicast bytes
+  if (r.rank == 0) {
+    mbar_wait_cluster(r.cempty(st), par ^ 1u);   // ... and so have the consumers of every CTA of the cluster
+    if (r.csize == 1) bulk_g2s(r.stage(st), src, bytes, r.full(st));
+    else bulk_g2s_multicast(r.stage(st), src, bytes, r.full(st), (uint16_t)((1u << r.csize) - 1u));
+  }
   r.g++;
 }
 // consumer side: returns the stage index once its bytes have landed; release with ring_pop
@@ -117,7 +163,7 @@ __device__ __forceinline__ int ring_front(Ring& r) {
 }
 __device__ __forceinline__ void ring_pop(Ring& r, int st, int lane) {
   __syncwarp();
-  if (lane == 0) mbar_arrive(r.empty(st));
+  if (lane == 0) { mbar_arrive(r.empty(st)); mbar_arrive_remote(r.cempty_rank0 + 8u * st); }
   r.g++;
 }
 
@@ -189,7 +235,7 @@ struct FwdSmem {
   float4 te[32];             // time embedding (Et <= 21)
   float4 th[MW];             // timenet hidden
   float4 red[4 * MW];        // partial sums of the four k-groups
-  uint64_t bars[2 * STAGES];
+  uint64_t bars[3 * STAGES];
 };
 constexpr size_t FWD_SMEM_BYTES = (size_t)STAGES * FWD_STAGE_BYTES + sizeof(FwdSmem);
 
@@ -198,7 +244,7 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_fwd_kernel(MlpFwd a) {
   FwdSmem& S = *reinterpret_cast<FwdSmem*>(mlp_smem + (size_t)STAGES * FWD_STAGE_BYTES);
   const int tid = threadIdx.x;
   const int row0 = blockIdx.x * ROWS;
-  const int rows = min(ROWS, a.rows - row0);
+  const int rows = max(0, min(ROWS, a.rows - row0));     // 0 for a CTA that only pads its cluster
   const MlpLayers& L = a.layers;
   const int Et = a.Et, Tt = a.Tt;
   const int in0 = EX + Tt;
@@ -214,6 +260,8 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_fwd_kernel(MlpFwd a) {
           ring_push(ring, src + (size_t)k0 * ly.NP, (uint32_t)(min(KCH, ly.K - k0) * ly.NP) * 4u);
       }
     }
+    __syncwarp();
+    cluster_sync_all();     // no CTA of the cluster leaves while copies or remote arrivals may still target it
     return;
   }
   float4 (*s_x)[INP_LD + MW] = S.x;
@@ -277,6 +325,7 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_fwd_kernel(MlpFwd a) {
   // heads: concatenated outputs [warp 3 | scaling 2 | rotation 4 | local 4 | opacity 1] -> (rows, NH)
   const MlpLayer& hd = L.layer[li];
   dense<false>(ring, hd.NP, hd.b, hd.N, s_x[cur ^ 1] + in0, MW, s_red, nullptr, a.out, a.NH, row0, rows, tid);
+  cluster_sync_all();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -365,7 +414,7 @@ struct BwdSmem {
   float4 gh[16];        // head gradients
   float4 gt[32];        // gradient of the time feature (Tt <= 30)
   float4 red[4 * MW];
-  uint64_t bars[2 * STAGES];
+  uint64_t bars[3 * STAGES];
 };
 constexpr size_t BWD_SMEM_BYTES_MLP = (size_t)STAGES * BWD_STAGE_BYTES + sizeof(BwdSmem);
 
@@ -374,7 +423,7 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_bwd_act_kernel(MlpBwd a) {
   BwdSmem& S = *reinterpret_cast<BwdSmem*>(mlp_smem + (size_t)STAGES * BWD_STAGE_BYTES);
   const int tid = threadIdx.x;
   const int row0 = blockIdx.x * ROWS;
-  const int rows = min(ROWS, a.rows - row0);
+  const int rows = max(0, min(ROWS, a.rows - row0));     // 0 for a CTA that only pads its cluster
   const MlpLayers& L = a.layers;
   const int Tt = a.Tt, in0 = EX + Tt;
   const int first_trunk = a.has_timenet ? 2 : 0;
@@ -390,6 +439,8 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_bwd_act_kernel(MlpBwd a) {
           ring_push(ring, ly.W + (size_t)n0 * ly.K, (uint32_t)(min(NCH, ly.N - n0) * ly.K) * 4u);
       }
     }
+    __syncwarp();
+    cluster_sync_all();
     return;
   }
   float4 (*s_g)[MW] = S.g;
@@ -444,6 +495,7 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_bwd_act_kernel(MlpBwd a) {
     g = relu_mask(g, h);
     store_rows(a.G_t1, MW, row0, rows, tid, g);
   }
+  cluster_sync_all();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -526,17 +578,37 @@ void mlp_launch_transpose(const MlpLayers& L, cudaStream_t s) {
   dim3 grid((maxK + 31) / 32, (maxN + 31) / 32, L.count);
   mlp_transpose_kernel<<<grid, 256, 0, s>>>(L);
 }
+#ifndef D2GS_MLP_CLUSTER
+#define D2GS_MLP_CLUSTER 4
+#endif
+// grid of ceil(rows / ROWS) CTAs, rounded up to whole clusters (a CTA without rows still takes part in the ring protocol)
+template <typename Kern, typename Arg>
+static void launch_clustered(Kern kern, const Arg& a, int rows, size_t smem, cudaStream_t s) {
+  const int ctas = (rows + ROWS - 1) / ROWS;
+  int cl = D2GS_MLP_CLUSTER;
+  while (cl > 1 && ctas < cl) cl >>= 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((ctas + cl - 1) / cl * cl), 1, 1);
+  cfg.blockDim = dim3(MLP_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, a);
+}
 void mlp_launch_forward(const MlpFwd& a, cudaStream_t s) {
   if (a.rows <= 0) return;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM_BYTES); attr = true; }
-  mlp_fwd_kernel<<<(a.rows + ROWS - 1) / ROWS, MLP_THREADS, FWD_SMEM_BYTES, s>>>(a);
+  launch_clustered(mlp_fwd_kernel, a, a.rows, FWD_SMEM_BYTES, s);
 }
 void mlp_launch_backward(const MlpBwd& a, const MlpWJobs& J, cudaStream_t s) {
   if (a.rows <= 0) return;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(mlp_bwd_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES_MLP); attr = true; }
-  mlp_bwd_act_kernel<<<(a.rows + ROWS - 1) / ROWS, MLP_THREADS, BWD_SMEM_BYTES_MLP, s>>>(a);
+  launch_clustered(mlp_bwd_act_kernel, a, a.rows, BWD_SMEM_BYTES_MLP, s);
   int tiles = 0;
   for (int j = 0; j < J.count; j++) tiles += J.job[j].tiles;
   mlp_bwd_w_kernel<<<tiles, 256, 0, s>>>(J, a.rows);

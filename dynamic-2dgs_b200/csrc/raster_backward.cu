@@ -523,7 +523,9 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_LW_MINBLOCKS) blend_bwd_
     for (int w = 0; w < BWD_WORDS; w++) {
       const int jj = w * 32 + lane;
       bool keep = jj < n;
-      if (keep && cull) {
+      if (hm_row) {
+        keep = keep && fmask[w] != 0u;       // the forward wrote 0 for the slots its cull box dropped (same box, same patch)
+      } else if (keep && cull) {
         const float4 bb = lds128(sb5 + ((uint32_t)jj << 4));
         keep = !(bb.z < pcx0 || bb.x > pcx1 || bb.w < pcy0 || bb.y > pcy1);
       }

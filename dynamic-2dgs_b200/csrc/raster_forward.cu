@@ -609,12 +609,17 @@ __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_lw_
     if (__all_sync(0xffffffffu, done)) continue;      // this patch is saturated: it only keeps the barriers company
     int w = 0;
     uint32_t m = keepmask[0];
+    uint32_t wmask = 0u;      // ballot of the prefilter for staged slot 32 w + lane (0 for a slot the cull box dropped)
     while (true) {
       // ---- phase 1: up to LW_CHUNK survivors, exact prefilter on all lanes, per-lane hit masks
       uint32_t hit_lo = 0u, hit_hi = 0u;
       int ord = 0;
       while (ord < LW_CHUNK) {
         if (m == 0u) {
+          // word w is finished: its 32 ballots go out as one coalesced 128-byte store (the backward reads them instead of
+          // repeating the prefilter; zeros tell it which slots to skip)
+          if (hm_row && w * 32 + lane < n) hm_row[i * BLEND_BATCH + w * 32 + lane] = wmask;
+          wmask = 0u;
           if (++w >= BLEND_BATCH / 32) break;
 #pragma unroll
           for (int q = 1; q < BLEND_BATCH / 32; q++) if (w == q) m = keepmask[q];
@@ -631,9 +636,9 @@ __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_lw_
         const float2 dd = {__fsub_rn(c.y, pixf.x), __fsub_rn(c.z, pixf.y)};
         const float rho2d = 2.0f * __fmaf_rn(dd.x, dd.x, __fmul_rn(dd.y, dd.y));
         const bool pass = !pair_rejected(p.x, p.y, p.z, rho2d, c.w) && p.z != 0.0f;
-        if (hm_row) {      // the backward reads the ballot instead of repeating the prefilter
+        if (hm_row) {
           const uint32_t hm = __ballot_sync(0xffffffffu, pass);
-          if (lane == 0) hm_row[i * BLEND_BATCH + j] = hm;
+          if ((j & 31) == lane) wmask = hm;
         }
         const uint32_t bit = pass ? 1u : 0u;
         if (LW_CHUNK <= 32 || ord < 32) hit_lo |= bit << ord; else hit_hi |= bit << (ord - 32);
