@@ -55,7 +55,10 @@ __global__ void __launch_bounds__(256) mlp_transpose_kernel(MlpLayers L) {
 // by load latency: 8 warps x 4 LDG.128 in flight per SM).
 constexpr int CONSUMERS = 256;               // 8 math warps
 constexpr int MLP_THREADS = CONSUMERS + 32;  // + 1 producer warp
-constexpr int STAGES = 3;
+#ifndef D2GS_MLP_STAGES
+#define D2GS_MLP_STAGES 4
+#endif
+constexpr int STAGES = D2GS_MLP_STAGES;
 constexpr int KCH = 32;                      // forward: k-rows of W^T per chunk (32 x NP floats <= 32 KB)
 constexpr int NCH = 32;                      // backward: n-rows of W per chunk (32 x K floats <= 44672 B at K = 349)
 constexpr int FWD_STAGE_BYTES = KCH * MW * 4;
@@ -101,7 +104,10 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t local_addr, uint32_t ra
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // relaxed: the shared-memory reads of the stage were consumed by the FMAs in front of this instruction, and the stage is
+  // overwritten through the async proxy only after rank 0 has OBSERVED the arrival (a .release.cluster arrive measured
+  // ~0.3 us each here — 8 warps x 85 chunks of them doubled the kernel)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok, spins = 0;
@@ -148,10 +154,11 @@ __device__ __forceinline__ void ring_push(Ring& r, const void* src, uint32_t byt
   const int st = r.g % STAGES; const uint32_t par = (uint32_t)(r.g / STAGES) & 1u;
   mbar_wait(r.empty(st), par ^ 1u);              // this CTA's consumers have left the stage
   mbar_expect_tx(r.full(st), bytes);             // arm the local "full" barrier for the multicast bytes
-  if (r.rank == 0) {
+  if (r.csize == 1) {
+    bulk_g2s(r.stage(st), src, bytes, r.full(st));
+  } else if (r.rank == 0) {
     mbar_wait_cluster(r.cempty(st), par ^ 1u);   // ... and so have the consumers of every CTA of the cluster
-    if (r.csize == 1) bulk_g2s(r.stage(st), src, bytes, r.full(st));
-    else bulk_g2s_multicast(r.stage(st), src, bytes, r.full(st), (uint16_t)((1u << r.csize) - 1u));
+    bulk_g2s_multicast(r.stage(st), src, bytes, r.full(st), (uint16_t)((1u << r.csize) - 1u));
   }
   r.g++;
 }
@@ -163,7 +170,7 @@ __device__ __forceinline__ int ring_front(Ring& r) {
 }
 __device__ __forceinline__ void ring_pop(Ring& r, int st, int lane) {
   __syncwarp();
-  if (lane == 0) { mbar_arrive(r.empty(st)); mbar_arrive_remote(r.cempty_rank0 + 8u * st); }
+  if (lane == 0) { mbar_arrive(r.empty(st)); if (r.csize > 1) mbar_arrive_remote(r.cempty_rank0 + 8u * st); }
   r.g++;
 }
 

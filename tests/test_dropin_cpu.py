@@ -124,3 +124,38 @@ def test_pytorch3d_stand_in_semantics():
     for i in range(50):
         hits = torch.nonzero(d[i] < 1.0).flatten()[:3]
         assert q.idx[0, i, :len(hits)].tolist() == hits.tolist() and (q.idx[0, i, len(hits):] == -1).all()
+
+
+def test_permute_surfels_reorders_parameters_state_and_buffers():
+    """layout.permute_surfels_: one permutation applied to every per-surfel tensor (parameters keep their identity, so the
+    optimiser state stays attached), optimiser moments and plain buffers; tensors of other sizes are left alone."""
+    import torch
+    from d2gs_b200 import layout
+    P = 37
+    g = torch.Generator().manual_seed(0)
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self._xyz = torch.nn.Parameter(torch.randn(P, 3, generator=g))
+            self._features_rest = torch.nn.Parameter(torch.randn(P, 15, 3, generator=g))
+            self.other = torch.nn.Parameter(torch.randn(5, 3, generator=g))
+            self.register_buffer("denom", torch.arange(P, dtype=torch.float32)[:, None])
+            self.max_radii2D = torch.arange(P, dtype=torch.float32) * 2
+    m = M()
+    opt = torch.optim.Adam([{"params": [m._xyz], "lr": 1e-2}, {"params": [m._features_rest], "lr": 1e-2}, {"params": [m.other], "lr": 1e-2}])
+    (m._xyz.sum() * 2 + (m._features_rest ** 2).sum() + m.other.sum()).backward()
+    opt.step()
+    before = {k: v.detach().clone() for k, v in dict(xyz=m._xyz, rest=m._features_rest, other=m.other, denom=m.denom, rad=m.max_radii2D,
+                                                      m1=opt.state[m._xyz]["exp_avg"], v2=opt.state[m._features_rest]["exp_avg_sq"]).items()}
+    ids = (id(m._xyz), id(m._features_rest))
+    perm = torch.randperm(P, generator=g)
+    n = layout.permute_surfels_(m, perm, optimizers=[opt])
+    assert n == 4 + 4          # 2 parameters + buffer + attribute, 2 x (exp_avg, exp_avg_sq)
+    assert (id(m._xyz), id(m._features_rest)) == ids and m._xyz.grad is None
+    assert torch.equal(m._xyz, before["xyz"][perm]) and torch.equal(m._features_rest, before["rest"][perm])
+    assert torch.equal(m.denom, before["denom"][perm]) and torch.equal(m.max_radii2D, before["rad"][perm])
+    assert torch.equal(opt.state[m._xyz]["exp_avg"], before["m1"][perm]) and torch.equal(opt.state[m._features_rest]["exp_avg_sq"], before["v2"][perm])
+    assert torch.equal(m.other, before["other"])
+    with pytest.raises(ValueError):
+        layout.permute_surfels_(m, torch.zeros(P, dtype=torch.long))
