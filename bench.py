@@ -58,7 +58,7 @@ class ClockSampler:
     read in-process; `nvidia-smi` is only the fallback when pynvml is missing.)"""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index: int, period_s: float = 0.02):
+    def __init__(self, gpu_index: int, period_s: float = 0.004):
         self.gpu, self.period, self.samples, self.stop_flag, self.thread = gpu_index, period_s, [], False, None
         self.h = None
         try:

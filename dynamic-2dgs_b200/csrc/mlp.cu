@@ -53,7 +53,11 @@ __global__ void __launch_bounds__(256) mlp_transpose_kernel(MlpLayers L) {
 // boundaries, so the next layer's first chunks land while the current layer is reduced and stored.  The copy engine
 // keeps the L2 -> SM pipe busy regardless of what the math warps are doing (the LDG version of this kernel was bound
 // by load latency: 8 warps x 4 LDG.128 in flight per SM).
-constexpr int CONSUMERS = 256;               // 8 math warps
+#ifndef D2GS_MLP_KGROUPS
+#define D2GS_MLP_KGROUPS 4
+#endif
+constexpr int KG = D2GS_MLP_KGROUPS;         // reduction groups: thread (group, quad) sums the k (or n) with index % KG == group
+constexpr int CONSUMERS = 64 * KG;           // math warps: 2 per group (one 116-KB CTA per SM: more warps = more latency hidden)
 constexpr int MLP_THREADS = CONSUMERS + 32;  // + 1 producer warp
 #ifndef D2GS_MLP_STAGES
 #define D2GS_MLP_STAGES 4
@@ -190,6 +194,18 @@ __device__ __forceinline__ void fma16(float4 (&acc)[4], const float4 wv, const f
   acc[3].x = fmaf(wv.w, xv.x, acc[3].x); acc[3].y = fmaf(wv.w, xv.y, acc[3].y); acc[3].z = fmaf(wv.w, xv.z, acc[3].z); acc[3].w = fmaf(wv.w, xv.w, acc[3].w);
 }
 
+// sum of the KG partial results of output `col` (pairwise, fixed order)
+__device__ __forceinline__ float4 sum_groups(const float4* s_red, int col) {
+  float4 p[KG];
+#pragma unroll
+  for (int g = 0; g < KG; g++) p[g] = s_red[g * MW + col];
+#pragma unroll
+  for (int st = 1; st < KG; st <<= 1)
+#pragma unroll
+    for (int g = 0; g + st < KG; g += 2 * st) { p[g].x += p[g + st].x; p[g].y += p[g + st].y; p[g].z += p[g + st].z; p[g].w += p[g + st].w; }
+  return p[0];
+}
+
 template <bool RELU>
 __device__ __forceinline__ void dense(Ring& ring, int NP, const float* __restrict__ bias, int N, const float4* s_in, int K,
                                       float4* s_red /*[4][256]*/, float4* s_out, float* g_out, int ld_out, int row0,
@@ -207,12 +223,12 @@ __device__ __forceinline__ void dense(Ring& ring, int NP, const float* __restric
     if (active) {
       if (kr == KCH) {
 #pragma unroll
-        for (int kk = 0; kk < KCH / 4; kk++) {
-          const int k = kg + 4 * kk;
+        for (int kk = 0; kk < KCH / KG; kk++) {
+          const int k = kg + KG * kk;
           fma16(acc, lds128(w + 16u * (uint32_t)(k * np4)), s_in[k0 + k]);
         }
       } else {
-        for (int k = kg; k < kr; k += 4) fma16(acc, lds128(w + 16u * (uint32_t)(k * np4)), s_in[k0 + k]);
+        for (int k = kg; k < kr; k += KG) fma16(acc, lds128(w + 16u * (uint32_t)(k * np4)), s_in[k0 + k]);
       }
     }
     ring_pop(ring, st, lane);
@@ -222,9 +238,8 @@ __device__ __forceinline__ void dense(Ring& ring, int NP, const float* __restric
   consumer_sync();
   if (tid < N) {
     const float b = bias ? __ldg(bias + tid) : 0.f;
-    const float4 p0 = s_red[tid], p1 = s_red[MW + tid], p2 = s_red[2 * MW + tid], p3 = s_red[3 * MW + tid];
-    float a0 = b + ((p0.x + p1.x) + (p2.x + p3.x)), a1 = b + ((p0.y + p1.y) + (p2.y + p3.y));
-    float a2 = b + ((p0.z + p1.z) + (p2.z + p3.z)), a3 = b + ((p0.w + p1.w) + (p2.w + p3.w));
+    const float4 ps = sum_groups(s_red, tid);
+    float a0 = b + ps.x, a1 = b + ps.y, a2 = b + ps.z, a3 = b + ps.w;
     if (RELU) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
     if (s_out) s_out[tid] = make_float4(a0, a1, a2, a3);
     if (g_out) {
@@ -241,7 +256,7 @@ struct FwdSmem {
   float4 x[2][INP_LD + MW];  // each buffer: [x_emb (63) | time feature (Tt)] at 0..in0-1, hidden at in0..in0+255
   float4 te[32];             // time embedding (Et <= 21)
   float4 th[MW];             // timenet hidden
-  float4 red[4 * MW];        // partial sums of the four k-groups
+  float4 red[KG * MW];       // partial sums of the k-groups
   uint64_t bars[3 * STAGES];
 };
 constexpr size_t FWD_SMEM_BYTES = (size_t)STAGES * FWD_STAGE_BYTES + sizeof(FwdSmem);
@@ -373,22 +388,21 @@ __device__ __forceinline__ float4 back_dense_k256(Ring& ring, int N, const float
     const int nr = min(NCH, N - n0);
     if (nr == NCH) {
 #pragma unroll
-      for (int nn = 0; nn < NCH / 4; nn++) {
-        const int n = ng + 4 * nn;
+      for (int nn = 0; nn < NCH / KG; nn++) {
+        const int n = ng + KG * nn;
         fma16(acc, lds128(w + 16u * (uint32_t)(n * (MW / 4))), s_g[n0 + n]);
       }
     } else {
-      for (int n = ng; n < nr; n += 4) fma16(acc, lds128(w + 16u * (uint32_t)(n * (MW / 4))), s_g[n0 + n]);
+      for (int n = ng; n < nr; n += KG) fma16(acc, lds128(w + 16u * (uint32_t)(n * (MW / 4))), s_g[n0 + n]);
     }
     ring_pop(ring, st, lane);
   }
 #pragma unroll
   for (int j = 0; j < 4; j++) s_red[ng * MW + 4 * kq + j] = acc[j];
   consumer_sync();
-  const float4 p0 = s_red[tid], p1 = s_red[MW + tid], p2 = s_red[2 * MW + tid], p3 = s_red[3 * MW + tid];
+  const float4 ps = sum_groups(s_red, tid & (MW - 1));      // threads >= 256 read a valid column and discard the value
   consumer_sync();
-  return make_float4((p0.x + p1.x) + (p2.x + p3.x), (p0.y + p1.y) + (p2.y + p3.y), (p0.z + p1.z) + (p2.z + p3.z),
-                     (p0.w + p1.w) + (p2.w + p3.w));
+  return ps;
 }
 // general K (the skip layer, K = 93 + 256, and layer 0, K = 93; rows are not 16-B aligned): thread tid accumulates input
 // column `col_main + tid` (when col_main >= 0) and, for tid < Tt, the time-feature column EX + tid.
@@ -402,7 +416,7 @@ __device__ __forceinline__ void back_dense_cols(Ring& ring, int K, int N, const 
     const int st = ring_front(ring);
     const uint32_t base = ring.stage(st);
     const int nr = min(NCH, N - n0);
-    if (col_main >= 0) {
+    if (col_main >= 0 && tid < MW) {
       const uint32_t w = base + 4u * (uint32_t)(col_main + tid);
 #pragma unroll 8
       for (int n = 0; n < nr; n++) fma4(g_main, lds32(w + 4u * (uint32_t)(n * K)), s_g[n0 + n]);
@@ -420,7 +434,7 @@ struct BwdSmem {
   float4 g[2][MW];      // pre-activation gradient of the current layer (ping-pong)
   float4 gh[16];        // head gradients
   float4 gt[32];        // gradient of the time feature (Tt <= 30)
-  float4 red[4 * MW];
+  float4 red[KG * MW];
   uint64_t bars[3 * STAGES];
 };
 constexpr size_t BWD_SMEM_BYTES_MLP = (size_t)STAGES * BWD_STAGE_BYTES + sizeof(BwdSmem);
@@ -460,10 +474,12 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_bwd_act_kernel(MlpBwd a) {
   int cur = 0;
   {
     float4 g = back_dense_k256(ring, hd.N, s_gh, s_red, tid);
-    const float4 h = load_rows(a.save_h + (size_t)(MD - 1) * a.rows * MW, MW, row0, rows, tid);
-    g = relu_mask(g, h);
-    s_g[cur][tid] = g;
-    store_rows(a.G + (size_t)(MD - 1) * a.rows * MW, MW, row0, rows, tid, g);
+    if (tid < MW) {
+      const float4 h = load_rows(a.save_h + (size_t)(MD - 1) * a.rows * MW, MW, row0, rows, tid);
+      g = relu_mask(g, h);
+      s_g[cur][tid] = g;
+      store_rows(a.G + (size_t)(MD - 1) * a.rows * MW, MW, row0, rows, tid, g);
+    }
   }
   consumer_sync();
   for (int l = MD - 1; l >= 1; l--) {
@@ -476,10 +492,12 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_bwd_act_kernel(MlpBwd a) {
     } else {
       g = back_dense_k256(ring, MW, s_g[cur], s_red, tid);
     }
-    const float4 h = load_rows(a.save_h + (size_t)(l - 1) * a.rows * MW, MW, row0, rows, tid);
-    g = relu_mask(g, h);
-    s_g[cur ^ 1][tid] = g;
-    store_rows(a.G + (size_t)(l - 1) * a.rows * MW, MW, row0, rows, tid, g);
+    if (tid < MW) {
+      const float4 h = load_rows(a.save_h + (size_t)(l - 1) * a.rows * MW, MW, row0, rows, tid);
+      g = relu_mask(g, h);
+      s_g[cur ^ 1][tid] = g;
+      store_rows(a.G + (size_t)(l - 1) * a.rows * MW, MW, row0, rows, tid, g);
+    }
     consumer_sync();
     cur ^= 1;
   }
@@ -498,9 +516,11 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_bwd_act_kernel(MlpBwd a) {
     if (tid < Tt) store_rows(a.g_tfeat, 32, row0, rows, tid, s_gt[tid]);
     const MlpLayer& t2 = L.layer[1];
     float4 g = back_dense_k256(ring, t2.N, s_gt, s_red, tid);
-    const float4 h = load_rows(a.save_th, MW, row0, rows, tid);
-    g = relu_mask(g, h);
-    store_rows(a.G_t1, MW, row0, rows, tid, g);
+    if (tid < MW) {
+      const float4 h = load_rows(a.save_th, MW, row0, rows, tid);
+      g = relu_mask(g, h);
+      store_rows(a.G_t1, MW, row0, rows, tid, g);
+    }
   }
   cluster_sync_all();
 }

@@ -483,7 +483,8 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_LW_MINBLOCKS) blend_bwd_
         const float4* r4 = reinterpret_cast<const float4*>(rec + id);
         const uint32_t dst = sq_base + (uint32_t)buf * (uint32_t)BWD_SMEM_Q1 + ((uint32_t)t << 4);
 #pragma unroll
-        for (int q = 0; q < REC_QUADS; q++) cp_async16(dst + q * QS, r4 + q);
+        for (int q = 0; q < REC_QUADS; q++)
+          if (q < 5 || hm_row == nullptr) cp_async16(dst + q * QS, r4 + q);   // the cull boxes (q5) are not needed with forward hit masks
       }
     }
     cp_async_commit();
