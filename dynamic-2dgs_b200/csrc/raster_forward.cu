@@ -511,7 +511,19 @@ __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_ker
 #ifndef D2GS_FWD_LW_CHUNK
 #define D2GS_FWD_LW_CHUNK 32
 #endif
-constexpr int LW_CHUNK = D2GS_FWD_LW_CHUNK;    // cull-box survivors per phase-1/phase-2 round (one or two 32-bit masks per lane)
+constexpr int LW_CHUNK = D2GS_FWD_LW_CHUNK;
+static_assert(D2GS_FWD_LW_CHUNK == 32, "the hit-mask transpose works on one 32-bit mask per lane");
+// 32 x 32 bit-matrix transpose across a warp: lane r holds row r, afterwards lane c holds column c (bit r = old row r's bit c).
+// Five block-swap steps (16, 8, 4, 2, 1), one shuffle each.
+__device__ __forceinline__ uint32_t transpose_bits32(uint32_t x, int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const uint32_t m = s == 16 ? 0x0000ffffu : s == 8 ? 0x00ff00ffu : s == 4 ? 0x0f0f0f0fu : s == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, s);
+    x = (lane & s) ? ((x & ~m) | ((y >> s) & m)) : ((x & m) | ((y << s) & ~m));
+  }
+  return x;
+}    // cull-box survivors per phase-1/phase-2 round (one or two 32-bit masks per lane)
 __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_lw_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
     const SurfelRec* __restrict__ rec, const float* __restrict__ bg, float* __restrict__ final_T,
@@ -519,7 +531,7 @@ __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_lw_
     const uint32_t* __restrict__ status, const uint32_t* __restrict__ tile_order, uint32_t gx,
     uint32_t* __restrict__ hit_mask) {
   __shared__ float4 s_q[2][REC_QUADS][BLEND_BATCH];
-  __shared__ uint8_t s_slot[FWD_NWARP][LW_CHUNK];
+  __shared__ uint8_t s_slot[FWD_NWARP][BLEND_BATCH];
 
   const int tid = threadIdx.x, lane = tid & 31;
   const uint32_t sub = blockIdx.x % FWD_Z;
@@ -607,27 +619,28 @@ __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_lw_
       keepmask[w] = __ballot_sync(0xffffffffu, keep);
     }
     if (__all_sync(0xffffffffu, done)) continue;      // this patch is saturated: it only keeps the barriers company
-    int w = 0;
-    uint32_t m = keepmask[0];
-    uint32_t wmask = 0u;      // ballot of the prefilter for staged slot 32 w + lane (0 for a slot the cull box dropped)
-    while (true) {
-      // ---- phase 1: up to LW_CHUNK survivors, exact prefilter on all lanes, per-lane hit masks
-      uint32_t hit_lo = 0u, hit_hi = 0u;
-      int ord = 0;
-      while (ord < LW_CHUNK) {
-        if (m == 0u) {
-          // word w is finished: its 32 ballots go out as one coalesced 128-byte store (the backward reads them instead of
-          // repeating the prefilter; zeros tell it which slots to skip)
-          if (hm_row && w * 32 + lane < n) hm_row[i * BLEND_BATCH + w * 32 + lane] = wmask;
-          wmask = 0u;
-          if (++w >= BLEND_BATCH / 32) break;
+    // compact list of the surviving slots (ballot compaction, one byte per survivor): the loops below walk it with a
+    // plain counter instead of bit-scanning four mask words
+    int ns = 0;
 #pragma unroll
-          for (int q = 1; q < BLEND_BATCH / 32; q++) if (w == q) m = keepmask[q];
-          continue;
-        }
-        const int j = w * 32 + (__ffs(m) - 1);
-        m &= m - 1u;
-        const uint32_t off = (uint32_t)j << 4;
+    for (int w = 0; w < BLEND_BATCH / 32; w++) {
+      const uint32_t km = keepmask[w];
+      if ((km >> lane) & 1u)
+        asm volatile("st.shared.u8 [%0], %1;" ::"r"(slot_base + (uint32_t)(ns + __popc(km & ((1u << lane) - 1u)))), "r"(w * 32 + lane) : "memory");
+      ns += __popc(km);
+      // hit masks for the backward: zeros first (slots the cull box dropped stay 0), survivors' ballots overwrite them below
+      if (hm_row && w * 32 + lane < n) hm_row[i * BLEND_BATCH + w * 32 + lane] = 0u;
+    }
+    __syncwarp();
+    for (int o0 = 0; o0 < ns; o0 += LW_CHUNK) {
+      // ---- phase 1: up to LW_CHUNK survivors, exact prefilter on all lanes, per-lane hit masks
+      const int nchunk = min(LW_CHUNK, ns - o0);
+      const uint32_t sbase = slot_base + (uint32_t)o0;
+      uint32_t mine = 0u;
+      for (int ord = 0; ord < nchunk; ord++) {
+        uint32_t j;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(j) : "r"(sbase + (uint32_t)ord));
+        const uint32_t off = j << 4;
         const float4 a = lds128(sb0 + off), b = lds128(sb1 + off), c = lds128(sb2 + off);
         const float3 k = {__fmaf_rn(pixf.x, b.z, -a.x), __fmaf_rn(pixf.x, b.w, -a.y), __fmaf_rn(pixf.x, c.x, -a.z)};
         const float3 l = {__fmaf_rn(pixf.y, b.z, -a.w), __fmaf_rn(pixf.y, b.w, -b.x), __fmaf_rn(pixf.y, c.x, -b.y)};
@@ -636,22 +649,21 @@ __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_lw_
         const float2 dd = {__fsub_rn(c.y, pixf.x), __fsub_rn(c.z, pixf.y)};
         const float rho2d = 2.0f * __fmaf_rn(dd.x, dd.x, __fmul_rn(dd.y, dd.y));
         const bool pass = !pair_rejected(p.x, p.y, p.z, rho2d, c.w) && p.z != 0.0f;
-        if (hm_row) {
-          const uint32_t hm = __ballot_sync(0xffffffffu, pass);
-          if ((j & 31) == lane) wmask = hm;
-        }
-        const uint32_t bit = pass ? 1u : 0u;
-        if (LW_CHUNK <= 32 || ord < 32) hit_lo |= bit << ord; else hit_hi |= bit << (ord - 32);
-        if (lane == 0) asm volatile("st.shared.u8 [%0], %1;" ::"r"(slot_base + (uint32_t)ord), "r"(j) : "memory");
-        ord++;
+        mine |= (pass ? 1u : 0u) << ord;
       }
-      if (ord == 0) break;
-      __syncwarp();
+      if (hm_row) {
+        // hit masks for the backward: lane p holds the chunk's hit bits of pixel p; the transposed bit matrix gives lane o the
+        // ballot of survivor o over the 32 pixels, stored at the survivor's list position (30 instructions per chunk instead
+        // of a ballot + select per survivor)
+        const uint32_t hm = transpose_bits32(mine, lane);
+        if (lane < nchunk && hm != 0u) {
+          uint32_t j;
+          asm volatile("ld.shared.u8 %0, [%1];" : "=r"(j) : "r"(sbase + (uint32_t)lane));
+          hm_row[i * BLEND_BATCH + j] = hm;
+        }
+      }
       // ---- phase 2: every lane consumes its own hits in list order
-#pragma unroll 1
-      for (int half = 0; half < (LW_CHUNK + 31) / 32; half++) {
-        uint32_t mine = half ? hit_hi : hit_lo;
-        const uint32_t sbase = slot_base + 32u * (uint32_t)half;
+      {
         while (mine != 0u && !done) {
           const uint32_t o = (uint32_t)(__ffs(mine) - 1);
           mine &= mine - 1u;
@@ -706,9 +718,8 @@ __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_lw_
           last_contributor = contributor;
         }
       }
-      __syncwarp();     // the slot map is rewritten by the next chunk
-      if (w >= BLEND_BATCH / 32) break;
     }
+    __syncwarp();     // the slot list is rewritten by the next batch
   }
   cp_async_wait<0>();
 

@@ -60,7 +60,15 @@ typedef struct D2gsConfig {
  *   "tile_sort"  (default 1): binning of d2gs_raster_forward by per-tile buckets (count, scan, atomic scatter, one sort per
  *                tile on depth bits | surfel id) instead of one global radix sort on tile | depth bits (0); the per-tile
  *                lists, ranges and everything downstream are bit-identical
- *   "deform_bwd_smem" (default 1): per-CTA shared accumulators in the incoherent d2gs_deform_backward path */
+ *   "deform_bwd_smem" (default 1): per-CTA shared accumulators in the incoherent d2gs_deform_backward path
+ *   "tile_order" (default 1): the blend kernels visit tiles longest list first (the tile scan writes the order); set it
+ *                before the forward of a frame
+ *   "lane_walk"  (default 7): bit 0 / bit 1: the forward / backward blend kernel lets every lane walk its OWN list of
+ *                prefilter hits (lanes of a warp work on different surfels at the same time) instead of visiting one surfel
+ *                per warp iteration; bit 2: the forward stores its prefilter ballots — one 32-bit word per (instance, 8x4
+ *                pixel patch of its tile), 32 B per instance at the end of the binning workspace — and the backward reads them
+ *                instead of repeating the prefilter.  Images, n_contrib and final_T are bit-identical in every setting;
+ *                gradients differ by the order of the floating-point sums */
 D2GS_API int d2gs_set_option(const char* name, int value);
 D2GS_API int d2gs_profile_enable(int on);
 D2GS_API int d2gs_profile_collect(double* total_ms, int64_t* launches);
