@@ -149,6 +149,18 @@ __device__ __forceinline__ void sts128(uint32_t addr, float x, float y, float z,
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
 
+// 32 x 32 bit-matrix transpose across a warp: lane r holds row r, afterwards lane c holds column c (bit r = old row r's bit c).
+// Five block-swap steps (16, 8, 4, 2, 1), one shuffle each.
+__device__ __forceinline__ uint32_t transpose_bits32(uint32_t x, int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const uint32_t m = s == 16 ? 0x0000ffffu : s == 8 ? 0x00ff00ffu : s == 4 ? 0x0f0f0f0fu : s == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, s);
+    x = (lane & s) ? ((x & ~m) | ((y >> s) & m)) : ((x & m) | ((y << s) & ~m));
+  }
+  return x;
+}    // cull-box survivors per phase-1/phase-2 round (one or two 32-bit masks per lane)
+
 // Tile rectangle of a surfel (reference: auxiliary.h:64-74).  Float arithmetic and the float->int truncation
 // are part of the contract: tile lists must be bit-exact.
 __device__ __forceinline__ RectU tile_rect(float px, float py, int max_radius, uint32_t gx, uint32_t gy) {

@@ -513,17 +513,6 @@ __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_ker
 #endif
 constexpr int LW_CHUNK = D2GS_FWD_LW_CHUNK;
 static_assert(D2GS_FWD_LW_CHUNK == 32, "the hit-mask transpose works on one 32-bit mask per lane");
-// 32 x 32 bit-matrix transpose across a warp: lane r holds row r, afterwards lane c holds column c (bit r = old row r's bit c).
-// Five block-swap steps (16, 8, 4, 2, 1), one shuffle each.
-__device__ __forceinline__ uint32_t transpose_bits32(uint32_t x, int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const uint32_t m = s == 16 ? 0x0000ffffu : s == 8 ? 0x00ff00ffu : s == 4 ? 0x0f0f0f0fu : s == 2 ? 0x33333333u : 0x55555555u;
-    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, s);
-    x = (lane & s) ? ((x & ~m) | ((y >> s) & m)) : ((x & m) | ((y << s) & ~m));
-  }
-  return x;
-}    // cull-box survivors per phase-1/phase-2 round (one or two 32-bit masks per lane)
 __global__ void __launch_bounds__(FWD_THREADS, D2GS_FWD_MINBLOCKS) blend_fwd_lw_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
     const SurfelRec* __restrict__ rec, const float* __restrict__ bg, float* __restrict__ final_T,
