@@ -552,7 +552,12 @@ def main():
     # (surfel tables whose gradient is final after the rasterizer backward start their all-reduce early, overlapped with
     # the deformation / MLP backward; `feature` also feeds the deformation blend, so it is not among them)
     early = [p for p in wl.pc.raster_parameters() if p is not getattr(wl.pc, "feature", None)]
-    bucket = ddist.FlatGradBucket(params, direct=(args.impl != "reference"), early=early if args.early_allreduce else None)
+    stages = {"raster": early}
+    if args.impl == "ours" and wl.use_deform:
+        # final after the deformation-blend backward (before the MLP backward): the hyper-coordinate table and the node geometry
+        cn = wl.deform.deform
+        stages["deform"] = [p for p in (wl.pc.feature, cn.nodes, cn._node_radius, cn._node_weight) if p.requires_grad]
+    bucket = ddist.FlatGradBucket(params, direct=(args.impl != "reference"), stages=stages if args.early_allreduce else None)
 
     def view_index(step):
         return ddist.view_for(step, rank, world, N_VIEWS)

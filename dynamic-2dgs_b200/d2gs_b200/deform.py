@@ -153,6 +153,7 @@ def _blend_backward(ctx, common, attr_ptrs, d_attr_ptrs, attr_stride, g_xyz, g_r
     a.dL_dfeature, a.dL_dmotion_mask = _p(d_feat), _p(d_mask)
     with torch.cuda.device(dev):
         _lib.check(L.d2gs_deform_backward(C.byref(a), _stream(dev)), "d2gs_deform_backward")
+    _dist.grads_ready("deform")     # hyper-coordinate table and node geometry are final: a bucket may start reducing them
     if d_mask is not None and ctx.mask_shape is not None:
         d_mask = d_mask.sum().reshape(ctx.mask_shape) if math.prod(ctx.mask_shape) == 1 else d_mask.reshape(ctx.mask_shape)
     return d_feat, d_nodes, d_rad, d_wl, d_mask

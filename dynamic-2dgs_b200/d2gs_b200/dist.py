@@ -73,8 +73,9 @@ _ACTIVE = []  # weak references to the direct-mode buckets, for grads_ready()
 
 def grads_ready(stage: str) -> None:
     """Called by the backward wrappers when a stage of the backward pass has written all its parameter gradients
-    ("raster": the per-surfel tables).  Buckets that declared those parameters `early` start their all-reduce now, on
-    the collective's own stream, overlapped with the rest of the backward (deformation blend, MLP)."""
+    ("raster": the per-surfel tables, after the per-surfel rasterizer backward; "deform": the hyper-coordinate table and the
+    node geometry, after the deformation blend backward).  Buckets that declared parameters for that stage start its
+    all-reduce now, on the collective's own stream, overlapped with the rest of the backward."""
     for ref in list(_ACTIVE):
         b = ref()
         if b is None:
@@ -99,14 +100,28 @@ class FlatGradBucket:
     ALIGN = 64   # floats
 
     def __init__(self, params: Iterable[torch.nn.Parameter], direct: bool = True, large_numel: int = 1 << 20,
-                 early: Optional[Iterable[torch.nn.Parameter]] = None):
+                 early: Optional[Iterable[torch.nn.Parameter]] = None, stages=None):
+        """``stages``: ``{"raster": [...], "deform": [...]}`` — parameters whose gradient is final when the named stage of
+        the backward pass reports ``grads_ready(stage)``; ``early=[...]`` is shorthand for ``{"raster": [...]}``."""
         ps = [p for p in params if p.requires_grad]
         assert ps, "no trainable parameters"
-        early_ids = {id(p) for p in (early or [])} if direct else set()
-        is_early = lambda p: id(p) in early_ids
+        stage_of = {}
+        if direct:
+            for name, plist in ({"raster": early or []} if stages is None else dict(stages)).items():
+                for p in plist:
+                    if p.requires_grad:
+                        stage_of[id(p)] = name
+        is_early = lambda p: id(p) in stage_of
         is_large = lambda p: p.numel() >= large_numel or is_early(p)
-        self.params = [p for p in ps if not is_large(p)] + [p for p in ps if is_large(p) and not is_early(p)] + \
-                      [p for p in ps if is_early(p)]
+        stage_names = []
+        for p in ps:
+            if is_early(p) and stage_of[id(p)] not in stage_names:
+                stage_names.append(stage_of[id(p)])
+        # staged parameters sit last, one contiguous range per stage; the stage that reports first ("raster") is the last range
+        stage_names.sort(key=lambda n: 0 if n == "raster" else -1)
+        self.params = [p for p in ps if not is_large(p)] + [p for p in ps if is_large(p) and not is_early(p)]
+        for name in stage_names:
+            self.params += [p for p in ps if is_early(p) and stage_of[id(p)] == name]
         dev = self.params[0].device
         # every slot starts on a 256-byte boundary, like a tensor from the CUDA caching allocator: the backward kernels
         # store gradients with 16-byte vector instructions
@@ -117,6 +132,7 @@ class FlatGradBucket:
         self.direct = direct
         self.slots: List[_Slot] = []
         self.early_slots: List[_Slot] = []
+        self.stage_ranges = {}        # name -> [begin, end, slots]
         off = 0
         self.early_begin = None
         for p in self.params:
@@ -127,13 +143,21 @@ class FlatGradBucket:
                     self.early_begin = off
                 sl.early_group = "default"
                 self.early_slots.append(sl)
+                r = self.stage_ranges.setdefault(stage_of[id(p)], [off, off, []])
+                r[1] = off + pad(p.numel())
+                r[2].append(sl)
             off += pad(p.numel())
-        self._early_work = None
+        self._stage_work = {}         # name -> async work handle of this step
         self._group = None
         if direct:
             import weakref
             _ACTIVE.append(weakref.ref(self))
         self.attach()
+
+    @property
+    def _early_work(self):
+        """The "raster" stage's work handle (kept for callers and tests written against the single early stage)."""
+        return self._stage_work.get("raster")
 
     def attach(self) -> None:
         for p, s in zip(self.params, self.slots):
@@ -153,9 +177,9 @@ class FlatGradBucket:
         if not self.direct:
             self.flat.zero_()
             return
-        if self._early_work is not None:       # a step that never reached all_reduce()
-            self._early_work.wait()
-            self._early_work = None
+        for w in self._stage_work.values():    # a step that never reached all_reduce()
+            w.wait()
+        self._stage_work = {}
         if self.n_small:
             self.flat[: self.n_small].zero_()
         for p, s in zip(self.params, self.slots):
@@ -173,19 +197,20 @@ class FlatGradBucket:
             sl.early_group = "default" if group is None else group
 
     def _on_stage(self, stage: str) -> None:
-        if stage != "raster" or not self.early_slots or self._early_work is not None:
+        r = self.stage_ranges.get(stage)
+        if r is None or stage in self._stage_work:
             return
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(self._group) > 1):
             return
-        if not all(s.claimed for s in self.early_slots):
-            return            # some table was not written by the kernels this step: everything goes at the end
-        self._early_work = dist.all_reduce(self.flat[self.early_begin:], op=dist.ReduceOp.SUM, group=self._group, async_op=True)
+        if not all(s.claimed for s in r[2]):
+            return            # some table was not written by the kernels this step: it goes with the final all-reduce
+        self._stage_work[stage] = dist.all_reduce(self.flat[r[0]:r[1]], op=dist.ReduceOp.SUM, group=self._group, async_op=True)
 
     def finalize(self) -> None:
         """After backward: every ``.grad`` is its bucket slice and the slice holds this step's gradient."""
         if not self.direct:
             return
-        early = set(map(id, self.early_slots)) if self._early_work is not None else ()
+        early = {id(sl) for name in self._stage_work for sl in self.stage_ranges[name][2]}
         for p, s in zip(self.params, self.slots):
             g = p.grad
             if g is None:
@@ -205,10 +230,21 @@ class FlatGradBucket:
     def all_reduce(self, group=None, average: bool = False) -> None:
         self.finalize()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            if self._early_work is not None:
-                dist.all_reduce(self.flat[: self.early_begin], op=dist.ReduceOp.SUM, group=group)
-                self._early_work.wait()
-                self._early_work = None
+            if self._stage_work:
+                # what no stage has started yet: the unstaged head plus the ranges of stages that never reported
+                end = self.early_begin
+                pending = [(b, e) for name, (b, e, _) in self.stage_ranges.items() if name not in self._stage_work]
+                for b, e in sorted(pending):
+                    if b == end:
+                        end = e               # contiguous with the head: one collective
+                if end > 0:
+                    dist.all_reduce(self.flat[:end], op=dist.ReduceOp.SUM, group=group)
+                for b, e in sorted(pending):
+                    if b >= end:
+                        dist.all_reduce(self.flat[b:e], op=dist.ReduceOp.SUM, group=group)
+                for w in self._stage_work.values():
+                    w.wait()
+                self._stage_work = {}
             else:
                 dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
             if average:

@@ -246,3 +246,41 @@ def test_early_reduced_slot_is_never_aliased_downstream(tmp_path):
     path = str(tmp_path / "alias.pt")
     mp.spawn(_alias_worker, args=(world, _free_port(), {"path": path}), nprocs=world, join=True)
     assert torch.load(path)["ok"]
+
+
+def _staged_worker(rank, world, port, out):
+    """Two named stages: 'raster' reports first, 'deform' second, the head goes with the final collective."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(3)
+    head = torch.nn.Parameter(torch.randn(7))
+    mid = torch.nn.Parameter(torch.randn(40, 2))
+    tab = torch.nn.Parameter(torch.randn(50, 3))
+    b = ddist.FlatGradBucket([head, mid, tab], stages={"raster": [tab], "deform": [mid]})
+    assert b.params == [head, mid, tab] and set(b.stage_ranges) == {"raster", "deform"}
+    assert b.stage_ranges["deform"][1] == b.stage_ranges["raster"][0] and b.early_begin == b.stage_ranges["deform"][0]
+    res = []
+    for step, report in enumerate([("raster", "deform"), ("raster",), ()]):
+        b.zero()
+        for p_, scale in ((head, 1.0), (mid, 2.0), (tab, 3.0)):
+            g = ddist.claim(p_, zeroed=False)
+            g.copy_(torch.full_like(p_, scale * (rank + 1) + step))
+            p_.grad = g
+        for st in report:
+            ddist.grads_ready(st)
+        launched = sorted(b._stage_work)
+        b.all_reduce()
+        res.append((launched, float(head.grad[0]), float(mid.grad[0, 0]), float(tab.grad[0, 0])))
+    if rank == 0:
+        torch.save(res, out["path"])
+    dist.destroy_process_group()
+
+
+def test_staged_allreduce_with_two_stages(tmp_path):
+    world = 2
+    path = str(tmp_path / "staged.pt")
+    mp.spawn(_staged_worker, args=(world, _free_port(), {"path": path}), nprocs=world, join=True)
+    res = torch.load(path)
+    assert [r[0] for r in res] == [["deform", "raster"], ["raster"], []]
+    for step, (_, h, m, t) in enumerate(res):       # sum over ranks 1 and 2 of scale * (rank + 1) + step
+        assert (h, m, t) == (1.0 * 3 + 2 * step, 2.0 * 3 + 2 * step, 3.0 * 3 + 2 * step)
