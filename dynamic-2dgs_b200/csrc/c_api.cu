@@ -882,7 +882,7 @@ int d2gs_mlp_backward(const D2gsMlpArgs* a, void* stream_) {
 // 3-D Gaussian rasterizer with depth and alpha outputs (gs3d.cu)
 // ------------------------------------------------------------------------------------------------------------
 namespace {
-struct G3GeomLayout { size_t rec, cov3D, clamped, tiles_touched, point_offsets, scan_temp, scan_temp_bytes, total; };
+struct G3GeomLayout { size_t rec, cov3D, clamped, tiles_touched, point_offsets, scan_temp, scan_temp_bytes, status, tile_box, total; };
 G3GeomLayout g3_geom_layout(int P) {
   G3GeomLayout L{};
   const size_t n = (size_t)(P > 0 ? P : 1);
@@ -896,16 +896,21 @@ G3GeomLayout g3_geom_layout(int P) {
   cub::DeviceScan::InclusiveSum(nullptr, tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
   L.scan_temp_bytes = tmp;
   L.scan_temp = o; o = align_up(o + tmp);
+  L.status = o; o = align_up(o + 4 * sizeof(uint32_t));   // {R, overflow flag, number of long tiles} of the per-tile binning
+  L.tile_box = o; o = align_up(o + 16 * n);
   L.total = o + 256;
   return L;
 }
-struct G3ImgLayout { size_t ranges, n_contrib, total; };
+struct G3ImgLayout { size_t ranges, n_contrib, tile_count, seg_begin, big_list, total; };
 G3ImgLayout g3_img_layout(int W, int H) {
   G3ImgLayout L{};
   const size_t tiles = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
   size_t o = 0;
   L.ranges = o; o = align_up(o + 8 * tiles);
   L.n_contrib = o; o = align_up(o + 4 * (size_t)W * H);
+  L.tile_count = o; o = align_up(o + 4 * tiles);
+  L.seg_begin = o; o = align_up(o + 4 * tiles);
+  L.big_list = o; o = align_up(o + 4 * tiles);
   L.total = o + 256;
   return L;
 }
@@ -977,39 +982,77 @@ int d2gs_gs3d_forward(const D2gsGs3dFwdArgs* a, void* stream_) {
   const G3Params p = g3_params(P, a->D, a->M, W, H, a->background, a->means3D, a->shs, a->colors_precomp, a->opacities, a->scales,
                                a->scale_modifier, a->rotations, a->cov3D_precomp, a->viewmatrix, a->projmatrix, a->campos,
                                a->tan_fovx, a->tan_fovy, a->prefiltered);
+  // Binning as in the surfel path (tile_binning.cu, option "tile_sort"): per-tile counters -> one-CTA scan (ranges, R,
+  // overflow flag) -> atomic scatter of (depth | id) keys -> one sort per tile; the same per-tile lists as the reference's
+  // global sort on (tile | depth) keys.  binning_capacity > 0 selects the deferred-count mode (no host readback).
+  const uint32_t tiles = p.gx * p.gy;
+  const bool tile_sort = g_tile_sort && tiles <= (uint32_t)TILE_SORT_MAX_TILES;
+  const bool deferred = a->binning_capacity > 0;
+  if (deferred && !tile_sort) return fail(D2GS_ERR_INVALID_ARG, "the deferred-count mode of gs3d needs the per-tile binning (tile_sort = 1)");
+  if (deferred && a->binning_capacity > 0xffffffffll) return fail(D2GS_ERR_INVALID_ARG, "binning_capacity exceeds 2^32-1 instances");
+  uint32_t* status = (uint32_t*)(gb + GL.status);
+  uint4* tile_box = (uint4*)(gb + GL.tile_box);
+  uint32_t* tile_count = (uint32_t*)(ib + IL.tile_count);
+  uint32_t* seg_begin = (uint32_t*)(ib + IL.seg_begin);
+  uint32_t* big_list = (uint32_t*)(ib + IL.big_list);
   if (!a->resume) {
-    g3_launch_preprocess_fwd(p, rec, cov3D, clamped, a->radii, tiles_touched, stream);
+    g3_launch_preprocess_fwd(p, rec, cov3D, clamped, a->radii, tiles_touched, tile_sort ? tile_box : nullptr, stream);
     D2GS_STAGE("gs3d preprocess", a->debug, stream);
-    size_t tmp = GL.scan_temp_bytes;
-    D2GS_CUDA_OK(cub::DeviceScan::InclusiveSum(gb + GL.scan_temp, tmp, tiles_touched, point_offsets, P, stream));
+    if (tile_sort) {
+      launch_tile_count(P, tile_box, p.gx, p.gy, tile_count, stream);
+      launch_tile_scan(tiles, deferred ? (uint32_t)a->binning_capacity : 0xffffffffu, tile_count, seg_begin, ranges, big_list, status,
+                       nullptr, stream);
+    } else {
+      size_t tmp = GL.scan_temp_bytes;
+      D2GS_CUDA_OK(cub::DeviceScan::InclusiveSum(gb + GL.scan_temp, tmp, tiles_touched, point_offsets, P, stream));
+    }
     D2GS_STAGE("gs3d scan", a->debug, stream);
   }
-  uint32_t R32 = 0;    // the reference's blocking readback (DGR/cuda_rasterizer/rasterizer_impl.cu:270-271)
-  D2GS_CUDA_OK(cudaMemcpyAsync(&R32, point_offsets + P - 1, 4, cudaMemcpyDeviceToHost, stream));
-  D2GS_CUDA_OK(cudaStreamSynchronize(stream));
-  const int64_t R = R32;
+  int64_t R = 0;
+  if (deferred) {
+    R = a->binning_capacity;
+  } else {
+    uint32_t R32 = 0;    // the reference's blocking readback (DGR/cuda_rasterizer/rasterizer_impl.cu:270-271)
+    D2GS_CUDA_OK(cudaMemcpyAsync(&R32, tile_sort ? status : point_offsets + P - 1, 4, cudaMemcpyDeviceToHost, stream));
+    D2GS_CUDA_OK(cudaStreamSynchronize(stream));
+    R = R32;
+  }
   *a->num_rendered = R;
   const BinLayout BL = bin_layout(R);
   if (a->binning_required) *a->binning_required = BL.total;
-  if (a->binning_bytes < BL.total || !a->binning_buffer) return D2GS_NEED_BINNING;
+  if (a->binning_bytes < BL.total || !a->binning_buffer) {
+    if (deferred) return fail(D2GS_ERR_WORKSPACE, "binning workspace smaller than binning_capacity instances need");
+    return D2GS_NEED_BINNING;
+  }
   char* bb = aligned_base(a->binning_buffer);
   uint64_t* keys_unsorted = (uint64_t*)(bb + BL.keys_unsorted);
   uint64_t* keys_sorted = (uint64_t*)(bb + BL.keys_sorted);
   uint32_t* vals_unsorted = (uint32_t*)(bb + BL.vals_unsorted);
   uint32_t* point_list = (uint32_t*)(bb + BL.point_list);
-  g3_launch_duplicate(P, rec, a->radii, point_offsets, keys_unsorted, vals_unsorted, p.gx, p.gy, stream);
-  D2GS_STAGE("gs3d duplicate", a->debug, stream);
-  if (R > 0) {
-    const int bit = (int)higher_msb(p.gx * p.gy);
-    size_t tmp = BL.sort_temp_bytes;
-    D2GS_CUDA_OK(cub::DeviceRadixSort::SortPairs(bb + BL.sort_temp, tmp, keys_unsorted, keys_sorted, vals_unsorted, point_list,
-                                                 (int)R, 0, 32 + bit, stream));
-    D2GS_STAGE("gs3d sort", a->debug, stream);
+  if (tile_sort) {
+    launch_tile_scatter(P, tile_box, p.gx, p.gy, seg_begin, tile_count, status, keys_unsorted, stream);
+    D2GS_STAGE("gs3d scatter", a->debug, stream);
+    if (deferred && a->num_rendered_async)
+      D2GS_CUDA_OK(cudaMemcpyAsync(a->num_rendered_async, status, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    if (R > 0) {
+      launch_tile_sort(tiles, ranges, big_list, status, keys_unsorted, keys_sorted, point_list, stream);
+      D2GS_STAGE("gs3d tile sort", a->debug, stream);
+    }
+  } else {
+    g3_launch_duplicate(P, rec, a->radii, point_offsets, keys_unsorted, vals_unsorted, p.gx, p.gy, stream);
+    D2GS_STAGE("gs3d duplicate", a->debug, stream);
+    if (R > 0) {
+      const int bit = (int)higher_msb(p.gx * p.gy);
+      size_t tmp = BL.sort_temp_bytes;
+      D2GS_CUDA_OK(cub::DeviceRadixSort::SortPairs(bb + BL.sort_temp, tmp, keys_unsorted, keys_sorted, vals_unsorted, point_list,
+                                                   (int)R, 0, 32 + bit, stream));
+      D2GS_STAGE("gs3d sort", a->debug, stream);
+    }
+    D2GS_CUDA_OK(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)p.gx * p.gy, stream));
+    launch_ranges(R, keys_sorted, ranges, stream);
+    D2GS_STAGE("gs3d ranges", a->debug, stream);
   }
-  D2GS_CUDA_OK(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)p.gx * p.gy, stream));
-  launch_ranges(R, keys_sorted, ranges, stream);
-  D2GS_STAGE("gs3d ranges", a->debug, stream);
-  g3_launch_blend_fwd(p, ranges, point_list, rec, a->out_color, a->out_depth, a->out_alpha, n_contrib, stream);
+  g3_launch_blend_fwd(p, ranges, point_list, rec, a->out_color, a->out_depth, a->out_alpha, n_contrib, deferred ? status : nullptr, stream);
   D2GS_STAGE("gs3d blend", a->debug, stream);
   return D2GS_OK;
 }
@@ -1066,7 +1109,10 @@ int d2gs_gs3d_export_state(int P, int width, int height, int64_t num_rendered, c
   if (binning_buffer && num_rendered > 0) {
     const BinLayout BL = bin_layout(num_rendered);
     char* bb = aligned_base(binning_buffer);
-    if (out->keys_sorted) D2GS_CUDA_OK(cudaMemcpyAsync(out->keys_sorted, bb + BL.keys_sorted, 8 * (size_t)num_rendered, cudaMemcpyDeviceToDevice, stream));
+    const bool tile_sort = g_tile_sort && tiles <= (size_t)TILE_SORT_MAX_TILES;
+    if (out->keys_sorted && tile_sort)     // per-tile keys are (depth << 32 | id): hand out the reference's (tile << 32 | depth)
+      launch_tile_export_keys((uint32_t)tiles, (const uint2*)(ib + IL.ranges), (const uint64_t*)(bb + BL.keys_sorted), out->keys_sorted, nullptr, stream);
+    else if (out->keys_sorted) D2GS_CUDA_OK(cudaMemcpyAsync(out->keys_sorted, bb + BL.keys_sorted, 8 * (size_t)num_rendered, cudaMemcpyDeviceToDevice, stream));
     if (out->point_list) D2GS_CUDA_OK(cudaMemcpyAsync(out->point_list, bb + BL.point_list, 4 * (size_t)num_rendered, cudaMemcpyDeviceToDevice, stream));
   }
   return D2GS_OK;

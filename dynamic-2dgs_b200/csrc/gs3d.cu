@@ -70,11 +70,12 @@ __device__ __forceinline__ Ewa ewa_project(v3 mean, float fx, float fy, float ta
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) g3_preprocess_fwd_kernel(G3Params p, G3Rec* __restrict__ rec, float* __restrict__ cov3Ds,
                                                                 uint8_t* __restrict__ clamped, int* __restrict__ radii,
-                                                                uint32_t* __restrict__ tiles_touched) {
+                                                                uint32_t* __restrict__ tiles_touched, uint4* __restrict__ tile_box) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= p.P) return;
   radii[idx] = 0;
   tiles_touched[idx] = 0;
+  if (tile_box) tile_box[idx] = make_uint4(0u, 0u, 0u, 0u);
   const v3 po = {p.means3D[3 * (size_t)idx], p.means3D[3 * (size_t)idx + 1], p.means3D[3 * (size_t)idx + 2]};
   const v3 p_view = xform4x3(po, p.view);
   if (p_view.z <= 0.2f) {
@@ -142,6 +143,8 @@ __global__ void __launch_bounds__(256) g3_preprocess_fwd_kernel(G3Params p, G3Re
   rec[idx] = g;
   radii[idx] = (int)my_radius;
   tiles_touched[idx] = (r.y1 - r.y0) * (r.x1 - r.x0);
+  // packed tile rectangle + depth bits for the per-tile binning (tile_binning.cu), as in the surfel path
+  if (tile_box) tile_box[idx] = make_uint4(r.x0 | (r.x1 << 16), r.y0 | (r.y1 << 16), __float_as_uint(p_view.z), 0u);
 }
 
 // one (tile | depth) key per tile of the Gaussian's rectangle (rasterizer_impl.cu:70-110)
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(256) g3_blend_fwd_kernel(const uint2* __restri
                                                            const G3Rec* __restrict__ rec, int W, int H, uint32_t gx,
                                                            const float* __restrict__ bg, float* __restrict__ out_color,
                                                            float* __restrict__ out_depth, float* __restrict__ out_alpha,
-                                                           uint32_t* __restrict__ n_contrib) {
+                                                           uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ status) {
   __shared__ G3Rec s_rec[256];
   const uint32_t tile = blockIdx.x;
   const uint32_t tx = tile % gx, ty = tile / gx;
@@ -223,9 +226,12 @@ __global__ void __launch_bounds__(256) g3_blend_fwd_kernel(const uint2* __restri
   if (inside) {
     const size_t pix = (size_t)pyi * W + pxi, HW = (size_t)H * W;
     n_contrib[pix] = last_contributor;
-    out_color[pix] = C0 + T * bg[0];
-    out_color[HW + pix] = C1 + T * bg[1];
-    out_color[2 * HW + pix] = C2 + T * bg[2];
+    // deferred-count mode: a frame whose instance count exceeded the binning capacity is never silently wrong
+    const bool poisoned = status != nullptr && status[1] != 0u;
+    const float qnan = __int_as_float(0x7fc00000);
+    out_color[pix] = poisoned ? qnan : C0 + T * bg[0];
+    out_color[HW + pix] = poisoned ? qnan : C1 + T * bg[1];
+    out_color[2 * HW + pix] = poisoned ? qnan : C2 + T * bg[2];
     out_alpha[pix] = weight;
     out_depth[pix] = D;
   }
@@ -486,9 +492,9 @@ __global__ void __launch_bounds__(256) g3_preprocess_bwd_kernel(G3Params p, cons
 }  // namespace
 
 void g3_launch_preprocess_fwd(const G3Params& p, G3Rec* rec, float* cov3Ds, uint8_t* clamped, int* radii, uint32_t* tiles_touched,
-                              cudaStream_t s) {
+                              uint4* tile_box, cudaStream_t s) {
   if (p.P == 0) return;
-  g3_preprocess_fwd_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p, rec, cov3Ds, clamped, radii, tiles_touched);
+  g3_preprocess_fwd_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p, rec, cov3Ds, clamped, radii, tiles_touched, tile_box);
 }
 void g3_launch_duplicate(int P, const G3Rec* rec, const int* radii, const uint32_t* offsets, uint64_t* keys, uint32_t* vals,
                          uint32_t gx, uint32_t gy, cudaStream_t s) {
@@ -496,9 +502,9 @@ void g3_launch_duplicate(int P, const G3Rec* rec, const int* radii, const uint32
   g3_duplicate_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, rec, radii, offsets, keys, vals, gx, gy);
 }
 void g3_launch_blend_fwd(const G3Params& p, const uint2* ranges, const uint32_t* point_list, const G3Rec* rec, float* out_color,
-                         float* out_depth, float* out_alpha, uint32_t* n_contrib, cudaStream_t s) {
+                         float* out_depth, float* out_alpha, uint32_t* n_contrib, const uint32_t* status, cudaStream_t s) {
   g3_blend_fwd_kernel<<<p.gx * p.gy, 256, 0, s>>>(ranges, point_list, rec, p.W, p.H, p.gx, p.bg, out_color, out_depth, out_alpha,
-                                                  n_contrib);
+                                                  n_contrib, status);
 }
 void g3_launch_blend_bwd(const G3Params& p, const uint2* ranges, const uint32_t* point_list, const G3Rec* rec, const float* alphas,
                          const uint32_t* n_contrib, const float* dL_dpix, const float* dL_ddepth, const float* dL_dalpha,

@@ -30,12 +30,14 @@ struct G3Params {
 
 constexpr int G3_GRAD_FLOATS = 12;   // per-Gaussian gradient record of the blend backward
 
+// tile_box (optional): packed tile rectangle + depth bits per Gaussian for the per-tile binning of tile_binning.cu
 void g3_launch_preprocess_fwd(const G3Params& p, G3Rec* rec, float* cov3Ds, uint8_t* clamped, int* radii, uint32_t* tiles_touched,
-                              cudaStream_t s);
+                              uint4* tile_box, cudaStream_t s);
 void g3_launch_duplicate(int P, const G3Rec* rec, const int* radii, const uint32_t* offsets, uint64_t* keys, uint32_t* vals,
                          uint32_t gx, uint32_t gy, cudaStream_t s);
+// status (optional): {R, overflow, ...} of the deferred-count binning; overflow poisons the colour planes with NaN
 void g3_launch_blend_fwd(const G3Params& p, const uint2* ranges, const uint32_t* point_list, const G3Rec* rec, float* out_color,
-                         float* out_depth, float* out_alpha, uint32_t* n_contrib, cudaStream_t s);
+                         float* out_depth, float* out_alpha, uint32_t* n_contrib, const uint32_t* status, cudaStream_t s);
 void g3_launch_blend_bwd(const G3Params& p, const uint2* ranges, const uint32_t* point_list, const G3Rec* rec, const float* alphas,
                          const uint32_t* n_contrib, const float* dL_dpix, const float* dL_ddepth, const float* dL_dalpha,
                          float* grad, cudaStream_t s);

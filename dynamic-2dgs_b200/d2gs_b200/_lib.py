@@ -47,7 +47,8 @@ class Gs3dFwdArgs(C.Structure):
                 ("out_color", C.c_void_p), ("out_depth", C.c_void_p), ("out_alpha", C.c_void_p), ("radii", C.c_void_p),
                 ("geom_buffer", C.c_void_p), ("geom_bytes", C.c_size_t), ("img_buffer", C.c_void_p), ("img_bytes", C.c_size_t),
                 ("binning_buffer", C.c_void_p), ("binning_bytes", C.c_size_t), ("resume", C.c_int),
-                ("num_rendered", C.POINTER(C.c_int64)), ("binning_required", C.POINTER(C.c_size_t))]
+                ("num_rendered", C.POINTER(C.c_int64)), ("binning_required", C.POINTER(C.c_size_t)),
+                ("binning_capacity", C.c_int64), ("num_rendered_async", C.c_void_p)]
 
 
 class Gs3dBwdArgs(C.Structure):

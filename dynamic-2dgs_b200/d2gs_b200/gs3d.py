@@ -12,15 +12,27 @@ from typing import Optional
 import torch
 
 from . import _lib
+from . import raster as _raster
 from .raster import _opt, _prep, _ptr, _stream_ptr, cpu_deep_copy_tuple
 
-_R_HINT: dict = {}      # (device index, P, W, H) -> last instance count: sizes the binning workspace so forward is one C call
 LAST_CONTEXT = None     # parity tests read the intermediates of the most recent forward through export_state()
 
 
 class Gs3dContext:
+    """``R`` = instance slots the binning workspace was laid out for (the C ABI's num_rendered in backward / export_state);
+    ``num_rendered`` = the true count (in deferred-count mode reading it waits for the asynchronous copy)."""
     __slots__ = ("P", "D", "M", "W", "H", "R", "geom", "img", "binning", "bg", "view", "proj", "campos", "tanfovx", "tanfovy",
-                 "scale_modifier", "debug")
+                 "scale_modifier", "debug", "_count", "_count_event", "_count_host")
+
+    @property
+    def num_rendered(self) -> int:
+        if self._count is None:
+            if self._count_event is None:
+                torch.cuda.synchronize(self.geom.device)
+            else:
+                self._count_event.synchronize()
+            self._count = int(self._count_host[0]) & 0xffffffff
+        return self._count
 
 
 def _forward(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs):
@@ -46,8 +58,27 @@ def _forward(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_p
     ctx.proj, ctx.campos = _prep(rs.projmatrix, "projmatrix"), _prep(rs.campos, "campos")
     ctx.tanfovx, ctx.tanfovy, ctx.scale_modifier, ctx.debug = float(rs.tanfovx), float(rs.tanfovy), float(rs.scale_modifier), bool(rs.debug)
     g, i, b = C.c_size_t(), C.c_size_t(), C.c_size_t()
-    key = (dev.index, P, W, H)
-    hint = int(_R_HINT.get(key, 4 * P + 1024) * 1.25) + 1024
+    key = ("gs3d", dev.index, P, W, H)
+    # Deferred-count mode: the same opt-in switch, warm-up and capacity rule as the surfel rasterizer
+    # (raster.set_deferred_count; always used under CUDA-graph capture) — see raster.raster_forward.
+    track = _raster._lru_get(_raster._TRACK, key, _raster._CountTrack, _raster._TRACK_MAX, on_evict=lambda k: _raster._R_HINT.pop(k, None))
+    capturing = torch.cuda.is_current_stream_capturing()
+    if capturing:
+        if ctx.debug or P == 0 or track.max_R <= 0:
+            raise _lib.D2gsError("CUDA-graph capture of the gs3d rasterizer needs debug=False and at least one eager frame of this "
+                                 "(P, width, height) first: the binning capacity comes from observed instance counts")
+        deferred = True
+    else:
+        track.poll(key)
+        track.raise_if_overflowed()
+        if not track.spare:
+            track.spare = [torch.zeros((2,), dtype=torch.int32).pin_memory() for _ in range(4)]
+        dcfg = _raster._DEFERRED
+        deferred = bool(dcfg["on"]) and P > 0 and not ctx.debug and track.frames >= dcfg["warmup"] and track.max_R > 0
+    if deferred:
+        hint = int(track.max_R * _raster._DEFERRED["margin"]) + 4096
+    else:
+        hint = int(_raster._R_HINT.get(key, 4 * P + 1024) * 1.25) + 1024
     _lib.check(L.d2gs_gs3d_workspace(P, W, H, hint, C.byref(g), C.byref(i), C.byref(b)), "d2gs_gs3d_workspace")
     u8 = dict(dtype=torch.uint8, device=dev)
     ctx.geom, ctx.img = torch.empty((g.value,), **u8), torch.empty((i.value,), **u8)
@@ -66,6 +97,16 @@ def _forward(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_p
     a.binning_buffer, a.binning_bytes = ctx.binning.data_ptr(), ctx.binning.numel()
     R, need = C.c_int64(0), C.c_size_t(0)
     a.num_rendered, a.binning_required = C.pointer(R), C.pointer(need)
+    ctx._count, ctx._count_event, ctx._count_host = None, None, None
+    if deferred:
+        if capturing:
+            if not track.spare:
+                raise _lib.D2gsError("more than 4 gs3d frames of one (P, width, height) captured without an eager frame in between")
+            host = track.spare.pop()
+        else:
+            host = torch.empty((2,), dtype=torch.int32, pin_memory=True)
+        a.binning_capacity, a.num_rendered_async = hint, host.data_ptr()
+        ctx._count_host = host
     with torch.cuda.device(dev):
         rc = L.d2gs_gs3d_forward(C.byref(a), _stream_ptr(dev))
         if rc == _lib.D2GS_NEED_BINNING:
@@ -73,8 +114,18 @@ def _forward(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_p
             a.binning_buffer, a.binning_bytes, a.resume = ctx.binning.data_ptr(), ctx.binning.numel(), 1
             rc = L.d2gs_gs3d_forward(C.byref(a), _stream_ptr(dev))
         _lib.check(rc, "d2gs_gs3d_forward")
+        if deferred and not capturing:
+            ctx._count_event = torch.cuda.Event()
+            ctx._count_event.record(torch.cuda.current_stream(dev))
     ctx.R = int(R.value)
-    _R_HINT[key] = ctx.R
+    if capturing:
+        track.captured.append((host, hint))
+    elif deferred:
+        track.pending.append((ctx._count_event, host, hint))
+    else:
+        ctx._count = ctx.R
+        track.observe(ctx.R)
+        _raster._R_HINT[key] = ctx.R
     return ctx, color, depth, alpha, radii, (means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp)
 
 

@@ -466,6 +466,12 @@ typedef struct D2gsGs3dFwdArgs {
   int resume;                     /* 1: per-Gaussian stage already done by a call that returned D2GS_NEED_BINNING */
   int64_t* num_rendered;          /* host */
   size_t* binning_required;       /* host */
+  /* Deferred-count mode, as in D2gsRasterFwdArgs: binning_capacity > 0 = bin into exactly that many instance slots without
+   * reading the count back (needs the per-tile binning, option "tile_sort"); *num_rendered = binning_capacity;
+   * num_rendered_async (pinned host, optional) receives {R, R > capacity} through an asynchronous copy on the stream;
+   * an overflowing frame renders nothing and its colour planes are NaN. */
+  int64_t binning_capacity;
+  int32_t* num_rendered_async;
 } D2gsGs3dFwdArgs;
 
 D2GS_API int d2gs_gs3d_forward(const D2gsGs3dFwdArgs* args, void* stream);

@@ -1,4 +1,5 @@
 """2-GPU (NCCL) check of the view-sharded step: the all-reduced gradients with the EARLY all-reduce of the surfel tables
+(and, in the third mode, the second stage that the deformation-blend backward reports)
 must equal those of the plain single all-reduce at the end — in particular the deformation-network / node gradients,
 which are computed downstream of dL/dxyz and dL/drotation while the early collective is already summing those tables
 across ranks (the deltas must not alias an early bucket slot).  Skipped on boxes with one GPU
@@ -31,7 +32,9 @@ def _worker(rank, world, port, path):
     sc = syn.make_scene(cfg["P"], cfg["seed"], cfg["s_med"], n_nodes=cfg["n_nodes"], hyper_dim=8)
     cams = syn.fibonacci_cameras(8, cfg["W"], cfg["H"])
     results = {}
-    for early_on in (False, True):
+    deform_stage_launched = []
+    for mode in ("off", "early", "staged"):
+        early_on = mode != "off"
         torch.manual_seed(0)
         pc = mdl.SurfelModel(sc, dev)
         dm = dfm.DeformModel(deform_type="node", is_blender=True, K=4, hyper_dim=8, node_num=cfg["n_nodes"], local_frame=True)
@@ -42,7 +45,13 @@ def _worker(rank, world, port, path):
                 h.weight.mul_(1e3)
         params = list(pc.raster_parameters()) + [p for p in dm.deform.parameters() if p.requires_grad]
         early = [p for p in pc.raster_parameters() if p is not pc.feature]
-        bucket = ddist.FlatGradBucket(params, large_numel=1 << 12, early=early if early_on else None)
+        cn = dm.deform
+        stages = None
+        if mode == "early":
+            stages = {"raster": early}
+        elif mode == "staged":      # + the tables that are final after the deformation-blend backward (ahead of the MLP backward)
+            stages = {"raster": early, "deform": [p for p in (pc.feature, cn.nodes, cn._node_radius, cn._node_weight) if p.requires_grad]}
+        bucket = ddist.FlatGradBucket(params, large_numel=1 << 12, stages=stages)
         assert ddist.reduces_early(pc._xyz) == early_on
         g = torch.Generator().manual_seed(3)
         w = (torch.randn((3, cfg["H"], cfg["W"]), generator=g) / (cfg["H"] * cfg["W"])).to(dev)
@@ -56,21 +65,23 @@ def _worker(rank, world, port, path):
             ((out["render"] * w).sum() + (out["depth"] * wd).sum() + (out["rend_normal"] * w).sum()).backward()
             launched = bucket._early_work is not None
             assert launched == early_on
+            if mode == "staged":
+                deform_stage_launched.append("deform" in bucket._stage_work)
             bucket.all_reduce()
             torch.cuda.synchronize(dev)
             acc = bucket.flat.clone() if acc is None else acc + bucket.flat
         names = {id(p): n for n, p in list(pc.named_parameters()) + list(dm.deform.named_parameters())}
-        results[early_on] = {names[id(p)]: p.grad.detach().cpu().numpy().copy() for p in bucket.params}
-        results[early_on]["__acc__"] = acc.cpu().numpy()
+        results[mode] = {names[id(p)]: p.grad.detach().cpu().numpy().copy() for p in bucket.params}
         bucket.detach()
     if rank == 0:
         bad = {}
-        for n in results[False]:
-            a, b = results[True][n], results[False][n]
-            e = float(np.linalg.norm(a.astype(np.float64) - b) / max(float(np.linalg.norm(b)), 1e-30))
-            if e > 1e-4:      # atomic ordering only; a race contaminates the network gradients at O(1)
-                bad[n] = e
-        torch.save({"bad": bad, "n": len(results[False])}, path)
+        for mode in ("early", "staged"):
+            for n in results["off"]:
+                a, b = results[mode][n], results["off"][n]
+                e = float(np.linalg.norm(a.astype(np.float64) - b) / max(float(np.linalg.norm(b)), 1e-30))
+                if e > 1e-4:      # atomic ordering only; a race contaminates the network gradients at O(1)
+                    bad[(mode, n)] = e
+        torch.save({"bad": bad, "n": len(results["off"]), "deform_stage_launched": deform_stage_launched}, path)
     dist.destroy_process_group()
 
 
@@ -82,3 +93,4 @@ def test_early_allreduce_matches_single_allreduce_on_two_gpus(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), path), nprocs=2, join=True)
     got = torch.load(path)
     assert got["n"] > 20 and not got["bad"], got["bad"]
+    assert got["deform_stage_launched"] == [True, True, True]      # the second stage really ran ahead of the MLP backward

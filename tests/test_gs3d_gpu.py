@@ -162,3 +162,111 @@ def test_api_errors_and_empty_scene(cuda_device):
     assert color.shape == (3, 48, 64) and float(color.abs().max()) == 0 and radii.numel() == 0 and float(alpha.abs().max()) == 0
     vis = r.markVisible(x)
     assert vis.dtype == torch.bool and vis.shape == (x.shape[0],)
+
+
+@pytest.mark.parametrize("name", ["G0", "G2"])
+def test_binning_modes_are_identical(name, cuda_device):
+    """The gs3d path bins like the surfel path (round 2): per-tile buckets + per-tile sort (default) or the reference's global
+    radix sort (`tile_sort = 0`), with the instance count read back (default) or deferred (no host synchronisation).  Tile
+    lists, ranges, n_contrib and images are bit-identical in all three settings; gradients agree to the order of the sums."""
+    import diff_gaussian_rasterization as ours
+    from d2gs_b200 import _lib, gs3d, raster
+    out = {}
+    try:
+        for mode in ("global", "tile", "deferred"):
+            _lib.set_option("tile_sort", 0 if mode == "global" else 1)
+            raster.set_deferred_count(mode == "deferred", warmup=1, margin=1.5)
+            if mode == "deferred":
+                run_module(ours, CASES[name], cuda_device)              # one synchronous frame establishes the capacity
+            res = run_module(ours, CASES[name], cuda_device)
+            ctx = gs3d.LAST_CONTEXT
+            st = {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in gs3d.export_state().items()}
+            out[mode] = (res, st, ctx.num_rendered, ctx.R)
+    finally:
+        _lib.set_option("tile_sort", 1)
+        raster.set_deferred_count(False)
+    ref, sref, Rref, _ = out["global"]
+    assert out["deferred"][3] > out["deferred"][2] == Rref > 0          # the deferred frame ran on capacity, not on the count
+    for mode in ("tile", "deferred"):
+        res, st, R, _ = out[mode]
+        assert R == Rref
+        assert np.array_equal(res["radii"], ref["radii"]) and np.array_equal(st["ranges"], sref["ranges"])
+        assert np.array_equal(st["point_list"][:R], sref["point_list"][:R]) and np.array_equal(st["keys_sorted"][:R], sref["keys_sorted"][:R])
+        assert np.array_equal(st["n_contrib"], sref["n_contrib"])
+        for k in ("color", "depth", "alpha"):
+            assert np.array_equal(res[k], ref[k]), (mode, k)
+        for k in GRAD_KEYS:
+            if k in res:
+                assert util.rel_err(res[k], ref[k]) < 2e-5, (mode, k)
+
+
+def test_deferred_overflow_is_loud_and_capturable(cuda_device):
+    """(1) A deferred frame whose instance count exceeds its slots renders NaN and the next call raises; (2) with no
+    synchronisation left, forward + backward of the gs3d op replays as a CUDA graph."""
+    import diff_gaussian_rasterization as ours
+    from d2gs_b200 import _lib, gs3d, raster, synthetic as syn
+    rng = np.random.default_rng(5)
+    P, W, H = 30_000, 400, 304
+    d = rng.normal(size=(P, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    cam = syn.fibonacci_cameras(16, W, H)[5]
+    q = rng.normal(size=(P, 4))
+    case = dict(inputs=dict(means3D=(d * rng.uniform(size=(P, 1)) ** (1 / 3)).astype(np.float32),
+                            opacities=rng.uniform(0.05, 0.95, size=(P, 1)).astype(np.float32),
+                            shs=np.concatenate([rng.normal(size=(P, 1, 3)), 0.1 * rng.normal(size=(P, 15, 3))], 1).astype(np.float32),
+                            sh_degree=3, scales=np.exp(np.log(0.01) + 0.5 * rng.normal(size=(P, 3))).astype(np.float32),
+                            rotations=(q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32), scale_modifier=1.0,
+                            bg=np.array([0.3, 0.1, 0.7], np.float32), viewmatrix=cam.world_view_transform,
+                            projmatrix=cam.full_proj_transform, campos=cam.camera_center, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, H=H, W=W),
+                g_color=rng.normal(size=(3, H, W)).astype(np.float32), g_depth=rng.normal(size=(1, H, W)).astype(np.float32),
+                g_alpha=rng.normal(size=(1, H, W)).astype(np.float32))       # tens of thousands of instances: far above the 4096-slot floor
+    try:
+        raster.set_deferred_count(True, warmup=1, margin=1.5)
+        run_module(ours, case, cuda_device)
+        want = run_module(ours, case, cuda_device)
+        assert gs3d.LAST_CONTEXT.num_rendered > 20_000
+        key = [k for k in raster._TRACK if k[0] == "gs3d"][-1]
+        raster._TRACK[key].poll(key, block=True)                        # fold in the pending counts, then ...
+        raster._TRACK[key].max_R = 10                                   # ... pretend the scene used to be tiny
+        bad = run_module(ours, case, cuda_device)
+        assert np.isnan(bad["color"]).all()
+        torch.cuda.synchronize()
+        with pytest.raises(_lib.D2gsError, match="deferred-count"):
+            run_module(ours, case, cuda_device)
+        again = run_module(ours, case, cuda_device)                     # the capacity has been raised
+        assert np.array_equal(again["color"], want["color"])
+        # CUDA graph: static inputs, capture fwd + bwd once, replay
+        dev = cuda_device
+        T = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32, device=dev)
+        inp = case["inputs"]
+        xyz = T(inp["means3D"]).requires_grad_(True)
+        rs = ours.GaussianRasterizationSettings(image_height=int(inp["H"]), image_width=int(inp["W"]), tanfovx=float(inp["tanfovx"]),
+                                                tanfovy=float(inp["tanfovy"]), bg=T(inp["bg"]), scale_modifier=float(inp["scale_modifier"]),
+                                                viewmatrix=T(inp["viewmatrix"]), projmatrix=T(inp["projmatrix"]), sh_degree=int(inp["sh_degree"]),
+                                                campos=T(inp["campos"]), prefiltered=False, debug=False)
+        kw = dict(means2D=torch.zeros_like(xyz), opacities=T(inp["opacities"]),
+                  scales=T(inp["scales"]) if inp.get("scales") is not None else None,
+                  rotations=T(inp["rotations"]) if inp.get("rotations") is not None else None)
+        if inp.get("shs") is not None:
+            kw["shs"] = T(inp["shs"])
+        else:
+            kw["colors_precomp"] = T(inp["colors_precomp"])
+        if inp.get("scales") is None:
+            kw.pop("scales"); kw.pop("rotations"); kw["cov3D_precomp"] = T(inp["cov3D_precomp"])
+        gcol = T(case["g_color"])
+
+        def step():
+            color, radii, depth, alpha = ours.GaussianRasterizer(rs)(means3D=xyz, **kw)
+            (g,) = torch.autograd.grad((color * gcol).sum() + depth.sum(), xyz)
+            return color, g
+        s = torch.cuda.Stream(dev)
+        with torch.cuda.stream(s):
+            c0, g0 = step()
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=s):
+                c1, g1 = step()
+            graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(c0, c1) and util.rel_err(g1.cpu().numpy(), g0.cpu().numpy()) < 2e-5
+    finally:
+        raster.set_deferred_count(False)
