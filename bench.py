@@ -829,7 +829,7 @@ def main():
                                      ("synchronous count readback" if args.sync_count else "deferred count (no host synchronisation in the step)")),
                          "launch": ("one CUDA graph per step (captured through the public API)" if graphed else "eager launches") +
                                    (" | e2e: graph incl. H2D/D2H copies" if e2e_graphed else " | e2e: eager"),
-                         "collective": ("NCCL all-reduce of the flat gradient bucket" + (", surfel tables early" if args.early_allreduce else "")) if world > 1 and args.impl == "ours"
+                         "collective": ("NCCL all-reduce of the flat gradient bucket" + (", surfel tables after the rasterizer backward, hyper-coordinate table + node geometry after the deformation backward" if args.early_allreduce else "")) if world > 1 and args.impl == "ours"
                                        else ("rank 0 only (the reference is single-GPU)" if world > 1 else "none")},
            "clocks": clocks,
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps}}

@@ -75,12 +75,15 @@ def _worker(rank, world, port, path):
         bucket.detach()
     if rank == 0:
         bad = {}
+        scale = max(float(np.linalg.norm(v)) for v in results["off"].values())
         for mode in ("early", "staged"):
             for n in results["off"]:
                 a, b = results[mode][n], results["off"][n]
-                e = float(np.linalg.norm(a.astype(np.float64) - b) / max(float(np.linalg.norm(b)), 1e-30))
-                if e > 1e-4:      # atomic ordering only; a race contaminates the network gradients at O(1)
-                    bad[(mode, n)] = e
+                err = float(np.linalg.norm(a.astype(np.float64) - b))
+                # atomic ordering only; a race contaminates the network gradients at O(1).  (`feature` has an analytically
+                # ~zero gradient here — all nodes share one radius — so its comparison needs the absolute term.)
+                if err > 1e-4 * float(np.linalg.norm(b)) + 1e-7 * scale:
+                    bad[(mode, n)] = (err, float(np.linalg.norm(b)), scale)
         torch.save({"bad": bad, "n": len(results["off"]), "deform_stage_launched": deform_stage_launched}, path)
     dist.destroy_process_group()
 
