@@ -149,6 +149,8 @@ int d2gs_set_option(const char* name, int value) {
   if (std::strcmp(name, "deform_bwd_smem") == 0) { g_deform_bwd_smem = value != 0; return D2GS_OK; }
   if (std::strcmp(name, "knn_filter") == 0) { g_knn_filter = value != 0; return D2GS_OK; }
   if (std::strcmp(name, "tile_sort") == 0) { g_tile_sort = value != 0; return D2GS_OK; }
+  if (std::strcmp(name, "mlp_cluster_fwd") == 0) { mlp_set_cluster(0, value); return D2GS_OK; }
+  if (std::strcmp(name, "mlp_cluster_bwd") == 0) { mlp_set_cluster(1, value); return D2GS_OK; }
   if (std::strcmp(name, "lane_walk") == 0) { g_lane_walk = value; return D2GS_OK; }
   if (std::strcmp(name, "tile_order") == 0) { g_tile_order = value != 0; return D2GS_OK; }
   return fail(D2GS_ERR_INVALID_ARG, std::string("unknown option ") + name);

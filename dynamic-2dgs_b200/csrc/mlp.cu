@@ -609,10 +609,17 @@ void mlp_launch_transpose(const MlpLayers& L, cudaStream_t s) {
 #define D2GS_MLP_CLUSTER 4
 #endif
 // grid of ceil(rows / ROWS) CTAs, rounded up to whole clusters (a CTA without rows still takes part in the ring protocol)
+// cluster sizes (option "mlp_cluster_fwd" / "mlp_cluster_bwd"): the forward multicasts across 4 CTAs; the backward gains nothing
+// from it (profiles/mlp_tensor_core_probe_r2.md) and runs next to the early all-reduce at N > 1, where whole clusters of free
+// SMs are scarce — it launches plain CTAs
+static int g_mlp_cluster[2] = {D2GS_MLP_CLUSTER, 1};
+void mlp_set_cluster(int which, int size) {
+  if (size == 1 || size == 2 || size == 4 || size == 8) g_mlp_cluster[which & 1] = size;
+}
 template <typename Kern, typename Arg>
-static void launch_clustered(Kern kern, const Arg& a, int rows, size_t smem, cudaStream_t s) {
+static void launch_clustered(Kern kern, const Arg& a, int rows, size_t smem, int cluster, cudaStream_t s) {
   const int ctas = (rows + ROWS - 1) / ROWS;
-  int cl = D2GS_MLP_CLUSTER;
+  int cl = cluster;
   while (cl > 1 && ctas < cl) cl >>= 1;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)((ctas + cl - 1) / cl * cl), 1, 1);
@@ -629,13 +636,13 @@ void mlp_launch_forward(const MlpFwd& a, cudaStream_t s) {
   if (a.rows <= 0) return;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM_BYTES); attr = true; }
-  launch_clustered(mlp_fwd_kernel, a, a.rows, FWD_SMEM_BYTES, s);
+  launch_clustered(mlp_fwd_kernel, a, a.rows, FWD_SMEM_BYTES, g_mlp_cluster[0], s);
 }
 void mlp_launch_backward(const MlpBwd& a, const MlpWJobs& J, cudaStream_t s) {
   if (a.rows <= 0) return;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(mlp_bwd_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES_MLP); attr = true; }
-  launch_clustered(mlp_bwd_act_kernel, a, a.rows, BWD_SMEM_BYTES_MLP, s);
+  launch_clustered(mlp_bwd_act_kernel, a, a.rows, BWD_SMEM_BYTES_MLP, g_mlp_cluster[1], s);
   int tiles = 0;
   for (int j = 0; j < J.count; j++) tiles += J.job[j].tiles;
   mlp_bwd_w_kernel<<<tiles, 256, 0, s>>>(J, a.rows);

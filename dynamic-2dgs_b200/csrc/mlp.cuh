@@ -50,6 +50,7 @@ struct MlpWJobs {
 };
 
 void mlp_launch_transpose(const MlpLayers& L, cudaStream_t s);
+void mlp_set_cluster(int which /*0 forward, 1 backward*/, int size /*1, 2, 4 or 8 CTAs*/);
 void mlp_launch_forward(const MlpFwd& a, cudaStream_t s);
 void mlp_launch_backward(const MlpBwd& a, const MlpWJobs& J, cudaStream_t s);
 

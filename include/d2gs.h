@@ -61,6 +61,8 @@ typedef struct D2gsConfig {
  *                tile on depth bits | surfel id) instead of one global radix sort on tile | depth bits (0); the per-tile
  *                lists, ranges and everything downstream are bit-identical
  *   "deform_bwd_smem" (default 1): per-CTA shared accumulators in the incoherent d2gs_deform_backward path
+ *   "mlp_cluster_fwd" (default 4) / "mlp_cluster_bwd" (default 1): thread-block cluster size of the MLP kernels; the CTAs of a
+ *                cluster receive the weight stream through ONE multicast bulk copy per chunk
  *   "tile_order" (default 1): the blend kernels visit tiles longest list first (the tile scan writes the order); set it
  *                before the forward of a frame
  *   "lane_walk"  (default 7): bit 0 / bit 1: the forward / backward blend kernel lets every lane walk its OWN list of

@@ -15,7 +15,7 @@ for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
     if m:
         cur = m.group(1); per[cur] = collections.Counter(); continue
-    m = re.search(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+    m = re.search(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Za-z0-9_.]+)", line)
     if cur and m:
         op = m.group(1)
         per[cur]["total"] += 1
@@ -26,12 +26,15 @@ print(f"# SASS census of `{os.path.relpath(lib, ROOT)}` ({', '.join(sorted(set(a
 print("| kernel | instr | " + " | ".join(keys) + " |")
 print("|---|---|" + "---|" * len(keys))
 def demangle(n):
-    try: return subprocess.run(["cu++filt", n], capture_output=True, text=True).stdout.strip().split("(")[0]
+    try:
+        d = subprocess.run(["cu++filt", n], capture_output=True, text=True).stdout.strip()
+        i = d.find("(")
+        return d if i < 0 else d[:i]
     except Exception: return n
 tot = collections.Counter()
 for f, c in per.items():
     if c["total"] < 40: continue
-    name = demangle(f).replace("d2gs::", "").replace("(anonymous namespace)::", "")[:60]
+    name = demangle(f).replace("d2gs::", "").replace("(anonymous namespace)::", "").replace("void ", "")[:48]
     print(f"| `{name}` | {c['total']} | " + " | ".join(str(c[k]) if c[k] else "" for k in keys) + " |")
     tot.update(c)
 print(f"| **all kernels** | {tot['total']} | " + " | ".join(str(tot[k]) if tot[k] else "0" for k in keys) + " |")
