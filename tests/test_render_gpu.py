@@ -189,3 +189,51 @@ def test_step_replays_as_cuda_graph(cuda_device):
     for a, b, p in zip(got[2:], grads_e, params):
         assert util.rel_err(a.cpu().numpy(), b.cpu().numpy()) < 2e-5, tuple(p.shape)
     assert float(got[0].std()) > 0.01
+
+
+def test_storage_order_changes_nothing(cuda_device):
+    """layout.permute_surfels_ (Morton-sorted storage): deform + render + backward + one FusedAdam step of a
+    permuted model equal those of the original model up to the permutation — images to fp32 round-off (the blend order inside a
+    tile is (depth, surfel id): exact depth ties are the only thing the ids can reorder), gradients and updated parameters
+    row for row."""
+    from d2gs_b200 import deform as dfm, layout, model as mdl, synthetic as syn
+    from d2gs_b200.optim import FusedAdam
+    from gaussian_renderer import render
+    dev = cuda_device
+    cfg = syn.CONFIGS["T1"]
+    sc = syn.make_scene(cfg["P"], cfg["seed"], cfg["s_med"], n_nodes=cfg["n_nodes"], hyper_dim=8)
+    cam = mdl.ViewCamera(syn.fibonacci_cameras(8, cfg["W"], cfg["H"])[3], dev)
+    g = torch.Generator().manual_seed(4)
+    w = (torch.randn((3, cfg["H"], cfg["W"]), generator=g) / (cfg["H"] * cfg["W"])).to(dev)
+    res = {}
+    perm = None
+    for mode in ("as_generated", "morton"):
+        torch.manual_seed(0)
+        pc = mdl.SurfelModel(sc, dev)
+        dm = dfm.DeformModel(deform_type="node", is_blender=True, K=4, hyper_dim=8, node_num=cfg["n_nodes"], local_frame=True)
+        with torch.no_grad():
+            dm.deform.nodes.copy_(torch.as_tensor(sc.nodes, device=dev))
+            dm.deform._node_radius.copy_(torch.as_tensor(sc.node_radius, device=dev))
+            dm.deform.network.gaussian_warp.weight.mul_(1e3)
+        opt = FusedAdam([{"params": [pc._xyz], "lr": 1e-3, "name": "xyz"}, {"params": [pc._features_rest], "lr": 1e-3, "name": "f_rest"}],
+                        lr=0.0, eps=1e-15)
+        if mode == "morton":
+            perm = layout.morton_permutation(pc.get_xyz)
+            n = layout.permute_surfels_(pc, perm, optimizers=[opt])
+            assert n >= 8 and not torch.equal(perm, torch.arange(perm.numel(), device=perm.device))
+        for step in range(2):            # second step: the optimiser state (first step's moments) is in play
+            d = dm.step(pc.get_xyz.detach(), dm.deform.expand_time(cam.fid), feature=pc.feature, motion_mask=pc.motion_mask)
+            out = render(cam, pc, mdl.PipelineParams(), torch.zeros(3, device=dev), d["d_xyz"], d["d_rotation"], d["d_scaling"])
+            loss = (out["render"] * w).sum() + 1e-3 * out["rend_dist"].sum()
+            for p_ in pc.parameters():
+                p_.grad = None
+            loss.backward()
+            opt.step()
+        torch.cuda.synchronize()
+        res[mode] = dict(img=out["render"].detach().cpu().numpy(), radii=out["radii"].cpu().numpy(), xyz=pc._xyz.detach().cpu().numpy(),
+                         g_rest=pc._features_rest.grad.cpu().numpy(), g_op=pc._opacity.grad.cpu().numpy())
+    a, b, p = res["as_generated"], res["morton"], perm.cpu().numpy()
+    assert np.array_equal(b["radii"], a["radii"][p])
+    assert util.rel_err(b["img"], a["img"]) < 1e-5
+    assert util.rel_err(b["xyz"], a["xyz"][p]) < 1e-6
+    assert util.rel_err(b["g_rest"], a["g_rest"][p]) < 1e-4 and util.rel_err(b["g_op"], a["g_op"][p]) < 1e-4
