@@ -473,6 +473,9 @@ def main():
     ap.add_argument("--tile-sort", type=int, default=None, choices=[0, 1],
                     help="binning: 1 = per-tile buckets + segmented sort, 0 = global radix sort (same lists); default: the library's")
     ap.add_argument("--no-clocks", action="store_true", help="diagnosis only: do not sample clocks during the timed region")
+    ap.add_argument("--view-schedule", choices=["balanced", "roundrobin"], default="balanced",
+                    help="N > 1 only: balanced = the views of one step (one per rank) are chosen to cost the same, so no rank waits for "
+                         "a slower one (every view still once per epoch); roundrobin = view (step * N + rank) mod 100")
     ap.add_argument("--storage", choices=["morton", "random"], default="morton",
                     help="storage order of the surfel tables (both arms): morton = sorted along a Morton curve once at set-up with "
                          "d2gs_b200.layout.permute_surfels_, as a trainer does after densification; random = as generated")
@@ -559,7 +562,26 @@ def main():
         stages["deform"] = [p for p in (wl.pc.feature, cn.nodes, cn._node_radius, cn._node_weight) if p.requires_grad]
     bucket = ddist.FlatGradBucket(params, direct=(args.impl != "reference"), stages=stages if args.early_allreduce else None)
 
+    # N > 1: every step waits for its slowest rank, so the `world` views of a step are chosen to cost the same (instance
+    # count of the view, measured once at set-up; dist.balanced_view_schedule).  Each view is still visited once per epoch.
+    schedule = None
+    if world > 1 and args.view_schedule == "balanced":
+        from gaussian_renderer import render as _render_ours
+        costs = []
+        with torch.no_grad():
+            for c in wl.cams:
+                if args.impl == "ours":
+                    d_ = wl.deform.step(wl.pc.get_xyz.detach(), wl.deform.deform.expand_time(c.fid), feature=wl.pc.feature,
+                                        motion_mask=wl.pc.motion_mask) if wl.use_deform else {"d_xyz": 0.0, "d_rotation": 0.0, "d_scaling": 0.0}
+                    o_ = _render_ours(c, wl.pc, wl.pipe, wl.bg, d_["d_xyz"], d_["d_rotation"], d_["d_scaling"])
+                    costs.append(int((o_["radii"].long() ** 2).sum()))          # ~ screen area of the surfels ~ instance count
+                else:
+                    costs.append(0)
+        schedule = ddist.balanced_view_schedule(costs, world)
+
     def view_index(step):
+        if schedule is not None:
+            return schedule[step % len(schedule)][rank]
         return ddist.view_for(step, rank, world, N_VIEWS)
 
     # ---- training tail (--train): what train_gui.py does between loss.backward() and the next iteration (:388-432)
@@ -820,7 +842,7 @@ def main():
                                   + (" + densification stats + Adam step of all parameters" if args.train else ""),
                       "loss": "seeded random-weighted sum over the render outputs + L1 (SURVEY 8(d))" if args.loss == "synthetic" else
                               "training loss of train_gui.py:292-313: L1 + D-SSIM(0.2) + normal(0.02) + distortion(1000)",
-                      "parallelism": f"view-sharded x{world}",
+                      "parallelism": f"view-sharded x{world}" + ((", views of a step balanced by instance count" if args.view_schedule == "balanced" else ", round-robin views") if world > 1 else ""),
                       "storage": ("surfel tables Morton-sorted once at set-up (d2gs_b200.layout.permute_surfels_, both arms)"
                                   if args.storage == "morton" else "surfel tables in generation (random) order"),
                       "l2_policy": "no explicit flush: per-step working set (params+grads+workspaces ~0.3 GB) exceeds the 126 MB L2 and the view changes every step"},

@@ -19,6 +19,22 @@ def view_for(step: int, rank: int, world: int, n_views: int) -> int:
     return (step * world + rank) % n_views
 
 
+def balanced_view_schedule(costs, world: int) -> List[List[int]]:
+    """Cost-balanced view schedule for synchronous data parallelism: every step waits for its slowest rank, so the ``world``
+    views of a step should cost the same.  Views are sorted by ``costs`` (e.g. the (surfel, tile) instance count of a view
+    from an earlier epoch) and cut into consecutive groups of ``world``; the group order is interleaved (cheap, expensive,
+    cheap, ...) so that the epoch has no trend.  Every view appears exactly once per epoch when ``len(costs)`` is a multiple
+    of ``world`` (the remainder wraps around to the cheapest views).  Returns ``schedule[step % len(schedule)][rank]``."""
+    order = sorted(range(len(costs)), key=lambda v: (float(costs[v]), v))
+    groups = [[order[(g * world + r) % len(order)] for r in range(world)] for g in range((len(order) + world - 1) // world)]
+    lo, hi, out = 0, len(groups) - 1, []
+    while lo <= hi:
+        out.append(groups[lo]); lo += 1
+        if lo <= hi:
+            out.append(groups[hi]); hi -= 1
+    return out
+
+
 def views_of_rank(rank: int, world: int, n_views: int) -> List[int]:
     """Static shard of a view list (rank r owns r, r+world, ...)."""
     return list(range(rank, n_views, world))

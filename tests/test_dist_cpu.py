@@ -284,3 +284,19 @@ def test_staged_allreduce_with_two_stages(tmp_path):
     assert [r[0] for r in res] == [["deform", "raster"], ["raster"], []]
     for step, (_, h, m, t) in enumerate(res):       # sum over ranks 1 and 2 of scale * (rank + 1) + step
         assert (h, m, t) == (1.0 * 3 + 2 * step, 2.0 * 3 + 2 * step, 3.0 * 3 + 2 * step)
+
+
+def test_balanced_view_schedule_is_an_epoch_of_equal_cost_groups():
+    import random
+    rnd = random.Random(0)
+    costs = [rnd.uniform(1.0, 2.0) for _ in range(96)]
+    sched = ddist.balanced_view_schedule(costs, 8)
+    assert len(sched) == 12 and all(len(g) == 8 for g in sched)
+    assert sorted(v for g in sched for v in g) == list(range(96))                    # every view once per epoch
+    spread = max(max(costs[v] for v in g) - min(costs[v] for v in g) for g in sched)
+    assert spread < 0.2 * (max(costs) - min(costs))                                   # the views of a step cost about the same
+    naive = max(max(costs[v] for v in range(s * 8, s * 8 + 8)) - min(costs[v] for v in range(s * 8, s * 8 + 8)) for s in range(12))
+    assert spread < 0.5 * naive
+    # 100 views on 8 ranks: the last group wraps around; still 8 per step
+    s100 = ddist.balanced_view_schedule([rnd.random() for _ in range(100)], 8)
+    assert len(s100) == 13 and all(len(g) == 8 for g in s100) and set(v for g in s100 for v in g) == set(range(100))
