@@ -1,4 +1,5 @@
 #!/bin/bash
+# 8-GPU configurations of DESIGN.md section 7 (gpurun --gpus 8).
 mkdir -p gpurun_out
 exec > gpurun_out/n8b.log 2>&1
 date
