@@ -11,6 +11,10 @@
 //     instead of the end of the tile list;
 //   * AABB backward, the transMat/normal/SH backward and the clearing of the gradient scratch are one
 //     per-surfel kernel; all outputs are fully written, so callers need no zero-fill.
+// Two blend kernels live here: blend_bwd_kernel (round 1: a warp visits one surfel per iteration; the description above) and
+// blend_bwd_lw_kernel (round 2, the default, option "lane_walk"): every lane walks its own list of prefilter hits — taken from
+// the hit masks the forward stored — writes one gradient row per (surfel, pixel) pair, and lanes then sum one (surfel, float4
+// of components) each and issue a 16-byte global reduction.  Same float operations per pair; see the comment at that kernel.
 #include "raster_common.cuh"
 
 namespace d2gs {
