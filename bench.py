@@ -876,7 +876,9 @@ def main():
         except Exception:
             pass
         out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                           "frac": achieved / hbm_peak, "traffic": traffic, "avg_launch_ms": avg_ms,
+                           "frac": achieved / hbm_peak, "traffic": traffic,
+                           "traffic_source": "profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture (profiles/ncu_r2.md), not measured in this run",
+                           "avg_launch_ms": avg_ms,
                            "algorithmic_bytes_per_launch": sb[dom], "peak_source": peak_src,
                            "frame": {"algorithmic_bytes": frame_bytes(P, R, HW, wl.use_deform),
                                      "achieved": frame_bytes(P, R, HW, wl.use_deform) / (ms / args.steps * 1e-3) / 1e9,
