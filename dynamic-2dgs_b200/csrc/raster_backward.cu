@@ -381,9 +381,6 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_MINBLOCKS) blend_bwd_ker
 #ifndef D2GS_BWD_LW_ROWS
 #define D2GS_BWD_LW_ROWS 64
 #endif
-#ifndef D2GS_BWD_LW_P3
-#define D2GS_BWD_LW_P3 5
-#endif
 constexpr int LW_ROWS = D2GS_BWD_LW_ROWS;      // gradient rows per warp (80 B each)
 constexpr int LW_ORD = 32;                      // survivors per chunk (one 32-bit hit mask per lane)
 constexpr size_t LWB_SMEM_Q = 2 * BWD_SMEM_Q1;
@@ -682,35 +679,6 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_LW_MINBLOCKS) blend_bwd_
           }
         }
         __syncwarp();
-#if D2GS_BWD_LW_P3 == 4
-        // ---- phase 3: every lane sums ONE (survivor, quarter row) over the survivor's rows — components 4g..4g+3 with one
-        // LDS.128 and component 16 + (g & 1) with one LDS.32 per row — and issues one 16-byte global reduction (plus a scalar one
-        // for g < 2): 4 lanes per survivor, up to 8 survivors per pass of the warp
-        for (int t = lane; t < 4 * ord; t += 32) {
-          const int o = t >> 2, gq = t & 3;
-          uint32_t hm, rj;
-          asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(hm), "=r"(rj) : "r"(meta_w + 8u * (uint32_t)o));
-          int nr = __popc(hm);
-          uint32_t ad = rows_w + (rj & 0xffffu) * (RED_STRIDE * 4) + 16u * (uint32_t)gq;
-          const uint32_t sgl = 64u + 4u * (uint32_t)(gq & 1) - 16u * (uint32_t)gq;     // offset of the single from `ad`
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          float acc1 = 0.f;
-          for (; nr >= 2; nr -= 2, ad += 2 * RED_STRIDE * 4) {
-            const float4 u = lds128(ad), v = lds128(ad + RED_STRIDE * 4);
-            const float u1 = lds32(ad + sgl), v1 = lds32(ad + sgl + RED_STRIDE * 4);
-            acc.x += u.x + v.x; acc.y += u.y + v.y; acc.z += u.z + v.z; acc.w += u.w + v.w;
-            acc1 += u1 + v1;
-          }
-          if (nr) {
-            const float4 u = lds128(ad);
-            acc1 += lds32(ad + sgl);
-            acc.x += u.x; acc.y += u.y; acc.z += u.z; acc.w += u.w;
-          }
-          float* dst = grad_rec + (size_t)cur_id[rj >> 16] * GRAD_REC_FLOATS;
-          if (acc.x != 0.f || acc.y != 0.f || acc.z != 0.f || acc.w != 0.f) atomicAdd(reinterpret_cast<float4*>(dst) + gq, acc);
-          if (gq < 2 && acc1 != 0.f) atomicAdd(dst + 16 + gq, acc1);
-        }
-#else
         // ---- phase 3: every lane sums ONE (survivor, group of 4 components) over the survivor's rows (LDS.128) and
         // issues one 16-byte global reduction: 5 lanes per survivor, ~6 survivors per pass of the warp
         for (int t = lane; t < 5 * ord; t += 32) {
@@ -732,7 +700,6 @@ __global__ void __launch_bounds__(BWD_THREADS, D2GS_BWD_LW_MINBLOCKS) blend_bwd_
           if (acc.x != 0.f || acc.y != 0.f || acc.z != 0.f || acc.w != 0.f)
             atomicAdd(reinterpret_cast<float4*>(grad_rec + (size_t)cur_id[rj >> 16] * GRAD_REC_FLOATS) + gq, acc);
         }
-#endif
         __syncwarp();     // rows and meta are rewritten by the next chunk
       }
       if (w >= BWD_WORDS) break;
