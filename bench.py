@@ -565,18 +565,15 @@ def main():
     # N > 1: every step waits for its slowest rank, so the `world` views of a step are chosen to cost the same (instance
     # count of the view, measured once at set-up; dist.balanced_view_schedule).  Each view is still visited once per epoch.
     schedule = None
-    if world > 1 and args.view_schedule == "balanced":
+    if world > 1 and args.view_schedule == "balanced" and args.impl == "ours":     # (the reference arm is single-GPU: plain order)
         from gaussian_renderer import render as _render_ours
         costs = []
         with torch.no_grad():
             for c in wl.cams:
-                if args.impl == "ours":
-                    d_ = wl.deform.step(wl.pc.get_xyz.detach(), wl.deform.deform.expand_time(c.fid), feature=wl.pc.feature,
-                                        motion_mask=wl.pc.motion_mask) if wl.use_deform else {"d_xyz": 0.0, "d_rotation": 0.0, "d_scaling": 0.0}
-                    o_ = _render_ours(c, wl.pc, wl.pipe, wl.bg, d_["d_xyz"], d_["d_rotation"], d_["d_scaling"])
-                    costs.append(int((o_["radii"].long() ** 2).sum()))          # ~ screen area of the surfels ~ instance count
-                else:
-                    costs.append(0)
+                d_ = wl.deform.step(wl.pc.get_xyz.detach(), wl.deform.deform.expand_time(c.fid), feature=wl.pc.feature,
+                                    motion_mask=wl.pc.motion_mask) if wl.use_deform else {"d_xyz": 0.0, "d_rotation": 0.0, "d_scaling": 0.0}
+                o_ = _render_ours(c, wl.pc, wl.pipe, wl.bg, d_["d_xyz"], d_["d_rotation"], d_["d_scaling"])
+                costs.append(int((o_["radii"].long() ** 2).sum()))          # ~ screen area of the surfels ~ instance count
         schedule = ddist.balanced_view_schedule(costs, world)
 
     def view_index(step):
@@ -842,11 +839,13 @@ def main():
                                   + (" + densification stats + Adam step of all parameters" if args.train else ""),
                       "loss": "seeded random-weighted sum over the render outputs + L1 (SURVEY 8(d))" if args.loss == "synthetic" else
                               "training loss of train_gui.py:292-313: L1 + D-SSIM(0.2) + normal(0.02) + distortion(1000)",
-                      "parallelism": f"view-sharded x{world}" + ((", views of a step balanced by instance count" if args.view_schedule == "balanced" else ", round-robin views") if world > 1 else ""),
+                      "parallelism": f"view-sharded x{world}",
                       "storage": ("surfel tables Morton-sorted once at set-up (d2gs_b200.layout.permute_surfels_, both arms)"
                                   if args.storage == "morton" else "surfel tables in generation (random) order"),
                       "l2_policy": "no explicit flush: per-step working set (params+grads+workspaces ~0.3 GB) exceeds the 126 MB L2 and the view changes every step"},
-           "execution": {"binning": ("reference extension: global radix sort, synchronous count readback" if args.impl == "reference" else
+           "execution": {"views": ("the views of one step (one per rank) are chosen to cost the same (dist.balanced_view_schedule); every view once per epoch"
+                                   if schedule is not None else "view (step * N + rank) mod 100"),
+                         "binning": ("reference extension: global radix sort, synchronous count readback" if args.impl == "reference" else
                                      ("global radix sort" if args.tile_sort == 0 else "per-tile buckets + per-tile sort") + ", " +
                                      ("synchronous count readback" if args.sync_count else "deferred count (no host synchronisation in the step)")),
                          "launch": ("one CUDA graph per step (captured through the public API)" if graphed else "eager launches") +
