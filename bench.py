@@ -473,9 +473,10 @@ def main():
     ap.add_argument("--tile-sort", type=int, default=None, choices=[0, 1],
                     help="binning: 1 = per-tile buckets + segmented sort, 0 = global radix sort (same lists); default: the library's")
     ap.add_argument("--no-clocks", action="store_true", help="diagnosis only: do not sample clocks during the timed region")
-    ap.add_argument("--view-schedule", choices=["balanced", "roundrobin"], default="balanced",
-                    help="N > 1 only: balanced = the views of one step (one per rank) are chosen to cost the same, so no rank waits for "
-                         "a slower one (every view still once per epoch); roundrobin = view (step * N + rank) mod 100")
+    ap.add_argument("--view-schedule", choices=["balanced", "roundrobin"], default="roundrobin",
+                    help="N > 1 only: roundrobin (default) = view (step * N + rank) mod 100, the same order as at N = 1; balanced = the views "
+                         "of one step (one per rank) are chosen to cost the same, so no rank waits for a slower one (every view still once "
+                         "per epoch; measured: 1.737 vs 1.749 ms at N = 8 — the views of this scene cost alike)")
     ap.add_argument("--storage", choices=["morton", "random"], default="morton",
                     help="storage order of the surfel tables (both arms): morton = sorted along a Morton curve once at set-up with "
                          "d2gs_b200.layout.permute_surfels_, as a trainer does after densification; random = as generated")
