@@ -552,7 +552,8 @@ def check_deferred_counts(device=None, wait: bool = True) -> None:
     if one of those frames overflowed its binning capacity.  For loops that only replay graphs — where no later
     rasterizer call would report it — call this after synchronising; an overflowed frame is NaN either way."""
     for key, track in list(_TRACK.items()):
-        if device is not None and key[0] != torch.device(device).index:
+        dev_index = key[1] if key[0] == "gs3d" else key[0]       # the gs3d side path shares the tracker under ("gs3d", device, P, W, H)
+        if device is not None and dev_index != torch.device(device).index:
             continue
         track.poll(key, block=wait)
         track.raise_if_overflowed()
