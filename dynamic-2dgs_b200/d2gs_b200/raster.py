@@ -551,9 +551,10 @@ def check_deferred_counts(device=None, wait: bool = True) -> None:
     """Fold in every outstanding asynchronous instance count (eager deferred frames and CUDA-graph replays) and raise
     if one of those frames overflowed its binning capacity.  For loops that only replay graphs — where no later
     rasterizer call would report it — call this after synchronising; an overflowed frame is NaN either way."""
+    want = None if device is None else torch.device(device).index        # "cuda" without an index = every device
     for key, track in list(_TRACK.items()):
         dev_index = key[1] if key[0] == "gs3d" else key[0]       # the gs3d side path shares the tracker under ("gs3d", device, P, W, H)
-        if device is not None and dev_index != torch.device(device).index:
+        if want is not None and dev_index != want:
             continue
         track.poll(key, block=wait)
         track.raise_if_overflowed()

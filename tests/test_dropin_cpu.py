@@ -159,3 +159,32 @@ def test_permute_surfels_reorders_parameters_state_and_buffers():
     assert torch.equal(m.other, before["other"])
     with pytest.raises(ValueError):
         layout.permute_surfels_(m, torch.zeros(P, dtype=torch.long))
+
+
+def test_deferred_count_check_filters_by_device_for_both_rasterizers():
+    """raster.check_deferred_counts(device): the surfel rasterizer tracks counts under (device, P, W, H), the depth/alpha
+    side rasterizer under ("gs3d", device, P, W, H) in the same table; a device filter must reach both, and "cuda"
+    without an index means every device."""
+    from d2gs_b200 import raster
+
+    class FakeTrack:
+        def __init__(self): self.polled = 0
+        def poll(self, key, block=True): self.polled += 1
+        def raise_if_overflowed(self): pass
+
+    saved = dict(raster._TRACK)
+    raster._TRACK.clear()
+    try:
+        keys = [(0, 10, 8, 8), (1, 10, 8, 8), ("gs3d", 0, 10, 8, 8), ("gs3d", 1, 10, 8, 8)]
+        for k in keys:
+            raster._TRACK[k] = FakeTrack()
+        raster.check_deferred_counts(torch.device("cuda", 0))
+        assert [raster._TRACK[k].polled for k in keys] == [1, 0, 1, 0]
+        raster.check_deferred_counts("cuda:1")
+        assert [raster._TRACK[k].polled for k in keys] == [1, 1, 1, 1]
+        raster.check_deferred_counts("cuda")
+        raster.check_deferred_counts(None)
+        assert [raster._TRACK[k].polled for k in keys] == [3, 3, 3, 3]
+    finally:
+        raster._TRACK.clear()
+        raster._TRACK.update(saved)
