@@ -87,3 +87,57 @@ def test_dropin_api_surface():
         r.forward(None, None, None, shs=1)
     with pytest.raises(Exception, match="scale/rotation pair"):
         r.forward(None, None, None, shs=1, scales=1, rotations=1, cov3D_precomp=1)
+
+
+_STRUCT_PAIRS = {
+    "D2gsConfig": "D2gsConfig", "D2gsRasterFwdArgs": "RasterFwdArgs", "D2gsRasterBwdArgs": "RasterBwdArgs",
+    "D2gsRasterState": "RasterState", "D2gsEpilogueArgs": "EpilogueArgs", "D2gsLossArgs": "LossArgs",
+    "D2gsAdamTensor": "AdamTensor", "D2gsMlpArgs": "MlpArgs", "D2gsDeformFwdArgs": "DeformFwdArgs",
+    "D2gsDeformBwdArgs": "DeformBwdArgs", "D2gsGs3dFwdArgs": "Gs3dFwdArgs", "D2gsGs3dBwdArgs": "Gs3dBwdArgs",
+    "D2gsGs3dState": "Gs3dState",
+}
+
+
+def _header_structs():
+    src = open(os.path.join(ROOT, "include", "d2gs.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    out = {}
+    for m in re.finditer(r"typedef struct (\w+) \{(.*?)\} \1;", src, flags=re.S):
+        names = []
+        for decl in m.group(2).split(";"):
+            for part in decl.strip().split(","):
+                nm = re.search(r"(\w+)\s*(\[\d+\])?$", part.strip())
+                if nm:
+                    names.append(nm.group(1))
+        out[m.group(1)] = names
+    return out
+
+
+def test_ctypes_mirrors_match_the_header_layout(tmp_path):
+    """The ctypes structures of d2gs_b200/_lib.py against include/d2gs.h as a C compiler lays it out: every struct the
+    header declares has a mirror, same field names in the same order, same offsets, same size (the header is plain C)."""
+    import shutil
+    import subprocess
+    structs = _header_structs()
+    assert sorted(structs) == sorted(_STRUCT_PAIRS), "a struct of include/d2gs.h has no ctypes mirror listed here"
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "d2gs.h"', "int main(void) {"]
+    for cname, fields in structs.items():
+        lines.append(f'  printf("{cname} . %zu\\n", sizeof({cname}));')
+        for f in fields:
+            lines.append(f'  printf("{cname} {f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    c_layout = {}
+    for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines():
+        s, f, v = line.split()
+        c_layout.setdefault(s, []).append((f, int(v)))
+    for cname, pyname in _STRUCT_PAIRS.items():
+        cls = getattr(_lib, pyname)
+        py = [(".", C.sizeof(cls))] + [(f[0], getattr(cls, f[0]).offset) for f in cls._fields_]
+        assert py == c_layout[cname], (cname, [(a, b) for a, b in zip(py, c_layout[cname]) if a != b][:4])
